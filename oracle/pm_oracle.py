@@ -1,0 +1,320 @@
+"""TEST INFRASTRUCTURE ONLY — CPU (numpy) restatement of CO*N*CEPT's particle-mesh
+gravity hot path.  It is the *checker* for the CUDA path; the product
+(concept_b200/) never imports it.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may use it.
+
+Parity status: PINNED.  Every function below is checked in
+tests/test_oracle_golden.py against tests/golden/*.npz, which hold outputs of the
+unmodified reference itself run in its pure-Python mode (tests/golden/gen_golden.py,
+oracle/ref_sandbox.py): final momenta after interactions.gravity('pm'|'p3m', …,
+'long-range') for NGP/CIC/TSC/PCS, differentiation orders 1,2,4,6,8 and 'fourier',
+interlacing, no-deconvolution, edge-positioned and clustered particles, plus taps
+of the density, potential and force grids, and Component.drift.
+
+All citations are file:line under /root/reference/src/.  Everything is float64
+like the reference (C2np['double'] everywhere, e.g. mesh.py:3794).
+"""
+import numpy as np
+
+MACHINE_EPS = float(np.finfo(np.float64).eps)  # commons.py:1814 machine_ϵ
+NGHOSTS_REF = 2  # commons.py:4411-4432 with default P(k) options; enters only through (1±ε) fudge
+
+
+# --------------------------------------------------------------------------
+# Coordinates and weights
+# --------------------------------------------------------------------------
+def grid_coords(pos, boxsize, gridsize, shift=(0.0, 0.0, 0.0), for_gather=False, nghosts=NGHOSTS_REF):
+    """Ghosted grid-unit coordinate of every particle, exactly as the reference
+    forms it (single domain, domain_bgn = 0, cell_centered = True).
+
+    deposit: mesh.py:1577-1606   offset = -(1+ε)(ng - ½ - shift)·h ; x = (pos - offset)·((1/h)(1-ε))
+    gather : mesh.py:405-432     same with +shift (sign of the lattice shift reversed)
+    Returns x[N,3] with  ng - ½ < x < G + ng - ½ .
+    """
+    pos = np.asarray(pos, dtype=np.float64)
+    cellsize = boxsize/gridsize
+    sgn = +1.0 if for_gather else -1.0
+    out = np.empty_like(pos)
+    scale = (1/cellsize)*(1 - MACHINE_EPS)
+    for d in range(3):
+        offset = 0.0 - (1 + MACHINE_EPS)*(nghosts - 0.5 + sgn*shift[d])*cellsize
+        out[:, d] = (pos[:, d] - offset)*scale
+    return out
+
+
+def weights_1d(x, order):
+    """Base index and the `order` weights along one axis.
+    NGP mesh.py:5305-5308, CIC :5319-5324, TSC :5338-5348, PCS :5365-5379.
+    x ≥ 0 always (ghosted frame) so int() == floor()."""
+    x = np.asarray(x, dtype=np.float64)
+    if order == 1:
+        index = (x + 0.5).astype(np.int64)
+        w = [np.ones_like(x)]
+    elif order == 2:
+        index = x.astype(np.int64)
+        dist = x - index
+        w = [1 - dist, dist]
+    elif order == 3:
+        index = (x + 0.5).astype(np.int64)
+        dist = x - index
+        index = index - 1
+        dist2 = dist**2
+        w0 = 0.125 + 0.5*(dist2 - dist)
+        w1 = 0.75 - dist2
+        w = [w0, w1, 1 - w0 - w1]
+    elif order == 4:
+        index = x.astype(np.int64) - 1
+        dist = x - index
+        tmp = 2 - dist
+        tmp2 = tmp**2
+        tmp3 = tmp*tmp2
+        w0 = 1./6.*tmp3
+        w2 = 2./3. - tmp2 + 0.5*tmp3
+        w3 = 1./6.*(dist - 1)**3
+        w = [w0, 1 - w0 - w2 - w3, w2, w3]
+    else:
+        raise ValueError(f'order = {order} ∉ {{1, 2, 3, 4}}')
+    return index, w
+
+
+# --------------------------------------------------------------------------
+# Deposit (a2) and gather (a12)
+# --------------------------------------------------------------------------
+def deposit(pos, boxsize, gridsize, order, contribution, shift=(0.0, 0.0, 0.0), nghosts=NGHOSTS_REF):
+    """interpolate_particles (mesh.py:1512-1636) + communicate_ghosts('+=')
+    (communication.py:563-660) on one rank == periodic wrap.  `contribution` is the
+    per-particle scalar  q·mass·(G/L)³·G⁻³  (mesh.py:1550-1573, 582).
+    Weight = (wx·contribution)·wy·wz  (mesh.py:5143-5154).  Returns rho[G,G,G]."""
+    G = int(gridsize)
+    x = grid_coords(pos, boxsize, G, shift, for_gather=False, nghosts=nghosts)
+    ix, wx = weights_1d(x[:, 0], order)
+    iy, wy = weights_1d(x[:, 1], order)
+    iz, wz = weights_1d(x[:, 2], order)
+    rho = np.zeros(G**3, dtype=np.float64)
+    for a in range(order):
+        ia = (ix + a - nghosts) % G
+        wa = wx[a]*contribution
+        for b in range(order):
+            ib = (iy + b - nghosts) % G
+            wab = wa*wy[b]
+            for c in range(order):
+                ic = (iz + c - nghosts) % G
+                rho += np.bincount((ia*G + ib)*G + ic, weights=wab*wz[c], minlength=G**3)
+    return rho.reshape(G, G, G)
+
+
+def gather(grid, pos, boxsize, order, shift=(0.0, 0.0, 0.0), nghosts=NGHOSTS_REF):
+    """interpolate_domaingrid_to_particles (mesh.py:376-459): value = Σ grid[cell]·w,
+    w = (wx·wy)·wz, accumulated in i,j,k-major order.  `grid` is ghost-free [G,G,G]."""
+    G = grid.shape[0]
+    x = grid_coords(pos, boxsize, G, shift, for_gather=True, nghosts=nghosts)
+    ix, wx = weights_1d(x[:, 0], order)
+    iy, wy = weights_1d(x[:, 1], order)
+    iz, wz = weights_1d(x[:, 2], order)
+    flat = grid.reshape(-1)
+    value = np.zeros(len(pos), dtype=np.float64)
+    for a in range(order):
+        ia = (ix + a - nghosts) % G
+        for b in range(order):
+            ib = (iy + b - nghosts) % G
+            wab = wx[a]*wy[b]
+            for c in range(order):
+                ic = (iz + c - nghosts) % G
+                value += flat[(ia*G + ib)*G + ic]*(wab*wz[c])
+    return value
+
+
+# --------------------------------------------------------------------------
+# k-space (a7, a8, a9, a10)
+# --------------------------------------------------------------------------
+def signed_wavenumbers(G):
+    k = np.arange(G)
+    return k - G*(k >= G//2)   # ki = i - G·[i ≥ G/2]; i = G/2 ↦ -G/2 (mesh.py:2720-2742)
+
+
+def mode_mask(G):
+    """True for modes visited by fourier_loop: all except the Nyquist planes ki = -G/2,
+    kj = -G/2, kk = +G/2 (mesh.py:2720-2742, 2833; nullify_modes 'nyquist' :3591-3622).
+    Natural rfftn layout [i, j, kk]."""
+    ki = signed_wavenumbers(G)
+    m1 = ki != -(G//2)
+    mk = np.arange(G//2 + 1) != G//2
+    return m1[:, None, None] & m1[None, :, None] & mk[None, None, :]
+
+
+def deconv_factor(G, deconv_order):
+    """[Π x_l/sin x_l]^D with x_l = k_l·π/G + ε (mesh.py:2775-2776, 2795-2798, 2848-2856),
+    in the reference's operation order ((xi·xj)·xk)/((si·sj)·sk) then **D."""
+    ki = signed_wavenumbers(G).astype(np.float64)
+    kk = np.arange(G//2 + 1, dtype=np.float64)
+    xi = ki*(np.pi/G) + MACHINE_EPS
+    xk = kk*(np.pi/G) + MACHINE_EPS
+    if not deconv_order:
+        return np.ones((G, G, G//2 + 1))
+    num = (xi[:, None, None]*xi[None, :, None])*xk[None, None, :]
+    den = (np.sin(xi)[:, None, None]*np.sin(xi)[None, :, None])*np.sin(xk)[None, None, :]
+    return (num/den)**deconv_order
+
+
+def k2_grid(G):
+    ki = signed_wavenumbers(G)
+    kk = np.arange(G//2 + 1)
+    return (ki[None, :, None]**2 + ki[:, None, None]**2) + kk[None, None, :]**2
+
+
+def potential_factor(G, boxsize, G_Newton, deconv_order, r_scale=0.0, n_lattices=1):
+    """Per-mode real factor applied in particle_mesh (interactions.py:2092-2118):
+    factor = deconv/n_lattices · (−L²·G_N/π)/k² [· exp(−k²(2π r_s/L)²)], origin and
+    Nyquist planes zero.  Natural layout [i, j, kk]."""
+    factor = deconv_factor(G, deconv_order)*(1/n_lattices)
+    k2 = k2_grid(G).astype(np.float64)
+    k2[0, 0, 0] = 1.0
+    pot = (-boxsize**2*G_Newton/np.pi)/k2
+    if r_scale:
+        pot = pot*np.exp(k2*(-(2*np.pi/boxsize*r_scale)**2))
+    factor = factor*pot
+    factor[0, 0, 0] = 0.0
+    factor[~mode_mask(G)] = 0.0
+    return factor
+
+
+def interlace_phase(G, shift):
+    """θ = −(2π/G)(ki·sx + kj·sy + kk·sz) (mesh.py:2873-2888); returns e^{iθ} [i,j,kk]."""
+    ki = signed_wavenumbers(G).astype(np.float64)
+    kk = np.arange(G//2 + 1, dtype=np.float64)
+    theta = ((ki*(-2*np.pi/G*shift[0]))[:, None, None] + (ki*(-2*np.pi/G*shift[1]))[None, :, None]) \
+        + (kk*(-2*np.pi/G*shift[2]))[None, None, :]
+    return np.cos(theta) + 1j*np.sin(theta)
+
+
+def forward_fft(rho):
+    """Unnormalised r2c (mesh.py:4078 np.fft.rfftn norm='backward'); natural layout."""
+    return np.fft.rfftn(rho)
+
+
+def backward_fft(slab, G):
+    """Unnormalised c2r (mesh.py:4131 irfftn norm='forward')."""
+    return np.fft.irfftn(slab, s=(G, G, G), axes=(0, 1, 2), norm='forward')
+
+
+def to_reference_slab_layout(slab_natural):
+    """[i, j, kk] complex → the reference's transposed, interleaved double layout
+    slab[j, i, 2·kk + {0: re, 1: im}] of shape (G, G, G+2) (fft.c:55-72; mesh.py:4081-4093)."""
+    t = np.ascontiguousarray(slab_natural.transpose(1, 0, 2))
+    return t.view(np.float64).reshape(t.shape[0], t.shape[1], 2*t.shape[2])
+
+
+# --------------------------------------------------------------------------
+# Finite differences (a11)
+# --------------------------------------------------------------------------
+FD_COEFFS = {  # mesh.py:4961-5015
+    2: [1/2],
+    4: [2/3, -1/12],
+    6: [3/4, -3/20, 1/60],
+    8: [4/5, -1/5, 4/105, -1/280],
+}
+
+
+def diff_grid(phi, dim, order, dx):
+    """diff_domaingrid (mesh.py:4874-5030), periodic.  order 1 = forward one-sided."""
+    if order == 1:
+        return (1/dx)*(np.roll(phi, -1, dim) - phi)
+    out = None
+    for n, c in enumerate(FD_COEFFS[order], start=1):
+        term = (abs(c)/dx)*(np.roll(phi, -n, dim) - np.roll(phi, n, dim))
+        if out is None:
+            out = term
+        else:
+            out = out + term if c > 0 else out - term
+    return out
+
+
+# --------------------------------------------------------------------------
+# One long-range PM kick (a16 orchestration of a2…a12)
+# --------------------------------------------------------------------------
+BCC_SHIFT = -0.5  # Lattice.shift_amount for cell-centred grids (mesh.py:85)
+
+
+def pm_kick(pos, mom, *, mass, boxsize, gridsize, order, G_Newton, dt_rho_over_dt1, dt_kick,
+            diff_order=2, deconvolve=True, interlace=False, r_scale=0.0, taps=None):
+    """interactions.gravity('pm'|'p3m', [c], [c], ᔑdt, 'long-range') for one particle
+    component (interactions.py:2854-2961 → particle_mesh :1985-2335).
+
+    dt_rho_over_dt1 = ᔑdt['a**(-3*w_eff-1)', name]/ᔑdt['1']   (mesh.py:1556)
+    dt_kick         = ᔑdt['a**(-3*w_eff)', name]              (interactions.py:2384-2387)
+    r_scale = shortrange_params['gravity']['scale'] for 'gravity long-range', else 0.
+    Returns the new momenta (pos unchanged)."""
+    G = int(gridsize)
+    pos = np.asarray(pos, dtype=np.float64)
+    mom = np.array(mom, dtype=np.float64, copy=True)
+    h = boxsize/G
+    # mesh.py:1556-1573: contribution = q·mass · factor·(G/L)³ with factor = G⁻³ (mesh.py:582)
+    contribution = dt_rho_over_dt1
+    contribution *= mass
+    contribution_factor = float(G)**(-3)*(G/boxsize)**3
+    contribution *= contribution_factor
+    shifts = [(0.0, 0.0, 0.0)] + ([(BCC_SHIFT,)*3] if interlace else [])
+    nl = len(shifts)
+    deconv_global = order*(2 if deconvolve else 0)   # interactions.py:2069-2080 (both promoted)
+    # Upstream: deposit each lattice, FFT, Nyquist-nullify, interlace-combine (mesh.py:598-616, 654-710)
+    slab = None
+    for n, s in enumerate(shifts):
+        rho = deposit(pos, boxsize, G, order, contribution, s)
+        if taps is not None:
+            taps['rho' if n == 0 else 'rho_shifted'] = rho
+        f = forward_fft(rho)
+        f[~mode_mask(G)] = 0
+        if nl > 1:
+            f = f*(1/nl)
+            if n > 0:
+                f = f*interlace_phase(G, s)
+        slab = f if slab is None else slab + f
+    slab = slab*potential_factor(G, boxsize, G_Newton, deconv_global, r_scale)
+    kick_factor = mass*(-dt_kick)
+    # Downstream: per sub-lattice (interactions.py:2214-2330)
+    for n, s in enumerate(shifts):
+        f = slab
+        if nl > 1:
+            f = f*(1/nl)
+            if n > 0:
+                f = f*interlace_phase(G, s)
+        if diff_order == 0:
+            # Fourier differentiation: ×i·(2π/L)·k_dim (mesh.py:3383-3392)
+            ki = signed_wavenumbers(G).astype(np.float64)
+            kvec = [ki[:, None, None], ki[None, :, None], np.arange(G//2 + 1, dtype=np.float64)[None, None, :]]
+            for dim in range(3):
+                force = backward_fft(1j*(2*np.pi/boxsize)*kvec[dim]*f, G)
+                if taps is not None:
+                    taps[f'forcegrid{dim}' + ('_shifted' if n else '')] = force
+                mom[:, dim] += gather(force, pos, boxsize, order, s)*kick_factor
+        else:
+            phi = backward_fft(f, G)
+            if taps is not None:
+                taps['phi' if n == 0 else 'phi_shifted'] = phi
+            for dim in range(3):
+                force = diff_grid(phi, dim, diff_order, h)
+                if taps is not None:
+                    taps[f'forcegrid{dim}' + ('_shifted' if n else '')] = force
+                mom[:, dim] += gather(force, pos, boxsize, order, s)*kick_factor
+    return mom
+
+
+# --------------------------------------------------------------------------
+# Drift (a13) and v_rms (a17)
+# --------------------------------------------------------------------------
+def drift(pos, mom, dt_over_mass, boxsize):
+    """Component.drift (species.py:2191-2196): pos ← mod(pos + mom·Δ, L), mod → [0, L) with
+    x == L ↦ 0 (commons.py:5102-5131)."""
+    x = np.mod(np.asarray(pos, dtype=np.float64) + np.asarray(mom, dtype=np.float64)*dt_over_mass, boxsize)
+    x[x == boxsize] = 0
+    return x
+
+
+def sum_mom2(mom):
+    """Σ mom² as in measure(component, 'v_rms') (analysis.py:3965-3972)."""
+    m = np.asarray(mom, dtype=np.float64).reshape(-1)
+    return float(np.dot(m, m))
+
+
+def v_rms(mom, N, a, mass, w_eff=0.0):
+    return np.sqrt(sum_mom2(mom)/N)/(a**(2 - 3*w_eff)*mass)
