@@ -1,0 +1,174 @@
+// pm_comm.cu — the exchange steps of the x-slab decomposition over NCCL (NVLink 5 / NVSwitch).
+//
+// Reference counterparts (file:line under the reference's src/):
+//   halo add / fill   communicate_ghosts(grid, '+=' | '=')   communication.py:563-660
+//   slab transpose    FFTW-MPI's internal all-to-all          fft.c:34-73, 240-257
+//   allreduce         analysis.py:3971, main.py:1202
+// One rank owns G/P consecutive x planes and, in Fourier space, G/P consecutive j rows; the
+// domain<->slab redistribution of mesh.py:2138-2411 does not exist in this layout.
+#include "pm_internal.cuh"
+
+namespace pm {
+
+template <typename T> struct NcclType;
+template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclDouble; };
+template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat; };
+
+// ---------------------------------------------------------------------------
+// halo planes
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) add_planes_kernel(T* __restrict__ dst, const T* __restrict__ src, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] += src[i];
+}
+
+constexpr int kDepositHalo = 2;  // PCS touches 2 planes beyond the slab on either side
+
+template <typename T>
+static int halo_add_t(pm_ctx* c) {
+    const Geom& g = c->g;
+    const size_t plane = (size_t)g.G * g.Gp;
+    const size_t cnt = plane * kDepositHalo;
+    T* base = reinterpret_cast<T*>(c->real);
+    T* lo_halo = base + (size_t)(g.halo - kDepositHalo) * plane;          // my planes x0-2 .. x0-1
+    T* hi_halo = base + (size_t)(g.halo + g.nxl) * plane;                 // my planes x0+nxl .. +1
+    T* first = base + (size_t)g.halo * plane;                             // interior, low end
+    T* last = base + (size_t)(g.halo + g.nxl - kDepositHalo) * plane;     // interior, high end
+    // staging: reuse the far halo planes that the deposit never touches? keep it simple: sendbuf
+    T* stage = reinterpret_cast<T*>(c->sendbuf);
+    const int next = (c->rank + 1) % c->nranks, prev = (c->rank + c->nranks - 1) % c->nranks;
+    PM_CHECK_NCCL(ncclGroupStart());
+    PM_CHECK_NCCL(ncclSend(hi_halo, cnt, NcclType<T>::v, next, c->comm, c->stream));
+    PM_CHECK_NCCL(ncclSend(lo_halo, cnt, NcclType<T>::v, prev, c->comm, c->stream));
+    PM_CHECK_NCCL(ncclRecv(stage, cnt, NcclType<T>::v, prev, c->comm, c->stream));        // prev's hi halo
+    PM_CHECK_NCCL(ncclRecv(stage + cnt, cnt, NcclType<T>::v, next, c->comm, c->stream));  // next's lo halo
+    PM_CHECK_NCCL(ncclGroupEnd());
+    PM_LAUNCH((add_planes_kernel<T>), kNumSMs * 4, 256, 0, c->stream, first, stage, cnt);
+    PM_LAUNCH((add_planes_kernel<T>), kNumSMs * 4, 256, 0, c->stream, last, stage + cnt, cnt);
+    return PM_OK;
+}
+
+int halo_add(pm_ctx* c) {
+    if (c->nranks == 1) return PM_OK;
+    PM_REQUIRE(c->comm_ready, "pm_halo_add: call pm_comm_init first");
+    PM_REQUIRE(c->g.nxl >= kDepositHalo, "slab thinner than the deposit halo");
+    return c->dtype == PM_GRID_F64 ? halo_add_t<double>(c) : halo_add_t<float>(c);
+}
+
+template <typename T>
+static int halo_fill_t(pm_ctx* c, int planes_lo, int planes_hi, int which) {
+    const Geom& g = c->g;
+    const size_t plane = (size_t)g.G * g.Gp;
+    T* base = reinterpret_cast<T*>(which == PM_TAP_FORCE ? c->force : c->real);
+    const int next = (c->rank + 1) % c->nranks, prev = (c->rank + c->nranks - 1) % c->nranks;
+    PM_CHECK_NCCL(ncclGroupStart());
+    // my first `planes_hi` interior planes become prev's high halo; my last `planes_lo` its next's low halo
+    PM_CHECK_NCCL(ncclSend(base + (size_t)g.halo * plane, plane * planes_hi, NcclType<T>::v, prev, c->comm, c->stream));
+    PM_CHECK_NCCL(ncclSend(base + (size_t)(g.halo + g.nxl - planes_lo) * plane, plane * planes_lo, NcclType<T>::v, next, c->comm, c->stream));
+    PM_CHECK_NCCL(ncclRecv(base + (size_t)(g.halo + g.nxl) * plane, plane * planes_hi, NcclType<T>::v, next, c->comm, c->stream));
+    PM_CHECK_NCCL(ncclRecv(base + (size_t)(g.halo - planes_lo) * plane, plane * planes_lo, NcclType<T>::v, prev, c->comm, c->stream));
+    PM_CHECK_NCCL(ncclGroupEnd());
+    return PM_OK;
+}
+
+int halo_fill(pm_ctx* c, int planes_lo, int planes_hi, int which) {
+    if (c->nranks == 1) return PM_OK;
+    PM_REQUIRE(c->comm_ready, "pm_halo_fill: call pm_comm_init first");
+    PM_REQUIRE(planes_lo <= c->g.halo && planes_hi <= c->g.halo && planes_lo <= c->g.nxl && planes_hi <= c->g.nxl,
+               "halo_fill: %d/%d planes exceed halo %d or slab %d", planes_lo, planes_hi, c->g.halo, c->g.nxl);
+    return c->dtype == PM_GRID_F64 ? halo_fill_t<double>(c, planes_lo, planes_hi, which)
+                                   : halo_fill_t<float>(c, planes_lo, planes_hi, which);
+}
+
+// ---------------------------------------------------------------------------
+// slab transpose
+// ---------------------------------------------------------------------------
+// 2-D spectra in the real buffer: complex [il][j][kk]  ->  send blocks [r][il][jl][kk], j = r·njl + jl
+template <typename C>
+__global__ void __launch_bounds__(256)
+pack_kernel(const C* __restrict__ src, C* __restrict__ dst, int nxl, int G, int Gc, int njl, bool unpack) {
+    const int64_t total = (int64_t)nxl * G * Gc;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int kk = (int)(idx % Gc);
+        const int j = (int)((idx / Gc) % G);
+        const int il = (int)(idx / ((int64_t)Gc * G));
+        const int r = j / njl, jl = j - r * njl;
+        const int64_t blk = (((int64_t)r * nxl + il) * njl + jl) * Gc + kk;
+        if (unpack) const_cast<C*>(src)[idx] = dst[blk];
+        else dst[blk] = src[idx];
+    }
+}
+
+template <typename T, typename C>
+static int transpose_t(pm_ctx* c, bool forward) {
+    const Geom& g = c->g;
+    const int P = c->nranks;
+    const size_t blk = (size_t)g.nxl * g.njl * g.Gc;   // complex elements per (src, dst) pair
+    C* spectra = reinterpret_cast<C*>(c->real_interior<T>());
+    C* stage = reinterpret_cast<C*>(c->sendbuf);
+    C* slab = reinterpret_cast<C*>(c->fourier);
+    if (forward) {
+        PM_LAUNCH((pack_kernel<C>), kNumSMs * 8, 256, 0, c->stream, spectra, stage, g.nxl, g.G, g.Gc, g.njl, false);
+    }
+    C* from = forward ? stage : slab;
+    C* to = forward ? slab : stage;
+    PM_CHECK_NCCL(ncclGroupStart());
+    for (int r = 0; r < P; ++r) {
+        if (r == c->rank) continue;
+        PM_CHECK_NCCL(ncclSend(from + r * blk, 2 * blk, NcclType<T>::v, r, c->comm, c->stream));
+        PM_CHECK_NCCL(ncclRecv(to + r * blk, 2 * blk, NcclType<T>::v, r, c->comm, c->stream));
+    }
+    PM_CHECK_NCCL(ncclGroupEnd());
+    PM_CHECK_CUDA(cudaMemcpyAsync(to + c->rank * blk, from + c->rank * blk, blk * sizeof(C),
+                                  cudaMemcpyDeviceToDevice, c->stream));
+    if (!forward) {
+        PM_LAUNCH((pack_kernel<C>), kNumSMs * 8, 256, 0, c->stream, spectra, stage, g.nxl, g.G, g.Gc, g.njl, true);
+    }
+    return PM_OK;
+}
+
+int transpose_forward(pm_ctx* c) {
+    PM_REQUIRE(c->comm_ready, "FFT transpose: call pm_comm_init first");
+    return c->dtype == PM_GRID_F64 ? transpose_t<double, double2>(c, true) : transpose_t<float, float2>(c, true);
+}
+
+int transpose_backward(pm_ctx* c) {
+    PM_REQUIRE(c->comm_ready, "FFT transpose: call pm_comm_init first");
+    return c->dtype == PM_GRID_F64 ? transpose_t<double, double2>(c, false) : transpose_t<float, float2>(c, false);
+}
+
+}  // namespace pm
+
+// ---------------------------------------------------------------------------
+// C ABI: communicator
+// ---------------------------------------------------------------------------
+extern "C" int pm_comm_unique_id(void* id_out_128) {
+    PM_REQUIRE(id_out_128 != nullptr, "pm_comm_unique_id: NULL");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    PM_CHECK_NCCL(ncclGetUniqueId(&id));
+    memcpy(id_out_128, &id, sizeof(id));
+    return PM_OK;
+}
+
+extern "C" int pm_comm_init(pm_ctx* c, const void* id_128) {
+    PM_REQUIRE(c && id_128, "pm_comm_init: NULL argument");
+    if (c->nranks == 1) return PM_OK;
+    PM_REQUIRE(!c->comm_ready, "pm_comm_init: communicator already initialised");
+    ncclUniqueId id;
+    memcpy(&id, id_128, sizeof(id));
+    PM_CHECK_CUDA(cudaSetDevice(c->device));
+    PM_CHECK_NCCL(ncclCommInitRank(&c->comm, c->nranks, id, c->rank));
+    c->comm_ready = true;
+    return PM_OK;
+}
+
+extern "C" int pm_allreduce_sum(pm_ctx* c, double* dev_values, int n) {
+    PM_REQUIRE(c && dev_values && n >= 0, "pm_allreduce_sum: bad argument");
+    if (c->nranks == 1 || n == 0) return PM_OK;
+    PM_REQUIRE(c->comm_ready, "pm_allreduce_sum: call pm_comm_init first");
+    PM_CHECK_NCCL(ncclAllReduce(dev_values, dev_values, n, ncclDouble, ncclSum, c->comm, c->stream));
+    return PM_OK;
+}

@@ -1,0 +1,172 @@
+// pm_internal.cuh — shared definitions for libpmgrav.so (sm_100a only).
+// Not part of the public ABI (that is include/pmgrav.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <nccl.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "pmgrav.h"
+
+namespace pm {
+
+// machine_ϵ and the reference's ghost count that enters the (1±ε) coordinate fudge
+// (reference mesh.py:1577-1606, commons.py:1814, :4411-4432)
+constexpr double kEps = 2.220446049250313e-16;
+constexpr int kNghostsRef = 2;
+constexpr int kNumSMs = 148;  // B200
+// x-halo planes kept on each side of a slab when nranks > 1:
+// PCS reach (2) + 8th-order difference reach (4)
+constexpr int kHalo = 6;
+
+extern std::atomic<int64_t> g_launches;
+void set_error(const char* fmt, ...);
+
+#define PM_CHECK_CUDA(expr)                                                         \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            pm::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__,            \
+                          cudaGetErrorName(_e), cudaGetErrorString(_e));            \
+            return PM_ERR_CUDA;                                                     \
+        }                                                                           \
+    } while (0)
+
+#define PM_CHECK_CUFFT(expr)                                                        \
+    do {                                                                            \
+        cufftResult _e = (expr);                                                    \
+        if (_e != CUFFT_SUCCESS) {                                                  \
+            pm::set_error("%s:%d cuFFT error %d", __FILE__, __LINE__, (int)_e);     \
+            return PM_ERR_CUDA;                                                     \
+        }                                                                           \
+    } while (0)
+
+#define PM_CHECK_NCCL(expr)                                                         \
+    do {                                                                            \
+        ncclResult_t _e = (expr);                                                   \
+        if (_e != ncclSuccess) {                                                    \
+            pm::set_error("%s:%d NCCL error %s", __FILE__, __LINE__,                \
+                          ncclGetErrorString(_e));                                  \
+            return PM_ERR_COMM;                                                     \
+        }                                                                           \
+    } while (0)
+
+#define PM_REQUIRE(cond, ...)                                                       \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            pm::set_error(__VA_ARGS__);                                             \
+            return PM_ERR_ARG;                                                      \
+        }                                                                           \
+    } while (0)
+
+#define PM_TRY(expr)                                                                \
+    do {                                                                            \
+        int _s = (expr);                                                            \
+        if (_s != PM_OK) return _s;                                                 \
+    } while (0)
+
+// Count + launch + check.  Every kernel of this library goes through here.
+#define PM_LAUNCH(kernel, grid, block, smem, stream, ...)                           \
+    do {                                                                            \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                 \
+        pm::g_launches.fetch_add(1, std::memory_order_relaxed);                     \
+        PM_CHECK_CUDA(cudaGetLastError());                                          \
+    } while (0)
+
+// Geometry of the local slab, passed by value to kernels
+struct Geom {
+    int G;        // global cells per side
+    int Gp;       // padded z length of the real grid: 2*(G/2+1)
+    int Gc;       // complex z length: G/2+1
+    int nxl;      // local x planes
+    int x0;       // global index of first local plane
+    int halo;     // halo planes on each side in x (0 when nranks == 1)
+    int wrap_x;   // 1: x wraps periodically in-kernel (nranks == 1)
+    int njl;      // local j rows of the Fourier slab
+    int j0;       // global index of first local j row
+};
+
+}  // namespace pm
+
+struct pm_ctx {
+    pm::Geom g;
+    double boxsize;
+    int dtype;      // PM_GRID_F64 / PM_GRID_F32
+    int rank, nranks, device;
+    cudaStream_t stream;
+    bool own_stream;
+    // buffers
+    void* real;       // [(nxl+2*halo)][G][Gp] of T ; the interior doubles as the in-place FFT slab
+    void* fourier;    // == interior of `real` when nranks == 1, else separate [G][njl][Gc] complex
+    void* saved;      // lazily allocated copy of the Fourier slab
+    void* force;      // lazily allocated scratch force grid, same shape as `real`
+    void* sendbuf;    // nranks > 1: packed transpose blocks
+    void* fft_work;   // shared cuFFT work area
+    size_t fft_work_bytes;
+    size_t real_elems;     // elements of T in `real`
+    size_t fourier_elems;  // complex elements in the Fourier slab
+    // k-space tables (device): x_l and sin(x_l) for l over signed wavenumbers / kk
+    double* tab_x;     // [G]   x(k_signed(i)) = k·π/G + ε
+    double* tab_sin;   // [G]
+    // cuFFT
+    cufftHandle plan_fwd, plan_bwd;        // nranks == 1: 3-D ; else batched 2-D
+    cufftHandle plan_x;                    // nranks > 1: strided 1-D c2c along i
+    bool plans_ready;
+    // NCCL
+    ncclComm_t comm;
+    bool comm_ready;
+    // scratch for reductions / exchange
+    double* d_scratch;        // small device scratch (>= 64 doubles)
+    int64_t* d_counts;        // exchange counters
+    void* xchg_buf;           // staging for migrating particles
+    size_t xchg_bytes;
+    int64_t bytes_allocated;
+    // state flags
+    bool space_fourier;       // working slab currently holds Fourier data
+
+    size_t elem_size() const { return dtype == PM_GRID_F64 ? 8 : 4; }
+    template <typename T> T* real_interior() const {
+        return reinterpret_cast<T*>(real) + (size_t)g.halo * g.G * g.Gp;
+    }
+};
+
+namespace pm {
+
+// implemented in pm_mesh.cu
+int launch_deposit(pm_ctx* c, const double* pos, int64_t n, int order, double contribution,
+                   const double* shift);
+int launch_gather(pm_ctx* c, int which, const double* pos, double* mom, int64_t n, int order,
+                  int dim, double factor, const double* shift);
+int launch_gather_kick(pm_ctx* c, const double* pos, double* mom, int64_t n, int order,
+                       int diff_order, double factor, const double* shift, double* sum_mom2);
+int launch_diff(pm_ctx* c, int dim, int order);
+int launch_halo_wrap_add(pm_ctx* c);   // single-rank no-op; multi-rank local part of halo add
+// implemented in pm_fourier.cu
+int make_plans(pm_ctx* c);
+void destroy_plans(pm_ctx* c);
+int fft_forward(pm_ctx* c);
+int fft_backward(pm_ctx* c);
+int launch_kspace(pm_ctx* c, double prefactor, int deconv_order, double gauss, double scale,
+                  const double* shift, int diff_dim, bool from_saved, bool potential);
+int slab_copy(pm_ctx* c, int mode);  // 0 save, 1 accumulate, 2 restore
+// implemented in pm_particles.cu
+int launch_drift(pm_ctx* c, double* pos, const double* mom, int64_t n, double dt_over_mass);
+int launch_sum_mom2(pm_ctx* c, const double* mom, int64_t n, double* out);
+int exchange_particles(pm_ctx* c, double* pos, double* mom, int64_t* ids, int64_t* n_inout,
+                       int64_t capacity);
+// implemented in pm_comm.cu
+int halo_add(pm_ctx* c);
+int halo_fill(pm_ctx* c, int planes_lo, int planes_hi, int which);
+int transpose_forward(pm_ctx* c);   // real-buffer 2-D spectra -> Fourier slab (all-to-all)
+int transpose_backward(pm_ctx* c);
+
+int ensure_saved(pm_ctx* c);
+int ensure_force(pm_ctx* c);
+
+}  // namespace pm

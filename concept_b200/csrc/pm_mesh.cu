@@ -1,0 +1,479 @@
+// pm_mesh.cu — particle <-> mesh kernels: mass deposit, finite-difference gradient,
+// force gather + kick.  sm_100a, HBM/L2-bound scatter/gather work: no tensor cores.
+//
+// Reference semantics (file:line under the reference's src/):
+//   coordinates   mesh.py:1577-1606 (deposit), :405-432 (gather; lattice shift sign flipped)
+//   weights       mesh.py:5305-5379 (set_weights_NGP/CIC/TSC/PCS)
+//   3-D weight    mesh.py:5138-5155: (wx·multiplier)·wy·wz
+//   deposit       mesh.py:1596-1632   grid[index] += contribution_weighted
+//   FD gradient   mesh.py:4961-5015   (coefficients (c/Δx) formed on the host exactly as there)
+//   gather/kick   mesh.py:427-459; interactions.py:2384-2387
+#include "pm_internal.cuh"
+
+#include <algorithm>
+
+namespace pm {
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+struct Coord {
+    double off[3];   // offset_x/y/z of the reference
+    double scale;    // (1/cellsize)*(1 - machine_ϵ)
+};
+
+static Coord make_coord(const pm_ctx* c, const double* shift, bool for_gather) {
+    // mesh.py:1577-1589 / :405-420 with domain_bgn = 0, cell_centered = True
+    Coord k;
+    const double cellsize = c->boxsize / c->g.G;
+    const double sgn = for_gather ? +1.0 : -1.0;
+    for (int d = 0; d < 3; ++d) {
+        const double s = shift ? shift[d] : 0.0;
+        k.off[d] = 0.0 - (1 + kEps) * (kNghostsRef - 0.5 + sgn * s) * cellsize;
+    }
+    k.scale = (1 / cellsize) * (1 - kEps);
+    return k;
+}
+
+// 1-D weights; returns the (ghost-free, unwrapped) index of the first cell.
+template <int ORDER>
+__device__ __forceinline__ int weights_1d(double x, double (&w)[ORDER]) {
+    int index;
+    if constexpr (ORDER == 1) {
+        index = (int)(x + 0.5);
+        w[0] = 1.0;
+    } else if constexpr (ORDER == 2) {
+        index = (int)x;
+        const double dist = x - index;
+        w[0] = 1 - dist;
+        w[1] = dist;
+    } else if constexpr (ORDER == 3) {
+        index = (int)(x + 0.5);
+        const double dist = x - index;
+        index -= 1;
+        const double dist2 = dist * dist;
+        const double w0 = 0.125 + 0.5 * (dist2 - dist);
+        const double w1 = 0.75 - dist2;
+        w[0] = w0;
+        w[1] = w1;
+        w[2] = 1 - w0 - w1;
+    } else {
+        index = (int)x;
+        index -= 1;
+        const double dist = x - index;
+        const double tmp = 2 - dist;
+        const double tmp2 = tmp * tmp;
+        const double tmp3 = tmp * tmp2;
+        const double w0 = 1. / 6. * tmp3;
+        const double w2 = 2. / 3. - tmp2 + 0.5 * tmp3;
+        const double dm1 = dist - 1;
+        const double w3 = 1. / 6. * (dm1 * dm1 * dm1);
+        w[0] = w0;
+        w[1] = 1 - w0 - w2 - w3;
+        w[2] = w2;
+        w[3] = w3;
+    }
+    return index - kNghostsRef;
+}
+
+__device__ __forceinline__ int wrap(int i, int G) {
+    // |i| excursions are at most a handful of cells beyond [0, G)
+    if (i < 0) i += G;
+    else if (i >= G) i -= G;
+    return i;
+}
+
+// x plane of the local buffer for global (unwrapped) plane index i, or -1 if outside
+__device__ __forceinline__ int local_plane(int i, const Geom& g) {
+    if (g.wrap_x) return wrap(i, g.G);
+    const int l = i - g.x0 + g.halo;
+    return (l >= 0 && l < g.nxl + 2 * g.halo) ? l : -1;
+}
+
+// Coalesced 128-bit staging of BLOCK particles (AoS double[3]) through shared memory.
+template <int BLOCK>
+__device__ __forceinline__ void stage_particles(const double* __restrict__ src, int64_t first,
+                                                int count, double* s) {
+    const double* p = src + first * 3;
+    const int nd = count * 3;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const double2* p2 = reinterpret_cast<const double2*>(p);
+        double2* s2 = reinterpret_cast<double2*>(s);
+        const int n2 = nd >> 1;
+        for (int t = threadIdx.x; t < n2; t += BLOCK) s2[t] = __ldg(p2 + t);
+        if ((nd & 1) && threadIdx.x == 0) s[nd - 1] = __ldg(p + nd - 1);
+    } else {
+        for (int t = threadIdx.x; t < nd; t += BLOCK) s[t] = __ldg(p + t);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// deposit
+// ---------------------------------------------------------------------------
+constexpr int kDepBlock = 256;
+
+template <int ORDER, typename T>
+__global__ void __launch_bounds__(kDepBlock)
+deposit_kernel(const double* __restrict__ pos, int64_t n, T* __restrict__ grid, Geom g, Coord co,
+               double contribution) {
+    __shared__ __align__(16) double spos[kDepBlock * 3];
+    const int64_t ntiles = (n + kDepBlock - 1) / kDepBlock;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t first = tile * kDepBlock;
+        const int count = (int)min((int64_t)kDepBlock, n - first);
+        __syncthreads();
+        stage_particles<kDepBlock>(pos, first, count, spos);
+        __syncthreads();
+        if ((int)threadIdx.x >= count) continue;
+        const double x = (spos[threadIdx.x * 3 + 0] - co.off[0]) * co.scale;
+        const double y = (spos[threadIdx.x * 3 + 1] - co.off[1]) * co.scale;
+        const double z = (spos[threadIdx.x * 3 + 2] - co.off[2]) * co.scale;
+        double wx[ORDER], wy[ORDER], wz[ORDER];
+        const int ix = weights_1d<ORDER>(x, wx);
+        const int iy = weights_1d<ORDER>(y, wy);
+        const int iz = weights_1d<ORDER>(z, wz);
+        int jy[ORDER], kz[ORDER];
+#pragma unroll
+        for (int b = 0; b < ORDER; ++b) {
+            jy[b] = wrap(iy + b, g.G) * g.Gp;
+            kz[b] = wrap(iz + b, g.G);
+        }
+#pragma unroll
+        for (int a = 0; a < ORDER; ++a) {
+            const int lx = local_plane(ix + a, g);
+            if (lx < 0) continue;
+            const double wa = wx[a] * contribution;
+            T* plane = grid + (size_t)lx * g.G * g.Gp;
+#pragma unroll
+            for (int b = 0; b < ORDER; ++b) {
+                const double wab = wa * wy[b];
+                T* row = plane + jy[b];
+#pragma unroll
+                for (int cc = 0; cc < ORDER; ++cc) {
+                    atomicAdd(row + kz[cc], (T)(wab * wz[cc]));
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+static int deposit_dispatch(pm_ctx* c, const double* pos, int64_t n, int order, double contribution,
+                            const Coord& co) {
+    const int64_t ntiles = (n + kDepBlock - 1) / kDepBlock;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * 16);
+    T* gptr = reinterpret_cast<T*>(c->real);
+    switch (order) {
+        case 1: PM_LAUNCH((deposit_kernel<1, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution); break;
+        case 2: PM_LAUNCH((deposit_kernel<2, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution); break;
+        case 3: PM_LAUNCH((deposit_kernel<3, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution); break;
+        case 4: PM_LAUNCH((deposit_kernel<4, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution); break;
+    }
+    return PM_OK;
+}
+
+int launch_deposit(pm_ctx* c, const double* pos, int64_t n, int order, double contribution,
+                   const double* shift) {
+    PM_REQUIRE(order >= 1 && order <= 4,
+               "pm_deposit called with order = %d not in {1 (NGP), 2 (CIC), 3 (TSC), 4 (PCS)}", order);
+    if (n == 0) return PM_OK;
+    const Coord co = make_coord(c, shift, false);
+    return c->dtype == PM_GRID_F64 ? deposit_dispatch<double>(c, pos, n, order, contribution, co)
+                                   : deposit_dispatch<float>(c, pos, n, order, contribution, co);
+}
+
+// ---------------------------------------------------------------------------
+// finite differences
+// ---------------------------------------------------------------------------
+struct FD {
+    int reach;        // neighbours used on each side
+    int forward;      // order 1: (φ[+1] - φ[0])/Δx
+    double c[4];      // |coefficient|/Δx ; signs alternate + - + -
+};
+
+static int make_fd(int order, double dx, FD* fd) {
+    // mesh.py:4961-5015; coefficients formed as (c)/Δx like the ℝ[...] constants there
+    fd->forward = 0;
+    for (double& v : fd->c) v = 0;
+    switch (order) {
+        case 1: fd->reach = 1; fd->forward = 1; fd->c[0] = 1 / dx; break;
+        case 2: fd->reach = 1; fd->c[0] = (1. / 2) / dx; break;
+        case 4: fd->reach = 2; fd->c[0] = (2. / 3) / dx; fd->c[1] = (1. / 12) / dx; break;
+        case 6: fd->reach = 3; fd->c[0] = (3. / 4) / dx; fd->c[1] = (3. / 20) / dx; fd->c[2] = (1. / 60) / dx; break;
+        case 8: fd->reach = 4; fd->c[0] = (4. / 5) / dx; fd->c[1] = (1. / 5) / dx; fd->c[2] = (4. / 105) / dx; fd->c[3] = (1. / 280) / dx; break;
+        default:
+            set_error("diff order = %d not in {1, 2, 4, 6, 8}", order);
+            return PM_ERR_ARG;
+    }
+    return PM_OK;
+}
+
+// Combine the ±n differences exactly in the reference's association:
+//   order 2:  c0*(u1-l1)
+//   order 4:  + c0*(u1-l1) - c1*(u2-l2)
+//   order 6:  c0*(u1-l1) - c1*(u2-l2) + c2*(u3-l3)
+//   order 8:  c0*(u1-l1) - c1*(u2-l2) + c2*(u3-l3) - c3*(u4-l4)
+template <int REACH>
+__device__ __forceinline__ double fd_combine(const double (&d)[REACH], const FD& fd) {
+    double v = fd.c[0] * d[0];
+    if constexpr (REACH >= 2) v = v - fd.c[1] * d[1];
+    if constexpr (REACH >= 3) v = v + fd.c[2] * d[2];
+    if constexpr (REACH >= 4) v = v - fd.c[3] * d[3];
+    return v;
+}
+
+// Explicit force grid (parity tap and the un-fused path): interior planes only.
+template <int REACH, typename T>
+__global__ void __launch_bounds__(256)
+diff_kernel(const T* __restrict__ phi, T* __restrict__ out, Geom g, FD fd, int dim) {
+    const int64_t total = (int64_t)g.nxl * g.G * g.G;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % g.G);
+        const int j = (int)((idx / g.G) % g.G);
+        const int il = (int)(idx / ((int64_t)g.G * g.G));
+        const int i = g.x0 + il;
+        double d[REACH];
+#pragma unroll
+        for (int m = 1; m <= REACH; ++m) {
+            int iu = i, ju = j, ku = k, idn = i, jd = j, kd = k;
+            if (dim == 0) { iu += m; idn -= fd.forward ? 0 : m; }
+            if (dim == 1) { ju = wrap(j + m, g.G); jd = fd.forward ? j : wrap(j - m, g.G); }
+            if (dim == 2) { ku = wrap(k + m, g.G); kd = fd.forward ? k : wrap(k - m, g.G); }
+            const int lu = local_plane(iu, g), ld = local_plane(idn, g);
+            const double up = (double)phi[((size_t)lu * g.G + ju) * g.Gp + ku];
+            const double lo = (double)phi[((size_t)ld * g.G + jd) * g.Gp + kd];
+            d[m - 1] = up - lo;
+        }
+        const int lc = local_plane(i, g);
+        out[((size_t)lc * g.G + j) * g.Gp + k] = (T)fd_combine<REACH>(d, fd);
+    }
+}
+
+int launch_diff(pm_ctx* c, int dim, int order) {
+    PM_REQUIRE(dim >= 0 && dim < 3, "pm_diff called with dim = %d not in {0, 1, 2}", dim);
+    FD fd;
+    PM_TRY(make_fd(order, c->boxsize / c->g.G, &fd));
+    PM_TRY(ensure_force(c));
+    const int grid = kNumSMs * 8;
+#define PM_DIFF_CASE(R, T)                                                                       \
+    PM_LAUNCH((diff_kernel<R, T>), grid, 256, 0, c->stream, reinterpret_cast<const T*>(c->real), \
+              reinterpret_cast<T*>(c->force), c->g, fd, dim)
+    if (c->dtype == PM_GRID_F64) {
+        switch (fd.reach) {
+            case 1: PM_DIFF_CASE(1, double); break;
+            case 2: PM_DIFF_CASE(2, double); break;
+            case 3: PM_DIFF_CASE(3, double); break;
+            case 4: PM_DIFF_CASE(4, double); break;
+        }
+    } else {
+        switch (fd.reach) {
+            case 1: PM_DIFF_CASE(1, float); break;
+            case 2: PM_DIFF_CASE(2, float); break;
+            case 3: PM_DIFF_CASE(3, float); break;
+            case 4: PM_DIFF_CASE(4, float); break;
+        }
+    }
+#undef PM_DIFF_CASE
+    return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// gather from an explicit grid (one dimension)
+// ---------------------------------------------------------------------------
+constexpr int kGatBlock = 256;
+
+template <int ORDER, typename T>
+__global__ void __launch_bounds__(kGatBlock)
+gather_kernel(const T* __restrict__ grid, const double* __restrict__ pos, double* __restrict__ mom,
+              int64_t n, Geom g, Coord co, int dim, double factor) {
+    __shared__ __align__(16) double spos[kGatBlock * 3];
+    const int64_t ntiles = (n + kGatBlock - 1) / kGatBlock;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t first = tile * kGatBlock;
+        const int count = (int)min((int64_t)kGatBlock, n - first);
+        __syncthreads();
+        stage_particles<kGatBlock>(pos, first, count, spos);
+        __syncthreads();
+        if ((int)threadIdx.x >= count) continue;
+        const double x = (spos[threadIdx.x * 3 + 0] - co.off[0]) * co.scale;
+        const double y = (spos[threadIdx.x * 3 + 1] - co.off[1]) * co.scale;
+        const double z = (spos[threadIdx.x * 3 + 2] - co.off[2]) * co.scale;
+        double wx[ORDER], wy[ORDER], wz[ORDER];
+        const int ix = weights_1d<ORDER>(x, wx);
+        const int iy = weights_1d<ORDER>(y, wy);
+        const int iz = weights_1d<ORDER>(z, wz);
+        double value = 0;
+#pragma unroll
+        for (int a = 0; a < ORDER; ++a) {
+            const int lx = local_plane(ix + a, g);
+            if (lx < 0) continue;
+#pragma unroll
+            for (int b = 0; b < ORDER; ++b) {
+                const double wab = wx[a] * wy[b];
+                const T* row = grid + ((size_t)lx * g.G + wrap(iy + b, g.G)) * g.Gp;
+#pragma unroll
+                for (int cc = 0; cc < ORDER; ++cc) {
+                    value += (double)row[wrap(iz + cc, g.G)] * (wab * wz[cc]);
+                }
+            }
+        }
+        if (factor != 1) value *= factor;
+        mom[(first + threadIdx.x) * 3 + dim] += value;
+    }
+}
+
+int launch_gather(pm_ctx* c, int which, const double* pos, double* mom, int64_t n, int order,
+                  int dim, double factor, const double* shift) {
+    PM_REQUIRE(order >= 1 && order <= 4, "pm_gather called with order = %d not in {1, 2, 3, 4}", order);
+    PM_REQUIRE(dim >= 0 && dim < 3, "pm_gather called with dim = %d not in {0, 1, 2}", dim);
+    PM_REQUIRE(which == PM_TAP_REAL || which == PM_TAP_FORCE, "pm_gather: which = %d", which);
+    if (which == PM_TAP_FORCE) PM_REQUIRE(c->force != nullptr, "pm_gather: no force grid (call pm_diff first)");
+    if (n == 0) return PM_OK;
+    const Coord co = make_coord(c, shift, true);
+    const int64_t ntiles = (n + kGatBlock - 1) / kGatBlock;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * 16);
+    const void* src = which == PM_TAP_REAL ? c->real : c->force;
+#define PM_GATHER_CASE(O, T)                                                                           \
+    PM_LAUNCH((gather_kernel<O, T>), grid, kGatBlock, 0, c->stream, reinterpret_cast<const T*>(src),  \
+              pos, mom, n, c->g, co, dim, factor)
+    if (c->dtype == PM_GRID_F64) {
+        switch (order) {
+            case 1: PM_GATHER_CASE(1, double); break;
+            case 2: PM_GATHER_CASE(2, double); break;
+            case 3: PM_GATHER_CASE(3, double); break;
+            case 4: PM_GATHER_CASE(4, double); break;
+        }
+    } else {
+        switch (order) {
+            case 1: PM_GATHER_CASE(1, float); break;
+            case 2: PM_GATHER_CASE(2, float); break;
+            case 3: PM_GATHER_CASE(3, float); break;
+            case 4: PM_GATHER_CASE(4, float); break;
+        }
+    }
+#undef PM_GATHER_CASE
+    return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fused gradient + gather + kick (+ Σ mom²)
+// ---------------------------------------------------------------------------
+template <int ORDER, int REACH, typename T>
+__global__ void __launch_bounds__(kGatBlock)
+gather_kick_kernel(const T* __restrict__ phi, const double* __restrict__ pos,
+                   double* __restrict__ mom, int64_t n, Geom g, Coord co, FD fd, double factor,
+                   double* __restrict__ sum_mom2) {
+    __shared__ __align__(16) double spos[kGatBlock * 3];
+    __shared__ double sred[kGatBlock / 32];
+    constexpr int W = ORDER + 2 * REACH;   // cells touched per axis
+    double mom2_acc = 0;
+    const int64_t ntiles = (n + kGatBlock - 1) / kGatBlock;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t first = tile * kGatBlock;
+        const int count = (int)min((int64_t)kGatBlock, n - first);
+        __syncthreads();
+        stage_particles<kGatBlock>(pos, first, count, spos);
+        __syncthreads();
+        if ((int)threadIdx.x >= count) continue;
+        const double x = (spos[threadIdx.x * 3 + 0] - co.off[0]) * co.scale;
+        const double y = (spos[threadIdx.x * 3 + 1] - co.off[1]) * co.scale;
+        const double z = (spos[threadIdx.x * 3 + 2] - co.off[2]) * co.scale;
+        double wx[ORDER], wy[ORDER], wz[ORDER];
+        const int ix = weights_1d<ORDER>(x, wx);
+        const int iy = weights_1d<ORDER>(y, wy);
+        const int iz = weights_1d<ORDER>(z, wz);
+        // element offsets of the W cells along each axis (pre-multiplied by strides)
+        size_t ox[W];
+        int oy[W], oz[W];
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const int lx = local_plane(ix + t - REACH, g);
+            ox[t] = (size_t)(lx < 0 ? 0 : lx) * g.G * g.Gp;
+            oy[t] = wrap(iy + t - REACH, g.G) * g.Gp;
+            oz[t] = wrap(iz + t - REACH, g.G);
+        }
+        double vx = 0, vy = 0, vz = 0;
+#pragma unroll
+        for (int a = 0; a < ORDER; ++a) {
+#pragma unroll
+            for (int b = 0; b < ORDER; ++b) {
+                const double wab = wx[a] * wy[b];
+#pragma unroll
+                for (int cc = 0; cc < ORDER; ++cc) {
+                    const double w = wab * wz[cc];
+                    const int A = a + REACH, B = b + REACH, C = cc + REACH;
+                    double dx_[REACH], dy_[REACH], dz_[REACH];
+#pragma unroll
+                    for (int m = 1; m <= REACH; ++m) {
+                        const int lo = fd.forward ? 0 : m;
+                        dx_[m - 1] = (double)phi[ox[A + m] + oy[B] + oz[C]] - (double)phi[ox[A - lo] + oy[B] + oz[C]];
+                        dy_[m - 1] = (double)phi[ox[A] + oy[B + m] + oz[C]] - (double)phi[ox[A] + oy[B - lo] + oz[C]];
+                        dz_[m - 1] = (double)phi[ox[A] + oy[B] + oz[C + m]] - (double)phi[ox[A] + oy[B] + oz[C - lo]];
+                    }
+                    vx += fd_combine<REACH>(dx_, fd) * w;
+                    vy += fd_combine<REACH>(dy_, fd) * w;
+                    vz += fd_combine<REACH>(dz_, fd) * w;
+                }
+            }
+        }
+        if (factor != 1) { vx *= factor; vy *= factor; vz *= factor; }
+        double* m = mom + (first + threadIdx.x) * 3;
+        const double mx = m[0] + vx, my = m[1] + vy, mz = m[2] + vz;
+        m[0] = mx; m[1] = my; m[2] = mz;
+        mom2_acc += mx * mx + my * my + mz * mz;
+    }
+    if (sum_mom2 != nullptr) {
+        __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mom2_acc += __shfl_xor_sync(0xffffffffu, mom2_acc, o);
+        if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = mom2_acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0;
+            for (int w = 0; w < kGatBlock / 32; ++w) t += sred[w];
+            atomicAdd(sum_mom2, t);
+        }
+    }
+}
+
+template <typename T>
+static int gather_kick_dispatch(pm_ctx* c, const double* pos, double* mom, int64_t n, int order,
+                                const FD& fd, double factor, const Coord& co, double* sum_mom2) {
+    const int64_t ntiles = (n + kGatBlock - 1) / kGatBlock;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * 8);
+    const T* phi = reinterpret_cast<const T*>(c->real);
+#define PM_GK(O, R)                                                                              \
+    PM_LAUNCH((gather_kick_kernel<O, R, T>), grid, kGatBlock, 0, c->stream, phi, pos, mom, n,    \
+              c->g, co, fd, factor, sum_mom2)
+#define PM_GK_ORDER(R)                                  \
+    switch (order) {                                    \
+        case 1: PM_GK(1, R); break;                     \
+        case 2: PM_GK(2, R); break;                     \
+        case 3: PM_GK(3, R); break;                     \
+        case 4: PM_GK(4, R); break;                     \
+    }
+    switch (fd.reach) {
+        case 1: PM_GK_ORDER(1); break;
+        case 2: PM_GK_ORDER(2); break;
+        case 3: PM_GK_ORDER(3); break;
+        case 4: PM_GK_ORDER(4); break;
+    }
+#undef PM_GK_ORDER
+#undef PM_GK
+    return PM_OK;
+}
+
+int launch_gather_kick(pm_ctx* c, const double* pos, double* mom, int64_t n, int order,
+                       int diff_order, double factor, const double* shift, double* sum_mom2) {
+    PM_REQUIRE(order >= 1 && order <= 4, "pm_gather_kick called with order = %d not in {1, 2, 3, 4}", order);
+    FD fd;
+    PM_TRY(make_fd(diff_order, c->boxsize / c->g.G, &fd));
+    if (n == 0) return PM_OK;
+    const Coord co = make_coord(c, shift, true);
+    return c->dtype == PM_GRID_F64
+               ? gather_kick_dispatch<double>(c, pos, mom, n, order, fd, factor, co, sum_mom2)
+               : gather_kick_dispatch<float>(c, pos, mom, n, order, fd, factor, co, sum_mom2);
+}
+
+}  // namespace pm

@@ -1,0 +1,208 @@
+"""PMContext — Python handle on one libpmgrav context (one grid size, one GPU/slab).
+
+It is the analogue of the reference's cached FFTW slab + plans (get_fftw_slab, mesh.py:3769-3866)
+plus the named scratch grids ('grid_updownstream', 'slab_global', 'force_downstream';
+communication.py:1666-1723).  All heavy lifting happens inside libpmgrav.so; particle arrays are
+torch CUDA tensors (float64, shape (N, 3), contiguous — the AoS layout of Component.pos/.mom,
+species.py:1411-1431) and only their device pointers cross the C ABI.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import KickParams, PM_GRID_F32, PM_GRID_F64, PM_TAP_FORCE, PM_TAP_FOURIER, PM_TAP_REAL, check, vec3
+
+BCC_SHIFT = (-0.5, -0.5, -0.5)   # Lattice.shift_amount for cell-centred grids (mesh.py:85)
+
+
+def _ptr(t, n=None):
+    if t is None:
+        return None
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+        raise TypeError('expected a contiguous CUDA tensor')
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _particles(t):
+    if t.dtype != torch.float64 or t.dim() != 2 or t.shape[1] != 3:
+        raise TypeError('particle arrays must be float64 of shape (N, 3)')
+    return _ptr(t)
+
+
+class PMContext:
+    def __init__(self, gridsize, boxsize, dtype='f64', rank=0, nranks=1, device=None, stream=None):
+        self.lib = _lib.load()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = int(device)
+        self.gridsize = int(gridsize)
+        self.boxsize = float(boxsize)
+        self.dtype = {'f64': PM_GRID_F64, 'f32': PM_GRID_F32, 'float64': PM_GRID_F64, 'float32': PM_GRID_F32}[str(dtype)]
+        self.rank, self.nranks = int(rank), int(nranks)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._h = ctypes.c_void_p()
+        check(self.lib.pm_create(ctypes.byref(self._h), self.gridsize, self.boxsize, self.dtype,
+                                 self.rank, self.nranks, self.device, ctypes.c_void_p(stream)))
+        nx, x0, nj, j0 = (ctypes.c_int64() for _ in range(4))
+        check(self.lib.pm_local_shape(self._h, *(ctypes.byref(v) for v in (nx, x0, nj, j0))))
+        self.nx_local, self.x_start, self.nj_local, self.j_start = nx.value, x0.value, nj.value, j0.value
+        self._sum = torch.zeros(8, dtype=torch.float64, device=f'cuda:{self.device}')
+
+    # -- life cycle ----------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self.lib.pm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream):
+        check(self.lib.pm_set_stream(self._h, ctypes.c_void_p(stream)))
+
+    def sync(self):
+        check(self.lib.pm_sync(self._h))
+
+    @property
+    def device_bytes(self):
+        return self.lib.pm_device_bytes(self._h)
+
+    # -- communicator ----------------------------------------------------------------
+    def comm_init(self, unique_id_bytes):
+        buf = ctypes.create_string_buffer(bytes(unique_id_bytes), 128)
+        check(self.lib.pm_comm_init(self._h, buf))
+
+    @staticmethod
+    def comm_unique_id():
+        lib = _lib.load()
+        buf = ctypes.create_string_buffer(128)
+        check(lib.pm_comm_unique_id(buf))
+        return buf.raw
+
+    def allreduce_sum(self, t):
+        check(self.lib.pm_allreduce_sum(self._h, _ptr(t), t.numel()))
+
+    # -- mesh operators ----------------------------------------------------------------
+    def grid_zero(self):
+        check(self.lib.pm_grid_zero(self._h))
+
+    def deposit(self, pos, order, contribution, shift=None):
+        check(self.lib.pm_deposit(self._h, _particles(pos), pos.shape[0], int(order), float(contribution), vec3(shift)))
+
+    def halo_add(self):
+        check(self.lib.pm_halo_add(self._h))
+
+    def halo_fill(self):
+        check(self.lib.pm_halo_fill(self._h))
+
+    def fft_forward(self):
+        check(self.lib.pm_fft_forward(self._h))
+
+    def fft_backward(self):
+        check(self.lib.pm_fft_backward(self._h))
+
+    def kspace_potential(self, prefactor, deconv_order, gauss=0.0, scale=1.0):
+        check(self.lib.pm_kspace_potential(self._h, float(prefactor), int(deconv_order), float(gauss), float(scale)))
+
+    def fourier_operate(self, deconv_order=0, shift=None, scale=1.0, diff_dim=-1, from_saved=False):
+        check(self.lib.pm_fourier_operate(self._h, int(deconv_order), vec3(shift), float(scale), int(diff_dim), int(from_saved)))
+
+    def slab_save(self):
+        check(self.lib.pm_slab_save(self._h))
+
+    def slab_accumulate(self):
+        check(self.lib.pm_slab_accumulate(self._h))
+
+    def slab_restore(self):
+        check(self.lib.pm_slab_restore(self._h))
+
+    def diff(self, dim, order):
+        check(self.lib.pm_diff(self._h, int(dim), int(order)))
+
+    def gather(self, which, pos, mom, order, dim, factor, shift=None):
+        check(self.lib.pm_gather(self._h, int(which), _particles(pos), _particles(mom), pos.shape[0], int(order),
+                                 int(dim), float(factor), vec3(shift)))
+
+    def gather_kick(self, pos, mom, order, diff_order, factor, shift=None, sum_mom2=None):
+        check(self.lib.pm_gather_kick(self._h, _particles(pos), _particles(mom), pos.shape[0], int(order),
+                                      int(diff_order), float(factor), vec3(shift), _ptr(sum_mom2)))
+
+    # -- particle operators ------------------------------------------------------------
+    def drift(self, pos, mom, dt_over_mass):
+        check(self.lib.pm_drift(self._h, _particles(pos), _particles(mom), pos.shape[0], float(dt_over_mass)))
+
+    def sum_mom2(self, mom, out=None):
+        """Σ mom² over the local particles → python float (synchronises)."""
+        acc = self._sum[:1] if out is None else out
+        if out is None:
+            acc.zero_()
+        check(self.lib.pm_sum_mom2(self._h, _particles(mom), mom.shape[0], _ptr(acc)))
+        return float(acc.item()) if out is None else None
+
+    def exchange(self, pos, mom, ids, n):
+        """Slab migration.  pos/mom(/ids) are capacity-sized buffers; returns the new local count."""
+        n_io = ctypes.c_int64(int(n))
+        check(self.lib.pm_exchange(self._h, _particles(pos), _particles(mom), _ptr(ids), ctypes.byref(n_io), pos.shape[0]))
+        return n_io.value
+
+    # -- whole kick -------------------------------------------------------------------
+    def kick_long(self, pos, mom, params, sum_mom2=None):
+        check(self.lib.pm_kick_long(self._h, _particles(pos), _particles(mom), pos.shape[0], ctypes.byref(params), _ptr(sum_mom2)))
+
+    def kick_long_host(self, pos_np, mom_np, params, dt_over_mass=0.0, want_sum=False):
+        """Host (numpy, C-contiguous float64 (N,3)) buffers in and out; returns Σmom² or None."""
+        for a in (pos_np, mom_np):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.ndim == 2 and a.shape[1] == 3):
+                raise TypeError('host particle arrays must be C-contiguous float64 (N, 3)')
+        s = ctypes.c_double(0.0)
+        check(self.lib.pm_kick_long_host(self._h, pos_np.ctypes.data_as(ctypes.c_void_p), mom_np.ctypes.data_as(ctypes.c_void_p),
+                                         pos_np.shape[0], ctypes.byref(params), float(dt_over_mass),
+                                         ctypes.byref(s) if want_sum else None))
+        return s.value if want_sum else None
+
+    # -- taps -------------------------------------------------------------------------
+    def get_grid(self, which=PM_TAP_REAL):
+        n = self.lib.pm_tap_size(self._h, int(which))
+        out = np.empty(n, dtype=np.float64)
+        check(self.lib.pm_get_grid(self._h, int(which), out.ctypes.data_as(ctypes.c_void_p)))
+        G = self.gridsize
+        if which == PM_TAP_FOURIER:
+            return out.view(np.complex128).reshape(G, self.nj_local, G//2 + 1)
+        return out.reshape(self.nx_local, G, G)
+
+    def set_grid(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        assert arr.shape == (self.nx_local, self.gridsize, self.gridsize)
+        check(self.lib.pm_set_grid(self._h, arr.ctypes.data_as(ctypes.c_void_p)))
+
+
+def make_kick_params(*, mass, boxsize, gridsize, order, G_Newton, dt_rho_over_dt1, dt_kick,
+                     diff_order=2, deconvolve=True, interlace=False, r_scale=0.0):
+    """Scalars of one long-range kick, formed exactly as the reference does on the host:
+    contribution  mesh.py:1550-1573 with fft_factor = G⁻³ (mesh.py:582)
+    deconv_order  interactions.py:2069-2080 (up + down promoted to the global slab)
+    prefactor     interactions.py:2105  ℝ[-boxsize**2*G_Newton/π]
+    gauss         interactions.py:2112  (2π/boxsize·scale)²
+    kick_factor   interactions.py:2386  mass·(−ᔑdt[ᔑdt_key])
+    """
+    G = int(gridsize)
+    contribution = dt_rho_over_dt1
+    contribution *= mass
+    contribution_factor = float(G)**(-3)*(G/boxsize)**3
+    contribution *= contribution_factor
+    p = KickParams()
+    p.order = int(order)
+    p.diff_order = int(diff_order)
+    p.deconv_order = int(order)*(2 if deconvolve else 0)
+    p.interlace = int(bool(interlace))
+    p.contribution = contribution
+    p.prefactor = -boxsize**2*G_Newton/np.pi
+    p.gauss = (2*np.pi/boxsize*r_scale)**2 if r_scale else 0.0
+    p.kick_factor = mass*(-dt_kick)
+    return p

@@ -1,0 +1,178 @@
+/* pmgrav.h — C ABI of libpmgrav.so: the B200 (sm_100a) particle-mesh gravity hot path.
+ *
+ * Drop-in boundary for CO*N*CEPT's PM long-range kick + drift.  Every entry point
+ * names the reference interface it replaces (file:line under the reference's src/).
+ * The reference's only native FFI is fft.c (fftw_setup / fftw_execute / fftw_clean,
+ * mesh.py:43-71, fft.c:75-83,105-112,281-285); pm_create / pm_fft / pm_destroy are the
+ * equivalents.  The remaining entry points replace functions that the reference
+ * compiles from Python to C through Cython (`cdef` functions inside mesh.so,
+ * interactions.so, species.so) and that a maintainer would re-bind with ctypes/cffi
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C types only; all particle/grid pointers are DEVICE pointers unless the
+ *     name says `_host`;
+ *   - particles are AoS double[n][3] (x,y,z interleaved) exactly like Component.pos /
+ *     .mom (species.py:1411-1431);
+ *   - every function returns 0 on success or a negative pm_status; pm_last_error()
+ *     gives the message.  Nothing falls back to a CPU path;
+ *   - work is enqueued on the context's CUDA stream; no hidden host synchronisation
+ *     except in the `_host` functions and pm_get_grid;
+ *   - one context per (rank, gridsize, grid dtype), reused forever — like the cached
+ *     slabs/plans of get_fftw_slab (mesh.py:3769-3866).
+ */
+#ifndef PMGRAV_H
+#define PMGRAV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pm_ctx pm_ctx;
+
+typedef enum {
+    PM_OK = 0,
+    PM_ERR_ARG = -1,       /* invalid argument (the reference abort()s, commons.py:1002) */
+    PM_ERR_CUDA = -2,      /* CUDA runtime / cuFFT failure */
+    PM_ERR_ALLOC = -3,
+    PM_ERR_STATE = -4,     /* call order violated (e.g. gather before solve) */
+    PM_ERR_COMM = -5,      /* NCCL failure / communicator missing */
+    PM_ERR_OVERFLOW = -6   /* a particle buffer is too small for migrating particles */
+} pm_status;
+
+enum { PM_GRID_F64 = 0, PM_GRID_F32 = 1 };
+
+/* Which internal grid pm_get_grid() copies out */
+enum {
+    PM_TAP_REAL = 0,     /* real-space grid [nx_local][G][G] (padding stripped): density after
+                            pm_deposit(+halo), potential after pm_fft_backward */
+    PM_TAP_FOURIER = 1,  /* Fourier slab as doubles (re,im interleaved):
+                            nranks==1: natural [i][j][kk];  nranks>1: [j_local][i][kk]
+                            (the FFTW-MPI transposed layout of fft.c:55-72) */
+    PM_TAP_FORCE = 2     /* scratch force grid written by pm_diff() */
+};
+
+/* ---- library ---------------------------------------------------------- */
+const char* pm_version(void);
+const char* pm_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t pm_launch_count(void);
+int pm_device_count(void);
+
+/* ---- context: replaces fftw_setup / get_fftw_slab (fft.c:105-212, mesh.py:3769-3866) */
+/* gridsize G: cells per side; must be even and G % nranks == 0 (mesh.py:3779-3783).
+ * boxsize  L: in the caller's length unit.
+ * grid_dtype: PM_GRID_F64 (reference-exact) or PM_GRID_F32 (mixed precision).
+ * rank/nranks: x-slab decomposition — rank r owns planes [r·G/P, (r+1)·G/P).
+ * device: CUDA device ordinal; stream: cudaStream_t (NULL = the legacy default stream). */
+int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype,
+              int rank, int nranks, int device, void* stream);
+int pm_destroy(pm_ctx* ctx);                                   /* fftw_clean, fft.c:281 */
+int pm_set_stream(pm_ctx* ctx, void* stream);
+int pm_sync(pm_ctx* ctx);
+/* local slab geometry, like fftw_return_struct (fft.c:75-83) */
+int pm_local_shape(const pm_ctx* ctx, int64_t* nx_local, int64_t* x_start,
+                   int64_t* nj_local, int64_t* j_start);
+int64_t pm_device_bytes(const pm_ctx* ctx);
+
+/* ---- multi-GPU: NCCL communicator owned by the library ------------------ */
+/* id_out: 128-byte ncclUniqueId created on rank 0 and broadcast by the host code */
+int pm_comm_unique_id(void* id_out_128);
+int pm_comm_init(pm_ctx* ctx, const void* id_128);
+/* sum a device array of n doubles over all ranks in place (allreduce, analysis.py:3971) */
+int pm_allreduce_sum(pm_ctx* ctx, double* dev_values, int n);
+
+/* ---- mesh operators ------------------------------------------------------ */
+/* get_buffer(..., nullify=True) for 'grid_updownstream' (mesh.py:600) */
+int pm_grid_zero(pm_ctx* ctx);
+/* interpolate_particles (mesh.py:1512-1636): grid[cell] += (wx·contribution)·wy·wz.
+ * order 1..4 = NGP, CIC, TSC, PCS (set_weights_*, mesh.py:5305-5379).
+ * contribution = q·mass·(G/L)³·G⁻³ (mesh.py:1550-1573, 582).
+ * shift[3]: lattice shift in grid units (mesh.py:85-100), NULL = (0,0,0). */
+int pm_deposit(pm_ctx* ctx, const double* pos, int64_t n, int order,
+               double contribution, const double* shift);
+/* communicate_ghosts(grid,'+=') (communication.py:563-660, mesh.py:609): fold the x-halo
+ * planes into the neighbour slabs.  No-op for nranks == 1 (periodic wrap is done in-kernel). */
+int pm_halo_add(pm_ctx* ctx);
+/* communicate_ghosts(grid,'=') after the inverse transform (mesh.py:2243): fill x-halo planes */
+int pm_halo_fill(pm_ctx* ctx);
+/* fft(slab,'forward'|'backward') (mesh.py:4012-4157 → fftw_execute): unnormalised, in place.
+ * forward also performs nullify_modes(slab,'nyquist') only when asked via pm_kspace_*. */
+int pm_fft_forward(pm_ctx* ctx);
+int pm_fft_backward(pm_ctx* ctx);
+/* The potential loop of particle_mesh (interactions.py:2092-2118) fused with
+ * nullify_modes 'nyquist' (mesh.py:3591-3622) and 'origin' (:3585-3590):
+ *   slab[k] *= [Π x_l/sin x_l]^deconv_order · scale · prefactor/k² · exp(−k²·gauss)
+ * prefactor = −L²·G_N/π ; gauss = (2π·r_s/L)² or 0 (plain PM) ; scale = 1/n_lattices.
+ * If prefactor == 0 the 1/k² and exp terms are skipped (pure deconvolution, used by
+ * the power-spectrum path, fourier_operate mesh.py:3327-3400). */
+int pm_kspace_potential(pm_ctx* ctx, double prefactor, int deconv_order, double gauss,
+                        double scale);
+/* fourier_operate (mesh.py:3327-3400): in-place deconvolution^deconv_order · scale,
+ * phase rotation by θ = −2π/G·k·shift, and (diff_dim ∈ {0,1,2}) ×i·(2π/L)·k_dim.
+ * If `from_saved` the operation reads the saved copy made by pm_slab_save and writes the
+ * working slab (the reference copies slab_downstream → slab_updownstream_subgroup). */
+int pm_fourier_operate(pm_ctx* ctx, int deconv_order, const double* shift, double scale,
+                       int diff_dim, int from_saved);
+int pm_slab_save(pm_ctx* ctx);      /* slab_updownstream_subgroup[...] = slab (interactions.py:2256) */
+int pm_slab_accumulate(pm_ctx* ctx);/* saved += working slab (copy_modes '+=' for interlacing) */
+int pm_slab_restore(pm_ctx* ctx);   /* working slab = saved */
+/* diff_domaingrid (mesh.py:4874-5030) into the scratch force grid; order ∈ {1,2,4,6,8} */
+int pm_diff(pm_ctx* ctx, int dim, int order);
+/* interpolate_domaingrid_to_particles (mesh.py:376-459) + apply_particle_mesh_force
+ * (interactions.py:2359-2402) for one dimension from an explicit force grid:
+ *   mom[dim] += factor · Σ W·grid[cell];  which = PM_TAP_REAL or PM_TAP_FORCE */
+int pm_gather(pm_ctx* ctx, int which, const double* pos, double* mom, int64_t n,
+              int order, int dim, double factor, const double* shift);
+/* Fused diff_domaingrid ×3 + gather ×3 + kick from the real-space potential:
+ *   mom[d] += factor · Σ W·(∂_d φ)[cell],  factor = −mass·ᔑdt['a**(-3*w_eff)'].
+ * diff_order ∈ {1,2,4,6,8}.  If sum_mom2 != NULL, Σ mom² of the updated momenta is
+ * ADDED to *sum_mom2 (device double; measure('v_rms'), analysis.py:3965-3972). */
+int pm_gather_kick(pm_ctx* ctx, const double* pos, double* mom, int64_t n, int order,
+                   int diff_order, double factor, const double* shift, double* sum_mom2);
+
+/* ---- particle operators ------------------------------------------------ */
+/* Component.drift (species.py:2179-2199): pos = mod(pos + mom·dt_over_mass, L) */
+int pm_drift(pm_ctx* ctx, double* pos, const double* mom, int64_t n, double dt_over_mass);
+/* measure(component,'v_rms') reduction: *out += Σ mom² (device double) */
+int pm_sum_mom2(pm_ctx* ctx, const double* mom, int64_t n, double* out);
+/* exchange(component) (communication.py:135-517) for the x-slab decomposition: particles
+ * whose owner floor(x/L·P) differs from this rank are sent to their owner.  pos/mom/ids are
+ * device arrays with room for `capacity` particles; *n_inout is updated (host int64).
+ * ids may be NULL. */
+int pm_exchange(pm_ctx* ctx, double* pos, double* mom, int64_t* ids, int64_t* n_inout,
+                int64_t capacity);
+
+/* ---- whole-path entry points --------------------------------------------- */
+typedef struct {
+    int order;            /* interpolation order 1..4 */
+    int diff_order;       /* 0 = Fourier differentiation, else 1,2,4,6,8 */
+    int deconv_order;     /* total deconvolution power (order·(up+down)), interactions.py:2069-2080 */
+    int interlace;        /* 0 / 1 (bcc, two lattices) */
+    double contribution;  /* deposit scalar, see pm_deposit */
+    double prefactor;     /* −L²·G_N/π */
+    double gauss;         /* (2π·r_s/L)² for 'gravity long-range', else 0 */
+    double kick_factor;   /* −mass·ᔑdt['a**(-3*w_eff)'] */
+} pm_kick_params;
+/* gravity('pm'|'p3m', [c], [c], ᔑdt, 'long-range') for one particle component
+ * (interactions.py:2854-2961 → particle_mesh :1985-2335).  sum_mom2 as in pm_gather_kick. */
+int pm_kick_long(pm_ctx* ctx, const double* pos, double* mom, int64_t n,
+                 const pm_kick_params* p, double* sum_mom2);
+/* Same, with HOST particle buffers: H2D, kick, optional drift (dt_over_mass != 0), D2H.
+ * pos_host is updated only when drifting. Synchronous. */
+int pm_kick_long_host(pm_ctx* ctx, double* pos_host, double* mom_host, int64_t n,
+                      const pm_kick_params* p, double dt_over_mass, double* sum_mom2_host);
+
+/* ---- parity taps ------------------------------------------------------------ */
+/* copies the chosen grid to host as float64; host_out must hold pm_tap_size() doubles */
+int64_t pm_tap_size(const pm_ctx* ctx, int which);
+int pm_get_grid(pm_ctx* ctx, int which, double* host_out);
+/* overwrite the real-space grid from host float64 [nx_local][G][G] (tests) */
+int pm_set_grid(pm_ctx* ctx, const double* host_in);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMGRAV_H */
