@@ -1,0 +1,296 @@
+"""Global state shared by the host-side mirror of the reference's operator surface:
+unit system, physical constants, the parameter-file loader and `universals`.
+
+Reference: commons.py — units :1826-1905, :2044-2135; parameter file execution :1921-2042
+(`exec_params`: statements are executed repeatedly until no further one succeeds, so a line may use
+a name that is assigned further down); hot-path parameters :2956-3269, :3664-3702, :3862-3926.
+
+Only the parameters that the PM hot path reads are normalised here.  Unlike the reference, the
+parameters are not frozen into module globals at import: `load_params()` may be called again
+(one process can run several configurations, which the tests rely on).
+"""
+import ast
+import math
+import os
+import sys
+import types
+
+import numpy as np
+
+π = math.pi
+τ = 2*math.pi
+machine_ϵ = float(np.finfo(np.float64).eps)
+ထ = float('inf')
+
+# ---------------------------------------------------------------------------
+# Unit system: everything is expressed in (unit_length, unit_time, unit_mass) =
+# (Mpc, Gyr, 10¹⁰ m☉) by default, like the reference.
+# ---------------------------------------------------------------------------
+
+
+def _unit_relations():
+    r = {'yr': 1.0, 'pc': 1.0, 'm_sun': 1.0}
+    r['kyr'], r['Myr'], r['Gyr'] = 1e3, 1e6, 1e9
+    r['day'] = 1/365.25
+    r['hr'] = r['day']/24
+    r['minutes'] = r['hr']/60
+    r['s'] = r['minutes']/60
+    r['kpc'], r['Mpc'], r['Gpc'] = 1e3, 1e6, 1e9
+    r['AU'] = τ/(60*60*360)
+    r['m'] = r['AU']/149597870700
+    r['mm'], r['cm'], r['km'] = 1e-3*r['m'], 1e-2*r['m'], 1e3*r['m']
+    r['ly'] = (299792458*r['m']/r['s'])*r['yr']
+    r['km_sun'], r['Mm_sun'], r['Gm_sun'] = 1e3, 1e6, 1e9
+    r['kg'] = 1/1.98841e30
+    r['g'] = 1e-3*r['kg']
+    r['G_Newton'] = 6.67430e-11*r['m']**3/(r['kg']*r['s']**2)
+    return r
+
+
+class Units(types.SimpleNamespace):
+    pass
+
+
+def build_units(unit_length='Mpc', unit_time='Gyr', unit_mass='10¹⁰ m☉'):
+    r = _unit_relations()
+    mass_alias = {'10¹⁰ m☉': 1e10, '1e+10*m_sun': 1e10, '10**10*m_sun': 1e10, 'm_sun': 1.0, 'm☉': 1.0}
+    yr = 1/r[unit_time]
+    pc = 1/r[unit_length]
+    m_sun = 1/(mass_alias[unit_mass] if unit_mass in mass_alias else r[unit_mass])
+    u = Units()
+    for name in ('yr', 'kyr', 'Myr', 'Gyr', 'day', 'hr', 'minutes', 's'):
+        setattr(u, name, r[name]*yr)
+    for name in ('pc', 'kpc', 'Mpc', 'Gpc', 'AU', 'm', 'mm', 'cm', 'km', 'ly'):
+        setattr(u, name, r[name]*pc)
+    for name in ('m_sun', 'km_sun', 'Mm_sun', 'Gm_sun', 'kg', 'g'):
+        setattr(u, name, r[name]*m_sun)
+    return u, r
+
+
+units, unit_relations = build_units()
+unit_length, unit_time, unit_mass = 'Mpc', 'Gyr', '10¹⁰ m☉'
+light_speed = units.ly/units.yr
+G_Newton = (unit_relations['G_Newton']/(unit_relations['m']**3/(unit_relations['kg']*unit_relations['s']**2))
+            * units.m**3/(units.kg*units.s**2))
+
+
+# ---------------------------------------------------------------------------
+# universals (commons.py `universals` struct)
+# ---------------------------------------------------------------------------
+universals = types.SimpleNamespace(t=0.0, a=1.0, t_begin=0.0, a_begin=1.0, z_begin=0.0, time_step=0)
+
+
+# ---------------------------------------------------------------------------
+# Printing / aborting
+# ---------------------------------------------------------------------------
+class ConceptAbort(SystemExit):
+    """Raised by abort(); the reference prints and terminates all ranks (commons.py:1002-1030)."""
+
+
+verbose = bool(int(os.environ.get('CONCEPT_B200_VERBOSE', '0')))
+
+
+def masterprint(*args, **kwargs):
+    if verbose and int(os.environ.get('RANK', '0')) == 0:
+        print(*args, **kwargs)
+        sys.stdout.flush()
+
+
+def masterwarn(*args, **kwargs):
+    if int(os.environ.get('RANK', '0')) == 0:
+        print('Warning:', *args, file=sys.stderr, **kwargs)
+
+
+def abort(*args, exit_code=1):
+    msg = ' '.join(str(a) for a in args)
+    print('Aborting:', msg, file=sys.stderr)
+    raise ConceptAbort(msg or exit_code)
+
+
+# ---------------------------------------------------------------------------
+# Parameter file
+# ---------------------------------------------------------------------------
+class Param:
+    """`param` object available inside parameter files (commons.py:1909): .path, .name, .dir"""
+
+    def __init__(self, path=''):
+        self.path = os.path.abspath(path) if path else ''
+        self.name = os.path.basename(self.path)
+        self.dir = os.path.dirname(self.path)
+
+    def __str__(self):
+        return self.path
+
+    __fspath__ = __str__
+
+
+def _param_namespace(param_path):
+    ns = {name: getattr(units, name) for name in vars(units)}
+    ns.update(
+        units=units, light_speed=light_speed, c=light_speed, G_Newton=G_Newton, G=G_Newton,
+        π=π, pi=π, τ=τ, tau=τ, ထ=ထ, inf=ထ, machine_ϵ=machine_ϵ, eps=machine_ϵ,
+        np=np, numpy=np, asarray=np.asarray, arange=np.arange, linspace=np.linspace, logspace=np.logspace,
+        zeros=np.zeros, ones=np.ones, empty=np.empty, array=np.array,
+        sqrt=np.sqrt, cbrt=np.cbrt, exp=np.exp, log=np.log, log2=np.log2, log10=np.log10,
+        sin=np.sin, cos=np.cos, tan=np.tan, min=min, max=max, sum=np.sum, prod=np.prod, mean=np.mean,
+        isint=lambda x: float(x).is_integer(), param=Param(param_path), os=os,
+    )
+    return ns
+
+
+def exec_params(content, namespace):
+    """Execute parameter-file text statement by statement, retrying failed statements until no
+    further one succeeds (commons.py:2001-2036) — a statement may use names assigned later."""
+    tree = ast.parse(content)
+    pending = [ast.Module(body=[node], type_ignores=[]) for node in tree.body]
+    progress = True
+    while pending and progress:
+        progress = False
+        still = []
+        for mod in pending:
+            try:
+                exec(compile(mod, '<param>', 'exec'), namespace)
+                progress = True
+            except Exception:
+                still.append(mod)
+        pending = still
+    return namespace
+
+
+_ORDER_NAMES = {'ngp': 1, 'cic': 2, 'tsc': 3, 'pcs': 4}
+
+
+def _lower_keys(d):
+    return {str(k).lower(): v for k, v in d.items()}
+
+
+class Params(types.SimpleNamespace):
+    """Normalised hot-path parameters (subset of commons.py:2470-4432)."""
+
+
+params = Params()
+user_params = {}
+
+
+def load_params(path_or_text='', extra='', **overrides):
+    """Load a CO*N*CEPT parameter file (path or literal text).  `extra` mimics `-c "name = value"`
+    (appended lines, doc/command_line_options.rst).  Keyword overrides are applied last."""
+    global params, user_params
+    if path_or_text and '\n' not in path_or_text and os.path.isfile(path_or_text):
+        with open(path_or_text, encoding='utf-8') as f:
+            content = f.read()
+        path = path_or_text
+    else:
+        content, path = path_or_text, ''
+    content = content + '\n' + extra + '\n'
+    # h is defined from H0 after the file (commons.py:1785-1798) — but files use it (`256*Mpc/h`), so
+    # it must be resolvable during the retry loop
+    content += '\ntry:\n    h = H0/(100*km/(s*Mpc))\nexcept NameError:\n    h = 1\nh = float("{:.15f}".format(h))\n'
+    ns = _param_namespace(path)
+    base_keys = set(ns)
+    exec_params(content, ns)
+    exec_params(content, ns)   # the reference executes the file twice (commons.py:2352, 2419)
+    up = {k: v for k, v in ns.items() if k not in base_keys and not k.startswith('__')}
+    up.update(overrides)
+    user_params = up
+    p = Params()
+    p.user = up
+    p.boxsize = float(up.get('boxsize', 512*units.Mpc))
+    p.H0 = float(up.get('H0', 67*units.km/(units.s*units.Mpc)))
+    p.Ωb = float(up.get('Ωb', 0.049))
+    p.Ωcdm = float(up.get('Ωcdm', 0.27))
+    p.Ωm = p.Ωb + p.Ωcdm
+    p.a_begin = float(up.get('a_begin', 1.0))
+    p.t_begin = float(up.get('t_begin', 0.0))
+    p.enable_Hubble = bool(up.get('enable_Hubble', True))
+    p.ρ_crit = 3*p.H0**2/(8*π*G_Newton)            # commons.py:4435
+    p.initial_conditions = up.get('initial_conditions', None)
+    p.output_times = up.get('output_times', {})
+    p.output_dirs = up.get('output_dirs', {})
+    p.random_seeds = up.get('random_seeds', {})
+    p.N_rungs = int(up.get('N_rungs', 8))
+    p.Δt_base_background_factor = float(up.get('Δt_base_background_factor', 1))
+    p.Δt_base_nonlinear_factor = float(up.get('Δt_base_nonlinear_factor', 1))
+    p.Δt_increase_max_factor = float(up.get('Δt_increase_max_factor', ထ))
+    p.Δt_rung_factor = float(up.get('Δt_rung_factor', 1))
+    p.Δa_max_early = float(up.get('Δa_max_early', 0.00153))
+    p.Δa_max_late = float(up.get('Δa_max_late', 0.022))
+    p.static_timestepping = up.get('static_timestepping', None)
+    p.cell_centered = bool(up.get('cell_centered', True))
+    p.grid_dtype = str(up.get('grid_dtype', 'f64'))     # extension: 'f32' selects the mixed-precision grid
+    # select_forces (commons.py:3664-3702): default for particles is gravity via P³M
+    sf = up.get('select_forces', {})
+    p.select_forces = {str(k): _lower_keys(v) if isinstance(v, dict) else {'gravity': str(v).lower()} for k, v in sf.items()}
+    # potential_options (commons.py:2958-3237)
+    po = up.get('potential_options', {})
+    if not isinstance(po, dict):
+        po = {'gridsize': po}
+    p.potential_options_raw = po
+    return p_finish(p)
+
+
+def _method_dict(spec, default_pm, default_p3m):
+    """Accepts a scalar, {'gravity': x}, {'gravity': {'pm': x, 'p3m': y}} → {'pm': x, 'p3m': y}"""
+    out = {'pm': default_pm, 'p3m': default_p3m}
+    if spec is None:
+        return out
+    if isinstance(spec, dict):
+        spec = _lower_keys(spec)
+        if 'default' in spec and isinstance(spec['default'], dict):
+            spec = _lower_keys(spec['default'])
+        if 'global' in spec or 'particles' in spec:
+            merged = {}
+            for key in ('global', 'particles'):
+                if isinstance(spec.get(key), dict):
+                    merged.update(_lower_keys(spec[key]))
+            spec = merged or spec
+        g = spec.get('gravity', spec if ('pm' in spec or 'p3m' in spec) else None)
+        if isinstance(g, dict):
+            g = _lower_keys(g)
+            for m in ('pm', 'p3m'):
+                if m in g:
+                    out[m] = g[m]
+        elif g is not None:
+            out = {'pm': g, 'p3m': g}
+    else:
+        out = {'pm': spec, 'p3m': spec}
+    return out
+
+
+def p_finish(p):
+    global params
+    po = _lower_keys(p.potential_options_raw)
+    p.gridsize_spec = _method_dict(po.get('gridsize'), None, None)
+    interp = _method_dict(po.get('interpolation'), 'CIC', 'CIC')
+    p.interpolation_order = {m: (_ORDER_NAMES[str(v).lower()] if isinstance(v, str) else int(v)) for m, v in interp.items()}
+    p.deconvolve = {m: (tuple(bool(x) for x in v) if isinstance(v, (tuple, list)) else (bool(v), bool(v)))
+                    for m, v in _method_dict(po.get('deconvolve'), (True, True), (True, True)).items()}
+    p.interlace = {m: (tuple(bool(x) for x in v) if isinstance(v, (tuple, list)) else (bool(v), bool(v)))
+                   for m, v in _method_dict(po.get('interlace'), (False, False), (False, False)).items()}
+    diff = _method_dict(po.get('differentiation'), 2, 4)
+    p.differentiation = {m: (0 if str(v).lower() == 'fourier' else int(v)) for m, v in diff.items()}
+    params = p
+    return p
+
+
+def gridsize_for(method, N):
+    """Default PM grid sizes: cbrt(N) for pm, 2·cbrt(N) for p3m (doc/parameters/numerics.rst:72-100)."""
+    g = params.gridsize_spec.get(method)
+    if isinstance(g, (tuple, list)):
+        g = g[0]
+    if g is None or g == -1:
+        n = round(N**(1/3))
+        g = n if method == 'pm' else 2*n
+    g = int(g)
+    return g + (g & 1)
+
+
+def shortrange_scale(gridsize):
+    """shortrange_params['gravity']['scale'] = 1.25·boxsize/gridsize (commons.py:3254-3269)"""
+    sp = user_params.get('shortrange_params', {})
+    if sp and not isinstance(list(sp.values())[0], dict):
+        sp = {'gravity': sp}
+    scale = sp.get('gravity', {}).get('scale', None)
+    if scale is None or isinstance(scale, str):
+        return 1.25*params.boxsize/gridsize
+    return float(scale)

@@ -345,7 +345,6 @@ int pm_kick_long(pm_ctx* c, const double* pos, double* mom, int64_t n, const pm_
         const double* shift = l == 0 ? nullptr : kBccShift;
         if (p->diff_order == 0) {
             for (int dim = 0; dim < 3; ++dim) {
-                c->space_fourier = true;
                 PM_TRY(launch_kspace(c, 0, 0, 0, lscale, shift, dim, true, false));
                 PM_TRY(fft_backward(c));
                 PM_TRY(halo_fill(c, hlo, hhi, PM_TAP_REAL));
@@ -353,7 +352,6 @@ int pm_kick_long(pm_ctx* c, const double* pos, double* mom, int64_t n, const pm_
             }
         } else {
             if (nl > 1) {
-                c->space_fourier = true;
                 PM_TRY(launch_kspace(c, 0, 0, 0, lscale, shift, -1, true, false));
             }
             PM_TRY(fft_backward(c));

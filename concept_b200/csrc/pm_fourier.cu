@@ -106,7 +106,8 @@ kspace_kernel(const typename Cplx<T>::type* __restrict__ src, typename Cplx<T>::
 
 int launch_kspace(pm_ctx* c, double prefactor, int deconv_order, double gauss, double scale,
                   const double* shift, int diff_dim, bool from_saved, bool potential) {
-    PM_REQUIRE(c->space_fourier, "k-space operation called while the slab holds real-space data");
+    // reading from the saved copy overwrites the working slab, whatever it held
+    PM_REQUIRE(from_saved || c->space_fourier, "k-space operation called while the slab holds real-space data");
     PM_REQUIRE(deconv_order >= 0 && deconv_order <= 64, "deconv_order = %d out of range", deconv_order);
     PM_REQUIRE(diff_dim >= -1 && diff_dim < 3, "fourier_operate called with diff_dim = %d not in {-1, 0, 1, 2}", diff_dim);
     if (from_saved) PM_REQUIRE(c->saved != nullptr, "pm_fourier_operate(from_saved) without pm_slab_save");
@@ -136,6 +137,7 @@ int launch_kspace(pm_ctx* c, double prefactor, int deconv_order, double gauss, d
                   reinterpret_cast<const float2*>(src), reinterpret_cast<float2*>(c->fourier), c->g, p,
                   c->tab_x, c->tab_sin);
     }
+    c->space_fourier = true;
     return PM_OK;
 }
 

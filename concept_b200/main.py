@@ -1,0 +1,321 @@
+"""Time loop of the host mirror: KDK leapfrog with long-range kicks half a step out of phase with
+the drifts (reference main.py:102-471), its time-step controller and the kick/drift drivers.
+
+Reference: timeloop :102, get_base_timestep_size :697-907, update_base_timestep_size :913-975,
+get_time_step_integrals :998-1073, kick_long :1104-1144, kick_short :1173, driftkick_short :1347-1624,
+constants :2325-2433.  Host-side scheduling stays Python; the only work done
+per step outside libpmgrav.so is O(1) scalar arithmetic.
+
+Out of scope here: fluids, autosave, component activation/termination, renders.
+"""
+import itertools
+import math
+import os
+
+import numpy as np
+
+from . import analysis, commons, communication, integration, interactions
+from .commons import abort, machine_ϵ, masterprint, masterwarn, universals, ထ
+from .integration import cosmic_time, hubble, init_time, scale_factor, scalefactor_integral
+
+# main.py:2325-2433
+Δt_initial_fac = 0.95
+Δt_reduce_fac = 0.94
+Δt_increase_fac = 0.96
+Δt_increase_min_factor = 1.01
+Δt_ratio_warn = 0.7
+Δt_ratio_abort = 0.01
+Δt_jump_fac = 0.95
+Δt_reltol = 1e-9
+Δt_period = 1*8
+bottleneck_static_timestepping = 'static time-stepping'
+initial_fac_times = set()
+ᔑdt_scalar = {}
+
+
+def _facs():
+    p = commons.params
+    return dict(
+        dynamical=0.056*p.Δt_base_background_factor, hubble=0.031*p.Δt_base_background_factor,
+        ẇ=0.0017*p.Δt_base_background_factor, Γ=0.0028*p.Δt_base_background_factor,
+        pm=0.13*p.Δt_base_nonlinear_factor, p3m=0.14*p.Δt_base_nonlinear_factor,
+        softening=0.025*p.Δt_rung_factor,
+    )
+
+
+def get_time_step_integrals(t_start, t_end, components):
+    """main.py:998-1073: every ᔑdt[...] = ∫ integrand(a(t)) dt over [t_start, t_end]."""
+    if not ᔑdt_scalar or ᔑdt_scalar.get('__names') != tuple(c.name for c in components):
+        ᔑdt_scalar.clear()
+        ᔑdt_scalar['__names'] = tuple(c.name for c in components)
+        for integrand in ('1', 'a**2', 'a**(-1)', 'a**(-2)', 'ȧ/a'):
+            ᔑdt_scalar[integrand] = 0
+        for c in components:
+            for integrand in ('a**(-3*w_eff)', 'a**(-3*(1+w_eff))', 'a**(-3*w_eff-1)', 'a**(3*w_eff-2)', 'a**(-3*w_eff)*Γ/H'):
+                ᔑdt_scalar[integrand, c.name] = 0
+        for c0, c1 in itertools.product(components, components):
+            ᔑdt_scalar['a**(-3*w_eff₀-3*w_eff₁-1)', c0.name, c1.name] = 0
+    for integrand in list(ᔑdt_scalar):
+        if integrand == '__names':
+            continue
+        ᔑdt_scalar[integrand] = scalefactor_integral(integrand, t_start, t_end, components)
+    return ᔑdt_scalar
+
+
+def get_base_timestep_size(components, static_timestepping_func=None):
+    """main.py:697-907 for particle components (no fluids, no decay, constant w)."""
+    p = commons.params
+    fac = _facs()
+    t, a = universals.t, universals.a
+    if static_timestepping_func is not None:
+        return static_timestepping_func(a), bottleneck_static_timestepping
+    H = hubble(a)
+    Δt_max, bottleneck = ထ, ''
+    ρ_bar = sum(a**(-3*(1 + c.w_eff(a=a)))*c.ϱ_bar for c in components)
+    Δt_dynamical = fac['dynamical']/(math.sqrt(commons.G_Newton*ρ_bar) + machine_ϵ)
+    if Δt_dynamical < Δt_max:
+        Δt_max, bottleneck = Δt_dynamical, 'the dynamical time scale'
+    if p.enable_Hubble:
+        a_next = a + p.Δa_max_late
+        if a_next < 1:
+            Δt_Δa_late = p.Δt_base_background_factor*(cosmic_time(a_next) - t)
+            if Δt_Δa_late < Δt_max:
+                Δt_max, bottleneck = Δt_Δa_late, 'the maximum allowed Δa (late)'
+        Δt_hubble, bottleneck_hubble = fac['hubble']/H, 'the Hubble time'
+        if p.Δa_max_early > 0:
+            a_next = a + p.Δa_max_early
+            if a_next < 1:
+                Δt_Δa_early = p.Δt_base_background_factor*(cosmic_time(a_next) - t)
+                if Δt_Δa_early > Δt_hubble:
+                    Δt_hubble, bottleneck_hubble = Δt_Δa_early, 'the maximum allowed Δa (early)'
+        if Δt_hubble < Δt_max:
+            Δt_max, bottleneck = Δt_hubble, bottleneck_hubble
+    measurements = {}
+
+    def v_rms_of(c):
+        if c not in measurements:
+            measurements[c] = analysis.measure(c, 'v_rms')
+        return max(measurements[c], machine_ϵ)
+    for c in components:     # PM limiter
+        if c.forces.get('gravity') != 'pm':
+            continue
+        resolution = max(c.potential_gridsizes['gravity']['pm'])
+        Δt_pm = fac['pm']*(p.boxsize/resolution)/v_rms_of(c)
+        if Δt_pm < Δt_max:
+            Δt_max, bottleneck = Δt_pm, f'the PM method of the gravity force for {c.name}'
+    for c in components:     # P³M limiter
+        if c.forces.get('gravity') != 'p3m':
+            continue
+        scale = commons.shortrange_scale(c.potential_gridsizes['gravity']['p3m'][0])
+        Δt_p3m = fac['p3m']*scale/v_rms_of(c)
+        if Δt_p3m < Δt_max:
+            Δt_max, bottleneck = Δt_p3m, f'the P³M method of the gravity force for {c.name}'
+    if t in initial_fac_times:
+        Δt_max *= Δt_initial_fac
+    return Δt_max, bottleneck
+
+
+def update_base_timestep_size(Δt, Δt_min, Δt_max, bottleneck, time_step=-1, time_step_last_sync=-1,
+                              *, allow_increase=True, tolerate_danger=False):
+    """main.py:913-975"""
+    p = commons.params
+    if Δt > Δt_max:
+        Δt_new = Δt_reduce_fac*Δt_max
+        Δt_ratio = Δt_new/Δt
+        if Δt_ratio < Δt_ratio_abort and not tolerate_danger:
+            abort(f'Due to {bottleneck}, the time step size needs to be rescaled by a factor {Δt_ratio:.1g}.')
+        elif Δt_ratio < Δt_ratio_warn:
+            masterwarn(f'Rescaling time step size by a factor {Δt_ratio:.1g} due to {bottleneck}')
+        if Δt_new < Δt_min:
+            abort(f'Time evolution effectively halted with a time step size of {Δt_new} {commons.unit_time}')
+        return Δt_new, bottleneck
+    if not allow_increase:
+        return Δt, bottleneck
+    Δt_new = Δt_increase_fac*Δt_max
+    if Δt_new < Δt:
+        Δt_new = Δt
+    period_frac = (time_step + 1 - time_step_last_sync)*(1/Δt_period)
+    period_frac = min(1, max(0, period_frac))
+    Δt_tmp = (1 + period_frac*(p.Δt_increase_max_factor - 1))*Δt
+    if Δt_new > Δt_tmp:
+        Δt_new = Δt_tmp
+    if p.enable_Hubble and universals.t + Δt_new > cosmic_time(1):
+        return Δt, 'a ≈ 1'
+    return Δt_new, ''
+
+
+def kick_long(components, Δt, sync_time, step_type):
+    """main.py:1104-1144"""
+    t_start = universals.t
+    t_end = t_start + (Δt/2 if step_type == 'init' else Δt)
+    if t_end + Δt_reltol*Δt + 2*machine_ϵ > sync_time:
+        t_end = sync_time
+    if t_start == t_end:
+        return
+    ᔑdt = get_time_step_integrals(t_start, t_end, components)
+    printout = True
+    for force, method, receivers, suppliers in interactions.find_interactions(components, 'long-range'):
+        getattr(interactions, force)(method, receivers, suppliers, ᔑdt, 'long-range', printout)
+
+
+def kick_short(components, Δt, fake=False):
+    """main.py:1173-1345.  Pure-PM runs have no short-range interactions: nothing to do."""
+    if not interactions.find_interactions(components, 'short-range'):
+        return
+    from . import shortrange
+    shortrange.kick_short(components, Δt, fake)
+
+
+def driftkick_short(components, Δt, sync_time):
+    """main.py:1347-1624.  Without short-range interactions: one drift over the whole base step."""
+    particle_components = [c for c in components if c.representation == 'particles']
+    if not particle_components:
+        return
+    if not interactions.find_interactions(particle_components, 'short-range'):
+        t_start = universals.t
+        t_end = t_start + Δt
+        if t_end + Δt_reltol*Δt + 2*machine_ϵ > sync_time:
+            t_end = sync_time
+        if t_start == t_end:
+            return
+        ᔑdt = get_time_step_integrals(t_start, t_end, particle_components)
+        for component in particle_components:
+            component.drift(ᔑdt)
+        return
+    from . import shortrange
+    shortrange.driftkick_short(components, Δt, sync_time)
+
+
+class DumpTime:
+    def __init__(self, a):
+        self.time_param, self.a, self.t = 'a', float(a), cosmic_time(float(a))
+
+
+def _dump_times():
+    ot = commons.params.output_times
+    values = set()
+    for kind, val in ot.items():
+        if isinstance(val, dict):      # {'a': {...}} / {'t': {...}} forms are not used by the hot-path configs
+            for v in val.values():
+                values.update(np.ravel(v).tolist())
+        else:
+            values.update(np.ravel(val).tolist())
+    return [DumpTime(a) for a in sorted(values) if a >= universals.a]
+
+
+def dump(components, dump_time, on_dump=None):
+    """main.py:1676-1712: snapshots are written as .npz (HDF5 is unavailable); `on_dump` is the hook the
+    tests use to capture the state."""
+    if on_dump is not None:
+        on_dump(components, dump_time)
+    out_dir = commons.params.output_dirs.get('snapshot') if isinstance(commons.params.output_dirs, dict) else None
+    wants_snapshot = 'snapshot' in commons.params.output_times
+    if out_dir and wants_snapshot:
+        for c in components:
+            pos, mom = c.gather_global()
+            if communication.master:
+                os.makedirs(out_dir, exist_ok=True)
+                np.savez(os.path.join(out_dir, f'snapshot_a={dump_time.a:.6g}_{c.name}.npz'), pos=pos, mom=mom,
+                         mass=c.mass, a=universals.a, t=universals.t, boxsize=commons.params.boxsize)
+    return False
+
+
+def timeloop(components, on_dump=None, on_step=None, max_steps=None):
+    """main.py:102-471 for particle components.  `components` replaces get_initial_conditions()
+    (snapshot loading / IC generation are out of scope).  Returns the number of base steps taken."""
+    init_time()
+    dump_times = _dump_times()
+    if not dump_times or not components:
+        return 0
+    ᔑdt_scalar.clear()
+    initial_fac_times.clear()
+    if dump_times[0].t == universals.t or dump_times[0].a == universals.a:
+        dump(components, dump_times[0], on_dump)
+        dump_times.pop(0)
+        if not dump_times:
+            return 0
+    initial_fac_times.add(universals.t)
+    Δt_max, bottleneck = get_base_timestep_size(components)
+    Δt_begin = Δt_max
+    if Δt_begin > dump_times[0].t - universals.t:
+        Δt_begin = dump_times[0].t - universals.t
+    Δt = Δt_begin
+    Δt_min = 1e-4*Δt_begin
+    get_time_step_integrals(0, 0, components)
+    kick_short(components, Δt, fake=True)       # initialize_rung_populations (main.py:1639)
+    time_step = 0
+    time_step_last_sync = 0
+    time_step_type = 'init'
+    sync_time = ထ
+    recompute_Δt_max = True
+    Δt_backup = -1
+    for dump_index, dump_time in enumerate(dump_times):
+        while True:
+            if max_steps is not None and time_step >= max_steps:
+                return time_step
+            universals.time_step = time_step
+            if time_step_type == 'init':
+                time_step_type = 'full'
+                kick_long(components, Δt, sync_time, 'init')
+                kick_short(components, Δt)
+                if dump_time.t - universals.t <= 1.5*Δt:
+                    sync_time = dump_time.t
+                    continue
+                Δt_max, bottleneck = get_base_timestep_size(components)
+                if Δt > Δt_max:
+                    sync_time = universals.t + 0.5*Δt
+                    recompute_Δt_max = False
+                    continue
+            elif time_step_type == 'full':
+                driftkick_short(components, Δt, sync_time)
+                universals.t += 0.5*Δt
+                if universals.t + Δt_reltol*Δt + 2*machine_ϵ > sync_time:
+                    universals.t = sync_time
+                universals.a = scale_factor(universals.t)
+                kick_long(components, Δt, sync_time, 'full')
+                universals.t += 0.5*Δt
+                if universals.t + Δt_reltol*Δt + 2*machine_ϵ > sync_time:
+                    universals.t = sync_time
+                universals.a = scale_factor(universals.t)
+                if on_step is not None:
+                    on_step(time_step, universals.t, universals.a, Δt)
+                if universals.t == sync_time:
+                    time_step_type = 'init'
+                    sync_time = ထ
+                    if Δt_backup != -1:
+                        if Δt < Δt_backup:
+                            Δt = Δt_backup
+                        Δt_backup = -1
+                    if recompute_Δt_max:
+                        Δt_max, bottleneck = get_base_timestep_size(components)
+                    recompute_Δt_max = True
+                    Δt, bottleneck = update_base_timestep_size(Δt, Δt_min, Δt_max, bottleneck, time_step, time_step_last_sync)
+                    time_step += 1
+                    time_step_last_sync = time_step
+                    if universals.t == dump_time.t:
+                        dump(components, dump_time, on_dump)
+                        if dump_index != len(dump_times) - 1:
+                            Δt_max = dump_times[dump_index + 1].t - universals.t
+                            if Δt > Δt_max:
+                                Δt_backup = Δt
+                                Δt = Δt_max
+                        break
+                    Δt_max = dump_time.t - universals.t
+                    if Δt > Δt_max:
+                        Δt_backup = Δt
+                        Δt = Δt_max
+                    continue
+                time_step += 1
+                if dump_time.t - universals.t <= 1.5*Δt:
+                    sync_time = dump_time.t
+                    continue
+                Δt_max, bottleneck = get_base_timestep_size(components)
+                if Δt > Δt_max:
+                    sync_time = universals.t + Δt
+                    recompute_Δt_max = False
+                    continue
+                if Δt_max > Δt_increase_min_factor*Δt and (time_step + 1 - time_step_last_sync) >= Δt_period:
+                    sync_time = universals.t + Δt
+                    recompute_Δt_max = False
+                    continue
+    return time_step

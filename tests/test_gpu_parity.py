@@ -1,9 +1,14 @@
 """GPU parity tests: libpmgrav (through the C ABI) vs the golden vectors produced by the reference
 itself (tests/golden) and vs the numpy oracle on seeded inputs.
 
-Tolerances (fp64 grid): the reference is built with -ffast-math and times its FFTW plans, its own
-cross-build tolerance is 1e-9 (test/optimizations/analyze.py:18-22); we require 1e-11 relative on
-the kick and 1e-12 on grids, which is what summation-order differences (atomics, cuFFT) allow.
+Tolerances (fp64 grid).  Bit parity is impossible by construction: the reference is built with
+-ffast-math and lets FFTW pick plans by timing; its own cross-build / cross-nprocs tolerance is 1e-9
+(test/optimizations/analyze.py:18-22, test/nprocs_pm/analyze.py:121).  Here:
+  grids (density, potential):  1e-12 relative to the grid maximum (summation order of atomics / cuFFT);
+  kick Δmom:                   KICK_RTOL = 1e-9 relative to max|Δmom| — the force is a difference of
+                               neighbouring potential values, so FFT rounding (1e-16·|φ|) is amplified
+                               by |φ|/|Δφ| ~ 1e4-1e5; measured errors are 1e-13 … 3e-11;
+  drift:                       bit exact.
 """
 import glob
 import os
@@ -18,6 +23,7 @@ from oracle import pm_oracle as O  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
 KICKS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, 'kick_*.npz')))
+KICK_RTOL = 1e-9
 
 
 def relerr(a, b):
@@ -48,7 +54,7 @@ def test_kick_long_matches_reference_golden(name):
     torch.cuda.synchronize()
     dmom = mom.cpu().numpy() - d['mom']
     dmom_ref = d['mom_out'] - d['mom']
-    assert relerr(dmom, dmom_ref) < 1e-11, name
+    assert relerr(dmom, dmom_ref) < KICK_RTOL, name
     assert np.array_equal(pos.cpu().numpy(), d['pos'])
     assert abs(s.item() - O.sum_mom2(d['mom_out'])) < 1e-12*O.sum_mom2(d['mom_out'])
     ctx.close()
@@ -81,7 +87,7 @@ def test_stages_match_reference_taps(name):
         ctx.gather(PM_TAP_FORCE, pos, mom, p.order, dim, p.kick_factor)
         got = mom.cpu().numpy()[:, dim] - d['mom'][:, dim]
         ref = d['mom_out'][:, dim] - d['mom'][:, dim]
-        assert relerr(got, ref) < 1e-11
+        assert relerr(got, ref) < KICK_RTOL
     ctx.close()
 
 
@@ -131,7 +137,7 @@ def test_kick_vs_oracle_seeded_32(order, diff_order, interlace):
     dpos, dmom = dev(pos), dev(mom)
     ctx.kick_long(dpos, dmom, make_kick_params(**kw))
     got = dmom.cpu().numpy()
-    assert relerr(got - mom, ref - mom) < 1e-11
+    assert relerr(got - mom, ref - mom) < KICK_RTOL
     ctx.close()
 
 
@@ -141,7 +147,7 @@ def test_kick_long_host_entry_point():
     ctx = PMContext(int(d['gridsize']), float(d['boxsize']))
     pos, mom = d['pos'].copy(), d['mom'].copy()
     s = ctx.kick_long_host(pos, mom, golden_params(d), dt_over_mass=0.0, want_sum=True)
-    assert relerr(mom - d['mom'], d['mom_out'] - d['mom']) < 1e-11
+    assert relerr(mom - d['mom'], d['mom_out'] - d['mom']) < KICK_RTOL
     assert abs(s - O.sum_mom2(d['mom_out'])) < 1e-12*s
     # with a drift folded in
     pos2, mom2 = d['pos'].copy(), d['mom'].copy()

@@ -1,0 +1,113 @@
+"""CPU-only tests of the host-side mirror: parameter files, units, background cosmology,
+time-step integrals — against values recorded from the reference's own full run
+(tests/golden/run_pm_8.npz, made by tests/golden/gen_golden_run.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from concept_b200 import commons, integration
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+PM8 = '''
+boxsize = 8*Mpc
+potential_options = {'gridsize': {'gravity': {'pm': 8}}}
+H0      = 70*km/s/Mpc
+Ωcdm    = 0.25
+Ωb      = 0.05
+a_begin = 0.02
+output_times = {'snapshot': (0.1, 0.5, 1)}
+select_forces = {'matter': {'gravity': 'pm'}}
+'''
+
+
+def test_units_match_reference():
+    d = np.load(os.path.join(GOLDEN, 'run_pm_8.npz'))
+    assert commons.G_Newton == float(d['G_Newton'])          # 4.4985024439973154e-05 Mpc³ (10¹⁰ m☉)⁻¹ Gyr⁻²
+    p = commons.load_params(PM8)
+    assert p.H0 == pytest.approx(float(d['H0']), rel=1e-15)
+    assert p.ρ_crit == pytest.approx(float(d['rho_crit']), rel=1e-14)
+    assert p.boxsize == 8.0 and p.Ωm == pytest.approx(0.3)
+
+
+def test_param_file_forward_references_and_h():
+    p = commons.load_params('''
+boxsize = 256*Mpc/h
+potential_options = 2*_size
+_size = 64
+H0 = 67*km/(s*Mpc)
+initial_conditions = {'species': 'matter', 'N': _size**3}
+''')
+    assert p.boxsize == pytest.approx(256/0.67, rel=1e-12)
+    assert commons.gridsize_for('p3m', 64**3) == 128 and commons.gridsize_for('pm', 64**3) == 128
+    assert p.interpolation_order == {'pm': 2, 'p3m': 2}
+    assert p.differentiation == {'pm': 2, 'p3m': 4}
+    assert p.deconvolve['pm'] == (True, True) and p.interlace['pm'] == (False, False)
+
+
+def test_example_basic_defaults_to_p3m():
+    """param/example_basic sets only potential_options = 128 ⇒ particles use P³M (commons.py:3664-3702)"""
+    commons.load_params('''
+initial_conditions = {'species': 'matter', 'N': 64**3}
+boxsize = 256*Mpc/h
+potential_options = 128
+H0 = 67*km/(s*Mpc)
+Ωb = 0.049
+Ωcdm = 0.27
+a_begin = 0.02
+''')
+    from concept_b200.species import Component
+    c = Component('matter', 'matter', N=64**3, mass=1.0)
+    assert c.forces == {'gravity': 'p3m'}
+    assert c.potential_gridsizes['gravity']['p3m'] == (128, 128)
+    assert c.potential_differentiations['gravity']['p3m'] == 4
+
+
+def test_potential_options_variants():
+    p = commons.load_params('''
+boxsize = 30*Mpc
+potential_options = {
+    'gridsize': {'gravity': {'pm': 12}},
+    'interpolation': {'gravity': {'pm': 'TSC'}},
+    'deconvolve': {'gravity': {'pm': (False, False)}},
+    'interlace': {'gravity': {'pm': (True, True)}},
+    'differentiation': {'default': {'gravity': {'pm': 'fourier', 'p3m': 6}}},
+}
+''')
+    assert p.interpolation_order['pm'] == 3 and p.deconvolve['pm'] == (False, False)
+    assert p.interlace['pm'] == (True, True) and p.differentiation == {'pm': 0, 'p3m': 6}
+    assert commons.gridsize_for('pm', 1000) == 12
+
+
+def test_background_and_time_step_integrals_match_reference_run():
+    """Every ᔑdt the reference used in its 160 kicks / 142 drifts is reproduced from our own
+    background (same ODE solver settings, same natural cubic splines)."""
+    d = np.load(os.path.join(GOLDEN, 'run_pm_8.npz'))
+    commons.load_params(PM8)
+    integration.init_time(reinitialize=True)
+    assert commons.universals.a == 0.02
+    for key in ('0.100000', '0.500000', '1.000000'):
+        assert integration.cosmic_time(float(key)) == pytest.approx(float(d[f'snap_t_{key}']), rel=1e-11)
+
+    class C:
+        name = 'matter'
+        def w_eff(self, a=-1, t=-1): return 0.0
+    comps = [C()]
+    # kicks: t_start = kick_t, t_end = t_start + ᔑdt['1']
+    for i in (0, 1, 2, 50, 100, 159):
+        t0, dt1 = float(d['kick_t'][i]), float(d['kick_dt1'][i])
+        assert integration.scalefactor_integral('1', t0, t0 + dt1, comps) == pytest.approx(dt1, rel=1e-12)
+        got = integration.scalefactor_integral(('a**(-3*w_eff-1)', 'matter'), t0, t0 + dt1, comps)
+        assert got == pytest.approx(float(d['kick_dtrho'][i]), rel=1e-10)
+        got = integration.scalefactor_integral(('a**(-3*w_eff)', 'matter'), t0, t0 + dt1, comps)
+        assert got == pytest.approx(float(d['kick_dtkick'][i]), rel=1e-10)
+
+
+def test_spline_matches_scipy_natural():
+    x = np.linspace(1, 3, 7)
+    s = integration.Spline(x, x**2, 'x²')
+    assert s.eval(2.0) == pytest.approx(4.0, rel=1e-3)
+    assert s.integrate(1, 3) == pytest.approx(26/3, rel=1e-3)
+    assert s.integrate(3, 1) == -s.integrate(1, 3)
+    with pytest.raises(SystemExit):
+        s.eval(10.0)     # outside the tabulated interval: abort, like the reference
