@@ -28,12 +28,15 @@ int ensure_force(pm_ctx* c) {
     return PM_OK;
 }
 
-static int halo_for_gather(int order, int diff_order, int* lo, int* hi) {
-    // cells touched along x relative to the slab: interpolation reach + difference reach
+static int halo_for_gather(int order, int diff_order, int interlace, int* lo, int* hi) {
+    // planes touched along x beyond the slab: interpolation reach + difference reach; the
+    // half-cell lattice shift of interlacing moves the footprint by up to one more plane
     const int reach = diff_order == 0 ? 0 : (diff_order <= 2 ? 1 : diff_order / 2);
-    const int interp = order <= 3 ? 1 : 2;   // NGP/CIC/TSC: 1 plane either side; PCS: 2
+    const int interp = (order <= 3 ? 1 : 2) + (interlace ? 1 : 0);   // NGP/CIC/TSC: 1; PCS: 2
     *lo = interp + reach;
     *hi = interp + reach;
+    if (*lo > kHalo) *lo = kHalo;
+    if (*hi > kHalo) *hi = kHalo;
     return PM_OK;
 }
 
@@ -339,7 +342,7 @@ int pm_kick_long(pm_ctx* c, const double* pos, double* mom, int64_t n, const pm_
     const bool need_copy = nl > 1 || p->diff_order == 0;
     if (need_copy) PM_TRY(slab_copy(c, 0));
     int hlo, hhi;
-    halo_for_gather(p->order, p->diff_order, &hlo, &hhi);
+    halo_for_gather(p->order, p->diff_order, p->interlace, &hlo, &hhi);
     // downstream (interactions.py:2214-2330)
     for (int l = 0; l < nl; ++l) {
         const double* shift = l == 0 ? nullptr : kBccShift;

@@ -22,8 +22,8 @@ constexpr double kEps = 2.220446049250313e-16;
 constexpr int kNghostsRef = 2;
 constexpr int kNumSMs = 148;  // B200
 // x-halo planes kept on each side of a slab when nranks > 1:
-// PCS reach (2) + 8th-order difference reach (4)
-constexpr int kHalo = 6;
+// PCS reach (2) + interlacing shift (1) + 8th-order difference reach (4)
+constexpr int kHalo = 7;
 
 extern std::atomic<int64_t> g_launches;
 void set_error(const char* fmt, ...);
