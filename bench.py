@@ -194,9 +194,16 @@ def run_gpu(args):
     n_total = pos.shape[0]
     ctx = PMContext(GRID, BOXSIZE, dtype='f64', rank=rank, nranks=world, device=local_rank)
     if world > 1:
-        uid = [PMContext.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(uid[0])
+        def _bcast(obj):
+            box = [obj]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+
+        def _allgather(obj):
+            out = [None]*world
+            dist.all_gather_object(out, obj)
+            return out
+        ctx.connect(_bcast, _allgather, rank == 0)
         owner = torch.clamp((pos[:, 0]*(GRID/BOXSIZE)).to(torch.int64), 0, GRID - 1)//ctx.nx_local
         keep = owner == rank
         n_local = int(keep.sum().item())
@@ -226,9 +233,12 @@ def run_gpu(args):
             ctx.grid_zero()
             ctx.deposit(p, params.order, params.contribution)
             ctx.halo_add()
-            ctx.fft_forward()
-            ctx.kspace_potential(params.prefactor, params.deconv_order, params.gauss, 1.0)
-            ctx.fft_backward()
+            if ctx.fused_solve_available:
+                ctx.solve_fused(params.prefactor, params.deconv_order, params.gauss)
+            else:
+                ctx.fft_forward()
+                ctx.kspace_potential(params.prefactor, params.deconv_order, params.gauss, 1.0)
+                ctx.fft_backward()
             if world > 1:
                 ctx.halo_fill()
             ev_k0[i].record()

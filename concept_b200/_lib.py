@@ -44,6 +44,8 @@ SIGNATURES = {
     'pm_comm_unique_id': (c_int, [c_void_p]),
     'pm_comm_init': (c_int, [c_void_p, c_void_p]),
     'pm_allreduce_sum': (c_int, [c_void_p, c_void_p, c_int]),
+    'pm_ipc_get_handle': (c_int, [c_void_p, c_void_p]),
+    'pm_ipc_open_peers': (c_int, [c_void_p, c_void_p]),
     'pm_grid_zero': (c_int, [c_void_p]),
     'pm_deposit': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, POINTER(c_double)]),
     'pm_halo_add': (c_int, [c_void_p]),
@@ -52,6 +54,9 @@ SIGNATURES = {
     'pm_fft_backward': (c_int, [c_void_p]),
     'pm_kspace_potential': (c_int, [c_void_p, c_double, c_int, c_double, c_double]),
     'pm_fourier_operate': (c_int, [c_void_p, c_int, POINTER(c_double), c_double, c_int, c_int]),
+    'pm_solve_fused': (c_int, [c_void_p, c_double, c_int, c_double]),
+    'pm_fused_solve_available': (c_int, [c_void_p]),
+    'pm_set_fused_solve': (c_int, [c_void_p, c_int]),
     'pm_slab_save': (c_int, [c_void_p]),
     'pm_slab_accumulate': (c_int, [c_void_p]),
     'pm_slab_restore': (c_int, [c_void_p]),

@@ -157,7 +157,7 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
     if (cudaMalloc(&c->tab_x, sizeof(double) * g.G) != cudaSuccess ||
         cudaMalloc(&c->tab_sin, sizeof(double) * g.G) != cudaSuccess ||
         cudaMalloc(&c->d_scratch, sizeof(double) * 64) != cudaSuccess ||
-        cudaMalloc(&c->d_counts, sizeof(int64_t) * (3 * nranks + (size_t)nranks * nranks + 8)) != cudaSuccess) {
+        cudaMalloc(&c->d_counts, sizeof(int64_t) * (3 * nranks + (size_t)nranks * nranks + 8 + kNumSMs * 4)) != cudaSuccess) {
         set_error("pm_create: cannot allocate tables");
         return fail(PM_ERR_ALLOC);
     }
@@ -165,7 +165,10 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
     cudaMemcpyAsync(c->tab_sin, ts.data(), sizeof(double) * g.G, cudaMemcpyHostToDevice, c->stream);
     cudaMemsetAsync(c->d_scratch, 0, sizeof(double) * 64, c->stream);
     cudaStreamSynchronize(c->stream);   // tx/ts go out of scope
-    int s = make_plans(c);
+    c->fused_solve = true;
+    int s = make_xsolve_tables(c);
+    if (s != PM_OK) return fail(s);
+    s = make_plans(c);
     if (s != PM_OK) return fail(s);
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
@@ -181,7 +184,12 @@ int pm_destroy(pm_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     destroy_plans(c);
+    if (c->peers_ready)
+        for (int r = 0; r < c->nranks; ++r)
+            if (r != c->rank && c->peer_real[r]) cudaIpcCloseMemHandle(c->peer_real[r]);
     if (c->comm_ready) ncclCommDestroy(c->comm);
+    cudaFree(c->xs_tw);
+    cudaFree(c->xs_sep);
     if (c->fourier && c->fourier != c->real) cudaFree(c->fourier);
     cudaFree(c->real);
     cudaFree(c->saved);
@@ -272,6 +280,19 @@ int pm_fourier_operate(pm_ctx* c, int deconv_order, const double* shift, double 
     return launch_kspace(c, 0, deconv_order, 0, scale, shift, diff_dim, from_saved != 0, false);
 }
 
+int pm_solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss) {
+    PM_REQUIRE(c != nullptr, "pm_solve_fused: NULL context");
+    return solve_fused(c, prefactor, deconv_order, gauss);
+}
+
+int pm_fused_solve_available(const pm_ctx* c) { return c && xsolve_supported(c) ? 1 : 0; }
+
+int pm_set_fused_solve(pm_ctx* c, int enable) {
+    PM_REQUIRE(c != nullptr, "pm_set_fused_solve: NULL context");
+    c->fused_solve = enable != 0;
+    return PM_OK;
+}
+
 int pm_slab_save(pm_ctx* c) { PM_REQUIRE(c != nullptr, "NULL context"); return slab_copy(c, 0); }
 int pm_slab_accumulate(pm_ctx* c) { PM_REQUIRE(c != nullptr, "NULL context"); return slab_copy(c, 1); }
 int pm_slab_restore(pm_ctx* c) { PM_REQUIRE(c != nullptr, "NULL context"); return slab_copy(c, 2); }
@@ -323,6 +344,17 @@ int pm_kick_long(pm_ctx* c, const double* pos, double* mom, int64_t n, const pm_
     PM_REQUIRE(p->interlace == 0 || p->interlace == 1, "pm_kick_long: interlace = %d", p->interlace);
     const int nl = p->interlace ? 2 : 1;
     const double lscale = 1.0 / nl;
+    if (c->fused_solve && nl == 1 && p->diff_order != 0 && xsolve_supported(c)) {
+        // default path: 2-D transforms + fused x pass (FFT · Green's function · inverse FFT)
+        int hlo, hhi;
+        halo_for_gather(p->order, p->diff_order, 0, &hlo, &hhi);
+        PM_TRY(pm_grid_zero(c));
+        PM_TRY(pm_deposit(c, pos, n, p->order, p->contribution, nullptr));
+        PM_TRY(halo_add(c));
+        PM_TRY(solve_fused(c, p->prefactor, p->deconv_order, p->gauss));
+        PM_TRY(halo_fill(c, hlo, hhi, PM_TAP_REAL));
+        return launch_gather_kick(c, pos, mom, n, p->order, p->diff_order, p->kick_factor, nullptr, sum_mom2);
+    }
     // upstream: interpolate_upstream(..., output_space='Fourier')  (mesh.py:492-616)
     for (int l = 0; l < nl; ++l) {
         const double* shift = l == 0 ? nullptr : kBccShift;

@@ -8,6 +8,8 @@
 // domain<->slab redistribution of mesh.py:2138-2411 does not exist in this layout.
 #include "pm_internal.cuh"
 
+#include <cstring>
+
 namespace pm {
 
 template <typename T> struct NcclType;
@@ -139,7 +141,47 @@ int transpose_backward(pm_ctx* c) {
     return c->dtype == PM_GRID_F64 ? transpose_t<double, double2>(c, false) : transpose_t<float, float2>(c, false);
 }
 
+int device_barrier(pm_ctx* c) {
+    if (c->nranks == 1) return PM_OK;
+    PM_REQUIRE(c->comm_ready, "device barrier: call pm_comm_init first");
+    double* token = c->d_scratch + 32;
+    PM_CHECK_NCCL(ncclAllReduce(token, token, 1, ncclDouble, ncclSum, c->comm, c->stream));
+    return PM_OK;
+}
+
 }  // namespace pm
+
+// ---------------------------------------------------------------------------
+// C ABI: peer mappings of the slabs (CUDA IPC) for the fused x-solve
+// ---------------------------------------------------------------------------
+extern "C" int pm_ipc_get_handle(pm_ctx* c, void* handle_out_64) {
+    PM_REQUIRE(c && handle_out_64, "pm_ipc_get_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    cudaIpcMemHandle_t h;
+    PM_CHECK_CUDA(cudaIpcGetMemHandle(&h, c->real));
+    memcpy(handle_out_64, &h, sizeof(h));
+    return PM_OK;
+}
+
+extern "C" int pm_ipc_open_peers(pm_ctx* c, const void* handles_nranks_x_64) {
+    PM_REQUIRE(c && handles_nranks_x_64, "pm_ipc_open_peers: NULL argument");
+    if (c->nranks == 1) return PM_OK;
+    PM_REQUIRE(c->nranks <= pm::kMaxPeers, "pm_ipc_open_peers: more than %d ranks", pm::kMaxPeers);
+    PM_REQUIRE(!c->peers_ready, "pm_ipc_open_peers: already opened");
+    PM_CHECK_CUDA(cudaSetDevice(c->device));
+    const unsigned char* hs = reinterpret_cast<const unsigned char*>(handles_nranks_x_64);
+    for (int r = 0; r < c->nranks; ++r) {
+        if (r == c->rank) {
+            c->peer_real[r] = c->real;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs + (size_t)r * 64, sizeof(h));
+        PM_CHECK_CUDA(cudaIpcOpenMemHandle(&c->peer_real[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->peers_ready = true;
+    return PM_OK;
+}
 
 // ---------------------------------------------------------------------------
 // C ABI: communicator

@@ -208,8 +208,27 @@ int make_plans(pm_ctx* c) {
         PM_CHECK_CUFFT(cufftMakePlanMany64(c->plan_x, 1, n1, e1, stride, 1, e1, stride, 1,
                                            f64 ? CUFFT_Z2Z : CUFFT_C2C, stride, &ws_x));
     }
+    size_t ws2_f = 0, ws2_b = 0;
+    c->plan2_ready = false;
+    if (c->nranks == 1 && c->xs_tw != nullptr) {
+        // batched 2-D (y,z) plans: the x direction is handled by the fused x-solve kernel
+        long long n2[2] = {g.G, g.G};
+        long long rembed[2] = {g.G, g.Gp};
+        long long cembed[2] = {g.G, g.Gc};
+        PM_CHECK_CUFFT(cufftCreate(&c->plan2_fwd));
+        PM_CHECK_CUFFT(cufftCreate(&c->plan2_bwd));
+        PM_CHECK_CUFFT(cufftSetAutoAllocation(c->plan2_fwd, 0));
+        PM_CHECK_CUFFT(cufftSetAutoAllocation(c->plan2_bwd, 0));
+        PM_CHECK_CUFFT(cufftMakePlanMany64(c->plan2_fwd, 2, n2, rembed, 1, (long long)g.G * g.Gp, cembed, 1,
+                                           (long long)g.G * g.Gc, f64 ? CUFFT_D2Z : CUFFT_R2C, g.nxl, &ws2_f));
+        PM_CHECK_CUFFT(cufftMakePlanMany64(c->plan2_bwd, 2, n2, cembed, 1, (long long)g.G * g.Gc, rembed, 1,
+                                           (long long)g.G * g.Gp, f64 ? CUFFT_Z2D : CUFFT_C2R, g.nxl, &ws2_b));
+        c->plan2_ready = true;
+    }
     size_t ws = ws_f > ws_b ? ws_f : ws_b;
     if (ws_x > ws) ws = ws_x;
+    if (ws2_f > ws) ws = ws2_f;
+    if (ws2_b > ws) ws = ws2_b;
     c->fft_work_bytes = ws;
     if (ws) {
         PM_CHECK_CUDA(cudaMalloc(&c->fft_work, ws));
@@ -223,6 +242,12 @@ int make_plans(pm_ctx* c) {
         PM_CHECK_CUFFT(cufftSetWorkArea(c->plan_x, c->fft_work));
         PM_CHECK_CUFFT(cufftSetStream(c->plan_x, c->stream));
     }
+    if (c->plan2_ready) {
+        PM_CHECK_CUFFT(cufftSetWorkArea(c->plan2_fwd, c->fft_work));
+        PM_CHECK_CUFFT(cufftSetWorkArea(c->plan2_bwd, c->fft_work));
+        PM_CHECK_CUFFT(cufftSetStream(c->plan2_fwd, c->stream));
+        PM_CHECK_CUFFT(cufftSetStream(c->plan2_bwd, c->stream));
+    }
     c->plans_ready = true;
     return PM_OK;
 }
@@ -232,6 +257,7 @@ void destroy_plans(pm_ctx* c) {
     cufftDestroy(c->plan_fwd);
     cufftDestroy(c->plan_bwd);
     if (c->nranks > 1) cufftDestroy(c->plan_x);
+    if (c->plan2_ready) { cufftDestroy(c->plan2_fwd); cufftDestroy(c->plan2_bwd); c->plan2_ready = false; }
     c->plans_ready = false;
 }
 
@@ -280,6 +306,28 @@ int fft_backward(pm_ctx* c) {
         PM_CHECK_CUFFT(cufftExecC2R(c->plan_bwd, reinterpret_cast<cufftComplex*>(r), r));
     }
     c->space_fourier = false;
+    return PM_OK;
+}
+
+// forward 2-D transforms → fused x pass (FFT · Green · inverse FFT) → inverse 2-D transforms.
+// Equivalent to pm_fft_forward + pm_kspace_potential + pm_fft_backward; the slab ends in real space.
+int solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss) {
+    PM_REQUIRE(!c->space_fourier, "pm_solve_fused: the slab holds Fourier data");
+    PM_REQUIRE(xsolve_supported(c), "pm_solve_fused: not available for this grid size / rank layout");
+    const bool f64 = c->dtype == PM_GRID_F64;
+    cufftHandle fwd = c->nranks == 1 ? c->plan2_fwd : c->plan_fwd;
+    cufftHandle bwd = c->nranks == 1 ? c->plan2_bwd : c->plan_bwd;
+    if (f64) {
+        double* r = c->real_interior<double>();
+        PM_CHECK_CUFFT(cufftExecD2Z(fwd, r, reinterpret_cast<cufftDoubleComplex*>(r)));
+        PM_TRY(xsolve(c, prefactor, deconv_order, gauss));
+        PM_CHECK_CUFFT(cufftExecZ2D(bwd, reinterpret_cast<cufftDoubleComplex*>(r), r));
+    } else {
+        float* r = c->real_interior<float>();
+        PM_CHECK_CUFFT(cufftExecR2C(fwd, r, reinterpret_cast<cufftComplex*>(r)));
+        PM_TRY(xsolve(c, prefactor, deconv_order, gauss));
+        PM_CHECK_CUFFT(cufftExecC2R(bwd, reinterpret_cast<cufftComplex*>(r), r));
+    }
     return PM_OK;
 }
 

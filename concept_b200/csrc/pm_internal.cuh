@@ -24,6 +24,7 @@ constexpr int kNumSMs = 148;  // B200
 // x-halo planes kept on each side of a slab when nranks > 1:
 // PCS reach (2) + interlacing shift (1) + 8th-order difference reach (4)
 constexpr int kHalo = 7;
+constexpr int kMaxPeers = 16;   // ranks whose slabs one kernel can address through peer pointers
 
 extern std::atomic<int64_t> g_launches;
 void set_error(const char* fmt, ...);
@@ -117,6 +118,8 @@ struct pm_ctx {
     // cuFFT
     cufftHandle plan_fwd, plan_bwd;        // nranks == 1: 3-D ; else batched 2-D
     cufftHandle plan_x;                    // nranks > 1: strided 1-D c2c along i
+    cufftHandle plan2_fwd, plan2_bwd;      // nranks == 1: batched 2-D (y,z) plans for the fused x-solve path
+    bool plan2_ready;
     bool plans_ready;
     // NCCL
     ncclComm_t comm;
@@ -127,6 +130,14 @@ struct pm_ctx {
     void* xchg_buf;           // staging for migrating particles
     size_t xchg_bytes;
     int64_t bytes_allocated;
+    // fused x-solve (pm_xsolve.cu)
+    double2* xs_tw;           // exp(−2πi·m/G)
+    double* xs_sep;           // separable k-space factor per axis index (cached for one (deconv, gauss))
+    int xs_sep_deconv;
+    double xs_sep_gauss;
+    bool fused_solve;         // use the fused path when supported
+    void* peer_real[pm::kMaxPeers];   // IPC mappings of every rank's `real` buffer (own pointer for self)
+    bool peers_ready;
     // state flags
     bool space_fourier;       // working slab currently holds Fourier data
 
@@ -165,6 +176,13 @@ int halo_add(pm_ctx* c);
 int halo_fill(pm_ctx* c, int planes_lo, int planes_hi, int which);
 int transpose_forward(pm_ctx* c);   // real-buffer 2-D spectra -> Fourier slab (all-to-all)
 int transpose_backward(pm_ctx* c);
+
+int device_barrier(pm_ctx* c);      // stream-ordered barrier over all ranks
+// implemented in pm_xsolve.cu
+bool xsolve_supported(const pm_ctx* c);
+int xsolve(pm_ctx* c, double prefactor, int deconv_order, double gauss);
+int make_xsolve_tables(pm_ctx* c);
+int solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss);   // pm_fourier.cu
 
 int ensure_saved(pm_ctx* c);
 int ensure_force(pm_ctx* c);

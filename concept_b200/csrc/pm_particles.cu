@@ -94,45 +94,102 @@ __device__ __forceinline__ int owner_of(double x, double cells_per_len, int G, i
     return cell / nxl;
 }
 
-// counts[r] = particles bound for rank r
-__global__ void __launch_bounds__(256)
+constexpr int kXchgBlocks = kNumSMs * 4;   // contiguous chunks of the particle array, one per CTA
+constexpr int kXchgThreads = 256;
+
+// Pass 1: counts[r] = particles bound for rank r (global); stay[b] = stayers in chunk b.
+__global__ void __launch_bounds__(kXchgThreads)
 owner_count_kernel(const double* __restrict__ pos, int64_t n, double cells_per_len, int G, int nxl,
-                   int nranks, unsigned long long* __restrict__ counts) {
+                   int rank, int nranks, unsigned long long* __restrict__ counts,
+                   unsigned int* __restrict__ stay) {
     extern __shared__ unsigned int scount[];
     for (int r = threadIdx.x; r < nranks; r += blockDim.x) scount[r] = 0;
     __syncthreads();
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
         atomicAdd(&scount[owner_of(pos[3 * i], cells_per_len, G, nxl)], 1u);
-    }
     __syncthreads();
     for (int r = threadIdx.x; r < nranks; r += blockDim.x)
         if (scount[r]) atomicAdd(&counts[r], (unsigned long long)scount[r]);
+    if (threadIdx.x == 0) stay[blockIdx.x] = scount[rank];
 }
 
-// Scatter every particle into the staging arrays grouped by owner:
-// [own | rank 0 | rank 1 | …] with `offsets[r]` the start of each group and `cursor[r]` a running
-// counter.  Order inside a group is not deterministic (atomics), like any parallel partition.
-__global__ void __launch_bounds__(256)
+// exclusive scan of the per-chunk stayer counts (one CTA; kXchgBlocks is small)
+__global__ void __launch_bounds__(1024) stay_scan_kernel(unsigned int* __restrict__ stay, int nblocks) {
+    __shared__ unsigned int s[1024];
+    unsigned int carry = 0;
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned int v = i < nblocks ? stay[i] : 0;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            const unsigned int t = threadIdx.x >= off ? s[threadIdx.x - off] : 0;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nblocks) stay[i] = carry + s[threadIdx.x] - v;
+        carry += s[1023];
+        __syncthreads();
+    }
+}
+
+// Pass 2: ORDER-PRESERVING partition.  Stayers keep their relative order (the memory order of the
+// particles — lattice / cell-sorted — is what makes deposit and gather cache-friendly, and it must not
+// be scrambled by every migration); movers are grouped by destination rank, order irrelevant.
+__global__ void __launch_bounds__(kXchgThreads)
 owner_scatter_kernel(const double* __restrict__ pos, const double* __restrict__ mom,
-                     const int64_t* __restrict__ ids, int64_t n, double cells_per_len, int G, int nxl,
+                     const int64_t* __restrict__ ids, int64_t n, double cells_per_len, int G, int nxl, int rank,
+                     const unsigned int* __restrict__ stay_offset,
                      const unsigned long long* __restrict__ offsets, unsigned long long* __restrict__ cursor,
                      double* __restrict__ pos_out, double* __restrict__ mom_out, int64_t* __restrict__ ids_out) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
-        const int r = owner_of(x, cells_per_len, G, nxl);
-        // warp-aggregated slot claim: one atomic per distinct owner per warp
-        const unsigned peers = __match_any_sync(__activemask(), r);
-        const int leader = __ffs(peers) - 1;
-        const int lane = threadIdx.x & 31;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(&cursor[r], (unsigned long long)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        const int64_t slot = (int64_t)(offsets[r] + base + __popc(peers & ((1u << lane) - 1)));
-        pos_out[3 * slot] = x; pos_out[3 * slot + 1] = y; pos_out[3 * slot + 2] = z;
-        mom_out[3 * slot] = mom[3 * i]; mom_out[3 * slot + 1] = mom[3 * i + 1]; mom_out[3 * slot + 2] = mom[3 * i + 2];
-        if (ids) ids_out[slot] = ids[i];
+    __shared__ unsigned int warp_tot[kXchgThreads / 32];
+    __shared__ unsigned int running;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = stay_offset[blockIdx.x];
+    __syncthreads();
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+    for (int64_t base = lo; base < hi; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const bool valid = i < hi;
+        double x = 0, y = 0, z = 0;
+        int r = -1;
+        if (valid) {
+            x = pos[3 * i]; y = pos[3 * i + 1]; z = pos[3 * i + 2];
+            r = owner_of(x, cells_per_len, G, nxl);
+        }
+        const bool stays = valid && r == rank;
+        const unsigned ball = __ballot_sync(0xffffffffu, stays);
+        if (lane == 0) warp_tot[warp] = __popc(ball);
+        __syncthreads();
+        unsigned int before = 0, total = 0;
+        for (int w = 0; w < kXchgThreads / 32; ++w) {
+            const unsigned int t = warp_tot[w];
+            if (w < warp) before += t;
+            total += t;
+        }
+        int64_t slot = -1;
+        if (stays) {
+            slot = (int64_t)running + before + __popc(ball & ((1u << lane) - 1));
+        } else if (valid) {
+            const unsigned peers = __match_any_sync(__activemask(), r);
+            const int leader = __ffs(peers) - 1;
+            unsigned long long b0 = 0;
+            if (lane == leader) b0 = atomicAdd(&cursor[r], (unsigned long long)__popc(peers));
+            b0 = __shfl_sync(peers, b0, leader);
+            slot = (int64_t)(offsets[r] + b0 + __popc(peers & ((1u << lane) - 1)));
+        }
+        if (slot >= 0) {
+            pos_out[3 * slot] = x; pos_out[3 * slot + 1] = y; pos_out[3 * slot + 2] = z;
+            mom_out[3 * slot] = mom[3 * i]; mom_out[3 * slot + 1] = mom[3 * i + 1]; mom_out[3 * slot + 2] = mom[3 * i + 2];
+            if (ids) ids_out[slot] = ids[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) running += total;
+        __syncthreads();
     }
 }
 
@@ -150,10 +207,13 @@ int exchange_particles(pm_ctx* c, double* pos, double* mom, int64_t* ids, int64_
     auto* d_offsets = d_counts + P;
     auto* d_cursor = d_offsets + P;
     auto* d_matrix = d_cursor + P;
+    auto* d_stay = reinterpret_cast<unsigned int*>(d_matrix + (size_t)P * P);   // [kXchgBlocks]
     PM_CHECK_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * 3 * P, c->stream));
+    PM_CHECK_CUDA(cudaMemsetAsync(d_stay, 0, sizeof(unsigned int) * kXchgBlocks, c->stream));
     if (n > 0) {
-        PM_LAUNCH(owner_count_kernel, kNumSMs * 4, 256, P * sizeof(unsigned int), c->stream, pos, n,
-                  cells_per_len, c->g.G, c->g.nxl, P, d_counts);
+        PM_LAUNCH(owner_count_kernel, kXchgBlocks, kXchgThreads, P * sizeof(unsigned int), c->stream, pos, n,
+                  cells_per_len, c->g.G, c->g.nxl, c->rank, P, d_counts, d_stay);
+        PM_LAUNCH(stay_scan_kernel, 1, 1024, 0, c->stream, d_stay, kXchgBlocks);
     }
     // everyone learns everyone's send counts
     PM_CHECK_NCCL(ncclAllGather(d_counts, d_matrix, P, ncclUint64, c->comm, c->stream));
@@ -194,8 +254,8 @@ int exchange_particles(pm_ctx* c, double* pos, double* mom, int64_t* ids, int64_
     PM_CHECK_CUDA(cudaMemcpyAsync(d_offsets, offsets.data(), sizeof(unsigned long long) * P,
                                   cudaMemcpyHostToDevice, c->stream));
     if (n > 0) {
-        PM_LAUNCH(owner_scatter_kernel, kNumSMs * 4, 256, 0, c->stream, pos, mom, ids, n, cells_per_len,
-                  c->g.G, c->g.nxl, d_offsets, d_cursor, spos, smom, ids ? sids : nullptr);
+        PM_LAUNCH(owner_scatter_kernel, kXchgBlocks, kXchgThreads, 0, c->stream, pos, mom, ids, n, cells_per_len,
+                  c->g.G, c->g.nxl, c->rank, d_stay, d_offsets, d_cursor, spos, smom, ids ? sids : nullptr);
     }
     // own particles back to the front of the live arrays
     const int64_t n_own = (int64_t)mine[c->rank];

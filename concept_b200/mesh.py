@@ -25,8 +25,7 @@ def get_context(gridsize, dtype=None):
         ctx = PMContext(gridsize, commons.params.boxsize, dtype=dtype, rank=communication.rank,
                         nranks=communication.nprocs, device=communication.local_rank)
         if communication.nprocs > 1:
-            uid = communication.bcast(PMContext.comm_unique_id() if communication.master else None)
-            ctx.comm_init(uid)
+            ctx.connect(communication.bcast, communication.allgather, communication.master)
         _contexts[key] = ctx
     return ctx
 

@@ -85,6 +85,24 @@ class PMContext:
         check(lib.pm_comm_unique_id(buf))
         return buf.raw
 
+    def connect(self, bcast, allgather, is_master):
+        """Join the ranks of one job: NCCL communicator (id broadcast from the master) and CUDA-IPC
+        peer mappings of every rank's slab (handles all-gathered in rank order).  `bcast(obj)` and
+        `allgather(obj)` are host-side helpers (torch.distributed object collectives)."""
+        uid = bcast(PMContext.comm_unique_id() if is_master else None)
+        self.comm_init(uid)
+        self.ipc_open_peers(allgather(self.ipc_handle()))
+
+    def ipc_handle(self):
+        buf = ctypes.create_string_buffer(64)
+        check(self.lib.pm_ipc_get_handle(self._h, buf))
+        return buf.raw
+
+    def ipc_open_peers(self, handles):
+        """handles: list of 64-byte handles in rank order (all-gathered by the host code)"""
+        blob = b''.join(bytes(h) for h in handles)
+        check(self.lib.pm_ipc_open_peers(self._h, ctypes.create_string_buffer(blob, len(blob))))
+
     def allreduce_sum(self, t):
         check(self.lib.pm_allreduce_sum(self._h, _ptr(t), t.numel()))
 
@@ -109,6 +127,16 @@ class PMContext:
 
     def kspace_potential(self, prefactor, deconv_order, gauss=0.0, scale=1.0):
         check(self.lib.pm_kspace_potential(self._h, float(prefactor), int(deconv_order), float(gauss), float(scale)))
+
+    def solve_fused(self, prefactor, deconv_order, gauss=0.0):
+        check(self.lib.pm_solve_fused(self._h, float(prefactor), int(deconv_order), float(gauss)))
+
+    @property
+    def fused_solve_available(self):
+        return bool(self.lib.pm_fused_solve_available(self._h))
+
+    def set_fused_solve(self, enable):
+        check(self.lib.pm_set_fused_solve(self._h, int(bool(enable))))
 
     def fourier_operate(self, deconv_order=0, shift=None, scale=1.0, diff_dim=-1, from_saved=False):
         check(self.lib.pm_fourier_operate(self._h, int(deconv_order), vec3(shift), float(scale), int(diff_dim), int(from_saved)))

@@ -83,6 +83,11 @@ int pm_comm_unique_id(void* id_out_128);
 int pm_comm_init(pm_ctx* ctx, const void* id_128);
 /* sum a device array of n doubles over all ranks in place (allreduce, analysis.py:3971) */
 int pm_allreduce_sum(pm_ctx* ctx, double* dev_values, int n);
+/* CUDA-IPC mapping of every rank's slab into every rank (same node, NVLink/NVSwitch peer access):
+ * each rank exports a 64-byte handle; the host code all-gathers them (rank order) and hands the
+ * nranks×64 bytes to pm_ipc_open_peers. */
+int pm_ipc_get_handle(pm_ctx* ctx, void* handle_out_64);
+int pm_ipc_open_peers(pm_ctx* ctx, const void* handles_nranks_x_64);
 
 /* ---- mesh operators ------------------------------------------------------ */
 /* get_buffer(..., nullify=True) for 'grid_updownstream' (mesh.py:600) */
@@ -116,6 +121,14 @@ int pm_kspace_potential(pm_ctx* ctx, double prefactor, int deconv_order, double 
  * working slab (the reference copies slab_downstream → slab_updownstream_subgroup). */
 int pm_fourier_operate(pm_ctx* ctx, int deconv_order, const double* shift, double scale,
                        int diff_dim, int from_saved);
+/* pm_fft_forward + pm_kspace_potential + pm_fft_backward in one call, with the x transforms and the
+ * k-space factor fused into a single kernel that addresses all ranks' slabs through peer pointers
+ * (the FFTW-MPI transpose of fft.c:34-73 never materialises).  Available for G ∈ {64, 512}; with
+ * several ranks pm_ipc_open_peers must have been called.  The slab ends in real space (potential). */
+int pm_solve_fused(pm_ctx* ctx, double prefactor, int deconv_order, double gauss);
+int pm_fused_solve_available(const pm_ctx* ctx);
+/* pm_kick_long uses the fused solve when available; enable = 0 forces the three-call path */
+int pm_set_fused_solve(pm_ctx* ctx, int enable);
 int pm_slab_save(pm_ctx* ctx);      /* slab_updownstream_subgroup[...] = slab (interactions.py:2256) */
 int pm_slab_accumulate(pm_ctx* ctx);/* saved += working slab (copy_modes '+=' for interlacing) */
 int pm_slab_restore(pm_ctx* ctx);   /* working slab = saved */

@@ -25,10 +25,14 @@ def relerr(a, b):
 
 def main():
     rank, P = communication.init()
-    G, L, N = 48, 60.0, 40000
+    L, N = 60.0, 40000
     failures = []
-    for order, diff, interlace, dtype in [(2, 2, False, 'f64'), (3, 4, False, 'f64'), (4, 8, False, 'f64'),
-                                          (2, 0, False, 'f64'), (3, 2, True, 'f64')]:
+    # G = 64: the fused x-solve over CUDA-IPC peer pointers; G = 48: cuFFT + NCCL all-to-all transpose
+    for G, order, diff, interlace, dtype in [(64, 2, 2, False, 'f64'), (64, 3, 4, False, 'f64'), (64, 4, 8, False, 'f64'),
+                                             (64, 2, 0, False, 'f64'), (64, 3, 2, True, 'f64'),
+                                             (48, 2, 2, False, 'f64'), (48, 3, 4, False, 'f64')]:
+        if G % P or G//P < 7:
+            continue
         interp = {2: 'CIC', 3: 'TSC', 4: 'PCS'}[order]
         commons.load_params(f'''
 boxsize = {L}*Mpc
@@ -50,7 +54,12 @@ select_forces = {{'matter': {{'gravity': 'pm'}}}}
         ᔑdt = {'1': 0.02, ('a**(-3*w_eff-1)', 'matter'): 0.041, ('a**(-3*w_eff)', 'matter'): 0.0199, 'a**(-2)': 0.08}
         interactions.gravity('pm', [c], [c], ᔑdt, 'long-range', False)
         got_pos, got_mom = c.gather_global()
+        fused = mesh.get_context(G).fused_solve_available
+        ids_before = set(c.ids[:c.N_local].cpu().numpy().tolist())
         c.drift(ᔑdt)                      # moves particles up to several cells → migration
+        ids_now = c.ids[:c.N_local].cpu().numpy()
+        stayers = ids_now[np.isin(ids_now, np.fromiter(ids_before, dtype=np.int64))]
+        order_kept = communication.allgather(bool(np.all(np.diff(stayers) > 0)))
         n_after = communication.allgather(c.N_local)
         drift_pos, drift_mom = c.gather_global()
         # ownership after migration
@@ -63,11 +72,12 @@ select_forces = {{'matter': {{'gravity': 'pm'}}}}
             e1 = relerr(got_mom - mom, ref - mom)
             ref_pos = O.drift(pos, ref, 0.08*1.0/mass, L)
             e2 = float(np.max(np.abs(drift_pos - O.drift(pos, got_mom, 0.08/mass, L))))
-            status = 'ok' if (e1 < 1e-9 and e2 == 0.0 and all(oks) and sum(n_after) == N and np.array_equal(got_pos, pos)) else 'FAIL'
-            print(f'[P={P}] order={order} diff={diff} interlace={interlace}: kick relerr {e1:.2e}, drift max|Δ| {e2:.1e}, '
-                  f'owners ok {all(oks)}, N {n_locals}->{n_after}  {status}', flush=True)
+            status = 'ok' if (e1 < 1e-9 and e2 == 0.0 and all(oks) and all(order_kept) and sum(n_after) == N
+                              and np.array_equal(got_pos, pos)) else 'FAIL'
+            print(f'[P={P}] G={G} fused={fused} order={order} diff={diff} interlace={interlace}: kick relerr {e1:.2e}, '
+                  f'drift max|Δ| {e2:.1e}, owners ok {all(oks)}, order kept {all(order_kept)}, N {n_locals}->{n_after}  {status}', flush=True)
             if status != 'ok':
-                failures.append((order, diff, interlace))
+                failures.append((G, order, diff, interlace))
         mesh.free_contexts()
     # f32 grid over several ranks: stated tolerance 1e-5 rms
     failures = communication.bcast(failures)

@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--dtype', default='f64')
     ap.add_argument('--sigma', type=float, default=0.3)
     ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--nofuse', action='store_true', help='three-call solve (cuFFT 3-D + k-space kernel) instead of the fused x-solve')
     ap.add_argument('--shuffle', action='store_true', help='random particle order (worst-case locality)')
     a = ap.parse_args()
     L = 512.0
@@ -38,9 +39,11 @@ def main():
     stages = [
         ('grid_zero', lambda: ctx.grid_zero()),
         ('deposit', lambda: ctx.deposit(pos, p.order, p.contribution)),
-        ('fft_forward', lambda: ctx.fft_forward()),
-        ('kspace', lambda: ctx.kspace_potential(p.prefactor, p.deconv_order, p.gauss, 1.0)),
-        ('fft_backward', lambda: ctx.fft_backward()),
+        *([('solve_fused', lambda: ctx.solve_fused(p.prefactor, p.deconv_order, p.gauss))]
+          if (ctx.fused_solve_available and not a.nofuse) else [
+            ('fft_forward', lambda: ctx.fft_forward()),
+            ('kspace', lambda: ctx.kspace_potential(p.prefactor, p.deconv_order, p.gauss, 1.0)),
+            ('fft_backward', lambda: ctx.fft_backward())]),
         ('gather_kick', lambda: ctx.gather_kick(pos, mom, p.order, p.diff_order, p.kick_factor, None, s)),
         ('drift', lambda: ctx.drift(pos, mom, 1e-4)),
     ]
@@ -59,7 +62,7 @@ def main():
             total.append(evs[0].elapsed_time(evs[-1]))
     G3 = a.grid**3
     es = 8 if a.dtype == 'f64' else 4
-    alg = {'grid_zero': es*G3, 'deposit': 24*N + es*G3, 'fft_forward': 2*es*G3, 'kspace': 2*es*G3, 'fft_backward': 2*es*G3,
+    alg = {'grid_zero': es*G3, 'deposit': 24*N + es*G3, 'fft_forward': 2*es*G3, 'kspace': 2*es*G3, 'fft_backward': 2*es*G3, 'solve_fused': 4*es*G3,
            'gather_kick': 72*N + es*G3, 'drift': 72*N}
     out = {'N': N, 'grid': a.grid, 'order': a.order, 'dtype': a.dtype, 'sigma': a.sigma, 'shuffle': a.shuffle,
            'device_bytes': ctx.device_bytes, 'stages_ms': {}, 'stages_GBps': {}}

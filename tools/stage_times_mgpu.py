@@ -20,9 +20,17 @@ def main():
     pos, mom = zeldovich_particles(n_side, L, 0.3, seed=0, device=dev)
     N = pos.shape[0]
     ctx = PMContext(G, L, rank=rank, nranks=world, device=lr)
-    uid = [PMContext.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    ctx.comm_init(uid[0])
+    def _bcast(obj):
+        box = [obj]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def _allgather(obj):
+        out = [None]*world
+        dist.all_gather_object(out, obj)
+        return out
+    ctx.connect(_bcast, _allgather, rank == 0)
+    fused = ctx.fused_solve_available and not int(os.environ.get('PM_NOFUSE', '0'))
     keep = torch.clamp((pos[:, 0]*(G/L)).to(torch.int64), 0, G - 1)//ctx.nx_local == rank
     n = int(keep.sum())
     cap = int(N/world*1.5) + 4096
@@ -36,9 +44,10 @@ def main():
         ('grid_zero', lambda: ctx.grid_zero()),
         ('deposit', lambda: ctx.deposit(pb[:st['n']], 2, p.contribution)),
         ('halo_add', lambda: ctx.halo_add()),
-        ('fft_forward', lambda: ctx.fft_forward()),
-        ('kspace', lambda: ctx.kspace_potential(p.prefactor, p.deconv_order, 0.0, 1.0)),
-        ('fft_backward', lambda: ctx.fft_backward()),
+        *([('solve_fused', lambda: ctx.solve_fused(p.prefactor, p.deconv_order, 0.0))] if fused else [
+            ('fft_forward', lambda: ctx.fft_forward()),
+            ('kspace', lambda: ctx.kspace_potential(p.prefactor, p.deconv_order, 0.0, 1.0)),
+            ('fft_backward', lambda: ctx.fft_backward())]),
         ('halo_fill', lambda: ctx.halo_fill()),
         ('gather_kick', lambda: ctx.gather_kick(pb[:st['n']], mb[:st['n']], 2, 2, p.kick_factor, None, s)),
         ('drift', lambda: ctx.drift(pb[:st['n']], mb[:st['n']], 1e-4)),
