@@ -190,6 +190,8 @@ int pm_destroy(pm_ctx* c) {
     if (c->comm_ready) ncclCommDestroy(c->comm);
     cudaFree(c->xs_tw);
     cudaFree(c->xs_sep);
+    cudaFree(c->sr_buf);
+    cudaFree(c->sr_tmp);
     if (c->fourier && c->fourier != c->real) cudaFree(c->fourier);
     cudaFree(c->real);
     cudaFree(c->saved);

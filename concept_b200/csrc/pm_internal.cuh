@@ -138,6 +138,11 @@ struct pm_ctx {
     bool fused_solve;         // use the fused path when supported
     void* peer_real[pm::kMaxPeers];   // IPC mappings of every rank's `real` buffer (own pointer for self)
     bool peers_ready;
+    // P3M short range scratch (pm_shortrange.cu)
+    void* sr_buf;
+    size_t sr_bytes;
+    void* sr_tmp;
+    size_t sr_tmp_bytes;
     // state flags
     bool space_fourier;       // working slab currently holds Fourier data
 

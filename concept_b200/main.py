@@ -186,6 +186,34 @@ def driftkick_short(components, Δt, sync_time):
     shortrange.driftkick_short(components, Δt, sync_time)
 
 
+def _uses_rungs(component):
+    return component.forces.get('gravity') == 'p3m' and commons.params.N_rungs > 1
+
+
+def initialize_rung_populations(components, Δt):
+    """main.py:1639-1675: all particles on rung 0, then a fake short kick assigns the rungs."""
+    if not any(_uses_rungs(c) for c in components):
+        return
+    if Δt == 0:
+        abort('Cannot initialise rung populations with Δt = 0')
+    from . import shortrange
+    for c in components:
+        if _uses_rungs(c):
+            shortrange.ensure_rung_state(c)
+            c.rung_indices.zero_()
+            c.rung_indices_jumped.zero_()
+            shortrange._set_populations(c, [c.N_local] + [0]*(commons.params.N_rungs - 1))
+    kick_short(components, Δt, fake=True)
+
+
+def _assign_rungs(components, Δt):
+    from . import shortrange
+    for c in components:
+        if _uses_rungs(c):
+            shortrange.ensure_rung_state(c)
+            shortrange.assign_rungs(c, Δt, _facs()['softening'])
+
+
 class DumpTime:
     def __init__(self, a):
         self.time_param, self.a, self.t = 'a', float(a), cosmic_time(float(a))
@@ -242,9 +270,10 @@ def timeloop(components, on_dump=None, on_step=None, max_steps=None):
     Δt = Δt_begin
     Δt_min = 1e-4*Δt_begin
     get_time_step_integrals(0, 0, components)
-    kick_short(components, Δt, fake=True)       # initialize_rung_populations (main.py:1639)
+    initialize_rung_populations(components, Δt)
     time_step = 0
     time_step_last_sync = 0
+    time_step_previous = -1
     time_step_type = 'init'
     sync_time = ထ
     recompute_Δt_max = True
@@ -253,7 +282,12 @@ def timeloop(components, on_dump=None, on_step=None, max_steps=None):
         while True:
             if max_steps is not None and time_step >= max_steps:
                 return time_step
-            universals.time_step = time_step
+            if time_step > time_step_previous:
+                time_step_previous = time_step
+                # at an "init" step all rungs are synchronised: re-assign them (main.py:225-227)
+                if time_step_type == 'init':
+                    _assign_rungs(components, Δt)
+                universals.time_step = time_step
             if time_step_type == 'init':
                 time_step_type = 'full'
                 kick_long(components, Δt, sync_time, 'init')

@@ -158,6 +158,33 @@ int pm_sum_mom2(pm_ctx* ctx, const double* mom, int64_t n, double* out);
 int pm_exchange(pm_ctx* ctx, double* pos, double* mom, int64_t* ids, int64_t* n_inout,
                 int64_t capacity);
 
+/* ---- P3M short range (single GPU in this round) ---------------------------- */
+/* gravity_pairwise_shortrange over all pairs within `range` (gravity.py:263-354; pair enumeration
+ * interactions.py:1353-1791), gather form:
+ *   dmom[i] = factors[rung_jumped[i]] · Σ_{j≠i, r²≤range²} (x_i − x_j)·table[int(r²·(tablesize−1)/maxr2)]
+ * for receivers with rung[i] ≥ lowest_active_rung (others untouched); periodic minimum image.
+ * factors (host, nfactors = 3·N_rungs−1) = G·m²·ᔑdt_rungs['a**(-3*w_eff₀-3*w_eff₁-1)'] (gravity.py:51-67);
+ * table_dev: device copy of get_shortrange_table() (gravity.py:373-421). */
+int pm_shortrange(pm_ctx* ctx, const double* pos, int64_t n, const signed char* rung,
+                  const signed char* rung_jumped, int lowest_active_rung, const double* factors_host,
+                  int nfactors, double range, const double* table_dev, int tablesize, double maxr2,
+                  double* dmom);
+/* apply_Δmom (species.py:2253-2266; skipped when apply = 0, the "fake" kick) then
+ * convert_Δmom_to_acc (species.py:2290-2325): dmom *= conv[rung_jumped], active rungs only */
+int pm_apply_dmom(pm_ctx* ctx, double* mom, double* dmom, int64_t n, const signed char* rung,
+                  const signed char* rung_jumped, int lowest_active_rung, const double* conv_host,
+                  int nconv, int apply);
+/* assign_rungs (species.py:2415-2435); rungs_N_host[n_rungs] receives the populations */
+int pm_assign_rungs(pm_ctx* ctx, const double* acc, int64_t n, double rung_factor, int n_rungs,
+                    signed char* rung, signed char* rung_jumped, int64_t* rungs_N_host);
+/* flag_rung_jumps (species.py:2461-2510); dt1_host = ᔑdt_rungs['1'] (3·n_rungs−1 doubles) */
+int pm_flag_rung_jumps(pm_ctx* ctx, const double* acc, int64_t n, const signed char* rung,
+                       signed char* rung_jumped, int lowest_active_rung, double rung_factor_up,
+                       double rung_factor_down, const double* dt1_host, int n_rungs, int* any_host);
+/* apply_rung_jumps (species.py:2523-2545) */
+int pm_apply_rung_jumps(pm_ctx* ctx, int64_t n, signed char* rung, signed char* rung_jumped, int n_rungs,
+                        int64_t* rungs_N_host);
+
 /* ---- whole-path entry points --------------------------------------------- */
 typedef struct {
     int order;            /* interpolation order 1..4 */

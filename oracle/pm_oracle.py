@@ -318,3 +318,72 @@ def sum_mom2(mom):
 
 def v_rms(mom, N, a, mass, w_eff=0.0):
     return np.sqrt(sum_mom2(mom)/N)/(a**(2 - 3*w_eff)*mass)
+
+
+# --------------------------------------------------------------------------
+# P³M short range (a18, a19)
+# --------------------------------------------------------------------------
+def softened_r3inv(r2, eps):
+    """get_softened_r3inv, spline kernel (interactions.py:1875-1897), h = 2.8·ε."""
+    from math import sqrt
+    h = 2.8*eps
+    r = sqrt(r2)
+    if r >= h:
+        return 1/(r2*r)
+    u = r/h
+    if u < 0.5:
+        return 32/h**3*(1./3. + u**2*(-6./5. + u))
+    return 32/(3*r**3)*(u**3*(2 + u*(-9./2. + u*(18./5. - u))) - 3./480.)
+
+
+def shortrange_table(scale, rng, tablesize, softening):
+    """get_shortrange_table (gravity.py:373-421): tabulated in r² at bin mid-points,
+    table[i] = −r⁻³(x/√π·e^{−x²/4} + erfc(x/2) − 1) − r⁻³_softened, x = r/scale; last entry NaN."""
+    from math import erfc, exp, pi, sqrt
+    maxr2 = (1 + 1/tablesize)*rng**2
+    r_tab = np.sqrt(np.linspace(0, maxr2, tablesize))
+    table = np.empty(tablesize)
+    for i in range(tablesize - 1):
+        r2 = 0.5*(r_tab[i]**2 + r_tab[i + 1]**2)
+        r = sqrt(r2)
+        x = r*(1/scale)
+        r3_inv = 1/(r2*r)
+        table[i] = -r3_inv*(1/sqrt(pi)*x*exp(-(0.5*x)**2) + (erfc(0.5*x) - 1)) - softened_r3inv(r2, softening)
+    table[tablesize - 1] = np.nan
+    return table, maxr2
+
+
+def shortrange_sums(pos, boxsize, rng, table, maxr2, active=None):
+    """S_i = Σ_{j≠i, r²≤R²} (x_i − x_j)·table[int(r²·(T−1)/maxr²)] with minimum-image separations
+    (gravity_pairwise_shortrange, gravity.py:263-354; pair enumeration interactions.py:1353-1791).
+    Brute force O(N²); `active` restricts the receivers."""
+    pos = np.asarray(pos, dtype=np.float64)
+    N = len(pos)
+    T = len(table)
+    scaling = (T - 1)/maxr2
+    S = np.zeros((N, 3))
+    idx = np.arange(N) if active is None else np.nonzero(active)[0]
+    tab = np.nan_to_num(table, nan=0.0)
+    for i in idx:
+        d = pos[i] - pos
+        d -= boxsize*np.round(d/boxsize)
+        r2 = (d*d).sum(1)
+        m = r2 <= rng**2
+        m[i] = False
+        f = tab[(r2[m]*scaling).astype(np.int64)]
+        S[i] = (d[m]*f[:, None]).sum(0)
+    return S
+
+
+def get_rung(acc, current, rung_factor, n_rungs):
+    """Component.get_rung (species.py:2340-2360) vectorised."""
+    acc2 = (np.asarray(acc)**2).sum(1)
+    with np.errstate(divide='ignore'):
+        rf = rung_factor + 0.25*np.log2(np.where(acc2 > 0, acc2, 1.0))
+    rung = np.where(rf < 0, 0, np.where(rf > n_rungs - 1, n_rungs - 1, 1 + np.floor(np.clip(rf, 0, n_rungs)).astype(np.int64)))
+    return np.where(acc2 == 0, current, rung).astype(np.int8)
+
+
+def rung_factor(dt, fac_softening, softening_length):
+    """Component.get_rung_factor (species.py:2362-2370)"""
+    return 0.5*np.log2(dt**2/(2*fac_softening*softening_length))
