@@ -157,6 +157,7 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
     if (cudaMalloc(&c->tab_x, sizeof(double) * g.G) != cudaSuccess ||
         cudaMalloc(&c->tab_sin, sizeof(double) * g.G) != cudaSuccess ||
         cudaMalloc(&c->d_scratch, sizeof(double) * 64) != cudaSuccess ||
+        cudaMalloc(&c->d_tilectr, sizeof(unsigned long long) * 4) != cudaSuccess ||
         cudaMalloc(&c->d_counts, sizeof(int64_t) * (3 * nranks + (size_t)nranks * nranks + 8 + kNumSMs * 4)) != cudaSuccess) {
         set_error("pm_create: cannot allocate tables");
         return fail(PM_ERR_ALLOC);
@@ -202,6 +203,7 @@ int pm_destroy(pm_ctx* c) {
     cudaFree(c->tab_sin);
     cudaFree(c->d_scratch);
     cudaFree(c->d_counts);
+    cudaFree(c->d_tilectr);
     cudaFree(c->xchg_buf);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;

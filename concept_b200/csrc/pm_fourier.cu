@@ -15,6 +15,7 @@
 #include "pm_internal.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace pm {
 
@@ -210,8 +211,14 @@ int make_plans(pm_ctx* c) {
     }
     size_t ws2_f = 0, ws2_b = 0;
     c->plan2_ready = false;
-    if (c->nranks == 1 && c->xs_tw != nullptr) {
-        // batched 2-D (y,z) plans: the x direction is handled by the fused x-solve kernel
+    if (c->xs_tw != nullptr) {
+        // batched 2-D (y,z) plans; the x direction is handled by the fused x-solve kernel.  PM_FFT_CHUNK
+        // (experiment knob) executes them over chunks of x planes.
+        int chunk = g.nxl;   // measured on B200 (r01): chunking (8…64 planes) is slower than whole-slab passes
+        if (const char* e = getenv("PM_FFT_CHUNK")) chunk = atoi(e);
+        if (chunk <= 0 || chunk > g.nxl) chunk = g.nxl;
+        while (g.nxl % chunk) --chunk;
+        c->fft_chunk = chunk;
         long long n2[2] = {g.G, g.G};
         long long rembed[2] = {g.G, g.Gp};
         long long cembed[2] = {g.G, g.Gc};
@@ -220,9 +227,9 @@ int make_plans(pm_ctx* c) {
         PM_CHECK_CUFFT(cufftSetAutoAllocation(c->plan2_fwd, 0));
         PM_CHECK_CUFFT(cufftSetAutoAllocation(c->plan2_bwd, 0));
         PM_CHECK_CUFFT(cufftMakePlanMany64(c->plan2_fwd, 2, n2, rembed, 1, (long long)g.G * g.Gp, cembed, 1,
-                                           (long long)g.G * g.Gc, f64 ? CUFFT_D2Z : CUFFT_R2C, g.nxl, &ws2_f));
+                                           (long long)g.G * g.Gc, f64 ? CUFFT_D2Z : CUFFT_R2C, chunk, &ws2_f));
         PM_CHECK_CUFFT(cufftMakePlanMany64(c->plan2_bwd, 2, n2, cembed, 1, (long long)g.G * g.Gc, rembed, 1,
-                                           (long long)g.G * g.Gp, f64 ? CUFFT_Z2D : CUFFT_C2R, g.nxl, &ws2_b));
+                                           (long long)g.G * g.Gp, f64 ? CUFFT_Z2D : CUFFT_C2R, chunk, &ws2_b));
         c->plan2_ready = true;
     }
     size_t ws = ws_f > ws_b ? ws_f : ws_b;
@@ -315,18 +322,30 @@ int solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss) {
     PM_REQUIRE(!c->space_fourier, "pm_solve_fused: the slab holds Fourier data");
     PM_REQUIRE(xsolve_supported(c), "pm_solve_fused: not available for this grid size / rank layout");
     const bool f64 = c->dtype == PM_GRID_F64;
-    cufftHandle fwd = c->nranks == 1 ? c->plan2_fwd : c->plan_fwd;
-    cufftHandle bwd = c->nranks == 1 ? c->plan2_bwd : c->plan_bwd;
+    const size_t plane = (size_t)c->g.G * c->g.Gp;
+    const int nchunks = c->g.nxl / c->fft_chunk;
     if (f64) {
         double* r = c->real_interior<double>();
-        PM_CHECK_CUFFT(cufftExecD2Z(fwd, r, reinterpret_cast<cufftDoubleComplex*>(r)));
+        for (int k = 0; k < nchunks; ++k) {
+            double* q = r + (size_t)k * c->fft_chunk * plane;
+            PM_CHECK_CUFFT(cufftExecD2Z(c->plan2_fwd, q, reinterpret_cast<cufftDoubleComplex*>(q)));
+        }
         PM_TRY(xsolve(c, prefactor, deconv_order, gauss));
-        PM_CHECK_CUFFT(cufftExecZ2D(bwd, reinterpret_cast<cufftDoubleComplex*>(r), r));
+        for (int k = 0; k < nchunks; ++k) {
+            double* q = r + (size_t)k * c->fft_chunk * plane;
+            PM_CHECK_CUFFT(cufftExecZ2D(c->plan2_bwd, reinterpret_cast<cufftDoubleComplex*>(q), q));
+        }
     } else {
         float* r = c->real_interior<float>();
-        PM_CHECK_CUFFT(cufftExecR2C(fwd, r, reinterpret_cast<cufftComplex*>(r)));
+        for (int k = 0; k < nchunks; ++k) {
+            float* q = r + (size_t)k * c->fft_chunk * plane;
+            PM_CHECK_CUFFT(cufftExecR2C(c->plan2_fwd, q, reinterpret_cast<cufftComplex*>(q)));
+        }
         PM_TRY(xsolve(c, prefactor, deconv_order, gauss));
-        PM_CHECK_CUFFT(cufftExecC2R(bwd, reinterpret_cast<cufftComplex*>(r), r));
+        for (int k = 0; k < nchunks; ++k) {
+            float* q = r + (size_t)k * c->fft_chunk * plane;
+            PM_CHECK_CUFFT(cufftExecC2R(c->plan2_bwd, reinterpret_cast<cufftComplex*>(q), q));
+        }
     }
     return PM_OK;
 }

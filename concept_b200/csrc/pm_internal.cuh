@@ -120,6 +120,7 @@ struct pm_ctx {
     cufftHandle plan_x;                    // nranks > 1: strided 1-D c2c along i
     cufftHandle plan2_fwd, plan2_bwd;      // nranks == 1: batched 2-D (y,z) plans for the fused x-solve path
     bool plan2_ready;
+    int fft_chunk;                         // x planes per 2-D plan execution
     bool plans_ready;
     // NCCL
     ncclComm_t comm;
@@ -127,6 +128,7 @@ struct pm_ctx {
     // scratch for reductions / exchange
     double* d_scratch;        // small device scratch (>= 64 doubles)
     int64_t* d_counts;        // exchange counters
+    unsigned long long* d_tilectr;   // dynamic tile counters of the particle kernels (4 entries)
     void* xchg_buf;           // staging for migrating particles
     size_t xchg_bytes;
     int64_t bytes_allocated;

@@ -100,11 +100,22 @@ __device__ __forceinline__ void stage_particles(const double* __restrict__ src, 
         const double2* p2 = reinterpret_cast<const double2*>(p);
         double2* s2 = reinterpret_cast<double2*>(s);
         const int n2 = nd >> 1;
-        for (int t = threadIdx.x; t < n2; t += BLOCK) s2[t] = __ldg(p2 + t);
-        if ((nd & 1) && threadIdx.x == 0) s[nd - 1] = __ldg(p + nd - 1);
+        for (int t = threadIdx.x; t < n2; t += BLOCK) s2[t] = __ldcs(p2 + t);   // streaming: do not displace the grid in L2
+        if ((nd & 1) && threadIdx.x == 0) s[nd - 1] = __ldcs(p + nd - 1);
     } else {
-        for (int t = threadIdx.x; t < nd; t += BLOCK) s[t] = __ldg(p + t);
+        for (int t = threadIdx.x; t < nd; t += BLOCK) s[t] = __ldcs(p + t);
     }
+}
+
+// Dynamic, in-order tile scheduler: CTAs take the next tile of BLOCK consecutive particles from a global
+// counter, so the set of tiles in flight stays a compact window of the (cell-ordered) particle array and
+// the grid planes it touches stay L2-resident.  A static blockIdx-strided loop lets fast and slow CTAs
+// drift tens of grid planes apart (measured: the potential grid was read 1.85x from DRAM).
+__device__ __forceinline__ int64_t next_tile(unsigned long long* counter, int64_t* s_tile) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_tile = (int64_t)atomicAdd(counter, 1ULL);
+    __syncthreads();
+    return *s_tile;
 }
 
 // ---------------------------------------------------------------------------
@@ -115,13 +126,13 @@ constexpr int kDepBlock = 256;
 template <int ORDER, typename T>
 __global__ void __launch_bounds__(kDepBlock)
 deposit_kernel(const double* __restrict__ pos, int64_t n, T* __restrict__ grid, Geom g, Coord co,
-               double contribution) {
+               double contribution, unsigned long long* __restrict__ tile_counter) {
     __shared__ __align__(16) double spos[kDepBlock * 3];
+    __shared__ int64_t s_tile;
     const int64_t ntiles = (n + kDepBlock - 1) / kDepBlock;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tile = next_tile(tile_counter, &s_tile); tile < ntiles; tile = next_tile(tile_counter, &s_tile)) {
         const int64_t first = tile * kDepBlock;
         const int count = (int)min((int64_t)kDepBlock, n - first);
-        __syncthreads();
         stage_particles<kDepBlock>(pos, first, count, spos);
         __syncthreads();
         if ((int)threadIdx.x >= count) continue;
@@ -163,11 +174,13 @@ static int deposit_dispatch(pm_ctx* c, const double* pos, int64_t n, int order, 
     const int64_t ntiles = (n + kDepBlock - 1) / kDepBlock;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * 16);
     T* gptr = reinterpret_cast<T*>(c->real);
+    unsigned long long* ctr = c->d_tilectr;
+    PM_CHECK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), c->stream));
     switch (order) {
-        case 1: PM_LAUNCH((deposit_kernel<1, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution); break;
-        case 2: PM_LAUNCH((deposit_kernel<2, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution); break;
-        case 3: PM_LAUNCH((deposit_kernel<3, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution); break;
-        case 4: PM_LAUNCH((deposit_kernel<4, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution); break;
+        case 1: PM_LAUNCH((deposit_kernel<1, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr); break;
+        case 2: PM_LAUNCH((deposit_kernel<2, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr); break;
+        case 3: PM_LAUNCH((deposit_kernel<3, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr); break;
+        case 4: PM_LAUNCH((deposit_kernel<4, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr); break;
     }
     return PM_OK;
 }
@@ -363,16 +376,16 @@ template <int ORDER, int REACH, typename T>
 __global__ void __launch_bounds__(kGatBlock)
 gather_kick_kernel(const T* __restrict__ phi, const double* __restrict__ pos,
                    double* __restrict__ mom, int64_t n, Geom g, Coord co, FD fd, double factor,
-                   double* __restrict__ sum_mom2) {
+                   double* __restrict__ sum_mom2, unsigned long long* __restrict__ tile_counter) {
     __shared__ __align__(16) double spos[kGatBlock * 3];
     __shared__ double sred[kGatBlock / 32];
+    __shared__ int64_t s_tile;
     constexpr int W = ORDER + 2 * REACH;   // cells touched per axis
     double mom2_acc = 0;
     const int64_t ntiles = (n + kGatBlock - 1) / kGatBlock;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tile = next_tile(tile_counter, &s_tile); tile < ntiles; tile = next_tile(tile_counter, &s_tile)) {
         const int64_t first = tile * kGatBlock;
         const int count = (int)min((int64_t)kGatBlock, n - first);
-        __syncthreads();
         stage_particles<kGatBlock>(pos, first, count, spos);
         __syncthreads();
         if ((int)threadIdx.x >= count) continue;
@@ -419,8 +432,8 @@ gather_kick_kernel(const T* __restrict__ phi, const double* __restrict__ pos,
         }
         if (factor != 1) { vx *= factor; vy *= factor; vz *= factor; }
         double* m = mom + (first + threadIdx.x) * 3;
-        const double mx = m[0] + vx, my = m[1] + vy, mz = m[2] + vz;
-        m[0] = mx; m[1] = my; m[2] = mz;
+        const double mx = __ldcs(m) + vx, my = __ldcs(m + 1) + vy, mz = __ldcs(m + 2) + vz;
+        __stcs(m, mx); __stcs(m + 1, my); __stcs(m + 2, mz);
         mom2_acc += mx * mx + my * my + mz * mz;
     }
     if (sum_mom2 != nullptr) {
@@ -443,9 +456,11 @@ static int gather_kick_dispatch(pm_ctx* c, const double* pos, double* mom, int64
     const int64_t ntiles = (n + kGatBlock - 1) / kGatBlock;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * 8);
     const T* phi = reinterpret_cast<const T*>(c->real);
+    unsigned long long* ctr = c->d_tilectr + 1;
+    PM_CHECK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), c->stream));
 #define PM_GK(O, R)                                                                              \
     PM_LAUNCH((gather_kick_kernel<O, R, T>), grid, kGatBlock, 0, c->stream, phi, pos, mom, n,    \
-              c->g, co, fd, factor, sum_mom2)
+              c->g, co, fd, factor, sum_mom2, ctr)
 #define PM_GK_ORDER(R)                                  \
     switch (order) {                                    \
         case 1: PM_GK(1, R); break;                     \
