@@ -57,6 +57,7 @@ SIGNATURES = {
     'pm_solve_fused': (c_int, [c_void_p, c_double, c_int, c_double]),
     'pm_fused_solve_available': (c_int, [c_void_p]),
     'pm_set_fused_solve': (c_int, [c_void_p, c_int]),
+    'pm_check_async_error': (c_int, [c_void_p]),
     'pm_slab_save': (c_int, [c_void_p]),
     'pm_slab_accumulate': (c_int, [c_void_p]),
     'pm_slab_restore': (c_int, [c_void_p]),

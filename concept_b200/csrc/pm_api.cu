@@ -167,7 +167,10 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
     cudaMemsetAsync(c->d_scratch, 0, sizeof(double) * 64, c->stream);
     cudaStreamSynchronize(c->stream);   // tx/ts go out of scope
     c->fused_solve = true;
+    c->solve_mode = PM_SOLVE_AUTO;
     int s = make_xsolve_tables(c);
+    if (s != PM_OK) return fail(s);
+    s = make_fft2_tables(c);
     if (s != PM_OK) return fail(s);
     s = make_plans(c);
     if (s != PM_OK) return fail(s);
@@ -190,6 +193,8 @@ int pm_destroy(pm_ctx* c) {
             if (r != c->rank && c->peer_real[r]) cudaIpcCloseMemHandle(c->peer_real[r]);
     if (c->comm_ready) ncclCommDestroy(c->comm);
     cudaFree(c->xs_tw);
+    cudaFree(c->f2_tw);
+    cudaFree(c->f2_ctr);
     cudaFree(c->xs_sep);
     cudaFree(c->sr_buf);
     cudaFree(c->sr_tmp);
@@ -289,12 +294,19 @@ int pm_solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss) 
     return solve_fused(c, prefactor, deconv_order, gauss);
 }
 
-int pm_fused_solve_available(const pm_ctx* c) { return c && xsolve_supported(c) ? 1 : 0; }
+int pm_fused_solve_available(const pm_ctx* c) { return c && (fft2_supported(c) || xsolve_supported(c)) ? 1 : 0; }
 
-int pm_set_fused_solve(pm_ctx* c, int enable) {
+int pm_set_fused_solve(pm_ctx* c, int mode) {
     PM_REQUIRE(c != nullptr, "pm_set_fused_solve: NULL context");
-    c->fused_solve = enable != 0;
+    PM_REQUIRE(mode >= PM_SOLVE_UNFUSED && mode <= PM_SOLVE_FFT2_L2, "pm_set_fused_solve: mode = %d", mode);
+    c->fused_solve = mode != PM_SOLVE_UNFUSED;
+    c->solve_mode = mode;
     return PM_OK;
+}
+
+int pm_check_async_error(pm_ctx* c) {
+    PM_REQUIRE(c != nullptr, "pm_check_async_error: NULL context");
+    return fft2_check_error(c);
 }
 
 int pm_slab_save(pm_ctx* c) { PM_REQUIRE(c != nullptr, "NULL context"); return slab_copy(c, 0); }
@@ -348,7 +360,7 @@ int pm_kick_long(pm_ctx* c, const double* pos, double* mom, int64_t n, const pm_
     PM_REQUIRE(p->interlace == 0 || p->interlace == 1, "pm_kick_long: interlace = %d", p->interlace);
     const int nl = p->interlace ? 2 : 1;
     const double lscale = 1.0 / nl;
-    if (c->fused_solve && nl == 1 && p->diff_order != 0 && xsolve_supported(c)) {
+    if (c->fused_solve && nl == 1 && p->diff_order != 0 && pm_fused_solve_available(c)) {
         // default path: 2-D transforms + fused x pass (FFT · Green's function · inverse FFT)
         int hlo, hhi;
         halo_for_gather(p->order, p->diff_order, 0, &hlo, &hhi);

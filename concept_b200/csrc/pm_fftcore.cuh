@@ -1,0 +1,378 @@
+// pm_fftcore.cuh — in-shared-memory FFT building blocks for the hand-written slab transform
+// (pm_fft.cu).  Everything here is __host__ __device__ and takes (tid, nthr) explicitly, so that the
+// very same code can be stepped through sequentially on the CPU (tests/fft_host_harness.cu) — stages
+// are separated by __syncthreads() on the device and touch thread-private positions in between.
+//
+// Transform length N = R1·8·8 with R1 ∈ {1, 2, 4, 8}.  Two flows over a tile of C independent lines:
+//
+//   DIT  (A, B, C):  input element a = a1 + R1·a2 + 8·R1·a3 at position 64·a1 + 8·a2 + a3
+//                    (stage A can gather it from a naturally ordered source), output natural.
+//   DIF  (1, 2, 3):  input natural, output element b = b1 + R1·b2 + 8·R1·b3 at position
+//                    64·b1 + 8·b2 + b3.
+//
+// so that   natural --DIT--> natural-order spectrum --(pointwise factor)--> DIF --> scattered store
+// needs no reordering pass, and DIT stage C / DIF stage 1 touch the same positions (the x-solve keeps
+// them in registers across the Green's-function multiply).
+//
+// Tile layouts (template policy L):
+//   ColLayout<C>      element (position p, line c) at p·C + c.  C·sizeof(complex) = 128 B, lanes run
+//                     over c first: every quarter-warp access is one contiguous 128 B — conflict-free
+//                     for any position stride.  Used for the y and x passes (lines are strided in
+//                     global memory; 128 B row segments).
+//   RowLayout<N>      element (p, c) at c·PITCH + p + (p>>3) + (p>>6).  Lanes run over positions; the
+//                     padding keeps the stride-8 and stride-64 accesses of the stages conflict-free.
+//                     Used for the z pass (lines are contiguous in global memory).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#ifndef PM_HD
+#ifdef __CUDACC__
+#define PM_HD __host__ __device__ __forceinline__
+#else
+#define PM_HD inline
+#endif
+#endif
+
+namespace pm {
+namespace fftc {
+
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+PM_HD double fma_(double a, double b, double c) { return fma(a, b, c); }
+PM_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+
+// ---------------------------------------------------------------------------------------------
+// small DFTs in registers, natural order in and out.  DIR = −1: e^{−2πi nk/R};  +1: e^{+2πi nk/R}
+// ---------------------------------------------------------------------------------------------
+template <int DIR, typename T>
+PM_HD void dft2(T (&r)[2], T (&i)[2]) {
+    const T ar = r[0] + r[1], ai = i[0] + i[1];
+    r[1] = r[0] - r[1]; i[1] = i[0] - i[1];
+    r[0] = ar; i[0] = ai;
+}
+
+template <int DIR, typename T>
+PM_HD void dft4(T (&r)[4], T (&i)[4]) {
+    const T s0r = r[0] + r[2], s0i = i[0] + i[2], d0r = r[0] - r[2], d0i = i[0] - i[2];
+    const T s1r = r[1] + r[3], s1i = i[1] + i[3], d1r = r[1] - r[3], d1i = i[1] - i[3];
+    // forward: −i·d1 = (d1i, −d1r);  inverse: +i·d1 = (−d1i, d1r)
+    const T tr = DIR < 0 ? d1i : -d1i;
+    const T ti = DIR < 0 ? -d1r : d1r;
+    r[0] = s0r + s1r; i[0] = s0i + s1i;
+    r[2] = s0r - s1r; i[2] = s0i - s1i;
+    r[1] = d0r + tr;  i[1] = d0i + ti;
+    r[3] = d0r - tr;  i[3] = d0i - ti;
+}
+
+template <int DIR, typename T>
+PM_HD void dft8(T (&r)[8], T (&i)[8]) {
+    const T h = (T)0.70710678118654752440;
+    T a0r = r[0] + r[4], a0i = i[0] + i[4], a4r = r[0] - r[4], a4i = i[0] - i[4];
+    T a1r = r[1] + r[5], a1i = i[1] + i[5], a5r = r[1] - r[5], a5i = i[1] - i[5];
+    T a2r = r[2] + r[6], a2i = i[2] + i[6], a6r = r[2] - r[6], a6i = i[2] - i[6];
+    T a3r = r[3] + r[7], a3i = i[3] + i[7], a7r = r[3] - r[7], a7i = i[3] - i[7];
+    T t;
+    if (DIR < 0) {
+        t = (a5r + a5i) * h; a5i = (a5i - a5r) * h; a5r = t;        // ·(1−i)/√2
+        t = a6i; a6i = -a6r; a6r = t;                               // ·(−i)
+        t = (a7i - a7r) * h; a7i = (-a7r - a7i) * h; a7r = t;       // ·(−1−i)/√2
+    } else {
+        t = (a5r - a5i) * h; a5i = (a5r + a5i) * h; a5r = t;        // ·(1+i)/√2
+        t = -a6i; a6i = a6r; a6r = t;                               // ·(+i)
+        t = (-a7r - a7i) * h; a7i = (a7r - a7i) * h; a7r = t;       // ·(−1+i)/√2
+    }
+    T b0r = a0r + a2r, b0i = a0i + a2i, b2r = a0r - a2r, b2i = a0i - a2i;
+    T b1r = a1r + a3r, b1i = a1i + a3i, b3r = a1r - a3r, b3i = a1i - a3i;
+    T b4r = a4r + a6r, b4i = a4i + a6i, b6r = a4r - a6r, b6i = a4i - a6i;
+    T b5r = a5r + a7r, b5i = a5i + a7i, b7r = a5r - a7r, b7i = a5i - a7i;
+    if (DIR < 0) {
+        t = b3i; b3i = -b3r; b3r = t;
+        t = b7i; b7i = -b7r; b7r = t;
+    } else {
+        t = -b3i; b3i = b3r; b3r = t;
+        t = -b7i; b7i = b7r; b7r = t;
+    }
+    r[0] = b0r + b1r; i[0] = b0i + b1i; r[4] = b0r - b1r; i[4] = b0i - b1i;
+    r[2] = b2r + b3r; i[2] = b2i + b3i; r[6] = b2r - b3r; i[6] = b2i - b3i;
+    r[1] = b4r + b5r; i[1] = b4i + b5i; r[5] = b4r - b5r; i[5] = b4i - b5i;
+    r[3] = b6r + b7r; i[3] = b6i + b7i; r[7] = b6r - b7r; i[7] = b6i - b7i;
+}
+
+template <int R, int DIR, typename T>
+PM_HD void dftR(T (&r)[R], T (&i)[R]) {
+    if constexpr (R == 2) dft2<DIR>(r, i);
+    else if constexpr (R == 4) dft4<DIR>(r, i);
+    else if constexpr (R == 8) dft8<DIR>(r, i);
+    // R == 1: identity
+}
+
+// (r, i) ·= w (DIR < 0) or ·= conj(w) (DIR > 0); the table holds w = e^{−2πi m/NT}
+template <int DIR, typename T, typename V>
+PM_HD void cmul(T& r, T& i, const V w) {
+    const T wi = DIR < 0 ? w.y : -w.y;
+    const T t = fma_(r, w.x, -(i * wi));
+    i = fma_(r, wi, i * w.x);
+    r = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layouts
+// ---------------------------------------------------------------------------------------------
+template <int C_>
+struct ColLayout {
+    static constexpr int C = C_;
+    static PM_HD int idx(int p, int c) { return p * C + c; }
+    // butterfly b of a stage with P butterflies per line  ->  (line, butterfly-in-line)
+    template <int P> static PM_HD void decode(int b, int& c, int& u) { c = b % C; u = b / C; }
+};
+
+template <int N_, int C_>
+struct RowLayout {
+    static constexpr int C = C_;
+    static constexpr int PITCH = N_ + N_ / 8 + N_ / 64 + 1;
+    static PM_HD int idx(int p, int c) { return c * PITCH + p + (p >> 3) + (p >> 6); }
+    template <int P> static PM_HD void decode(int b, int& c, int& u) { u = b % P; c = b / P; }
+};
+
+// natural-order raw tile as the loads leave it
+template <int C_>
+struct ColRaw {   // [position][C]
+    static PM_HD int idx(int p, int c) { return p * C_ + c; }
+};
+template <int N_>
+struct RowRaw {   // [line][N]
+    static PM_HD int idx(int p, int c) { return c * N_ + p; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// DIT flow
+// ---------------------------------------------------------------------------------------------
+// Stage A: gathers element a = u + (N/8)·a3 (u = a1 + R1·a2) from the naturally ordered `src`,
+// 8-point DFT over a3 -> b3, result at position 64·a1 + 8·a2 + b3 of `dst`.
+template <class L, class RAW, typename T, int N, int DIR, typename V>
+PM_HD void dit_stageA(const V* src, V* dst, int tid, int nthr) {
+    constexpr int R1 = N / 64;
+    constexpr int P = N / 8;
+    for (int b = tid; b < P * L::C; b += nthr) {
+        int c, u;
+        L::template decode<P>(b, c, u);
+        const int a1 = u % R1, a2 = u / R1;
+        T r[8], i[8];
+#pragma unroll
+        for (int a3 = 0; a3 < 8; ++a3) {
+            const V v = src[RAW::idx(u + P * a3, c)];
+            r[a3] = v.x; i[a3] = v.y;
+        }
+        dft8<DIR>(r, i);
+        const int p0 = 64 * a1 + 8 * a2;
+#pragma unroll
+        for (int b3 = 0; b3 < 8; ++b3) {
+            V v; v.x = r[b3]; v.y = i[b3];
+            dst[L::idx(p0 + b3, c)] = v;
+        }
+    }
+}
+
+// Stage A in place: the inputs already sit at positions 64·a1 + 8·a2 + a3 (c2r_pre puts them there).
+template <class L, typename T, int N, int DIR, typename V>
+PM_HD void dit_stageA_inplace(V* tile, int tid, int nthr) {
+    constexpr int P = N / 8;
+    for (int b = tid; b < P * L::C; b += nthr) {
+        int c, u;
+        L::template decode<P>(b, c, u);   // u = a2 + 8·a1: positions 8·u + a3
+        T r[8], i[8];
+#pragma unroll
+        for (int a3 = 0; a3 < 8; ++a3) {
+            const V v = tile[L::idx(8 * u + a3, c)];
+            r[a3] = v.x; i[a3] = v.y;
+        }
+        dft8<DIR>(r, i);
+#pragma unroll
+        for (int b3 = 0; b3 < 8; ++b3) {
+            V v; v.x = r[b3]; v.y = i[b3];
+            tile[L::idx(8 * u + b3, c)] = v;
+        }
+    }
+}
+
+// Stage B: positions 64·a1 + 8·a2 + b3 over a2; input a2 times ω64^(a2·b3); DFT8 -> b2, in place.
+// tw[m] = e^{−2πi m/NT}; NT is a multiple of 64.
+template <class L, typename T, int N, int NT, int DIR, typename V>
+PM_HD void dit_stageB(V* tile, const V* tw, int tid, int nthr) {
+    constexpr int P = N / 8;
+    for (int b = tid; b < P * L::C; b += nthr) {
+        int c, u;
+        L::template decode<P>(b, c, u);
+        const int b3 = u & 7, a1 = u >> 3;
+        const int p0 = 64 * a1 + b3;
+        T r[8], i[8];
+#pragma unroll
+        for (int a2 = 0; a2 < 8; ++a2) {
+            const V v = tile[L::idx(p0 + 8 * a2, c)];
+            r[a2] = v.x; i[a2] = v.y;
+            if (a2) cmul<DIR>(r[a2], i[a2], tw[(a2 * b3) * (NT / 64)]);
+        }
+        dft8<DIR>(r, i);
+#pragma unroll
+        for (int b2 = 0; b2 < 8; ++b2) {
+            V v; v.x = r[b2]; v.y = i[b2];
+            tile[L::idx(p0 + 8 * b2, c)] = v;
+        }
+    }
+}
+
+// Stage C: positions 64·a1 + q over a1 (q = 8·b2 + b3); input a1 times ωN^(a1·q); DFT_R1 -> b1;
+// result (natural index 64·b1 + q) handed to sink(c, index, re, im).
+template <class L, typename T, int N, int NT, int DIR, typename V, class Sink>
+PM_HD void dit_stageC(const V* tile, const V* tw, int tid, int nthr, Sink& sink) {
+    constexpr int R1 = N / 64;
+    for (int b = tid; b < 64 * L::C; b += nthr) {
+        int c, q;
+        L::template decode<64>(b, c, q);
+        T r[R1], i[R1];
+#pragma unroll
+        for (int a1 = 0; a1 < R1; ++a1) {
+            const V v = tile[L::idx(64 * a1 + q, c)];
+            r[a1] = v.x; i[a1] = v.y;
+            if (a1) cmul<DIR>(r[a1], i[a1], tw[(a1 * q) * (NT / N)]);
+        }
+        dftR<R1, DIR>(r, i);
+#pragma unroll
+        for (int b1 = 0; b1 < R1; ++b1) sink(c, 64 * b1 + q, r[b1], i[b1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DIF flow
+// ---------------------------------------------------------------------------------------------
+// Stage 1 on values already in registers (natural index 64·a1 + q): DFT_R1 -> b1, times ωN^(b1·q),
+// written to position 64·b1 + q.
+template <class L, typename T, int N, int NT, int DIR, typename V>
+PM_HD void dif_stage1_regs(T (&r)[N / 64], T (&i)[N / 64], V* tile, const V* tw, int c, int q) {
+    constexpr int R1 = N / 64;
+    dftR<R1, DIR>(r, i);
+#pragma unroll
+    for (int b1 = 0; b1 < R1; ++b1) {
+        if (b1) cmul<DIR>(r[b1], i[b1], tw[(b1 * q) * (NT / N)]);
+        V v; v.x = r[b1]; v.y = i[b1];
+        tile[L::idx(64 * b1 + q, c)] = v;
+    }
+}
+
+// Stage 2: positions 64·b1 + 8·a2 + a3 over a2: DFT8 -> b2, times ω64^(a3·b2), in place.
+template <class L, typename T, int N, int NT, int DIR, typename V>
+PM_HD void dif_stage2(V* tile, const V* tw, int tid, int nthr) {
+    constexpr int P = N / 8;
+    for (int b = tid; b < P * L::C; b += nthr) {
+        int c, u;
+        L::template decode<P>(b, c, u);
+        const int a3 = u & 7, b1 = u >> 3;
+        const int p0 = 64 * b1 + a3;
+        T r[8], i[8];
+#pragma unroll
+        for (int a2 = 0; a2 < 8; ++a2) {
+            const V v = tile[L::idx(p0 + 8 * a2, c)];
+            r[a2] = v.x; i[a2] = v.y;
+        }
+        dft8<DIR>(r, i);
+#pragma unroll
+        for (int b2 = 0; b2 < 8; ++b2) {
+            if (b2) cmul<DIR>(r[b2], i[b2], tw[(a3 * b2) * (NT / 64)]);
+            V v; v.x = r[b2]; v.y = i[b2];
+            tile[L::idx(p0 + 8 * b2, c)] = v;
+        }
+    }
+}
+
+// Stage 3: positions 8·u + a3 (u = b2 + 8·b1) over a3: DFT8 -> b3; element b1 + R1·b2 + 8·R1·b3
+// handed to sink(c, element, re, im).
+template <class L, typename T, int N, int DIR, typename V, class Sink>
+PM_HD void dif_stage3(const V* tile, int tid, int nthr, Sink& sink) {
+    constexpr int R1 = N / 64;
+    constexpr int P = N / 8;
+    for (int b = tid; b < P * L::C; b += nthr) {
+        int c, u;
+        L::template decode<P>(b, c, u);
+        const int b2 = u & 7, b1 = u >> 3;
+        T r[8], i[8];
+#pragma unroll
+        for (int a3 = 0; a3 < 8; ++a3) {
+            const V v = tile[L::idx(8 * u + a3, c)];
+            r[a3] = v.x; i[a3] = v.y;
+        }
+        dft8<DIR>(r, i);
+        const int e0 = b1 + R1 * b2;
+#pragma unroll
+        for (int b3 = 0; b3 < 8; ++b3) sink(c, e0 + 8 * R1 * b3, r[b3], i[b3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// real <-> half-length complex packing (z pass).  M complex points per line, real length 2M = NT.
+// ---------------------------------------------------------------------------------------------
+// After the forward M-point transform of z_n = x_2n + i·x_2n+1 (natural order in `tile`):
+//   X_k = E + ω^k·O,   E = (Z_k + conj Z_{M−k})/2,   O = −i·(Z_k − conj Z_{M−k})/2,   ω = e^{−2πi/2M}
+//   X_{M−k} = conj(E) − conj(ω^k·O)
+// for k = 0 … M/2; sink(c, k, re, im) receives k = 0 … M−1 (X_M — the Nyquist mode, which the potential
+// nullifies, mesh.py:3615-3622 — is delivered as zero at k = M).
+template <class L, typename T, int M, typename V, class Sink>
+PM_HD void r2c_post(const V* tile, const V* tw, int tid, int nthr, Sink& sink) {
+    constexpr int P = M / 2 + 1;
+    for (int b = tid; b < P * L::C; b += nthr) {
+        int c, k;
+        L::template decode<P>(b, c, k);
+        const int kp = (M - k) & (M - 1);
+        const V zk = tile[L::idx(k, c)];
+        const V zp = tile[L::idx(kp, c)];
+        const T er = (T)0.5 * (zk.x + zp.x), ei = (T)0.5 * (zk.y - zp.y);
+        // D = Z_k − conj Z_p = (zk.x − zp.x, zk.y + zp.y);  O = −i·D/2 = (D.y/2, −D.x/2)
+        T orr = (T)0.5 * (zk.y + zp.y), oi = (T)-0.5 * (zk.x - zp.x);
+        cmul<-1>(orr, oi, tw[k]);
+        sink(c, k, er + orr, ei + oi);
+        if (k == 0) sink(c, M, (T)0, (T)0);
+        else if (k != kp) sink(c, kp, er - orr, -ei + oi);
+    }
+}
+
+// Before the inverse M-point transform:  Z_k = A + i·U,  Z_{M−k} = conj(A) + i·conj(U),
+//   A = X_k + conj X_{M−k},  U = conj(ω^k)·(X_k − conj X_{M−k}),  with X_M := 0 and Im X_0 ignored.
+// `raw` holds X_0 … X_{M−1} in natural order; Z_k goes to its DIT input position of `tile`.
+template <class L, class RAW, typename T, int M, typename V>
+PM_HD void c2r_pre(const V* raw, V* tile, const V* tw, int tid, int nthr) {
+    constexpr int R1 = M / 64;
+    constexpr int P = M / 2 + 1;
+    for (int b = tid; b < P * L::C; b += nthr) {
+        int c, k;
+        L::template decode<P>(b, c, k);
+        const int kp = (M - k) & (M - 1);
+        V zk, zp;
+        if (k == 0) {
+            const T x0 = raw[RAW::idx(0, c)].x;
+            zk.x = x0; zk.y = x0;
+            zp = zk;
+        } else {
+            const V xk = raw[RAW::idx(k, c)];
+            const V xp = raw[RAW::idx(kp, c)];
+            const T ar = xk.x + xp.x, ai = xk.y - xp.y;
+            T ur = xk.x - xp.x, ui = xk.y + xp.y;
+            cmul<+1>(ur, ui, tw[k]);
+            zk.x = ar - ui; zk.y = ai + ur;      // A + i·U
+            zp.x = ar + ui; zp.y = -ai + ur;     // conj(A) + i·conj(U)
+        }
+        // DIT input position of element a: a = a1 + R1·a2 + 8·R1·a3  ->  64·a1 + 8·a2 + a3
+        {
+            const int a1 = k % R1, a2 = (k / R1) & 7, a3 = k / (8 * R1);
+            tile[L::idx(64 * a1 + 8 * a2 + a3, c)] = zk;
+        }
+        if (k != kp) {
+            const int a1 = kp % R1, a2 = (kp / R1) & 7, a3 = kp / (8 * R1);
+            tile[L::idx(64 * a1 + 8 * a2 + a3, c)] = zp;
+        }
+    }
+}
+
+}  // namespace fftc
+}  // namespace pm

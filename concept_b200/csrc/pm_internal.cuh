@@ -138,6 +138,12 @@ struct pm_ctx {
     int xs_sep_deconv;
     double xs_sep_gauss;
     bool fused_solve;         // use the fused path when supported
+    int solve_mode;           // PM_SOLVE_* (pmgrav.h): which implementation pm_solve_fused / pm_kick_long use
+    // hand-written slab transform (pm_fft.cu)
+    void* f2_tw;              // e^{−2πi m/G} in the grid's precision
+    unsigned* f2_ctr;         // tickets, per-plane completion counters, error flag (last entry)
+    size_t f2_nctr;
+    int f2_lag;
     void* peer_real[pm::kMaxPeers];   // IPC mappings of every rank's `real` buffer (own pointer for self)
     bool peers_ready;
     // P3M short range scratch (pm_shortrange.cu)
@@ -189,6 +195,12 @@ int device_barrier(pm_ctx* c);      // stream-ordered barrier over all ranks
 bool xsolve_supported(const pm_ctx* c);
 int xsolve(pm_ctx* c, double prefactor, int deconv_order, double gauss);
 int make_xsolve_tables(pm_ctx* c);
+int update_sep_table(pm_ctx* c, int deconv_order, double gauss);
+// implemented in pm_fft.cu
+bool fft2_supported(const pm_ctx* c);
+int make_fft2_tables(pm_ctx* c);
+int solve_fft2(pm_ctx* c, double prefactor, int deconv_order, double gauss, bool l2_fused);
+int fft2_check_error(pm_ctx* c);
 int solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss);   // pm_fourier.cu
 
 int ensure_saved(pm_ctx* c);

@@ -339,6 +339,27 @@ bool xsolve_supported(const pm_ctx* c) {
     return true;
 }
 
+// separable per-axis factor (x_l/sin x_l)^D · exp(−gauss·k_l²), x_l = k_l·π/G + ε (mesh.py:2775-2776),
+// cached for one (deconv_order, gauss)
+int update_sep_table(pm_ctx* c, int deconv_order, double gauss) {
+    const Geom& g = c->g;
+    if (c->xs_sep != nullptr && c->xs_sep_deconv == deconv_order && c->xs_sep_gauss == gauss) return PM_OK;
+    std::vector<double> sep(g.G);
+    for (int l = 0; l < g.G; ++l) {
+        const int k = l - (l >= g.G / 2 ? g.G : 0);
+        const double x = k * (M_PI / g.G) + kEps;
+        double v = 1.0;
+        for (int e = 0; e < deconv_order; ++e) v *= x / sin(x);
+        sep[l] = v * exp(-gauss * (double)k * (double)k);
+    }
+    if (c->xs_sep == nullptr) PM_CHECK_CUDA(cudaMalloc(&c->xs_sep, sizeof(double) * g.G));
+    PM_CHECK_CUDA(cudaStreamSynchronize(c->stream));   // a previous launch may still read the table
+    PM_CHECK_CUDA(cudaMemcpy(c->xs_sep, sep.data(), sizeof(double) * g.G, cudaMemcpyHostToDevice));
+    c->xs_sep_deconv = deconv_order;
+    c->xs_sep_gauss = gauss;
+    return PM_OK;
+}
+
 template <typename T>
 static int xsolve_t(pm_ctx* c, double prefactor, int deconv_order, double gauss) {
     using V = typename Vec2<T>::type;
@@ -351,22 +372,7 @@ static int xsolve_t(pm_ctx* c, double prefactor, int deconv_order, double gauss)
         for (int r = 0; r < c->nranks; ++r)
             p.base[r] = reinterpret_cast<T*>(c->peer_real[r]) + (size_t)g.halo * g.G * g.Gp;
     }
-    if (c->xs_sep == nullptr || c->xs_sep_deconv != deconv_order || c->xs_sep_gauss != gauss) {
-        // separable per-axis factor (x_l/sin x_l)^D · exp(−gauss·k_l²), x_l = k_l·π/G + ε (mesh.py:2775-2776)
-        std::vector<double> sep(g.G);
-        for (int l = 0; l < g.G; ++l) {
-            const int k = l - (l >= g.G / 2 ? g.G : 0);
-            const double x = k * (M_PI / g.G) + kEps;
-            double v = 1.0;
-            for (int e = 0; e < deconv_order; ++e) v *= x / sin(x);
-            sep[l] = v * exp(-gauss * (double)k * (double)k);
-        }
-        if (c->xs_sep == nullptr) PM_CHECK_CUDA(cudaMalloc(&c->xs_sep, sizeof(double) * g.G));
-        PM_CHECK_CUDA(cudaStreamSynchronize(c->stream));   // a previous launch may still read the table
-        PM_CHECK_CUDA(cudaMemcpy(c->xs_sep, sep.data(), sizeof(double) * g.G, cudaMemcpyHostToDevice));
-        c->xs_sep_deconv = deconv_order;
-        c->xs_sep_gauss = gauss;
-    }
+    PM_TRY(update_sep_table(c, deconv_order, gauss));
     p.tw = c->xs_tw;
     p.sep = c->xs_sep;
     p.prefactor = prefactor;

@@ -135,8 +135,17 @@ class PMContext:
     def fused_solve_available(self):
         return bool(self.lib.pm_fused_solve_available(self._h))
 
-    def set_fused_solve(self, enable):
-        check(self.lib.pm_set_fused_solve(self._h, int(bool(enable))))
+    # PM_SOLVE_* of include/pmgrav.h
+    SOLVE_MODES = {'unfused': 0, 'auto': 1, 'cufft2d': 2, 'fft2_split': 3, 'fft2_l2': 4}
+
+    def set_fused_solve(self, mode):
+        """mode: bool (False = three-call path, True = best fused implementation) or a SOLVE_MODES key."""
+        if isinstance(mode, str):
+            mode = self.SOLVE_MODES[mode]
+        check(self.lib.pm_set_fused_solve(self._h, int(mode)))
+
+    def check_async_error(self):
+        check(self.lib.pm_check_async_error(self._h))
 
     def fourier_operate(self, deconv_order=0, shift=None, scale=1.0, diff_dim=-1, from_saved=False):
         check(self.lib.pm_fourier_operate(self._h, int(deconv_order), vec3(shift), float(scale), int(diff_dim), int(from_saved)))

@@ -121,14 +121,26 @@ int pm_kspace_potential(pm_ctx* ctx, double prefactor, int deconv_order, double 
  * working slab (the reference copies slab_downstream → slab_updownstream_subgroup). */
 int pm_fourier_operate(pm_ctx* ctx, int deconv_order, const double* shift, double scale,
                        int diff_dim, int from_saved);
-/* pm_fft_forward + pm_kspace_potential + pm_fft_backward in one call, with the x transforms and the
- * k-space factor fused into a single kernel that addresses all ranks' slabs through peer pointers
- * (the FFTW-MPI transpose of fft.c:34-73 never materialises).  Available for G ∈ {64, 512}; with
- * several ranks pm_ipc_open_peers must have been called.  The slab ends in real space (potential). */
+/* pm_fft_forward + pm_kspace_potential + pm_fft_backward in one call: 2-D (y,z) transforms per x plane,
+ * then ONE kernel for the x direction — forward transform, Green's function, inverse transform — that
+ * addresses all ranks' slabs through peer pointers (the FFTW-MPI transpose of fft.c:34-73 never
+ * materialises), then the inverse 2-D transforms.  The slab ends in real space (potential).
+ * Implementations (pm_set_fused_solve):
+ *   PM_SOLVE_FFT2_L2        hand-written transforms, G ∈ {128, 256, 512}; the two passes of each 2-D
+ *                           transform run dependency-ordered in one launch so the intermediate plane
+ *                           stays in L2 (fp64 grids; fp32 grids use PM_SOLVE_FFT2_SPLIT)
+ *   PM_SOLVE_FFT2_SPLIT     same kernels, one launch per pass
+ *   PM_SOLVE_CUFFT2D_XSOLVE batched cuFFT 2-D plans + the x kernel, G ∈ {64, 512}
+ *   PM_SOLVE_UNFUSED        pm_kick_long uses the three-call path (cuFFT 3-D + k-space kernel)
+ *   PM_SOLVE_AUTO           the first available of the above (default)
+ * With several ranks pm_ipc_open_peers must have been called. */
+enum { PM_SOLVE_UNFUSED = 0, PM_SOLVE_AUTO = 1, PM_SOLVE_CUFFT2D_XSOLVE = 2, PM_SOLVE_FFT2_SPLIT = 3, PM_SOLVE_FFT2_L2 = 4 };
 int pm_solve_fused(pm_ctx* ctx, double prefactor, int deconv_order, double gauss);
 int pm_fused_solve_available(const pm_ctx* ctx);
-/* pm_kick_long uses the fused solve when available; enable = 0 forces the three-call path */
-int pm_set_fused_solve(pm_ctx* ctx, int enable);
+int pm_set_fused_solve(pm_ctx* ctx, int mode);
+/* Host-synchronising check of the asynchronous give-up flag of the dependency-ordered kernels
+ * (a tile dependency that was not satisfied within seconds); PM_ERR_ARG with a message if set. */
+int pm_check_async_error(pm_ctx* ctx);
 int pm_slab_save(pm_ctx* ctx);      /* slab_updownstream_subgroup[...] = slab (interactions.py:2256) */
 int pm_slab_accumulate(pm_ctx* ctx);/* saved += working slab (copy_modes '+=' for interlacing) */
 int pm_slab_restore(pm_ctx* ctx);   /* working slab = saved */

@@ -1,0 +1,282 @@
+// CPU walk-through of the shared-memory FFT building blocks (concept_b200/csrc/pm_fftcore.cuh):
+// the device stages are executed sequentially for tid = 0 … nthr−1 and compared with an O(N²)
+// long-double DFT.  Built and run by tests/test_fftcore_host.py (no GPU needed).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "pm_fftops.cuh"
+
+using namespace pm::fftc;
+
+static const long double PI = 3.14159265358979323846264338327950288L;
+
+template <typename V>
+static std::vector<V> make_tw(int NT) {
+    std::vector<V> tw(NT);
+    for (int m = 0; m < NT; ++m) {
+        const long double a = -2.0L * PI * m / NT;
+        tw[m].x = (decltype(tw[m].x))cosl(a);
+        tw[m].y = (decltype(tw[m].y))sinl(a);
+    }
+    return tw;
+}
+
+template <typename T> struct Store {
+    T* re; T* im; int N;   // out[c][index]
+    void operator()(int c, int idx, T r, T i) { re[c * N + idx] = r; im[c * N + idx] = i; }
+};
+
+template <typename T, class L> struct StoreTile {
+    typename Vec2<T>::type* tile;
+    void operator()(int c, int idx, T r, T i) { typename Vec2<T>::type v; v.x = r; v.y = i; tile[L::idx(idx, c)] = v; }
+};
+
+static double frand() { return rand() / (double)RAND_MAX - 0.5; }
+
+// reference DFT of line c (natural order), sign dir
+template <typename T>
+static void ref_dft(const std::vector<T>& xr, const std::vector<T>& xi, int N, int dir, std::vector<long double>& yr,
+                    std::vector<long double>& yi) {
+    yr.assign(N, 0); yi.assign(N, 0);
+    for (int k = 0; k < N; ++k) {
+        long double sr = 0, si = 0;
+        for (int n = 0; n < N; ++n) {
+            const long double a = dir * 2.0L * PI * ((long long)n * k % N) / N;
+            const long double cr = cosl(a), ci = sinl(a);
+            sr += xr[n] * cr - xi[n] * ci;
+            si += xr[n] * ci + xi[n] * cr;
+        }
+        yr[k] = sr; yi[k] = si;
+    }
+}
+
+template <typename T, int N, int C, bool ROW>
+static double test_complex(int nthr) {
+    using V = typename Vec2<T>::type;
+    using L = typename std::conditional<ROW, RowLayout<N, C>, ColLayout<C>>::type;
+    using RAW = typename std::conditional<ROW, RowRaw<N>, ColRaw<C>>::type;
+    constexpr int NT = N;
+    auto tw = make_tw<V>(NT);
+    std::vector<V> raw(N * C), tile((size_t)(N + N / 8 + N / 64 + 1) * C + 16);
+    std::vector<std::vector<T>> xr(C, std::vector<T>(N)), xi(C, std::vector<T>(N));
+    for (int c = 0; c < C; ++c)
+        for (int n = 0; n < N; ++n) {
+            xr[c][n] = (T)frand(); xi[c][n] = (T)frand();
+            V v; v.x = xr[c][n]; v.y = xi[c][n];
+            raw[RAW::idx(n, c)] = v;
+        }
+    double err = 0;
+    for (int dir = -1; dir <= 1; dir += 2) {
+        std::vector<T> ore(C * N), oim(C * N);
+        Store<T> st{ore.data(), oim.data(), N};
+        // ---- DIT: natural -> natural
+        for (int t = 0; t < nthr; ++t) {
+            if (dir < 0) dit_stageA<L, RAW, T, N, -1>(raw.data(), tile.data(), t, nthr);
+            else dit_stageA<L, RAW, T, N, +1>(raw.data(), tile.data(), t, nthr);
+        }
+        for (int t = 0; t < nthr; ++t) {
+            if (dir < 0) dit_stageB<L, T, N, NT, -1>(tile.data(), tw.data(), t, nthr);
+            else dit_stageB<L, T, N, NT, +1>(tile.data(), tw.data(), t, nthr);
+        }
+        for (int t = 0; t < nthr; ++t) {
+            if (dir < 0) dit_stageC<L, T, N, NT, -1>(tile.data(), tw.data(), t, nthr, st);
+            else dit_stageC<L, T, N, NT, +1>(tile.data(), tw.data(), t, nthr, st);
+        }
+        std::vector<long double> yr, yi;
+        for (int c = 0; c < C; ++c) {
+            ref_dft(xr[c], xi[c], N, dir, yr, yi);
+            for (int k = 0; k < N; ++k) {
+                err = fmax(err, fabs((double)(ore[c * N + k] - yr[k])));
+                err = fmax(err, fabs((double)(oim[c * N + k] - yi[k])));
+            }
+        }
+        // ---- DIF: natural (registers) -> scattered elements
+        std::vector<T> dre(C * N), dim_(C * N);
+        Store<T> st2{dre.data(), dim_.data(), N};
+        constexpr int R1 = N / 64;
+        for (int t = 0; t < nthr; ++t)
+            for (int b = t; b < 64 * L::C; b += nthr) {
+                int c, q;
+                L::template decode<64>(b, c, q);
+                T r[R1], i[R1];
+                for (int a1 = 0; a1 < R1; ++a1) { r[a1] = xr[c][64 * a1 + q]; i[a1] = xi[c][64 * a1 + q]; }
+                if (dir < 0) dif_stage1_regs<L, T, N, NT, -1>(r, i, tile.data(), tw.data(), c, q);
+                else dif_stage1_regs<L, T, N, NT, +1>(r, i, tile.data(), tw.data(), c, q);
+            }
+        for (int t = 0; t < nthr; ++t) {
+            if (dir < 0) dif_stage2<L, T, N, NT, -1>(tile.data(), tw.data(), t, nthr);
+            else dif_stage2<L, T, N, NT, +1>(tile.data(), tw.data(), t, nthr);
+        }
+        for (int t = 0; t < nthr; ++t) {
+            if (dir < 0) dif_stage3<L, T, N, -1>(tile.data(), t, nthr, st2);
+            else dif_stage3<L, T, N, +1>(tile.data(), t, nthr, st2);
+        }
+        for (int c = 0; c < C; ++c) {
+            ref_dft(xr[c], xi[c], N, dir, yr, yi);
+            for (int k = 0; k < N; ++k) {
+                err = fmax(err, fabs((double)(dre[c * N + k] - yr[k])));
+                err = fmax(err, fabs((double)(dim_[c * N + k] - yi[k])));
+            }
+        }
+    }
+    return err;
+}
+
+// z pass: 2M reals per line <-> M+1 complex (Nyquist dropped)
+template <typename T, int M, int C>
+static double test_real(int nthr) {
+    using V = typename Vec2<T>::type;
+    using L = RowLayout<M, C>;
+    using RAW = RowRaw<M>;
+    constexpr int NT = 2 * M;
+    auto tw = make_tw<V>(NT);
+    std::vector<V> raw(M * C), tile((size_t)L::PITCH * C + 16);
+    std::vector<std::vector<T>> x(C, std::vector<T>(2 * M));
+    for (int c = 0; c < C; ++c)
+        for (int n = 0; n < M; ++n) {
+            x[c][2 * n] = (T)frand(); x[c][2 * n + 1] = (T)frand();
+            V v; v.x = x[c][2 * n]; v.y = x[c][2 * n + 1];
+            raw[RAW::idx(n, c)] = v;
+        }
+    double err = 0;
+    // forward
+    StoreTile<T, L> stt{tile.data()};
+    for (int t = 0; t < nthr; ++t) dit_stageA<L, RAW, T, M, -1>(raw.data(), tile.data(), t, nthr);
+    for (int t = 0; t < nthr; ++t) dit_stageB<L, T, M, NT, -1>(tile.data(), tw.data(), t, nthr);
+    for (int t = 0; t < nthr; ++t) dit_stageC<L, T, M, NT, -1>(tile.data(), tw.data(), t, nthr, stt);
+    std::vector<T> ore(C * (M + 1)), oim(C * (M + 1));
+    Store<T> st{ore.data(), oim.data(), M + 1};
+    for (int t = 0; t < nthr; ++t) r2c_post<L, T, M>(tile.data(), tw.data(), t, nthr, st);
+    std::vector<std::vector<long double>> Xr(C, std::vector<long double>(M + 1)), Xi(C, std::vector<long double>(M + 1));
+    for (int c = 0; c < C; ++c) {
+        for (int k = 0; k <= M; ++k) {
+            long double sr = 0, si = 0;
+            for (int n = 0; n < 2 * M; ++n) {
+                const long double a = -2.0L * PI * ((long long)n * k % (2 * M)) / (2 * M);
+                sr += x[c][n] * cosl(a); si += x[c][n] * sinl(a);
+            }
+            Xr[c][k] = sr; Xi[c][k] = si;
+            if (k < M) {
+                err = fmax(err, fabs((double)(ore[c * (M + 1) + k] - sr)));
+                err = fmax(err, fabs((double)(oim[c * (M + 1) + k] - si)));
+            } else {
+                err = fmax(err, fabs((double)ore[c * (M + 1) + k]) + fabs((double)oim[c * (M + 1) + k]));   // delivered as zero
+            }
+        }
+    }
+    // inverse: feed the exact spectrum with X_M := 0; expected x'_n = Σ_{k} X_k e^{+…} with the Nyquist term missing
+    for (int c = 0; c < C; ++c)
+        for (int k = 0; k < M; ++k) {
+            V v; v.x = (T)Xr[c][k]; v.y = (T)Xi[c][k];
+            raw[RAW::idx(k, c)] = v;
+        }
+    for (int t = 0; t < nthr; ++t) c2r_pre<L, RAW, T, M>(raw.data(), tile.data(), tw.data(), t, nthr);
+    for (int t = 0; t < nthr; ++t) dit_stageA_inplace<L, T, M, +1>(tile.data(), t, nthr);
+    for (int t = 0; t < nthr; ++t) dit_stageB<L, T, M, NT, +1>(tile.data(), tw.data(), t, nthr);
+    std::vector<T> zre(C * M), zim(C * M);
+    Store<T> stz{zre.data(), zim.data(), M};
+    for (int t = 0; t < nthr; ++t) dit_stageC<L, T, M, NT, +1>(tile.data(), tw.data(), t, nthr, stz);
+    for (int c = 0; c < C; ++c)
+        for (int n = 0; n < 2 * M; ++n) {
+            // 2M·x_n minus the dropped Nyquist term X_M·(−1)^n
+            const long double expect = 2.0L * M * x[c][n] - Xr[c][M] * ((n & 1) ? -1 : 1);
+            const T got = (n & 1) ? zim[c * M + n / 2] : zre[c * M + n / 2];
+            err = fmax(err, fabs((double)(got - expect)) / (2.0 * M));
+        }
+    return err;
+}
+
+
+// ---- a whole fused solve on the CPU: z/y forward per plane, x solve, y/z inverse ------------------
+struct HostCopy {
+    template <typename V> void operator()(V* dst, const V* src) const { *dst = *src; }
+};
+
+template <typename T, int G>
+static int solve3d(const char* fin, const char* fsep, const char* fout, double prefactor, int nranks) {
+    using S = SlabFFT<T, G>;
+    using V = typename S::V;
+    const int nthr = 512;
+    const int nxl = G / nranks;
+    std::vector<double> in((size_t)G * G * G), sep(G);
+    FILE* f = fopen(fin, "rb");
+    if (!f || fread(in.data(), sizeof(double), in.size(), f) != in.size()) return 2;
+    fclose(f);
+    f = fopen(fsep, "rb");
+    if (!f || fread(sep.data(), sizeof(double), G, f) != (size_t)G) return 2;
+    fclose(f);
+    // one padded slab per "rank"
+    std::vector<std::vector<T>> slab(nranks, std::vector<T>((size_t)nxl * G * S::Gp, (T)7));   // padding holds garbage
+    for (int i = 0; i < G; ++i)
+        for (int j = 0; j < G; ++j)
+            for (int k = 0; k < G; ++k)
+                slab[i / nxl][((size_t)(i % nxl) * G + j) * S::Gp + k] = (T)in[((size_t)i * G + j) * G + k];
+    auto tw = make_tw<V>(S::NT);
+    std::vector<V> raw(S::kRawElems), work(S::kWorkElems + 16);
+    HostCopy cp;
+    auto run = [&](auto& op) {
+        for (int t = 0; t < nthr; ++t) op.load(raw.data(), t, nthr, cp);
+        for (int ph = 0; ph < op.kPhases; ++ph)
+            for (int t = 0; t < nthr; ++t) op.phase(ph, raw.data(), work.data(), tw.data(), t, nthr);
+    };
+    for (int r = 0; r < nranks; ++r)
+        for (int p = 0; p < nxl; ++p) {
+            T* plane = slab[r].data() + (size_t)p * G * S::Gp;
+            for (int t = 0; t < S::kZTilesPerPlane; ++t) { typename S::ZFwd op{plane, t * S::CZ}; run(op); }
+            for (int t = 0; t < S::kYTilesPerPlane; ++t) { typename S::template YPass<-1> op{reinterpret_cast<V*>(plane), t * S::CY}; run(op); }
+        }
+    typename S::XGeom xg;
+    for (int r = 0; r < kMaxFftPeers; ++r) xg.base[r] = r < nranks ? reinterpret_cast<V*>(slab[r].data()) : nullptr;
+    xg.nxl_shift = 0;
+    while ((1 << xg.nxl_shift) < nxl) ++xg.nxl_shift;
+    xg.sep = sep.data();
+    xg.prefactor = prefactor;
+    for (int j = 0; j < G; ++j)
+        for (int t = 0; t < S::kYTilesPerPlane; ++t) { typename S::XSolve op{&xg, j, t * S::CY}; run(op); }
+    for (int r = 0; r < nranks; ++r)
+        for (int p = 0; p < nxl; ++p) {
+            T* plane = slab[r].data() + (size_t)p * G * S::Gp;
+            for (int t = 0; t < S::kYTilesPerPlane; ++t) { typename S::template YPass<+1> op{reinterpret_cast<V*>(plane), t * S::CY}; run(op); }
+            for (int t = 0; t < S::kZTilesPerPlane; ++t) { typename S::ZInv op{plane, t * S::CZ}; run(op); }
+        }
+    std::vector<double> out((size_t)G * G * G);
+    for (int i = 0; i < G; ++i)
+        for (int j = 0; j < G; ++j)
+            for (int k = 0; k < G; ++k)
+                out[((size_t)i * G + j) * G + k] = (double)slab[i / nxl][((size_t)(i % nxl) * G + j) * S::Gp + k];
+    f = fopen(fout, "wb");
+    if (!f || fwrite(out.data(), sizeof(double), out.size(), f) != out.size()) return 2;
+    fclose(f);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc >= 8 && std::string(argv[1]) == "solve3d") {
+        // solve3d <f64|f32> <in.bin> <sep.bin> <out.bin> <prefactor> <nranks>     (G = 128)
+        const double pre = atof(argv[6]);
+        const int nr = atoi(argv[7]);
+        return std::string(argv[2]) == "f64" ? solve3d<double, 128>(argv[3], argv[4], argv[5], pre, nr)
+                                             : solve3d<float, 128>(argv[3], argv[4], argv[5], pre, nr);
+    }
+    int fails = 0;
+    auto report = [&](const char* name, double err, double tol) {
+        printf("%-40s max err %.3e %s\n", name, err, err < tol ? "ok" : "FAIL");
+        if (!(err < tol)) ++fails;
+    };
+    report("col f64 N=512 C=8  nthr=512", test_complex<double, 512, 8, false>(512), 1e-12);
+    report("col f64 N=256 C=8  nthr=512", test_complex<double, 256, 8, false>(512), 1e-12);
+    report("col f64 N=128 C=8  nthr=512", test_complex<double, 128, 8, false>(512), 1e-12);
+    report("col f64 N=64  C=8  nthr=512", test_complex<double, 64, 8, false>(512), 1e-12);
+    report("col f32 N=512 C=16 nthr=512", test_complex<float, 512, 16, false>(512), 2e-4);
+    report("col f32 N=128 C=16 nthr=256", test_complex<float, 128, 16, false>(256), 1e-4);
+    report("row f64 N=256 C=16 nthr=512", test_complex<double, 256, 16, true>(512), 1e-12);
+    report("row f64 N=64  C=16 nthr=512", test_complex<double, 64, 16, true>(512), 1e-12);
+    report("real f64 M=256 C=16", test_real<double, 256, 16>(512), 1e-12);
+    report("real f64 M=128 C=16", test_real<double, 128, 16>(512), 1e-12);
+    report("real f64 M=64  C=16", test_real<double, 64, 16>(512), 1e-12);
+    report("real f32 M=256 C=16", test_real<float, 256, 16>(512), 2e-4);
+    return fails;
+}

@@ -1,0 +1,124 @@
+"""GPU parity of the hand-written slab transform (pm_fft.cu) behind pm_solve_fused / pm_kick_long:
+against the numpy oracle (G = 128), against the cuFFT-based paths of the same library (G = 128, 256,
+512), run-to-run bit stability of the dependency-ordered (L2-resident) schedule, and the whole kick."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+G_NEWTON = 4.4985024439973154e-05
+
+
+def _ctx(G, L, dtype='f64'):
+    from concept_b200.pmsolver import PMContext
+    return PMContext(G, L, dtype=dtype)
+
+
+def _solve(ctx, rho, mode, pre, deconv, gauss=0.0):
+    ctx.set_fused_solve(mode)
+    ctx.set_grid(rho)
+    if mode == 'unfused':
+        ctx.fft_forward()
+        ctx.kspace_potential(pre, deconv, gauss, 1.0)
+        ctx.fft_backward()
+    else:
+        ctx.solve_fused(pre, deconv, gauss)
+        ctx.check_async_error()
+    return ctx.get_grid()
+
+
+def _numpy_solve(rho, pre, deconv, gauss):
+    G = rho.shape[0]
+    l = np.arange(G)
+    k = np.where(l >= G//2, l - G, l).astype(float)
+    x = k*(np.pi/G) + 2.220446049250313e-16
+    d = x/np.sin(x)
+    kz = k[:G//2 + 1].copy(); kz[-1] = G//2
+    dz = d[:G//2 + 1]
+    k2 = k[:, None, None]**2 + k[None, :, None]**2 + kz[None, None, :]**2
+    fac = ((d[:, None, None]*d[None, :, None])*dz[None, None, :])**deconv*pre/np.where(k2 == 0, 1, k2)*np.exp(-gauss*k2)
+    fac[k2 == 0] = 0
+    fac[G//2, :, :] = 0; fac[:, G//2, :] = 0; fac[:, :, G//2] = 0
+    return np.fft.irfftn(np.fft.rfftn(rho)*fac, s=rho.shape, axes=(0, 1, 2), norm='forward')
+
+
+@pytest.mark.parametrize('mode', ['fft2_l2', 'fft2_split'])
+@pytest.mark.parametrize('gauss', [0.0, 3e-3])
+def test_solve_G128_against_numpy(mode, gauss):
+    G, L = 128, 100.0
+    rho = np.random.default_rng(1).standard_normal((G, G, G))
+    ctx = _ctx(G, L)
+    got = _solve(ctx, rho, mode, -2.5, 4, gauss)
+    ref = _numpy_solve(rho, -2.5, 4, gauss)
+    ctx.close()
+    assert np.max(np.abs(got - ref))/np.max(np.abs(ref)) < 1e-12
+
+
+@pytest.mark.parametrize('G', [128, 256, 512])
+def test_solve_matches_cufft_paths(G):
+    L = 300.0
+    rng = np.random.default_rng(G)
+    rho = rng.standard_normal((G, G, G))
+    ctx = _ctx(G, L)
+    ref = _solve(ctx, rho, 'unfused', -1.7, 6)
+    scale = np.max(np.abs(ref))
+    for mode in ('fft2_l2', 'fft2_split'):
+        got = _solve(ctx, rho, mode, -1.7, 6)
+        assert np.max(np.abs(got - ref))/scale < 1e-12, mode
+    if G == 512:
+        got = _solve(ctx, rho, 'cufft2d', -1.7, 6)
+        assert np.max(np.abs(got - ref))/scale < 1e-12
+    ctx.close()
+
+
+def test_l2_schedule_is_bit_stable():
+    """The dependency-ordered schedule must not depend on timing: 12 runs, identical bits."""
+    G, L = 512, 512.0
+    rho = np.random.default_rng(3).standard_normal((G, G, G))
+    ctx = _ctx(G, L)
+    first = _solve(ctx, rho, 'fft2_l2', -1.0, 4)
+    split = _solve(ctx, rho, 'fft2_split', -1.0, 4)
+    assert np.array_equal(first, split)
+    for _ in range(11):
+        assert np.array_equal(_solve(ctx, rho, 'fft2_l2', -1.0, 4), first)
+    ctx.close()
+
+
+@pytest.mark.parametrize('G', [128, 512])
+def test_solve_fp32_grid(G):
+    L = 200.0
+    rho = np.random.default_rng(7).standard_normal((G, G, G))
+    c64 = _ctx(G, L)
+    ref = _solve(c64, rho, 'unfused', -1.3, 6)
+    c64.close()
+    c32 = _ctx(G, L, 'f32')
+    got = _solve(c32, rho, 'auto', -1.3, 6)
+    got_cufft = _solve(c32, rho, 'unfused', -1.3, 6)
+    c32.close()
+    scale = np.max(np.abs(ref))
+    e_new, e_cufft = np.max(np.abs(got - ref))/scale, np.max(np.abs(got_cufft - ref))/scale
+    assert e_new < 2e-5, e_new
+    assert e_new < 4*e_cufft + 1e-6, (e_new, e_cufft)    # as accurate as the library transform in fp32
+
+
+@pytest.mark.parametrize('G,order,diff', [(128, 2, 2), (256, 3, 4)])
+def test_kick_against_oracle(G, order, diff):
+    """Whole long-range kick through the hand-written transforms vs the numpy oracle."""
+    from concept_b200.pmsolver import make_kick_params
+    from oracle import pm_oracle as O
+    L, N = 256.0, 200_000
+    rng = np.random.default_rng(11)
+    pos_h, mom_h = rng.random((N, 3))*L, rng.standard_normal((N, 3))
+    kw = dict(mass=2.1, boxsize=L, gridsize=G, order=order, G_Newton=G_NEWTON, dt_rho_over_dt1=2.0, dt_kick=0.01, diff_order=diff)
+    ref = O.pm_kick(pos_h, mom_h, **kw) - mom_h
+    ctx = _ctx(G, L)
+    assert ctx.fused_solve_available
+    ctx.set_fused_solve('fft2_l2')
+    pos, mom = torch.as_tensor(pos_h, device='cuda'), torch.as_tensor(mom_h, device='cuda')
+    ctx.kick_long(pos, mom, make_kick_params(**kw))
+    ctx.check_async_error()
+    got = mom.cpu().numpy() - mom_h
+    ctx.close()
+    # tolerance: tests/test_gpu_parity.py (Δmom 1e-9 of max|Δmom|)
+    assert np.max(np.abs(got - ref))/np.max(np.abs(ref)) < 1e-9

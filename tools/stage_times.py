@@ -24,6 +24,7 @@ def main():
     ap.add_argument('--sigma', type=float, default=0.3)
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--nofuse', action='store_true', help='three-call solve (cuFFT 3-D + k-space kernel) instead of the fused x-solve')
+    ap.add_argument('--solve-mode', default='auto', help='auto | fft2_l2 | fft2_split | cufft2d (see PMContext.SOLVE_MODES)')
     ap.add_argument('--shuffle', action='store_true', help='random particle order (worst-case locality)')
     a = ap.parse_args()
     L = 512.0
@@ -33,6 +34,7 @@ def main():
         pos, mom = pos[perm].contiguous(), mom[perm].contiguous()
     N = pos.shape[0]
     ctx = PMContext(a.grid, L, dtype=a.dtype)
+    ctx.set_fused_solve(a.solve_mode)
     p = make_kick_params(mass=1.0, boxsize=L, gridsize=a.grid, order=a.order, G_Newton=4.4985024439973154e-05,
                          dt_rho_over_dt1=2.0, dt_kick=1e-3, diff_order=a.diff)
     s = torch.zeros(1, dtype=torch.float64, device='cuda')
@@ -64,7 +66,8 @@ def main():
     es = 8 if a.dtype == 'f64' else 4
     alg = {'grid_zero': es*G3, 'deposit': 24*N + es*G3, 'fft_forward': 2*es*G3, 'kspace': 2*es*G3, 'fft_backward': 2*es*G3, 'solve_fused': 4*es*G3,
            'gather_kick': 72*N + es*G3, 'drift': 72*N}
-    out = {'N': N, 'grid': a.grid, 'order': a.order, 'dtype': a.dtype, 'sigma': a.sigma, 'shuffle': a.shuffle,
+    ctx.check_async_error()
+    out = {'N': N, 'grid': a.grid, 'solve_mode': a.solve_mode, 'order': a.order, 'dtype': a.dtype, 'sigma': a.sigma, 'shuffle': a.shuffle,
            'device_bytes': ctx.device_bytes, 'stages_ms': {}, 'stages_GBps': {}}
     for k in times:
         t = sorted(times[k])[len(times[k])//2]
