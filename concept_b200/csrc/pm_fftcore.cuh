@@ -6,7 +6,8 @@
 // Transform length N = R1·8·8 with R1 ∈ {1, 2, 4, 8}.  Two flows over a tile of C independent lines:
 //
 //   DIT  (A, B, C):  input element a = a1 + R1·a2 + 8·R1·a3 at position 64·a1 + 8·a2 + a3
-//                    (stage A can gather it from a naturally ordered source), output natural.
+//                    (stage A gathers it straight from global memory through a Source functor),
+//                    output natural.
 //   DIF  (1, 2, 3):  input natural, output element b = b1 + R1·b2 + 8·R1·b3 at position
 //                    64·b1 + 8·b2 + b3.
 //
@@ -137,23 +138,36 @@ struct RowLayout {
     template <int P> static PM_HD void decode(int b, int& c, int& u) { u = b % P; c = b / P; }
 };
 
-// natural-order raw tile as the loads leave it
-template <int C_>
-struct ColRaw {   // [position][C]
-    static PM_HD int idx(int p, int c) { return p * C_ + c; }
+// Twiddle tables of one grid size G (all e^{−2πi·…}), laid out so that the lanes of a warp read
+// consecutive entries (row layout) or one broadcast entry per quarter-warp (column layout):
+//   B[a·8 + b]   = ω64^(a·b)            a, b < 8        middle stages
+//   C[a·64 + q]  = ωG^(a·q)             a < G/64, q < 64   first/last stage of a G-point transform; an
+//                                                       M = G/2-point transform uses rows 2a (ωM = ωG²)
+//   R[k]         = ωG^k                 k ≤ G/8         real<->complex packing; k up to G/4 by symmetry
+template <typename V>
+struct Twiddles {
+    const V* B;
+    const V* C;
+    const V* R;
 };
-template <int N_>
-struct RowRaw {   // [line][N]
-    static PM_HD int idx(int p, int c) { return c * N_ + p; }
-};
+template <int G> constexpr int twiddle_entries() { return 64 + G + G / 8 + 1; }
+
+// ω_{2M}^k for 0 ≤ k ≤ M/2 from R (entries k ≤ M/4):  ω^k = −i·conj(ω^(M/2−k))
+template <int M, typename V>
+PM_HD V tw_r(const V* R, int k) {
+    if (k <= M / 4) return R[k];
+    const V w = R[M / 2 - k];
+    V o; o.x = -w.y; o.y = -w.x;
+    return o;
+}
 
 // ---------------------------------------------------------------------------------------------
-// DIT flow
+// DIT flow.  TWS = G/N: row stride into the C table (1 for a G-point transform, 2 for G/2 points).
 // ---------------------------------------------------------------------------------------------
-// Stage A: gathers element a = u + (N/8)·a3 (u = a1 + R1·a2) from the naturally ordered `src`,
+// Stage A: gathers element a = u + (N/8)·a3 (u = a1 + R1·a2) of line c through src(c, a),
 // 8-point DFT over a3 -> b3, result at position 64·a1 + 8·a2 + b3 of `dst`.
-template <class L, class RAW, typename T, int N, int DIR, typename V>
-PM_HD void dit_stageA(const V* src, V* dst, int tid, int nthr) {
+template <class L, typename T, int N, int DIR, typename V, class Source>
+PM_HD void dit_stageA(const Source& src, V* dst, int tid, int nthr) {
     constexpr int R1 = N / 64;
     constexpr int P = N / 8;
     for (int b = tid; b < P * L::C; b += nthr) {
@@ -163,7 +177,7 @@ PM_HD void dit_stageA(const V* src, V* dst, int tid, int nthr) {
         T r[8], i[8];
 #pragma unroll
         for (int a3 = 0; a3 < 8; ++a3) {
-            const V v = src[RAW::idx(u + P * a3, c)];
+            const V v = src(c, u + P * a3);
             r[a3] = v.x; i[a3] = v.y;
         }
         dft8<DIR>(r, i);
@@ -199,9 +213,8 @@ PM_HD void dit_stageA_inplace(V* tile, int tid, int nthr) {
 }
 
 // Stage B: positions 64·a1 + 8·a2 + b3 over a2; input a2 times ω64^(a2·b3); DFT8 -> b2, in place.
-// tw[m] = e^{−2πi m/NT}; NT is a multiple of 64.
-template <class L, typename T, int N, int NT, int DIR, typename V>
-PM_HD void dit_stageB(V* tile, const V* tw, int tid, int nthr) {
+template <class L, typename T, int N, int DIR, typename V>
+PM_HD void dit_stageB(V* tile, const V* twB, int tid, int nthr) {
     constexpr int P = N / 8;
     for (int b = tid; b < P * L::C; b += nthr) {
         int c, u;
@@ -213,7 +226,7 @@ PM_HD void dit_stageB(V* tile, const V* tw, int tid, int nthr) {
         for (int a2 = 0; a2 < 8; ++a2) {
             const V v = tile[L::idx(p0 + 8 * a2, c)];
             r[a2] = v.x; i[a2] = v.y;
-            if (a2) cmul<DIR>(r[a2], i[a2], tw[(a2 * b3) * (NT / 64)]);
+            if (a2) cmul<DIR>(r[a2], i[a2], twB[a2 * 8 + b3]);
         }
         dft8<DIR>(r, i);
 #pragma unroll
@@ -226,8 +239,8 @@ PM_HD void dit_stageB(V* tile, const V* tw, int tid, int nthr) {
 
 // Stage C: positions 64·a1 + q over a1 (q = 8·b2 + b3); input a1 times ωN^(a1·q); DFT_R1 -> b1;
 // result (natural index 64·b1 + q) handed to sink(c, index, re, im).
-template <class L, typename T, int N, int NT, int DIR, typename V, class Sink>
-PM_HD void dit_stageC(const V* tile, const V* tw, int tid, int nthr, Sink& sink) {
+template <class L, typename T, int N, int TWS, int DIR, typename V, class Sink>
+PM_HD void dit_stageC(const V* tile, const V* twC, int tid, int nthr, const Sink& sink) {
     constexpr int R1 = N / 64;
     for (int b = tid; b < 64 * L::C; b += nthr) {
         int c, q;
@@ -237,7 +250,7 @@ PM_HD void dit_stageC(const V* tile, const V* tw, int tid, int nthr, Sink& sink)
         for (int a1 = 0; a1 < R1; ++a1) {
             const V v = tile[L::idx(64 * a1 + q, c)];
             r[a1] = v.x; i[a1] = v.y;
-            if (a1) cmul<DIR>(r[a1], i[a1], tw[(a1 * q) * (NT / N)]);
+            if (a1) cmul<DIR>(r[a1], i[a1], twC[(a1 * TWS) * 64 + q]);
         }
         dftR<R1, DIR>(r, i);
 #pragma unroll
@@ -250,21 +263,21 @@ PM_HD void dit_stageC(const V* tile, const V* tw, int tid, int nthr, Sink& sink)
 // ---------------------------------------------------------------------------------------------
 // Stage 1 on values already in registers (natural index 64·a1 + q): DFT_R1 -> b1, times ωN^(b1·q),
 // written to position 64·b1 + q.
-template <class L, typename T, int N, int NT, int DIR, typename V>
-PM_HD void dif_stage1_regs(T (&r)[N / 64], T (&i)[N / 64], V* tile, const V* tw, int c, int q) {
+template <class L, typename T, int N, int TWS, int DIR, typename V>
+PM_HD void dif_stage1_regs(T (&r)[N / 64], T (&i)[N / 64], V* tile, const V* twC, int c, int q) {
     constexpr int R1 = N / 64;
     dftR<R1, DIR>(r, i);
 #pragma unroll
     for (int b1 = 0; b1 < R1; ++b1) {
-        if (b1) cmul<DIR>(r[b1], i[b1], tw[(b1 * q) * (NT / N)]);
+        if (b1) cmul<DIR>(r[b1], i[b1], twC[(b1 * TWS) * 64 + q]);
         V v; v.x = r[b1]; v.y = i[b1];
         tile[L::idx(64 * b1 + q, c)] = v;
     }
 }
 
 // Stage 2: positions 64·b1 + 8·a2 + a3 over a2: DFT8 -> b2, times ω64^(a3·b2), in place.
-template <class L, typename T, int N, int NT, int DIR, typename V>
-PM_HD void dif_stage2(V* tile, const V* tw, int tid, int nthr) {
+template <class L, typename T, int N, int DIR, typename V>
+PM_HD void dif_stage2(V* tile, const V* twB, int tid, int nthr) {
     constexpr int P = N / 8;
     for (int b = tid; b < P * L::C; b += nthr) {
         int c, u;
@@ -280,7 +293,7 @@ PM_HD void dif_stage2(V* tile, const V* tw, int tid, int nthr) {
         dft8<DIR>(r, i);
 #pragma unroll
         for (int b2 = 0; b2 < 8; ++b2) {
-            if (b2) cmul<DIR>(r[b2], i[b2], tw[(a3 * b2) * (NT / 64)]);
+            if (b2) cmul<DIR>(r[b2], i[b2], twB[b2 * 8 + a3]);
             V v; v.x = r[b2]; v.y = i[b2];
             tile[L::idx(p0 + 8 * b2, c)] = v;
         }
@@ -290,7 +303,7 @@ PM_HD void dif_stage2(V* tile, const V* tw, int tid, int nthr) {
 // Stage 3: positions 8·u + a3 (u = b2 + 8·b1) over a3: DFT8 -> b3; element b1 + R1·b2 + 8·R1·b3
 // handed to sink(c, element, re, im).
 template <class L, typename T, int N, int DIR, typename V, class Sink>
-PM_HD void dif_stage3(const V* tile, int tid, int nthr, Sink& sink) {
+PM_HD void dif_stage3(const V* tile, int tid, int nthr, const Sink& sink) {
     constexpr int R1 = N / 64;
     constexpr int P = N / 8;
     for (int b = tid; b < P * L::C; b += nthr) {
@@ -311,7 +324,7 @@ PM_HD void dif_stage3(const V* tile, int tid, int nthr, Sink& sink) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// real <-> half-length complex packing (z pass).  M complex points per line, real length 2M = NT.
+// real <-> half-length complex packing (z pass).  M complex points per line, real length 2M = G.
 // ---------------------------------------------------------------------------------------------
 // After the forward M-point transform of z_n = x_2n + i·x_2n+1 (natural order in `tile`):
 //   X_k = E + ω^k·O,   E = (Z_k + conj Z_{M−k})/2,   O = −i·(Z_k − conj Z_{M−k})/2,   ω = e^{−2πi/2M}
@@ -319,7 +332,7 @@ PM_HD void dif_stage3(const V* tile, int tid, int nthr, Sink& sink) {
 // for k = 0 … M/2; sink(c, k, re, im) receives k = 0 … M−1 (X_M — the Nyquist mode, which the potential
 // nullifies, mesh.py:3615-3622 — is delivered as zero at k = M).
 template <class L, typename T, int M, typename V, class Sink>
-PM_HD void r2c_post(const V* tile, const V* tw, int tid, int nthr, Sink& sink) {
+PM_HD void r2c_post(const V* tile, const V* twR, int tid, int nthr, const Sink& sink) {
     constexpr int P = M / 2 + 1;
     for (int b = tid; b < P * L::C; b += nthr) {
         int c, k;
@@ -330,7 +343,7 @@ PM_HD void r2c_post(const V* tile, const V* tw, int tid, int nthr, Sink& sink) {
         const T er = (T)0.5 * (zk.x + zp.x), ei = (T)0.5 * (zk.y - zp.y);
         // D = Z_k − conj Z_p = (zk.x − zp.x, zk.y + zp.y);  O = −i·D/2 = (D.y/2, −D.x/2)
         T orr = (T)0.5 * (zk.y + zp.y), oi = (T)-0.5 * (zk.x - zp.x);
-        cmul<-1>(orr, oi, tw[k]);
+        cmul<-1>(orr, oi, tw_r<M>(twR, k));
         sink(c, k, er + orr, ei + oi);
         if (k == 0) sink(c, M, (T)0, (T)0);
         else if (k != kp) sink(c, kp, er - orr, -ei + oi);
@@ -339,9 +352,9 @@ PM_HD void r2c_post(const V* tile, const V* tw, int tid, int nthr, Sink& sink) {
 
 // Before the inverse M-point transform:  Z_k = A + i·U,  Z_{M−k} = conj(A) + i·conj(U),
 //   A = X_k + conj X_{M−k},  U = conj(ω^k)·(X_k − conj X_{M−k}),  with X_M := 0 and Im X_0 ignored.
-// `raw` holds X_0 … X_{M−1} in natural order; Z_k goes to its DIT input position of `tile`.
-template <class L, class RAW, typename T, int M, typename V>
-PM_HD void c2r_pre(const V* raw, V* tile, const V* tw, int tid, int nthr) {
+// src(c, k) delivers X_k (k < M) from global memory; Z_k goes to its DIT input position of `tile`.
+template <class L, typename T, int M, typename V, class Source>
+PM_HD void c2r_pre(const Source& src, V* tile, const V* twR, int tid, int nthr) {
     constexpr int R1 = M / 64;
     constexpr int P = M / 2 + 1;
     for (int b = tid; b < P * L::C; b += nthr) {
@@ -350,15 +363,15 @@ PM_HD void c2r_pre(const V* raw, V* tile, const V* tw, int tid, int nthr) {
         const int kp = (M - k) & (M - 1);
         V zk, zp;
         if (k == 0) {
-            const T x0 = raw[RAW::idx(0, c)].x;
+            const T x0 = src(c, 0).x;
             zk.x = x0; zk.y = x0;
             zp = zk;
         } else {
-            const V xk = raw[RAW::idx(k, c)];
-            const V xp = raw[RAW::idx(kp, c)];
+            const V xk = src(c, k);
+            const V xp = src(c, kp);
             const T ar = xk.x + xp.x, ai = xk.y - xp.y;
             T ur = xk.x - xp.x, ui = xk.y + xp.y;
-            cmul<+1>(ur, ui, tw[k]);
+            cmul<+1>(ur, ui, tw_r<M>(twR, k));
             zk.x = ar - ui; zk.y = ai + ur;      // A + i·U
             zp.x = ar + ui; zp.y = -ai + ur;     // conj(A) + i·conj(U)
         }

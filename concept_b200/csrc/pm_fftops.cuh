@@ -1,17 +1,19 @@
 // pm_fftops.cuh — the tile operations of the hand-written slab transform (pm_fft.cu), built from
 // the stages in pm_fftcore.cuh.  Each operation is a sequence of phases separated by a block barrier;
 // phases take (tid, nthr) so the CPU harness (tests/fft_host_harness.cu) can walk through a whole
-// 3-D solve with exactly this code.  Global loads go through a Copy functor (cp.async on the device).
+// 3-D solve with exactly this code.  Phase 0 reads its inputs straight from global memory
+// (ld.global.cg, 128-byte row segments) into registers; the last phase stores from registers; in
+// between the tile lives in ONE shared-memory buffer that every stage updates in place.
 //
 // Slab layout (per rank): real T[nxl][G][Gp], Gp = G + 2; in place complex V[nxl][G][Gc], Gc = G/2 + 1
 // (what fft.c:124 calls the padded slab).  The kk = G/2 column is never read or transformed: the
 // potential nullifies that Nyquist plane (mesh.py:3615-3622); the forward z pass stores a zero there.
 //
-//   ZFwd   16 rows of one plane: r2c along z               (contiguous 4 KB rows)
+//   ZFwd   CZ rows of one plane: r2c along z               (contiguous 4 KB rows)
 //   YPass  CY adjacent kk columns of one plane: c2c along y (forward or inverse; 128 B row segments)
 //   XSolve CY adjacent kk columns of one j row, all planes (of all ranks): forward c2c along x,
 //          Green's function (interactions.py:2092-2118, mesh.py:2775-2856, :3585-3622), inverse c2c
-//   ZInv   16 rows of one plane: c2r along z
+//   ZInv   CZ rows of one plane: c2r along z
 #pragma once
 
 #include "pm_fftcore.cuh"
@@ -21,56 +23,64 @@ namespace fftc {
 
 constexpr int kMaxFftPeers = 16;
 
+// streaming global load: L2 only (the 2-D kernels hand tiles from one SM to another inside a launch,
+// which L1 would not notice; nothing here is re-read anyway)
+template <typename V>
+PM_HD V ld_stream(const V* p) {
+#ifdef __CUDA_ARCH__
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+
 template <typename T, int G_>
 struct SlabFFT {
     using V = typename Vec2<T>::type;
+    using TW = Twiddles<V>;
     static constexpr int G = G_;
     static constexpr int M = G / 2;          // complex points of the packed real transform
     static constexpr int Gc = M + 1;
     static constexpr int Gp = 2 * Gc;
-    static constexpr int NT = G;             // twiddle table length: e^{−2πi m/G}
     static constexpr int CY = 128 / (int)sizeof(V);   // columns per y/x tile (8 in fp64, 16 in fp32)
-    static constexpr int CZ = 16;                     // rows per z tile
+    static constexpr int CZ = 8;                      // rows per z tile
     using LZ = RowLayout<M, CZ>;
-    using RZ = RowRaw<M>;
     using LY = ColLayout<CY>;
-    using RY = ColRaw<CY>;
     static constexpr int kZTileElems = LZ::PITCH * CZ;
     static constexpr int kYTileElems = G * CY;
-    static constexpr int kRawElems = (M * CZ > kYTileElems) ? M * CZ : kYTileElems;
     static constexpr int kWorkElems = (kZTileElems > kYTileElems) ? kZTileElems : kYTileElems;
     static constexpr int kZTilesPerPlane = G / CZ;
     static constexpr int kYTilesPerPlane = M / CY;    // kk = 0 … G/2−1
     static_assert(G % 64 == 0 && M % 64 == 0 && G / 64 <= 8, "G must be 128, 256 or 512");
 
+    struct RowSource {     // complex element k of row c
+        const T* plane; int row0;
+        PM_HD V operator()(int c, int k) const {
+            return ld_stream(reinterpret_cast<const V*>(plane + (size_t)(row0 + c) * Gp) + k);
+        }
+    };
+    struct RowSink {
+        T* plane; int row0;
+        PM_HD void operator()(int c, int k, T r, T i) const {
+            V v; v.x = r; v.y = i;
+            reinterpret_cast<V*>(plane + (size_t)(row0 + c) * Gp)[k] = v;
+        }
+    };
+
     // ------------------------------------------------------------------ z forward (r2c)
     struct ZFwd {
         T* plane;     // first real of the x plane
         int row0;     // first of the CZ rows
-        template <class Copy>
-        PM_HD void load(V* raw, int tid, int nthr, Copy& cp) const {
-            for (int e = tid; e < M * CZ; e += nthr) {
-                const int c = e / M, n = e - c * M;
-                cp(raw + RZ::idx(n, c), reinterpret_cast<const V*>(plane + (size_t)(row0 + c) * Gp) + n);
-            }
-        }
         struct ToTile {
             V* tile;
             PM_HD void operator()(int c, int idx, T r, T i) const { V v; v.x = r; v.y = i; tile[LZ::idx(idx, c)] = v; }
         };
-        struct ToRow {
-            T* plane; int row0;
-            PM_HD void operator()(int c, int k, T r, T i) const {
-                V v; v.x = r; v.y = i;
-                reinterpret_cast<V*>(plane + (size_t)(row0 + c) * Gp)[k] = v;
-            }
-        };
         static constexpr int kPhases = 4;
-        PM_HD void phase(int ph, const V* raw, V* work, const V* tw, int tid, int nthr) const {
-            if (ph == 0) dit_stageA<LZ, RZ, T, M, -1>(raw, work, tid, nthr);
-            else if (ph == 1) dit_stageB<LZ, T, M, NT, -1>(work, tw, tid, nthr);
-            else if (ph == 2) { ToTile s{work}; dit_stageC<LZ, T, M, NT, -1>(work, tw, tid, nthr, s); }
-            else { ToRow s{plane, row0}; r2c_post<LZ, T, M>(work, tw, tid, nthr, s); }
+        PM_HD void phase(int ph, V* work, const TW& tw, int tid, int nthr) const {
+            if (ph == 0) dit_stageA<LZ, T, M, -1>(RowSource{plane, row0}, work, tid, nthr);
+            else if (ph == 1) dit_stageB<LZ, T, M, -1>(work, tw.B, tid, nthr);
+            else if (ph == 2) dit_stageC<LZ, T, M, 2, -1>(work, tw.C, tid, nthr, ToTile{work});
+            else r2c_post<LZ, T, M>(work, tw.R, tid, nthr, RowSink{plane, row0});
         }
     };
 
@@ -78,26 +88,12 @@ struct SlabFFT {
     struct ZInv {
         T* plane;
         int row0;
-        template <class Copy>
-        PM_HD void load(V* raw, int tid, int nthr, Copy& cp) const {
-            for (int e = tid; e < M * CZ; e += nthr) {
-                const int c = e / M, k = e - c * M;
-                cp(raw + RZ::idx(k, c), reinterpret_cast<const V*>(plane + (size_t)(row0 + c) * Gp) + k);
-            }
-        }
-        struct ToRow {   // z_m = x_2m + i·x_2m+1
-            T* plane; int row0;
-            PM_HD void operator()(int c, int m, T r, T i) const {
-                V v; v.x = r; v.y = i;
-                reinterpret_cast<V*>(plane + (size_t)(row0 + c) * Gp)[m] = v;
-            }
-        };
         static constexpr int kPhases = 4;
-        PM_HD void phase(int ph, const V* raw, V* work, const V* tw, int tid, int nthr) const {
-            if (ph == 0) c2r_pre<LZ, RZ, T, M>(raw, work, tw, tid, nthr);
+        PM_HD void phase(int ph, V* work, const TW& tw, int tid, int nthr) const {
+            if (ph == 0) c2r_pre<LZ, T, M>(RowSource{plane, row0}, work, tw.R, tid, nthr);
             else if (ph == 1) dit_stageA_inplace<LZ, T, M, +1>(work, tid, nthr);
-            else if (ph == 2) dit_stageB<LZ, T, M, NT, +1>(work, tw, tid, nthr);
-            else { ToRow s{plane, row0}; dit_stageC<LZ, T, M, NT, +1>(work, tw, tid, nthr, s); }
+            else if (ph == 2) dit_stageB<LZ, T, M, +1>(work, tw.B, tid, nthr);
+            else dit_stageC<LZ, T, M, 2, +1>(work, tw.C, tid, nthr, RowSink{plane, row0});   // z_m = x_2m + i·x_2m+1
         }
     };
 
@@ -106,13 +102,10 @@ struct SlabFFT {
     struct YPass {
         V* plane;     // complex view of the x plane: [G][Gc]
         int kk0;      // first of the CY columns
-        template <class Copy>
-        PM_HD void load(V* raw, int tid, int nthr, Copy& cp) const {
-            for (int e = tid; e < G * CY; e += nthr) {
-                const int j = e / CY, c = e - j * CY;
-                cp(raw + RY::idx(j, c), plane + (size_t)j * Gc + kk0 + c);
-            }
-        }
+        struct Source {
+            const V* plane; int kk0;
+            PM_HD V operator()(int c, int j) const { return ld_stream(plane + (size_t)j * Gc + kk0 + c); }
+        };
         struct ToPlane {
             V* plane; int kk0;
             PM_HD void operator()(int c, int j, T r, T i) const {
@@ -121,10 +114,10 @@ struct SlabFFT {
             }
         };
         static constexpr int kPhases = 3;
-        PM_HD void phase(int ph, const V* raw, V* work, const V* tw, int tid, int nthr) const {
-            if (ph == 0) dit_stageA<LY, RY, T, G, DIR>(raw, work, tid, nthr);
-            else if (ph == 1) dit_stageB<LY, T, G, NT, DIR>(work, tw, tid, nthr);
-            else { ToPlane s{plane, kk0}; dit_stageC<LY, T, G, NT, DIR>(work, tw, tid, nthr, s); }
+        PM_HD void phase(int ph, V* work, const TW& tw, int tid, int nthr) const {
+            if (ph == 0) dit_stageA<LY, T, G, DIR>(Source{plane, kk0}, work, tid, nthr);
+            else if (ph == 1) dit_stageB<LY, T, G, DIR>(work, tw.B, tid, nthr);
+            else dit_stageC<LY, T, G, 1, DIR>(work, tw.C, tid, nthr, ToPlane{plane, kk0});
         }
     };
 
@@ -143,13 +136,10 @@ struct SlabFFT {
         const XGeom* g;
         int j;        // global j row
         int kk0;      // first of the CY columns
-        template <class Copy>
-        PM_HD void load(V* raw, int tid, int nthr, Copy& cp) const {
-            for (int e = tid; e < G * CY; e += nthr) {
-                const int i = e / CY, c = e - i * CY;
-                cp(raw + RY::idx(i, c), g->at(i, j, kk0 + c));
-            }
-        }
+        struct Source {
+            const XGeom* g; int j, kk0;
+            PM_HD V operator()(int c, int i) const { return ld_stream(g->at(i, j, kk0 + c)); }
+        };
         struct ToSlab {
             const XGeom* g; int j, kk0;
             PM_HD void operator()(int c, int i, T r, T im) const {
@@ -172,10 +162,10 @@ struct SlabFFT {
 #endif
         }
         static constexpr int kPhases = 5;
-        PM_HD void phase(int ph, const V* raw, V* work, const V* tw, int tid, int nthr) const {
+        PM_HD void phase(int ph, V* work, const TW& tw, int tid, int nthr) const {
             constexpr int R1 = G / 64;
-            if (ph == 0) dit_stageA<LY, RY, T, G, -1>(raw, work, tid, nthr);
-            else if (ph == 1) dit_stageB<LY, T, G, NT, -1>(work, tw, tid, nthr);
+            if (ph == 0) dit_stageA<LY, T, G, -1>(Source{g, j, kk0}, work, tid, nthr);
+            else if (ph == 1) dit_stageB<LY, T, G, -1>(work, tw.B, tid, nthr);
             else if (ph == 2) {
                 // forward stage C, Green's function, inverse stage 1 — all on the same R1 registers
                 const int kj = j - (j >= M ? G : 0);
@@ -187,7 +177,7 @@ struct SlabFFT {
                     for (int a1 = 0; a1 < R1; ++a1) {
                         const V v = work[LY::idx(64 * a1 + q, c)];
                         r[a1] = v.x; im[a1] = v.y;
-                        if (a1) cmul<-1>(r[a1], im[a1], tw[(a1 * q) * (NT / G)]);
+                        if (a1) cmul<-1>(r[a1], im[a1], tw.C[a1 * 64 + q]);
                     }
                     dftR<R1, -1>(r, im);
                     const int kk = kk0 + c;
@@ -199,10 +189,10 @@ struct SlabFFT {
                         const T f = (T)factor(64 * b1 + q, sep_jk, kj2_kk2, line_nyq);
                         r[b1] *= f; im[b1] *= f;
                     }
-                    dif_stage1_regs<LY, T, G, NT, +1>(r, im, work, tw, c, q);
+                    dif_stage1_regs<LY, T, G, 1, +1>(r, im, work, tw.C, c, q);
                 }
-            } else if (ph == 3) dif_stage2<LY, T, G, NT, +1>(work, tw, tid, nthr);
-            else { ToSlab s{g, j, kk0}; dif_stage3<LY, T, G, +1>(work, tid, nthr, s); }
+            } else if (ph == 3) dif_stage2<LY, T, G, +1>(work, tw.B, tid, nthr);
+            else dif_stage3<LY, T, G, +1>(work, tid, nthr, ToSlab{g, j, kk0});
         }
     };
 };

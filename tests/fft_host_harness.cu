@@ -13,25 +13,37 @@ using namespace pm::fftc;
 
 static const long double PI = 3.14159265358979323846264338327950288L;
 
+// B | C | R tables of pm_fftcore.cuh for grid size G
 template <typename V>
-static std::vector<V> make_tw(int NT) {
-    std::vector<V> tw(NT);
-    for (int m = 0; m < NT; ++m) {
-        const long double a = -2.0L * PI * m / NT;
-        tw[m].x = (decltype(tw[m].x))cosl(a);
-        tw[m].y = (decltype(tw[m].y))sinl(a);
+struct HostTw {
+    std::vector<V> data;
+    Twiddles<V> tw;
+    explicit HostTw(int G) : data(64 + G + G / 8 + 1) {
+        auto w = [&](long double num, long double den) {
+            const long double a = -2.0L * PI * num / den;
+            V v; v.x = (decltype(v.x))cosl(a); v.y = (decltype(v.y))sinl(a);
+            return v;
+        };
+        for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) data[a * 8 + b] = w(a * b, 64);
+        for (int a = 0; a < G / 64; ++a) for (int q = 0; q < 64; ++q) data[64 + a * 64 + q] = w(a * q, G);
+        for (int k = 0; k <= G / 8; ++k) data[64 + G + k] = w(k, G);
+        tw.B = data.data(); tw.C = data.data() + 64; tw.R = data.data() + 64 + G;
     }
-    return tw;
-}
+};
+
+template <typename T> struct NatSource {   // natural-order host arrays [c][n]
+    const std::vector<std::vector<T>>*re, *im;
+    typename Vec2<T>::type operator()(int c, int n) const { typename Vec2<T>::type v; v.x = (*re)[c][n]; v.y = (*im)[c][n]; return v; }
+};
 
 template <typename T> struct Store {
     T* re; T* im; int N;   // out[c][index]
-    void operator()(int c, int idx, T r, T i) { re[c * N + idx] = r; im[c * N + idx] = i; }
+    void operator()(int c, int idx, T r, T i) const { re[c * N + idx] = r; im[c * N + idx] = i; }
 };
 
 template <typename T, class L> struct StoreTile {
     typename Vec2<T>::type* tile;
-    void operator()(int c, int idx, T r, T i) { typename Vec2<T>::type v; v.x = r; v.y = i; tile[L::idx(idx, c)] = v; }
+    void operator()(int c, int idx, T r, T i) const { typename Vec2<T>::type v; v.x = r; v.y = i; tile[L::idx(idx, c)] = v; }
 };
 
 static double frand() { return rand() / (double)RAND_MAX - 0.5; }
@@ -57,33 +69,29 @@ template <typename T, int N, int C, bool ROW>
 static double test_complex(int nthr) {
     using V = typename Vec2<T>::type;
     using L = typename std::conditional<ROW, RowLayout<N, C>, ColLayout<C>>::type;
-    using RAW = typename std::conditional<ROW, RowRaw<N>, ColRaw<C>>::type;
-    constexpr int NT = N;
-    auto tw = make_tw<V>(NT);
-    std::vector<V> raw(N * C), tile((size_t)(N + N / 8 + N / 64 + 1) * C + 16);
+    HostTw<V> ht(N);
+    const Twiddles<V>& tw = ht.tw;
+    std::vector<V> tile((size_t)(N + N / 8 + N / 64 + 1) * C + 16);
     std::vector<std::vector<T>> xr(C, std::vector<T>(N)), xi(C, std::vector<T>(N));
     for (int c = 0; c < C; ++c)
-        for (int n = 0; n < N; ++n) {
-            xr[c][n] = (T)frand(); xi[c][n] = (T)frand();
-            V v; v.x = xr[c][n]; v.y = xi[c][n];
-            raw[RAW::idx(n, c)] = v;
-        }
+        for (int n = 0; n < N; ++n) { xr[c][n] = (T)frand(); xi[c][n] = (T)frand(); }
+    NatSource<T> src{&xr, &xi};
     double err = 0;
     for (int dir = -1; dir <= 1; dir += 2) {
         std::vector<T> ore(C * N), oim(C * N);
         Store<T> st{ore.data(), oim.data(), N};
         // ---- DIT: natural -> natural
         for (int t = 0; t < nthr; ++t) {
-            if (dir < 0) dit_stageA<L, RAW, T, N, -1>(raw.data(), tile.data(), t, nthr);
-            else dit_stageA<L, RAW, T, N, +1>(raw.data(), tile.data(), t, nthr);
+            if (dir < 0) dit_stageA<L, T, N, -1>(src, tile.data(), t, nthr);
+            else dit_stageA<L, T, N, +1>(src, tile.data(), t, nthr);
         }
         for (int t = 0; t < nthr; ++t) {
-            if (dir < 0) dit_stageB<L, T, N, NT, -1>(tile.data(), tw.data(), t, nthr);
-            else dit_stageB<L, T, N, NT, +1>(tile.data(), tw.data(), t, nthr);
+            if (dir < 0) dit_stageB<L, T, N, -1>(tile.data(), tw.B, t, nthr);
+            else dit_stageB<L, T, N, +1>(tile.data(), tw.B, t, nthr);
         }
         for (int t = 0; t < nthr; ++t) {
-            if (dir < 0) dit_stageC<L, T, N, NT, -1>(tile.data(), tw.data(), t, nthr, st);
-            else dit_stageC<L, T, N, NT, +1>(tile.data(), tw.data(), t, nthr, st);
+            if (dir < 0) dit_stageC<L, T, N, 1, -1>(tile.data(), tw.C, t, nthr, st);
+            else dit_stageC<L, T, N, 1, +1>(tile.data(), tw.C, t, nthr, st);
         }
         std::vector<long double> yr, yi;
         for (int c = 0; c < C; ++c) {
@@ -103,12 +111,12 @@ static double test_complex(int nthr) {
                 L::template decode<64>(b, c, q);
                 T r[R1], i[R1];
                 for (int a1 = 0; a1 < R1; ++a1) { r[a1] = xr[c][64 * a1 + q]; i[a1] = xi[c][64 * a1 + q]; }
-                if (dir < 0) dif_stage1_regs<L, T, N, NT, -1>(r, i, tile.data(), tw.data(), c, q);
-                else dif_stage1_regs<L, T, N, NT, +1>(r, i, tile.data(), tw.data(), c, q);
+                if (dir < 0) dif_stage1_regs<L, T, N, 1, -1>(r, i, tile.data(), tw.C, c, q);
+                else dif_stage1_regs<L, T, N, 1, +1>(r, i, tile.data(), tw.C, c, q);
             }
         for (int t = 0; t < nthr; ++t) {
-            if (dir < 0) dif_stage2<L, T, N, NT, -1>(tile.data(), tw.data(), t, nthr);
-            else dif_stage2<L, T, N, NT, +1>(tile.data(), tw.data(), t, nthr);
+            if (dir < 0) dif_stage2<L, T, N, -1>(tile.data(), tw.B, t, nthr);
+            else dif_stage2<L, T, N, +1>(tile.data(), tw.B, t, nthr);
         }
         for (int t = 0; t < nthr; ++t) {
             if (dir < 0) dif_stage3<L, T, N, -1>(tile.data(), t, nthr, st2);
@@ -130,26 +138,25 @@ template <typename T, int M, int C>
 static double test_real(int nthr) {
     using V = typename Vec2<T>::type;
     using L = RowLayout<M, C>;
-    using RAW = RowRaw<M>;
-    constexpr int NT = 2 * M;
-    auto tw = make_tw<V>(NT);
-    std::vector<V> raw(M * C), tile((size_t)L::PITCH * C + 16);
-    std::vector<std::vector<T>> x(C, std::vector<T>(2 * M));
+    HostTw<V> ht(2 * M);
+    const Twiddles<V>& tw = ht.tw;
+    std::vector<V> tile((size_t)L::PITCH * C + 16);
+    std::vector<std::vector<T>> x(C, std::vector<T>(2 * M)), zr(C, std::vector<T>(M)), zi(C, std::vector<T>(M));
     for (int c = 0; c < C; ++c)
         for (int n = 0; n < M; ++n) {
             x[c][2 * n] = (T)frand(); x[c][2 * n + 1] = (T)frand();
-            V v; v.x = x[c][2 * n]; v.y = x[c][2 * n + 1];
-            raw[RAW::idx(n, c)] = v;
+            zr[c][n] = x[c][2 * n]; zi[c][n] = x[c][2 * n + 1];
         }
+    NatSource<T> src{&zr, &zi};
     double err = 0;
     // forward
     StoreTile<T, L> stt{tile.data()};
-    for (int t = 0; t < nthr; ++t) dit_stageA<L, RAW, T, M, -1>(raw.data(), tile.data(), t, nthr);
-    for (int t = 0; t < nthr; ++t) dit_stageB<L, T, M, NT, -1>(tile.data(), tw.data(), t, nthr);
-    for (int t = 0; t < nthr; ++t) dit_stageC<L, T, M, NT, -1>(tile.data(), tw.data(), t, nthr, stt);
+    for (int t = 0; t < nthr; ++t) dit_stageA<L, T, M, -1>(src, tile.data(), t, nthr);
+    for (int t = 0; t < nthr; ++t) dit_stageB<L, T, M, -1>(tile.data(), tw.B, t, nthr);
+    for (int t = 0; t < nthr; ++t) dit_stageC<L, T, M, 2, -1>(tile.data(), tw.C, t, nthr, stt);
     std::vector<T> ore(C * (M + 1)), oim(C * (M + 1));
     Store<T> st{ore.data(), oim.data(), M + 1};
-    for (int t = 0; t < nthr; ++t) r2c_post<L, T, M>(tile.data(), tw.data(), t, nthr, st);
+    for (int t = 0; t < nthr; ++t) r2c_post<L, T, M>(tile.data(), tw.R, t, nthr, st);
     std::vector<std::vector<long double>> Xr(C, std::vector<long double>(M + 1)), Xi(C, std::vector<long double>(M + 1));
     for (int c = 0; c < C; ++c) {
         for (int k = 0; k <= M; ++k) {
@@ -167,18 +174,17 @@ static double test_real(int nthr) {
             }
         }
     }
-    // inverse: feed the exact spectrum with X_M := 0; expected x'_n = Σ_{k} X_k e^{+…} with the Nyquist term missing
+    // inverse: feed the exact spectrum with X_M := 0
+    std::vector<std::vector<T>> sr(C, std::vector<T>(M)), si(C, std::vector<T>(M));
     for (int c = 0; c < C; ++c)
-        for (int k = 0; k < M; ++k) {
-            V v; v.x = (T)Xr[c][k]; v.y = (T)Xi[c][k];
-            raw[RAW::idx(k, c)] = v;
-        }
-    for (int t = 0; t < nthr; ++t) c2r_pre<L, RAW, T, M>(raw.data(), tile.data(), tw.data(), t, nthr);
+        for (int k = 0; k < M; ++k) { sr[c][k] = (T)Xr[c][k]; si[c][k] = (T)Xi[c][k]; }
+    NatSource<T> spec{&sr, &si};
+    for (int t = 0; t < nthr; ++t) c2r_pre<L, T, M>(spec, tile.data(), tw.R, t, nthr);
     for (int t = 0; t < nthr; ++t) dit_stageA_inplace<L, T, M, +1>(tile.data(), t, nthr);
-    for (int t = 0; t < nthr; ++t) dit_stageB<L, T, M, NT, +1>(tile.data(), tw.data(), t, nthr);
+    for (int t = 0; t < nthr; ++t) dit_stageB<L, T, M, +1>(tile.data(), tw.B, t, nthr);
     std::vector<T> zre(C * M), zim(C * M);
     Store<T> stz{zre.data(), zim.data(), M};
-    for (int t = 0; t < nthr; ++t) dit_stageC<L, T, M, NT, +1>(tile.data(), tw.data(), t, nthr, stz);
+    for (int t = 0; t < nthr; ++t) dit_stageC<L, T, M, 2, +1>(tile.data(), tw.C, t, nthr, stz);
     for (int c = 0; c < C; ++c)
         for (int n = 0; n < 2 * M; ++n) {
             // 2M·x_n minus the dropped Nyquist term X_M·(−1)^n
@@ -189,17 +195,12 @@ static double test_real(int nthr) {
     return err;
 }
 
-
 // ---- a whole fused solve on the CPU: z/y forward per plane, x solve, y/z inverse ------------------
-struct HostCopy {
-    template <typename V> void operator()(V* dst, const V* src) const { *dst = *src; }
-};
-
 template <typename T, int G>
 static int solve3d(const char* fin, const char* fsep, const char* fout, double prefactor, int nranks) {
     using S = SlabFFT<T, G>;
     using V = typename S::V;
-    const int nthr = 512;
+    const int nthr = 256;
     const int nxl = G / nranks;
     std::vector<double> in((size_t)G * G * G), sep(G);
     FILE* f = fopen(fin, "rb");
@@ -214,13 +215,11 @@ static int solve3d(const char* fin, const char* fsep, const char* fout, double p
         for (int j = 0; j < G; ++j)
             for (int k = 0; k < G; ++k)
                 slab[i / nxl][((size_t)(i % nxl) * G + j) * S::Gp + k] = (T)in[((size_t)i * G + j) * G + k];
-    auto tw = make_tw<V>(S::NT);
-    std::vector<V> raw(S::kRawElems), work(S::kWorkElems + 16);
-    HostCopy cp;
+    HostTw<V> ht(G);
+    std::vector<V> work(S::kWorkElems + 16);
     auto run = [&](auto& op) {
-        for (int t = 0; t < nthr; ++t) op.load(raw.data(), t, nthr, cp);
         for (int ph = 0; ph < op.kPhases; ++ph)
-            for (int t = 0; t < nthr; ++t) op.phase(ph, raw.data(), work.data(), tw.data(), t, nthr);
+            for (int t = 0; t < nthr; ++t) op.phase(ph, work.data(), ht.tw, t, nthr);
     };
     for (int r = 0; r < nranks; ++r)
         for (int p = 0; p < nxl; ++p) {

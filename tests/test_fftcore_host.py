@@ -63,6 +63,6 @@ def test_whole_solve_against_numpy(harness, dtype, nranks, tol):
     fac[G//2, :, :] = 0
     fac[:, G//2, :] = 0
     fac[:, :, G//2] = 0
-    ref = np.fft.irfftn(np.fft.rfftn(rho)*fac, s=(G, G, G), norm='forward')
+    ref = np.fft.irfftn(np.fft.rfftn(rho)*fac, s=(G, G, G), axes=(0, 1, 2), norm='forward')
     err = np.max(np.abs(got - ref))/np.max(np.abs(ref))
     assert err < tol, err
