@@ -227,9 +227,9 @@ def run_gpu(args):
         p, m = pbuf[:n], mbuf[:n]
         sum2.zero_()
         if i is None:
-            ctx.kick_long(p, m, params, sum_mom2=sum2)
+            ctx.kick_drift(p, m, params, DT_OVER_MASS, sum_mom2=sum2)
         else:
-            # same sequence as pm_kick_long, split so that the dominant kernel can be bracketed by events
+            # same sequence as pm_kick_drift, split so that the dominant kernel can be bracketed by events
             ctx.grid_zero()
             ctx.deposit(p, params.order, params.contribution)
             ctx.halo_add()
@@ -242,9 +242,8 @@ def run_gpu(args):
             if world > 1:
                 ctx.halo_fill()
             ev_k0[i].record()
-            ctx.gather_kick(p, m, params.order, params.diff_order, params.kick_factor, None, sum2)
+            ctx.gather_kick_drift(p, m, params.order, params.diff_order, params.kick_factor, DT_OVER_MASS, None, sum2)
             ev_k1[i].record()
-        ctx.drift(p, m, DT_OVER_MASS)
         if world > 1:
             ctx.allreduce_sum(sum2)
             state['n'] = ctx.exchange(pbuf, mbuf, None, n)
@@ -328,10 +327,10 @@ def run_gpu(args):
         peak, peak_src = measured_peaks()
         n_per = n_total/world
         g3_per = GRID**3/world
-        kern_bytes = 72*n_per + 8*g3_per      # read pos+mom 48N, write mom 24N, read φ 8G³ (per rank)
+        kern_bytes = 96*n_per + 8*g3_per      # read pos+mom 48N, write pos+mom 48N, read φ 8G³ (per rank)
         achieved = kern_bytes/(kern_ms_avg*1e-3)/1e9
         b_alg = 120*n_total + 48*GRID**3
-        roofline = {'bound': 'hbm', 'kernel': 'gather_kick_kernel<2,1,double> (fused gradient + CIC gather + kick + sum mom^2)',
+        roofline = {'bound': 'hbm', 'kernel': 'gather_kick_kernel<2,1,double,drift> (fused gradient + CIC gather + kick + sum mom^2 + drift)',
                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved/peak, 'traffic': None,
                     'peak_source': peak_src, 'kernel_ms': kern_ms_avg, 'algorithmic_bytes_per_launch': kern_bytes,
                     'cycle': {'algorithmic_bytes': b_alg, 'achieved_GBps_per_gpu': b_alg/world/(ms_step*1e-3)/1e9,

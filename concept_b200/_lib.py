@@ -64,6 +64,7 @@ SIGNATURES = {
     'pm_diff': (c_int, [c_void_p, c_int, c_int]),
     'pm_gather': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_double, POINTER(c_double)]),
     'pm_gather_kick': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_double, POINTER(c_double), c_void_p]),
+    'pm_gather_kick_drift': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_double, POINTER(c_double), c_void_p, c_double]),
     'pm_drift': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double]),
     'pm_sum_mom2': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     'pm_exchange': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64]),
@@ -75,6 +76,7 @@ SIGNATURES = {
                                    POINTER(c_double), c_int, POINTER(c_int)]),
     'pm_apply_rung_jumps': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, POINTER(c_int64)]),
     'pm_kick_long': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(KickParams), c_void_p]),
+    'pm_kick_drift': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(KickParams), c_double, c_void_p]),
     'pm_kick_long_host': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(KickParams), c_double, POINTER(c_double)]),
     'pm_tap_size': (c_int64, [c_void_p, c_int]),
     'pm_get_grid': (c_int, [c_void_p, c_int, c_void_p]),

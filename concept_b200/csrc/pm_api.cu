@@ -332,7 +332,14 @@ int pm_gather_kick(pm_ctx* c, const double* pos, double* mom, int64_t n, int ord
                    double factor, const double* shift, double* sum_mom2) {
     PM_REQUIRE(c != nullptr && n >= 0, "pm_gather_kick: bad argument");
     PM_REQUIRE(!c->space_fourier, "pm_gather_kick: the slab holds Fourier data (call pm_fft_backward)");
-    return launch_gather_kick(c, pos, mom, n, order, diff_order, factor, shift, sum_mom2);
+    return launch_gather_kick(c, const_cast<double*>(pos), mom, n, order, diff_order, factor, shift, sum_mom2);
+}
+
+int pm_gather_kick_drift(pm_ctx* c, double* pos, double* mom, int64_t n, int order, int diff_order,
+                         double factor, const double* shift, double* sum_mom2, double dt_over_mass) {
+    PM_REQUIRE(c != nullptr && n >= 0, "pm_gather_kick_drift: bad argument");
+    PM_REQUIRE(!c->space_fourier, "pm_gather_kick_drift: the slab holds Fourier data (call pm_fft_backward)");
+    return launch_gather_kick(c, pos, mom, n, order, diff_order, factor, shift, sum_mom2, dt_over_mass != 0, dt_over_mass);
 }
 
 // ---- particle operators -------------------------------------------------------
@@ -354,8 +361,10 @@ int pm_exchange(pm_ctx* c, double* pos, double* mom, int64_t* ids, int64_t* n_in
 // ---- whole-path entry points -----------------------------------------------------
 static const double kBccShift[3] = {-0.5, -0.5, -0.5};   // Lattice.shift_amount, mesh.py:85
 
-int pm_kick_long(pm_ctx* c, const double* pos, double* mom, int64_t n, const pm_kick_params* p,
-                 double* sum_mom2) {
+// kick (+ drift of the same particles with the kicked momenta when dt_over_mass != 0)
+static int kick_long_impl(pm_ctx* c, double* pos, double* mom, int64_t n, const pm_kick_params* p,
+                          double* sum_mom2, double dt_over_mass) {
+    const bool drift = dt_over_mass != 0;
     PM_REQUIRE(c != nullptr && p != nullptr && n >= 0, "pm_kick_long: bad argument");
     PM_REQUIRE(p->interlace == 0 || p->interlace == 1, "pm_kick_long: interlace = %d", p->interlace);
     const int nl = p->interlace ? 2 : 1;
@@ -369,7 +378,8 @@ int pm_kick_long(pm_ctx* c, const double* pos, double* mom, int64_t n, const pm_
         PM_TRY(halo_add(c));
         PM_TRY(solve_fused(c, p->prefactor, p->deconv_order, p->gauss));
         PM_TRY(halo_fill(c, hlo, hhi, PM_TAP_REAL));
-        return launch_gather_kick(c, pos, mom, n, p->order, p->diff_order, p->kick_factor, nullptr, sum_mom2);
+        return launch_gather_kick(c, pos, mom, n, p->order, p->diff_order, p->kick_factor, nullptr, sum_mom2,
+                                  drift, dt_over_mass);
     }
     // upstream: interpolate_upstream(..., output_space='Fourier')  (mesh.py:492-616)
     for (int l = 0; l < nl; ++l) {
@@ -413,7 +423,18 @@ int pm_kick_long(pm_ctx* c, const double* pos, double* mom, int64_t n, const pm_
         }
     }
     if (p->diff_order == 0 && sum_mom2) PM_TRY(launch_sum_mom2(c, mom, n, sum_mom2));
+    if (drift) PM_TRY(launch_drift(c, pos, mom, n, dt_over_mass));
     return PM_OK;
+}
+
+int pm_kick_long(pm_ctx* c, const double* pos, double* mom, int64_t n, const pm_kick_params* p,
+                 double* sum_mom2) {
+    return kick_long_impl(c, const_cast<double*>(pos), mom, n, p, sum_mom2, 0.0);
+}
+
+int pm_kick_drift(pm_ctx* c, double* pos, double* mom, int64_t n, const pm_kick_params* p,
+                  double dt_over_mass, double* sum_mom2) {
+    return kick_long_impl(c, pos, mom, n, p, sum_mom2, dt_over_mass);
 }
 
 int pm_kick_long_host(pm_ctx* c, double* pos_host, double* mom_host, int64_t n, const pm_kick_params* p,
@@ -436,11 +457,8 @@ int pm_kick_long_host(pm_ctx* c, double* pos_host, double* mom_host, int64_t n, 
         dsum = c->d_scratch;
         PM_CHECK_CUDA(cudaMemsetAsync(dsum, 0, sizeof(double), c->stream));
     }
-    PM_TRY(pm_kick_long(c, dpos, dmom, n, p, dsum));
-    if (dt_over_mass != 0) {
-        PM_TRY(launch_drift(c, dpos, dmom, n, dt_over_mass));
-        PM_CHECK_CUDA(cudaMemcpyAsync(pos_host, dpos, bytes, cudaMemcpyDeviceToHost, c->stream));
-    }
+    PM_TRY(kick_long_impl(c, dpos, dmom, n, p, dsum, dt_over_mass));
+    if (dt_over_mass != 0) PM_CHECK_CUDA(cudaMemcpyAsync(pos_host, dpos, bytes, cudaMemcpyDeviceToHost, c->stream));
     PM_CHECK_CUDA(cudaMemcpyAsync(mom_host, dmom, bytes, cudaMemcpyDeviceToHost, c->stream));
     if (sum_mom2_host)
         PM_CHECK_CUDA(cudaMemcpyAsync(sum_mom2_host, dsum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));

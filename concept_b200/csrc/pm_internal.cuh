@@ -167,8 +167,9 @@ int launch_deposit(pm_ctx* c, const double* pos, int64_t n, int order, double co
                    const double* shift);
 int launch_gather(pm_ctx* c, int which, const double* pos, double* mom, int64_t n, int order,
                   int dim, double factor, const double* shift);
-int launch_gather_kick(pm_ctx* c, const double* pos, double* mom, int64_t n, int order,
-                       int diff_order, double factor, const double* shift, double* sum_mom2);
+int launch_gather_kick(pm_ctx* c, double* pos, double* mom, int64_t n, int order,
+                       int diff_order, double factor, const double* shift, double* sum_mom2,
+                       bool drift = false, double drift_dt = 0.0);
 int launch_diff(pm_ctx* c, int dim, int order);
 int launch_halo_wrap_add(pm_ctx* c);   // single-rank no-op; multi-rank local part of halo add
 // implemented in pm_fourier.cu

@@ -76,6 +76,14 @@ __device__ __forceinline__ int weights_1d(double x, double (&w)[ORDER]) {
     return index - kNghostsRef;
 }
 
+// np.mod(x, L) with the reference's x == L → 0 guard (commons.py:5102-5131); same as pm_particles.cu
+__device__ __forceinline__ double mod_box(double x, double L) {
+    double r = fmod(x, L);
+    if (r < 0) r += L;
+    if (r == L) r = 0;
+    return r;
+}
+
 __device__ __forceinline__ int wrap(int i, int G) {
     // |i| excursions are at most a handful of cells beyond [0, G)
     if (i < 0) i += G;
@@ -107,15 +115,20 @@ __device__ __forceinline__ void stage_particles(const double* __restrict__ src, 
     }
 }
 
-// Dynamic, in-order tile scheduler: CTAs take the next tile of BLOCK consecutive particles from a global
-// counter, so the set of tiles in flight stays a compact window of the (cell-ordered) particle array and
-// the grid planes it touches stay L2-resident.  A static blockIdx-strided loop lets fast and slow CTAs
-// drift tens of grid planes apart (measured: the potential grid was read 1.85x from DRAM).
-__device__ __forceinline__ int64_t next_tile(unsigned long long* counter, int64_t* s_tile) {
+// Dynamic, in-order chunk scheduler: CTAs take the next chunk of kChunkTiles·BLOCK consecutive particles
+// from a global counter, so the set of chunks in flight stays a compact window of the (cell-ordered)
+// particle array and the grid planes it touches stay L2-resident.  (A static blockIdx-strided loop lets
+// fast and slow CTAs drift tens of grid planes apart — measured: the potential grid was read 1.85x from
+// DRAM.)  One block-wide atomic per chunk, not per tile: with a ticket per 256-particle tile 64 % of the
+// deposit's warp stalls were the barrier around the ticket (ncu, r01).  Inside a chunk the warps run
+// free; consecutive tiles of a chunk share grid rows, which the SM's L1 keeps for the gather.
+constexpr int kChunkTiles = 8;
+
+__device__ __forceinline__ int64_t next_chunk(unsigned long long* counter, int64_t* s_slot) {
     __syncthreads();
-    if (threadIdx.x == 0) *s_tile = (int64_t)atomicAdd(counter, 1ULL);
+    if (threadIdx.x == 0) *s_slot = (int64_t)atomicAdd(counter, 1ULL);
     __syncthreads();
-    return *s_tile;
+    return *s_slot;
 }
 
 // ---------------------------------------------------------------------------
@@ -127,41 +140,40 @@ template <int ORDER, typename T>
 __global__ void __launch_bounds__(kDepBlock)
 deposit_kernel(const double* __restrict__ pos, int64_t n, T* __restrict__ grid, Geom g, Coord co,
                double contribution, unsigned long long* __restrict__ tile_counter) {
-    __shared__ __align__(16) double spos[kDepBlock * 3];
-    __shared__ int64_t s_tile;
-    const int64_t ntiles = (n + kDepBlock - 1) / kDepBlock;
-    for (int64_t tile = next_tile(tile_counter, &s_tile); tile < ntiles; tile = next_tile(tile_counter, &s_tile)) {
-        const int64_t first = tile * kDepBlock;
-        const int count = (int)min((int64_t)kDepBlock, n - first);
-        stage_particles<kDepBlock>(pos, first, count, spos);
-        __syncthreads();
-        if ((int)threadIdx.x >= count) continue;
-        const double x = (spos[threadIdx.x * 3 + 0] - co.off[0]) * co.scale;
-        const double y = (spos[threadIdx.x * 3 + 1] - co.off[1]) * co.scale;
-        const double z = (spos[threadIdx.x * 3 + 2] - co.off[2]) * co.scale;
-        double wx[ORDER], wy[ORDER], wz[ORDER];
-        const int ix = weights_1d<ORDER>(x, wx);
-        const int iy = weights_1d<ORDER>(y, wy);
-        const int iz = weights_1d<ORDER>(z, wz);
-        int jy[ORDER], kz[ORDER];
-#pragma unroll
-        for (int b = 0; b < ORDER; ++b) {
-            jy[b] = wrap(iy + b, g.G) * g.Gp;
-            kz[b] = wrap(iz + b, g.G);
-        }
-#pragma unroll
-        for (int a = 0; a < ORDER; ++a) {
-            const int lx = local_plane(ix + a, g);
-            if (lx < 0) continue;
-            const double wa = wx[a] * contribution;
-            T* plane = grid + (size_t)lx * g.G * g.Gp;
+    __shared__ int64_t s_slot;
+    constexpr int64_t kChunk = (int64_t)kDepBlock * kChunkTiles;
+    const int64_t nchunks = (n + kChunk - 1) / kChunk;
+    for (int64_t chunk = next_chunk(tile_counter, &s_slot); chunk < nchunks; chunk = next_chunk(tile_counter, &s_slot)) {
+        const int64_t end = min(n, (chunk + 1) * kChunk);
+        for (int64_t ip = chunk * kChunk + threadIdx.x; ip < end; ip += kDepBlock) {
+            const double* pp = pos + ip * 3;   // streaming: do not displace the grid in L2
+            const double x = (__ldcs(pp + 0) - co.off[0]) * co.scale;
+            const double y = (__ldcs(pp + 1) - co.off[1]) * co.scale;
+            const double z = (__ldcs(pp + 2) - co.off[2]) * co.scale;
+            double wx[ORDER], wy[ORDER], wz[ORDER];
+            const int ix = weights_1d<ORDER>(x, wx);
+            const int iy = weights_1d<ORDER>(y, wy);
+            const int iz = weights_1d<ORDER>(z, wz);
+            int jy[ORDER], kz[ORDER];
 #pragma unroll
             for (int b = 0; b < ORDER; ++b) {
-                const double wab = wa * wy[b];
-                T* row = plane + jy[b];
+                jy[b] = wrap(iy + b, g.G) * g.Gp;
+                kz[b] = wrap(iz + b, g.G);
+            }
 #pragma unroll
-                for (int cc = 0; cc < ORDER; ++cc) {
-                    atomicAdd(row + kz[cc], (T)(wab * wz[cc]));
+            for (int a = 0; a < ORDER; ++a) {
+                const int lx = local_plane(ix + a, g);
+                if (lx < 0) continue;
+                const double wa = wx[a] * contribution;
+                T* plane = grid + (size_t)lx * g.G * g.Gp;
+#pragma unroll
+                for (int b = 0; b < ORDER; ++b) {
+                    const double wab = wa * wy[b];
+                    T* row = plane + jy[b];
+#pragma unroll
+                    for (int cc = 0; cc < ORDER; ++cc) {
+                        atomicAdd(row + kz[cc], (T)(wab * wz[cc]));
+                    }
                 }
             }
         }
@@ -171,8 +183,8 @@ deposit_kernel(const double* __restrict__ pos, int64_t n, T* __restrict__ grid, 
 template <typename T>
 static int deposit_dispatch(pm_ctx* c, const double* pos, int64_t n, int order, double contribution,
                             const Coord& co) {
-    const int64_t ntiles = (n + kDepBlock - 1) / kDepBlock;
-    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * 16);
+    const int64_t nchunks = (n + (int64_t)kDepBlock * kChunkTiles - 1) / ((int64_t)kDepBlock * kChunkTiles);
+    const int grid = (int)std::min<int64_t>(nchunks, (int64_t)kNumSMs * 8);
     T* gptr = reinterpret_cast<T*>(c->real);
     unsigned long long* ctr = c->d_tilectr;
     PM_CHECK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), c->stream));
@@ -294,7 +306,8 @@ int launch_diff(pm_ctx* c, int dim, int order) {
 // ---------------------------------------------------------------------------
 // gather from an explicit grid (one dimension)
 // ---------------------------------------------------------------------------
-constexpr int kGatBlock = 256;
+constexpr int kGatBlock = 256;    // gather_kernel (one dimension, explicit grid)
+constexpr int kGkBlock = 128;     // gather_kick_kernel: ~100 registers per thread — small CTAs keep 20 warps per SM
 
 template <int ORDER, typename T>
 __global__ void __launch_bounds__(kGatBlock)
@@ -370,71 +383,135 @@ int launch_gather(pm_ctx* c, int which, const double* pos, double* mom, int64_t 
 }
 
 // ---------------------------------------------------------------------------
-// fused gradient + gather + kick (+ Σ mom²)
+// fused gradient + gather + kick (+ Σ mom²) (+ drift)
 // ---------------------------------------------------------------------------
-template <int ORDER, int REACH, typename T>
-__global__ void __launch_bounds__(kGatBlock)
-gather_kick_kernel(const T* __restrict__ phi, const double* __restrict__ pos,
+// Per particle the finite differences need the ORDER³ cells under the interpolation stencil plus, per
+// dimension, 2·REACH "arm" cells beyond it on every line: ORDER³ + 3·ORDER²·2·REACH distinct loads (32
+// for CIC/order 2) instead of the 6·REACH·ORDER³ (48) of the straightforward double loop.  Warps run
+// independently (no shared-memory staging, no barrier inside a chunk).  x and y sums run over their
+// line index innermost, so their summation order differs from the reference's (a, b, c) nest by a
+// reassociation (last-bit differences; the stated kick tolerance is 1e-9).
+constexpr int kGkChunkTiles = 16;  // 2048 consecutive particles per ticket
+
+template <int ORDER, int REACH, typename T, bool DRIFT>
+__global__ void __launch_bounds__(kGkBlock)
+gather_kick_kernel(const T* __restrict__ phi, double* __restrict__ pos,
                    double* __restrict__ mom, int64_t n, Geom g, Coord co, FD fd, double factor,
-                   double* __restrict__ sum_mom2, unsigned long long* __restrict__ tile_counter) {
-    __shared__ __align__(16) double spos[kGatBlock * 3];
-    __shared__ double sred[kGatBlock / 32];
-    __shared__ int64_t s_tile;
+                   double* __restrict__ sum_mom2, unsigned long long* __restrict__ tile_counter,
+                   double drift_dt, double boxsize) {
+    __shared__ double sred[kGkBlock / 32];
+    __shared__ int64_t s_slot;
     constexpr int W = ORDER + 2 * REACH;   // cells touched per axis
+    constexpr int64_t kChunk = (int64_t)kGkBlock * kGkChunkTiles;
     double mom2_acc = 0;
-    const int64_t ntiles = (n + kGatBlock - 1) / kGatBlock;
-    for (int64_t tile = next_tile(tile_counter, &s_tile); tile < ntiles; tile = next_tile(tile_counter, &s_tile)) {
-        const int64_t first = tile * kGatBlock;
-        const int count = (int)min((int64_t)kGatBlock, n - first);
-        stage_particles<kGatBlock>(pos, first, count, spos);
-        __syncthreads();
-        if ((int)threadIdx.x >= count) continue;
-        const double x = (spos[threadIdx.x * 3 + 0] - co.off[0]) * co.scale;
-        const double y = (spos[threadIdx.x * 3 + 1] - co.off[1]) * co.scale;
-        const double z = (spos[threadIdx.x * 3 + 2] - co.off[2]) * co.scale;
-        double wx[ORDER], wy[ORDER], wz[ORDER];
-        const int ix = weights_1d<ORDER>(x, wx);
-        const int iy = weights_1d<ORDER>(y, wy);
-        const int iz = weights_1d<ORDER>(z, wz);
-        // element offsets of the W cells along each axis (pre-multiplied by strides)
-        size_t ox[W];
-        int oy[W], oz[W];
+    const int64_t nchunks = (n + kChunk - 1) / kChunk;
+    for (int64_t chunk = next_chunk(tile_counter, &s_slot); chunk < nchunks; chunk = next_chunk(tile_counter, &s_slot)) {
+        const int64_t end = min(n, (chunk + 1) * kChunk);
+        for (int64_t ip = chunk * kChunk + threadIdx.x; ip < end; ip += kGkBlock) {
+            double* pp = pos + ip * 3;
+            const double px = __ldcs(pp), py = __ldcs(pp + 1), pz = __ldcs(pp + 2);
+            const double x = (px - co.off[0]) * co.scale;
+            const double y = (py - co.off[1]) * co.scale;
+            const double z = (pz - co.off[2]) * co.scale;
+            double wx[ORDER], wy[ORDER], wz[ORDER];
+            const int ix = weights_1d<ORDER>(x, wx);
+            const int iy = weights_1d<ORDER>(y, wy);
+            const int iz = weights_1d<ORDER>(z, wz);
+            // element offsets of the W cells along each axis (pre-multiplied by strides)
+            size_t ox[W];
+            int oy[W], oz[W];
 #pragma unroll
-        for (int t = 0; t < W; ++t) {
-            const int lx = local_plane(ix + t - REACH, g);
-            ox[t] = (size_t)(lx < 0 ? 0 : lx) * g.G * g.Gp;
-            oy[t] = wrap(iy + t - REACH, g.G) * g.Gp;
-            oz[t] = wrap(iz + t - REACH, g.G);
-        }
-        double vx = 0, vy = 0, vz = 0;
+            for (int t = 0; t < W; ++t) {
+                const int lx = local_plane(ix + t - REACH, g);
+                ox[t] = (size_t)(lx < 0 ? 0 : lx) * g.G * g.Gp;
+                oy[t] = wrap(iy + t - REACH, g.G) * g.Gp;
+                oz[t] = wrap(iz + t - REACH, g.G);
+            }
+            // the cells under the interpolation stencil
+            T core[ORDER][ORDER][ORDER];
 #pragma unroll
-        for (int a = 0; a < ORDER; ++a) {
+            for (int a = 0; a < ORDER; ++a)
+#pragma unroll
+                for (int b = 0; b < ORDER; ++b)
+#pragma unroll
+                    for (int cc = 0; cc < ORDER; ++cc)
+                        core[a][b][cc] = phi[ox[a + REACH] + oy[b + REACH] + oz[cc + REACH]];
+            double vx = 0, vy = 0, vz = 0;
+            // ---- x: lines along a for every (b, c)
 #pragma unroll
             for (int b = 0; b < ORDER; ++b) {
-                const double wab = wx[a] * wy[b];
 #pragma unroll
                 for (int cc = 0; cc < ORDER; ++cc) {
-                    const double w = wab * wz[cc];
-                    const int A = a + REACH, B = b + REACH, C = cc + REACH;
-                    double dx_[REACH], dy_[REACH], dz_[REACH];
+                    T line[W];
 #pragma unroll
-                    for (int m = 1; m <= REACH; ++m) {
-                        const int lo = fd.forward ? 0 : m;
-                        dx_[m - 1] = (double)phi[ox[A + m] + oy[B] + oz[C]] - (double)phi[ox[A - lo] + oy[B] + oz[C]];
-                        dy_[m - 1] = (double)phi[ox[A] + oy[B + m] + oz[C]] - (double)phi[ox[A] + oy[B - lo] + oz[C]];
-                        dz_[m - 1] = (double)phi[ox[A] + oy[B] + oz[C + m]] - (double)phi[ox[A] + oy[B] + oz[C - lo]];
+                    for (int t = 0; t < W; ++t)
+                        line[t] = (t >= REACH && t < REACH + ORDER) ? core[t - REACH][b][cc]
+                                                                  : phi[ox[t] + oy[b + REACH] + oz[cc + REACH]];
+#pragma unroll
+                    for (int a = 0; a < ORDER; ++a) {
+                        const double w = (wx[a] * wy[b]) * wz[cc];
+                        double d[REACH];
+#pragma unroll
+                        for (int m = 1; m <= REACH; ++m)
+                            d[m - 1] = (double)line[a + REACH + m] - (double)(fd.forward ? line[a + REACH] : line[a + REACH - m]);
+                        vx += fd_combine<REACH>(d, fd) * w;
                     }
-                    vx += fd_combine<REACH>(dx_, fd) * w;
-                    vy += fd_combine<REACH>(dy_, fd) * w;
-                    vz += fd_combine<REACH>(dz_, fd) * w;
                 }
             }
+            // ---- y: lines along b for every (a, c)
+#pragma unroll
+            for (int a = 0; a < ORDER; ++a) {
+#pragma unroll
+                for (int cc = 0; cc < ORDER; ++cc) {
+                    T line[W];
+#pragma unroll
+                    for (int t = 0; t < W; ++t)
+                        line[t] = (t >= REACH && t < REACH + ORDER) ? core[a][t - REACH][cc]
+                                                                  : phi[ox[a + REACH] + oy[t] + oz[cc + REACH]];
+#pragma unroll
+                    for (int b = 0; b < ORDER; ++b) {
+                        const double w = (wx[a] * wy[b]) * wz[cc];
+                        double d[REACH];
+#pragma unroll
+                        for (int m = 1; m <= REACH; ++m)
+                            d[m - 1] = (double)line[b + REACH + m] - (double)(fd.forward ? line[b + REACH] : line[b + REACH - m]);
+                        vy += fd_combine<REACH>(d, fd) * w;
+                    }
+                }
+            }
+            // ---- z: lines along c for every (a, b)
+#pragma unroll
+            for (int a = 0; a < ORDER; ++a) {
+#pragma unroll
+                for (int b = 0; b < ORDER; ++b) {
+                    T line[W];
+#pragma unroll
+                    for (int t = 0; t < W; ++t)
+                        line[t] = (t >= REACH && t < REACH + ORDER) ? core[a][b][t - REACH]
+                                                                  : phi[ox[a + REACH] + oy[b + REACH] + oz[t]];
+#pragma unroll
+                    for (int cc = 0; cc < ORDER; ++cc) {
+                        const double w = (wx[a] * wy[b]) * wz[cc];
+                        double d[REACH];
+#pragma unroll
+                        for (int m = 1; m <= REACH; ++m)
+                            d[m - 1] = (double)line[cc + REACH + m] - (double)(fd.forward ? line[cc + REACH] : line[cc + REACH - m]);
+                        vz += fd_combine<REACH>(d, fd) * w;
+                    }
+                }
+            }
+            if (factor != 1) { vx *= factor; vy *= factor; vz *= factor; }
+            double* m = mom + ip * 3;
+            const double mx = __ldcs(m) + vx, my = __ldcs(m + 1) + vy, mz = __ldcs(m + 2) + vz;
+            __stcs(m, mx); __stcs(m + 1, my); __stcs(m + 2, mz);
+            mom2_acc += mx * mx + my * my + mz * mz;
+            if constexpr (DRIFT) {
+                // Component.drift (species.py:2191-2196) with the freshly kicked momenta
+                __stcs(pp, mod_box(px + mx * drift_dt, boxsize));
+                __stcs(pp + 1, mod_box(py + my * drift_dt, boxsize));
+                __stcs(pp + 2, mod_box(pz + mz * drift_dt, boxsize));
+            }
         }
-        if (factor != 1) { vx *= factor; vy *= factor; vz *= factor; }
-        double* m = mom + (first + threadIdx.x) * 3;
-        const double mx = __ldcs(m) + vx, my = __ldcs(m + 1) + vy, mz = __ldcs(m + 2) + vz;
-        __stcs(m, mx); __stcs(m + 1, my); __stcs(m + 2, mz);
-        mom2_acc += mx * mx + my * my + mz * mz;
     }
     if (sum_mom2 != nullptr) {
         __syncthreads();
@@ -444,23 +521,30 @@ gather_kick_kernel(const T* __restrict__ phi, const double* __restrict__ pos,
         __syncthreads();
         if (threadIdx.x == 0) {
             double t = 0;
-            for (int w = 0; w < kGatBlock / 32; ++w) t += sred[w];
+            for (int w = 0; w < kGkBlock / 32; ++w) t += sred[w];
             atomicAdd(sum_mom2, t);
         }
     }
 }
 
 template <typename T>
-static int gather_kick_dispatch(pm_ctx* c, const double* pos, double* mom, int64_t n, int order,
-                                const FD& fd, double factor, const Coord& co, double* sum_mom2) {
-    const int64_t ntiles = (n + kGatBlock - 1) / kGatBlock;
-    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * 8);
+static int gather_kick_dispatch(pm_ctx* c, double* pos, double* mom, int64_t n, int order,
+                                const FD& fd, double factor, const Coord& co, double* sum_mom2,
+                                bool drift, double drift_dt) {
+    const int64_t nchunks = (n + (int64_t)kGkBlock * kGkChunkTiles - 1) / ((int64_t)kGkBlock * kGkChunkTiles);
+    const int grid = (int)std::min<int64_t>(nchunks, (int64_t)kNumSMs * 8);
     const T* phi = reinterpret_cast<const T*>(c->real);
     unsigned long long* ctr = c->d_tilectr + 1;
     PM_CHECK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), c->stream));
-#define PM_GK(O, R)                                                                              \
-    PM_LAUNCH((gather_kick_kernel<O, R, T>), grid, kGatBlock, 0, c->stream, phi, pos, mom, n,    \
-              c->g, co, fd, factor, sum_mom2, ctr)
+#define PM_GK(O, R)                                                                                     \
+    do {                                                                                                \
+        if (drift)                                                                                      \
+            PM_LAUNCH((gather_kick_kernel<O, R, T, true>), grid, kGkBlock, 0, c->stream, phi, pos, mom, n, \
+                      c->g, co, fd, factor, sum_mom2, ctr, drift_dt, c->boxsize);                       \
+        else                                                                                            \
+            PM_LAUNCH((gather_kick_kernel<O, R, T, false>), grid, kGkBlock, 0, c->stream, phi, pos, mom, n, \
+                      c->g, co, fd, factor, sum_mom2, ctr, drift_dt, c->boxsize);                       \
+    } while (0)
 #define PM_GK_ORDER(R)                                  \
     switch (order) {                                    \
         case 1: PM_GK(1, R); break;                     \
@@ -479,16 +563,17 @@ static int gather_kick_dispatch(pm_ctx* c, const double* pos, double* mom, int64
     return PM_OK;
 }
 
-int launch_gather_kick(pm_ctx* c, const double* pos, double* mom, int64_t n, int order,
-                       int diff_order, double factor, const double* shift, double* sum_mom2) {
+int launch_gather_kick(pm_ctx* c, double* pos, double* mom, int64_t n, int order,
+                       int diff_order, double factor, const double* shift, double* sum_mom2,
+                       bool drift, double drift_dt) {
     PM_REQUIRE(order >= 1 && order <= 4, "pm_gather_kick called with order = %d not in {1, 2, 3, 4}", order);
     FD fd;
     PM_TRY(make_fd(diff_order, c->boxsize / c->g.G, &fd));
     if (n == 0) return PM_OK;
     const Coord co = make_coord(c, shift, true);
     return c->dtype == PM_GRID_F64
-               ? gather_kick_dispatch<double>(c, pos, mom, n, order, fd, factor, co, sum_mom2)
-               : gather_kick_dispatch<float>(c, pos, mom, n, order, fd, factor, co, sum_mom2);
+               ? gather_kick_dispatch<double>(c, pos, mom, n, order, fd, factor, co, sum_mom2, drift, drift_dt)
+               : gather_kick_dispatch<float>(c, pos, mom, n, order, fd, factor, co, sum_mom2, drift, drift_dt);
 }
 
 }  // namespace pm

@@ -170,6 +170,10 @@ class PMContext:
         check(self.lib.pm_gather_kick(self._h, _particles(pos), _particles(mom), pos.shape[0], int(order),
                                       int(diff_order), float(factor), vec3(shift), _ptr(sum_mom2)))
 
+    def gather_kick_drift(self, pos, mom, order, diff_order, factor, dt_over_mass, shift=None, sum_mom2=None):
+        check(self.lib.pm_gather_kick_drift(self._h, _particles(pos), _particles(mom), pos.shape[0], int(order),
+                                            int(diff_order), float(factor), vec3(shift), _ptr(sum_mom2), float(dt_over_mass)))
+
     # -- particle operators ------------------------------------------------------------
     def drift(self, pos, mom, dt_over_mass):
         check(self.lib.pm_drift(self._h, _particles(pos), _particles(mom), pos.shape[0], float(dt_over_mass)))
@@ -191,6 +195,11 @@ class PMContext:
     # -- whole kick -------------------------------------------------------------------
     def kick_long(self, pos, mom, params, sum_mom2=None):
         check(self.lib.pm_kick_long(self._h, _particles(pos), _particles(mom), pos.shape[0], ctypes.byref(params), _ptr(sum_mom2)))
+
+    def kick_drift(self, pos, mom, params, dt_over_mass, sum_mom2=None):
+        """kick_long + Component.drift of the same particles in one call (drift fused into the gather/kick kernel)."""
+        check(self.lib.pm_kick_drift(self._h, _particles(pos), _particles(mom), pos.shape[0], ctypes.byref(params),
+                                     float(dt_over_mass), _ptr(sum_mom2)))
 
     def kick_long_host(self, pos_np, mom_np, params, dt_over_mass=0.0, want_sum=False):
         """Host (numpy, C-contiguous float64 (N,3)) buffers in and out; returns Σmom² or None."""

@@ -158,6 +158,12 @@ int pm_gather(pm_ctx* ctx, int which, const double* pos, double* mom, int64_t n,
 int pm_gather_kick(pm_ctx* ctx, const double* pos, double* mom, int64_t n, int order,
                    int diff_order, double factor, const double* shift, double* sum_mom2);
 
+/* pm_gather_kick with Component.drift (species.py:2179-2199) of the same particles fused in:
+ * after the kick, pos = mod(pos + mom·dt_over_mass, L) with the kicked momenta (dt_over_mass == 0: none).
+ * pos and mom cross HBM once for both operators. */
+int pm_gather_kick_drift(pm_ctx* ctx, double* pos, double* mom, int64_t n, int order, int diff_order,
+                         double factor, const double* shift, double* sum_mom2, double dt_over_mass);
+
 /* ---- particle operators ------------------------------------------------ */
 /* Component.drift (species.py:2179-2199): pos = mod(pos + mom·dt_over_mass, L) */
 int pm_drift(pm_ctx* ctx, double* pos, const double* mom, int64_t n, double dt_over_mass);
@@ -212,6 +218,13 @@ typedef struct {
  * (interactions.py:2854-2961 → particle_mesh :1985-2335).  sum_mom2 as in pm_gather_kick. */
 int pm_kick_long(pm_ctx* ctx, const double* pos, double* mom, int64_t n,
                  const pm_kick_params* p, double* sum_mom2);
+/* kick_long immediately followed by Component.drift (species.py:2179-2199) of the same particles with
+ * the kicked momenta, pos = mod(pos + mom·dt_over_mass, L) — what main.timeloop does across a step
+ * boundary (kick_long at the end of one step, driftkick_short's drift at the start of the next,
+ * main.py:255-361) whenever the next step's Δt is already fixed.  On the default path the drift is
+ * fused into the gather/kick kernel (pos and mom cross HBM once).  dt_over_mass == 0: no drift. */
+int pm_kick_drift(pm_ctx* ctx, double* pos, double* mom, int64_t n, const pm_kick_params* p,
+                  double dt_over_mass, double* sum_mom2);
 /* Same, with HOST particle buffers: H2D, kick, optional drift (dt_over_mass != 0), D2H.
  * pos_host is updated only when drifting. Synchronous. */
 int pm_kick_long_host(pm_ctx* ctx, double* pos_host, double* mom_host, int64_t n,

@@ -122,3 +122,37 @@ def test_kick_against_oracle(G, order, diff):
     ctx.close()
     # tolerance: tests/test_gpu_parity.py (Δmom 1e-9 of max|Δmom|)
     assert np.max(np.abs(got - ref))/np.max(np.abs(ref)) < 1e-9
+
+
+@pytest.mark.parametrize('order,diff,dtype', [(2, 2, 'f64'), (3, 4, 'f64'), (4, 8, 'f64'), (1, 1, 'f64'), (3, 2, 'f32')])
+def test_kick_drift_equals_kick_then_drift(order, diff, dtype):
+    """pm_kick_drift (drift fused into the gather/kick kernel) == pm_kick_long followed by pm_drift,
+    and the deduplicated gather matches the numpy oracle."""
+    from concept_b200.pmsolver import make_kick_params
+    from oracle import pm_oracle as O
+    G, L, N = 64, 128.0, 50_000
+    rng = np.random.default_rng(order*10 + diff)
+    pos_h, mom_h = rng.random((N, 3))*L, rng.standard_normal((N, 3))
+    pos_h[:64] = np.floor(pos_h[:64]/(L/G))*(L/G)          # particles exactly on cell edges
+    pos_h[64] = np.nextafter(L, 0)
+    kw = dict(mass=0.7, boxsize=L, gridsize=G, order=order, G_Newton=G_NEWTON, dt_rho_over_dt1=1.5, dt_kick=0.02, diff_order=diff)
+    params = make_kick_params(**kw)
+    dtm = 0.37
+    ctx = _ctx(G, L, dtype)
+    p1, m1 = torch.as_tensor(pos_h, device='cuda'), torch.as_tensor(mom_h, device='cuda')
+    s1 = torch.zeros(1, dtype=torch.float64, device='cuda')
+    ctx.kick_long(p1, m1, params, sum_mom2=s1)
+    ctx.drift(p1, m1, dtm)
+    p2, m2 = torch.as_tensor(pos_h, device='cuda'), torch.as_tensor(mom_h, device='cuda')
+    s2 = torch.zeros(1, dtype=torch.float64, device='cuda')
+    ctx.kick_drift(p2, m2, params, dtm, sum_mom2=s2)
+    ctx.close()
+    dm = (m1 - torch.as_tensor(mom_h, device='cuda')).abs().max().item()
+    # the deposit's atomics make the two potentials differ in the last bits
+    assert (m1 - m2).abs().max().item() < (1e-11 if dtype == 'f64' else 1e-5)*dm
+    assert torch.equal(p2, torch.as_tensor(O.drift(pos_h, m2.cpu().numpy(), dtm, L), device='cuda'))
+    assert abs(s1.item() - s2.item()) < 1e-9*abs(s1.item())
+    if dtype == 'f64':
+        ref = O.pm_kick(pos_h, mom_h, **kw) - mom_h
+        got = m2.cpu().numpy() - mom_h
+        assert np.max(np.abs(got - ref))/np.max(np.abs(ref)) < 1e-9

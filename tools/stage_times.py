@@ -25,6 +25,7 @@ def main():
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--nofuse', action='store_true', help='three-call solve (cuFFT 3-D + k-space kernel) instead of the fused x-solve')
     ap.add_argument('--solve-mode', default='auto', help='auto | fft2_l2 | fft2_split | cufft2d (see PMContext.SOLVE_MODES)')
+    ap.add_argument('--nodriftfuse', action='store_true', help='separate gather_kick and drift kernels')
     ap.add_argument('--shuffle', action='store_true', help='random particle order (worst-case locality)')
     a = ap.parse_args()
     L = 512.0
@@ -46,8 +47,10 @@ def main():
             ('fft_forward', lambda: ctx.fft_forward()),
             ('kspace', lambda: ctx.kspace_potential(p.prefactor, p.deconv_order, p.gauss, 1.0)),
             ('fft_backward', lambda: ctx.fft_backward())]),
-        ('gather_kick', lambda: ctx.gather_kick(pos, mom, p.order, p.diff_order, p.kick_factor, None, s)),
-        ('drift', lambda: ctx.drift(pos, mom, 1e-4)),
+        *([('gather_kick_drift', lambda: ctx.gather_kick_drift(pos, mom, p.order, p.diff_order, p.kick_factor, 1e-4, None, s))]
+          if not a.nodriftfuse else [
+            ('gather_kick', lambda: ctx.gather_kick(pos, mom, p.order, p.diff_order, p.kick_factor, None, s)),
+            ('drift', lambda: ctx.drift(pos, mom, 1e-4))]),
     ]
     times = {k: [] for k, _ in stages}
     total = []
@@ -65,7 +68,7 @@ def main():
     G3 = a.grid**3
     es = 8 if a.dtype == 'f64' else 4
     alg = {'grid_zero': es*G3, 'deposit': 24*N + es*G3, 'fft_forward': 2*es*G3, 'kspace': 2*es*G3, 'fft_backward': 2*es*G3, 'solve_fused': 4*es*G3,
-           'gather_kick': 72*N + es*G3, 'drift': 72*N}
+           'gather_kick': 72*N + es*G3, 'drift': 72*N, 'gather_kick_drift': 96*N + es*G3}
     ctx.check_async_error()
     out = {'N': N, 'grid': a.grid, 'solve_mode': a.solve_mode, 'order': a.order, 'dtype': a.dtype, 'sigma': a.sigma, 'shuffle': a.shuffle,
            'device_bytes': ctx.device_bytes, 'stages_ms': {}, 'stages_GBps': {}}
