@@ -218,9 +218,11 @@ def run_gpu(args):
         pbuf, mbuf = pos, mom
     params = make_kick_params(**KICK)
     sum2 = torch.zeros(1, dtype=torch.float64, device=dev)
-    ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # stages of one cycle, each bracketed by CUDA events inside the timed region
+    STAGES = ['grid_zero', 'deposit', 'halo_add', 'fft2d_forward', 'xsolve', 'fft2d_inverse', 'halo_fill', 'gather_kick_drift', 'migrate']
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(STAGES) + 1)] for _ in range(args.steps)]
     state = {'n': n_local}
+    staged = ctx.hand_fft_available
 
     def cycle(i=None):
         n = state['n']
@@ -229,24 +231,34 @@ def run_gpu(args):
         if i is None:
             ctx.kick_drift(p, m, params, DT_OVER_MASS, sum_mom2=sum2)
         else:
-            # same sequence as pm_kick_drift, split so that the dominant kernel can be bracketed by events
-            ctx.grid_zero()
-            ctx.deposit(p, params.order, params.contribution)
-            ctx.halo_add()
-            if ctx.fused_solve_available:
-                ctx.solve_fused(params.prefactor, params.deconv_order, params.gauss)
+            # same sequence as pm_kick_drift, split so that every kernel can be bracketed by events
+            e = evs[i]
+            e[0].record()
+            ctx.grid_zero(); e[1].record()
+            ctx.deposit(p, params.order, params.contribution); e[2].record()
+            ctx.halo_add(); e[3].record()
+            if staged:
+                ctx.solve_fused_stage(params.prefactor, params.deconv_order, params.gauss, 1); e[4].record()
+                ctx.solve_fused_stage(params.prefactor, params.deconv_order, params.gauss, 2); e[5].record()
+                ctx.solve_fused_stage(params.prefactor, params.deconv_order, params.gauss, 3); e[6].record()
             else:
-                ctx.fft_forward()
-                ctx.kspace_potential(params.prefactor, params.deconv_order, params.gauss, 1.0)
-                ctx.fft_backward()
+                if ctx.fused_solve_available:
+                    ctx.solve_fused(params.prefactor, params.deconv_order, params.gauss)
+                else:
+                    ctx.fft_forward()
+                    ctx.kspace_potential(params.prefactor, params.deconv_order, params.gauss, 1.0)
+                    ctx.fft_backward()
+                e[4].record(); e[5].record(); e[6].record()
             if world > 1:
                 ctx.halo_fill()
-            ev_k0[i].record()
+            e[7].record()
             ctx.gather_kick_drift(p, m, params.order, params.diff_order, params.kick_factor, DT_OVER_MASS, None, sum2)
-            ev_k1[i].record()
+            e[8].record()
         if world > 1:
             ctx.allreduce_sum(sum2)
             state['n'] = ctx.exchange(pbuf, mbuf, None, n)
+        if i is not None:
+            evs[i][9].record()
 
     def barrier():
         if world > 1:
@@ -270,12 +282,12 @@ def run_gpu(args):
     launches = lib.pm_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
-    kern_ms = [a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)]
-    t = torch.tensor([ms_total, sum(kern_ms)/len(kern_ms)], dtype=torch.float64, device=dev)
+    stage_ms = [sum(e[k].elapsed_time(e[k + 1]) for e in evs)/len(evs) for k in range(len(STAGES))]
+    t = torch.tensor([ms_total] + stage_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t[0].item()/args.steps
-    kern_ms_avg = t[1].item()
+    stage_ms = [v.item() for v in t[1:]]
     value = n_total/(ms_step*1e-3)
 
     # ---- end-to-end through the host-buffer C-ABI entry point (rank-local slab) ----
@@ -296,7 +308,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
         e2e_sec = (time.perf_counter() - t0)/e2e_steps
         e2e = {'value': n_total/e2e_sec, 'unit': UNIT, 'h2d_bytes_per_step': 2*24*n, 'd2h_bytes_per_step': 2*24*n + 8,
-               'ms_per_step': e2e_sec*1e3, 'api': 'pm_kick_long_host (pinned host pos/mom in, kick + drift, pos/mom out)'}
+               'ms_per_step': e2e_sec*1e3, 'api': 'pm_kick_long_host (pinned host pos/mom in, kick + fused drift, pos/mom out)'}
     else:
         # every rank moves its own slab's particles host<->device around the same distributed cycle
         def e2e_step():
@@ -327,12 +339,24 @@ def run_gpu(args):
         peak, peak_src = measured_peaks()
         n_per = n_total/world
         g3_per = GRID**3/world
-        kern_bytes = 96*n_per + 8*g3_per      # read pos+mom 48N, write pos+mom 48N, read φ 8G³ (per rank)
-        achieved = kern_bytes/(kern_ms_avg*1e-3)/1e9
+        es = 8
+        # algorithmic bytes per launch (SURVEY §8d / DESIGN §4), per rank
+        alg = {'grid_zero': es*g3_per, 'deposit': 24*n_per + es*g3_per, 'fft2d_forward': 2*es*g3_per, 'xsolve': 2*es*g3_per,
+               'fft2d_inverse': 2*es*g3_per, 'gather_kick_drift': 96*n_per + es*g3_per}
+        kernels = {k: {'ms': ms, 'algorithmic_GB': alg[k]/1e9 if k in alg else None,
+                       'achieved_GBps': (alg[k]/(ms*1e-3)/1e9 if (k in alg and ms > 0) else None)}
+                   for k, ms in zip(STAGES, stage_ms)}
+        names = {'fft2d_forward': 'fft2d_kernel<double,512,-1> (r2c along z + c2c along y per x plane, L2-resident hand-over)',
+                 'xsolve': 'xsolve2_kernel<double,512> (c2c along x, Green\'s function, inverse c2c along x)',
+                 'fft2d_inverse': 'fft2d_kernel<double,512,+1> (inverse c2c along y + c2r along z per x plane)',
+                 'gather_kick_drift': 'gather_kick_kernel<2,1,double,drift> (fused gradient + CIC gather + kick + sum mom^2 + drift)',
+                 'deposit': 'deposit_kernel<2,double> (CIC scatter, red.global.add.f64)', 'grid_zero': 'cudaMemsetAsync'}
+        dom = max((k for k in alg if k in names), key=lambda k: kernels[k]['ms'])
         b_alg = 120*n_total + 48*GRID**3
-        roofline = {'bound': 'hbm', 'kernel': 'gather_kick_kernel<2,1,double,drift> (fused gradient + CIC gather + kick + sum mom^2 + drift)',
-                    'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved/peak, 'traffic': None,
-                    'peak_source': peak_src, 'kernel_ms': kern_ms_avg, 'algorithmic_bytes_per_launch': kern_bytes,
+        roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': kernels[dom]['achieved_GBps'], 'peak': peak, 'unit': 'GB/s',
+                    'frac': kernels[dom]['achieved_GBps']/peak, 'traffic': None,
+                    'peak_source': peak_src, 'kernel_ms': kernels[dom]['ms'], 'algorithmic_bytes_per_launch': alg[dom],
+                    'kernels': kernels,
                     'cycle': {'algorithmic_bytes': b_alg, 'achieved_GBps_per_gpu': b_alg/world/(ms_step*1e-3)/1e9,
                               'frac': b_alg/world/(ms_step*1e-3)/1e9/peak}}
         cpu = None

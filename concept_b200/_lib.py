@@ -55,6 +55,7 @@ SIGNATURES = {
     'pm_kspace_potential': (c_int, [c_void_p, c_double, c_int, c_double, c_double]),
     'pm_fourier_operate': (c_int, [c_void_p, c_int, POINTER(c_double), c_double, c_int, c_int]),
     'pm_solve_fused': (c_int, [c_void_p, c_double, c_int, c_double]),
+    'pm_solve_fused_stage': (c_int, [c_void_p, c_double, c_int, c_double, c_int]),
     'pm_fused_solve_available': (c_int, [c_void_p]),
     'pm_set_fused_solve': (c_int, [c_void_p, c_int]),
     'pm_check_async_error': (c_int, [c_void_p]),

@@ -294,6 +294,11 @@ int pm_solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss) 
     return solve_fused(c, prefactor, deconv_order, gauss);
 }
 
+int pm_solve_fused_stage(pm_ctx* c, double prefactor, int deconv_order, double gauss, int stage) {
+    PM_REQUIRE(c != nullptr, "pm_solve_fused_stage: NULL context");
+    return solve_fused(c, prefactor, deconv_order, gauss, stage);
+}
+
 int pm_fused_solve_available(const pm_ctx* c) { return c && (fft2_supported(c) || xsolve_supported(c)) ? 1 : 0; }
 
 int pm_set_fused_solve(pm_ctx* c, int mode) {

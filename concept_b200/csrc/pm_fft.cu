@@ -387,38 +387,46 @@ static int launch_xsolve2(pm_ctx* c, double prefactor) {
     return PM_OK;
 }
 
+// stage: 0 = whole solve; 1 = forward 2-D transforms, 2 = x solve, 3 = inverse 2-D transforms (for timing
+// the three kernels separately; the caller runs 1, 2, 3 in order)
 template <typename T, int G>
-static int solve_fft2_tg(pm_ctx* c, double prefactor, bool l2_fused) {
-    PM_CHECK_CUDA(cudaMemsetAsync(c->f2_ctr, 0, sizeof(unsigned) * c->f2_nctr, c->stream));
-    if (l2_fused) {
-        PM_TRY((launch_fft2d<T, G, -1>(c, 0)));
-    } else {
-        PM_TRY((launch_fft2d<T, G, -1>(c, 1)));
-        PM_TRY((launch_fft2d<T, G, -1>(c, 2)));
+static int solve_fft2_tg(pm_ctx* c, double prefactor, bool l2_fused, int stage) {
+    if (stage == 0 || stage == 1) {
+        PM_CHECK_CUDA(cudaMemsetAsync(c->f2_ctr, 0, sizeof(unsigned) * c->f2_nctr, c->stream));
+        if (l2_fused) {
+            PM_TRY((launch_fft2d<T, G, -1>(c, 0)));
+        } else {
+            PM_TRY((launch_fft2d<T, G, -1>(c, 1)));
+            PM_TRY((launch_fft2d<T, G, -1>(c, 2)));
+        }
     }
-    if (c->nranks > 1) PM_TRY(device_barrier(c));   // every rank's 2-D spectra are complete
-    PM_TRY((launch_xsolve2<T, G>(c, prefactor)));
-    if (c->nranks > 1) PM_TRY(device_barrier(c));   // all peers have written our planes
-    if (l2_fused) {
-        PM_TRY((launch_fft2d<T, G, +1>(c, 0)));
-    } else {
-        PM_TRY((launch_fft2d<T, G, +1>(c, 1)));
-        PM_TRY((launch_fft2d<T, G, +1>(c, 2)));
+    if (stage == 0 || stage == 2) {
+        if (c->nranks > 1) PM_TRY(device_barrier(c));   // every rank's 2-D spectra are complete
+        PM_TRY((launch_xsolve2<T, G>(c, prefactor)));
+        if (c->nranks > 1) PM_TRY(device_barrier(c));   // all peers have written our planes
+    }
+    if (stage == 0 || stage == 3) {
+        if (l2_fused) {
+            PM_TRY((launch_fft2d<T, G, +1>(c, 0)));
+        } else {
+            PM_TRY((launch_fft2d<T, G, +1>(c, 1)));
+            PM_TRY((launch_fft2d<T, G, +1>(c, 2)));
+        }
     }
     return PM_OK;
 }
 
 // forward 2-D transforms → fused x pass → inverse 2-D transforms with the hand-written kernels.
 // l2_fused: dependency-ordered single launch per 2-D transform.
-int solve_fft2(pm_ctx* c, double prefactor, int deconv_order, double gauss, bool l2_fused) {
+int solve_fft2(pm_ctx* c, double prefactor, int deconv_order, double gauss, bool l2_fused, int stage) {
     PM_REQUIRE(fft2_supported(c) && c->f2_tw != nullptr, "hand-written FFT path not available for this grid size / rank layout");
     PM_TRY(update_sep_table(c, deconv_order, gauss));
     const bool f64 = c->dtype == PM_GRID_F64;
     int s;
     switch (c->g.G) {
-        case 128: s = f64 ? solve_fft2_tg<double, 128>(c, prefactor, l2_fused) : solve_fft2_tg<float, 128>(c, prefactor, l2_fused); break;
-        case 256: s = f64 ? solve_fft2_tg<double, 256>(c, prefactor, l2_fused) : solve_fft2_tg<float, 256>(c, prefactor, l2_fused); break;
-        default:  s = f64 ? solve_fft2_tg<double, 512>(c, prefactor, l2_fused) : solve_fft2_tg<float, 512>(c, prefactor, l2_fused); break;
+        case 128: s = f64 ? solve_fft2_tg<double, 128>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 128>(c, prefactor, l2_fused, stage); break;
+        case 256: s = f64 ? solve_fft2_tg<double, 256>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 256>(c, prefactor, l2_fused, stage); break;
+        default:  s = f64 ? solve_fft2_tg<double, 512>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 512>(c, prefactor, l2_fused, stage); break;
     }
     return s;
 }

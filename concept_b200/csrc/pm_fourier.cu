@@ -318,13 +318,15 @@ int fft_backward(pm_ctx* c) {
 
 // forward 2-D transforms → fused x pass (FFT · Green · inverse FFT) → inverse 2-D transforms.
 // Equivalent to pm_fft_forward + pm_kspace_potential + pm_fft_backward; the slab ends in real space.
-int solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss) {
+int solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss, int stage) {
     PM_REQUIRE(!c->space_fourier, "pm_solve_fused: the slab holds Fourier data");
+    PM_REQUIRE(stage >= 0 && stage <= 3, "pm_solve_fused_stage: stage = %d", stage);
     int mode = c->solve_mode;
     if (mode == PM_SOLVE_AUTO || mode == PM_SOLVE_UNFUSED)
         mode = fft2_supported(c) ? PM_SOLVE_FFT2_L2 : PM_SOLVE_CUFFT2D_XSOLVE;
     if (mode == PM_SOLVE_FFT2_L2 || mode == PM_SOLVE_FFT2_SPLIT)
-        return solve_fft2(c, prefactor, deconv_order, gauss, mode == PM_SOLVE_FFT2_L2);
+        return solve_fft2(c, prefactor, deconv_order, gauss, mode == PM_SOLVE_FFT2_L2, stage);
+    PM_REQUIRE(stage == 0, "pm_solve_fused_stage: staged execution needs the hand-written transforms");
     PM_REQUIRE(xsolve_supported(c), "pm_solve_fused: not available for this grid size / rank layout");
     const bool f64 = c->dtype == PM_GRID_F64;
     const size_t plane = (size_t)c->g.G * c->g.Gp;

@@ -200,9 +200,9 @@ int update_sep_table(pm_ctx* c, int deconv_order, double gauss);
 // implemented in pm_fft.cu
 bool fft2_supported(const pm_ctx* c);
 int make_fft2_tables(pm_ctx* c);
-int solve_fft2(pm_ctx* c, double prefactor, int deconv_order, double gauss, bool l2_fused);
+int solve_fft2(pm_ctx* c, double prefactor, int deconv_order, double gauss, bool l2_fused, int stage = 0);
 int fft2_check_error(pm_ctx* c);
-int solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss);   // pm_fourier.cu
+int solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss, int stage = 0);   // pm_fourier.cu
 
 int ensure_saved(pm_ctx* c);
 int ensure_force(pm_ctx* c);

@@ -131,6 +131,14 @@ class PMContext:
     def solve_fused(self, prefactor, deconv_order, gauss=0.0):
         check(self.lib.pm_solve_fused(self._h, float(prefactor), int(deconv_order), float(gauss)))
 
+    def solve_fused_stage(self, prefactor, deconv_order, gauss, stage):
+        check(self.lib.pm_solve_fused_stage(self._h, float(prefactor), int(deconv_order), float(gauss), int(stage)))
+
+    @property
+    def hand_fft_available(self):
+        """True when pm_solve_fused runs the hand-written slab transform (G ∈ {128, 256, 512})."""
+        return self.gridsize in (128, 256, 512) and self.fused_solve_available
+
     @property
     def fused_solve_available(self):
         return bool(self.lib.pm_fused_solve_available(self._h))

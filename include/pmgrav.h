@@ -136,6 +136,9 @@ int pm_fourier_operate(pm_ctx* ctx, int deconv_order, const double* shift, doubl
  * With several ranks pm_ipc_open_peers must have been called. */
 enum { PM_SOLVE_UNFUSED = 0, PM_SOLVE_AUTO = 1, PM_SOLVE_CUFFT2D_XSOLVE = 2, PM_SOLVE_FFT2_SPLIT = 3, PM_SOLVE_FFT2_L2 = 4 };
 int pm_solve_fused(pm_ctx* ctx, double prefactor, int deconv_order, double gauss);
+/* One kernel of pm_solve_fused at a time, for per-kernel timing: stage 1 = forward 2-D transforms,
+ * 2 = x solve, 3 = inverse 2-D transforms (call 1, 2, 3 in order; 0 = all).  Hand-written transforms only. */
+int pm_solve_fused_stage(pm_ctx* ctx, double prefactor, int deconv_order, double gauss, int stage);
 int pm_fused_solve_available(const pm_ctx* ctx);
 int pm_set_fused_solve(pm_ctx* ctx, int mode);
 /* Host-synchronising check of the asynchronous give-up flag of the dependency-ordered kernels

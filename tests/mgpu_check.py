@@ -27,8 +27,9 @@ def main():
     rank, P = communication.init()
     L, N = 60.0, 40000
     failures = []
-    # G = 64: the fused x-solve over CUDA-IPC peer pointers; G = 48: cuFFT + NCCL all-to-all transpose
-    for G, order, diff, interlace, dtype in [(64, 2, 2, False, 'f64'), (64, 3, 4, False, 'f64'), (64, 4, 8, False, 'f64'),
+    # G = 128: hand-written slab transform, x-solve over CUDA-IPC peer pointers; G = 64: cuFFT 2-D + the
+    # first-generation x-solve over peer pointers; G = 48: cuFFT + NCCL all-to-all transpose
+    for G, order, diff, interlace, dtype in [(128, 2, 2, False, 'f64'), (128, 3, 4, False, 'f64'), (64, 2, 2, False, 'f64'), (64, 3, 4, False, 'f64'), (64, 4, 8, False, 'f64'),
                                              (64, 2, 0, False, 'f64'), (64, 3, 2, True, 'f64'),
                                              (48, 2, 2, False, 'f64'), (48, 3, 4, False, 'f64')]:
         if G % P or G//P < 7:
