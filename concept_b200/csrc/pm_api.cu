@@ -2,6 +2,7 @@
 // over the kernels, the whole-kick orchestration and the parity taps.
 #include "pm_internal.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -210,6 +211,11 @@ int pm_destroy(pm_ctx* c) {
     cudaFree(c->d_counts);
     cudaFree(c->d_tilectr);
     cudaFree(c->xchg_buf);
+    if (c->pipe_ready) {
+        cudaStreamDestroy(c->s_h2d);
+        cudaStreamDestroy(c->s_d2h);
+        for (cudaEvent_t& e : c->ev_pipe) cudaEventDestroy(e);
+    }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return PM_OK;
@@ -442,6 +448,21 @@ int pm_kick_drift(pm_ctx* c, double* pos, double* mom, int64_t n, const pm_kick_
     return kick_long_impl(c, pos, mom, n, p, sum_mom2, dt_over_mass);
 }
 
+// Host buffers in, host buffers out.  On the default path the transfers are pipelined against the kernels in
+// kHostChunks chunks over two copy streams (PCIe is full duplex):
+//   H2D pos[k] → deposit[k] …; H2D mom[k] runs under the solve; gather/kick/drift[k] → D2H mom[k], pos[k] …
+// so the wall time approaches  H2D(pos) + solve + D2H(pos, mom)  instead of the sum of everything.
+constexpr int kHostChunks = 8;
+
+static int ensure_pipe(pm_ctx* c) {
+    if (c->pipe_ready) return PM_OK;
+    PM_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    PM_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : c->ev_pipe) PM_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->pipe_ready = true;
+    return PM_OK;
+}
+
 int pm_kick_long_host(pm_ctx* c, double* pos_host, double* mom_host, int64_t n, const pm_kick_params* p,
                       double dt_over_mass, double* sum_mom2_host) {
     PM_REQUIRE(c != nullptr && p != nullptr && n >= 0 && pos_host && mom_host, "pm_kick_long_host: bad argument");
@@ -455,19 +476,73 @@ int pm_kick_long_host(pm_ctx* c, double* pos_host, double* mom_host, int64_t n, 
     }
     double* dpos = reinterpret_cast<double*>(c->xchg_buf);
     double* dmom = dpos + 3 * n;
-    PM_CHECK_CUDA(cudaMemcpyAsync(dpos, pos_host, bytes, cudaMemcpyHostToDevice, c->stream));
-    PM_CHECK_CUDA(cudaMemcpyAsync(dmom, mom_host, bytes, cudaMemcpyHostToDevice, c->stream));
     double* dsum = nullptr;
     if (sum_mom2_host) {
         dsum = c->d_scratch;
         PM_CHECK_CUDA(cudaMemsetAsync(dsum, 0, sizeof(double), c->stream));
     }
-    PM_TRY(kick_long_impl(c, dpos, dmom, n, p, dsum, dt_over_mass));
-    if (dt_over_mass != 0) PM_CHECK_CUDA(cudaMemcpyAsync(pos_host, dpos, bytes, cudaMemcpyDeviceToHost, c->stream));
-    PM_CHECK_CUDA(cudaMemcpyAsync(mom_host, dmom, bytes, cudaMemcpyDeviceToHost, c->stream));
+    const bool drift = dt_over_mass != 0;
+    const bool pipelined = c->fused_solve && p->interlace == 0 && p->diff_order != 0 && pm_fused_solve_available(c) &&
+                           n >= (int64_t)kHostChunks * 65536;
+    if (!pipelined) {
+        PM_CHECK_CUDA(cudaMemcpyAsync(dpos, pos_host, bytes, cudaMemcpyHostToDevice, c->stream));
+        PM_CHECK_CUDA(cudaMemcpyAsync(dmom, mom_host, bytes, cudaMemcpyHostToDevice, c->stream));
+        PM_TRY(kick_long_impl(c, dpos, dmom, n, p, dsum, dt_over_mass));
+        if (drift) PM_CHECK_CUDA(cudaMemcpyAsync(pos_host, dpos, bytes, cudaMemcpyDeviceToHost, c->stream));
+        PM_CHECK_CUDA(cudaMemcpyAsync(mom_host, dmom, bytes, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        PM_TRY(ensure_pipe(c));
+        cudaEvent_t* ev_pos = c->ev_pipe;
+        cudaEvent_t* ev_mom = c->ev_pipe + 16;
+        cudaEvent_t* ev_out = c->ev_pipe + 32;
+        const int64_t per = ((n + kHostChunks - 1) / kHostChunks + 2047) / 2048 * 2048;
+        auto lo = [&](int k) { return std::min<int64_t>(n, (int64_t)k * per); };
+        auto cnt = [&](int k) { return lo(k + 1) - lo(k); };
+        // the copy streams start after whatever the context's stream has queued so far
+        PM_CHECK_CUDA(cudaEventRecord(ev_out[kHostChunks], c->stream));
+        PM_CHECK_CUDA(cudaStreamWaitEvent(c->s_h2d, ev_out[kHostChunks], 0));
+        for (int k = 0; k < kHostChunks; ++k) {
+            if (cnt(k) > 0)
+                PM_CHECK_CUDA(cudaMemcpyAsync(dpos + 3 * lo(k), pos_host + 3 * lo(k), sizeof(double) * 3 * cnt(k),
+                                              cudaMemcpyHostToDevice, c->s_h2d));
+            PM_CHECK_CUDA(cudaEventRecord(ev_pos[k], c->s_h2d));
+        }
+        for (int k = 0; k < kHostChunks; ++k) {
+            if (cnt(k) > 0)
+                PM_CHECK_CUDA(cudaMemcpyAsync(dmom + 3 * lo(k), mom_host + 3 * lo(k), sizeof(double) * 3 * cnt(k),
+                                              cudaMemcpyHostToDevice, c->s_h2d));
+            PM_CHECK_CUDA(cudaEventRecord(ev_mom[k], c->s_h2d));
+        }
+        PM_TRY(pm_grid_zero(c));
+        for (int k = 0; k < kHostChunks; ++k) {
+            PM_CHECK_CUDA(cudaStreamWaitEvent(c->stream, ev_pos[k], 0));
+            if (cnt(k) > 0) PM_TRY(pm_deposit(c, dpos + 3 * lo(k), cnt(k), p->order, p->contribution, nullptr));
+        }
+        int hlo, hhi;
+        halo_for_gather(p->order, p->diff_order, 0, &hlo, &hhi);
+        PM_TRY(halo_add(c));
+        PM_TRY(solve_fused(c, p->prefactor, p->deconv_order, p->gauss));
+        PM_TRY(halo_fill(c, hlo, hhi, PM_TAP_REAL));
+        for (int k = 0; k < kHostChunks; ++k) {
+            PM_CHECK_CUDA(cudaStreamWaitEvent(c->stream, ev_mom[k], 0));
+            if (cnt(k) > 0)
+                PM_TRY(launch_gather_kick(c, dpos + 3 * lo(k), dmom + 3 * lo(k), cnt(k), p->order, p->diff_order, p->kick_factor,
+                                          nullptr, dsum, drift, dt_over_mass));
+            PM_CHECK_CUDA(cudaEventRecord(ev_out[k], c->stream));
+            PM_CHECK_CUDA(cudaStreamWaitEvent(c->s_d2h, ev_out[k], 0));
+            if (cnt(k) > 0) {
+                PM_CHECK_CUDA(cudaMemcpyAsync(mom_host + 3 * lo(k), dmom + 3 * lo(k), sizeof(double) * 3 * cnt(k),
+                                              cudaMemcpyDeviceToHost, c->s_d2h));
+                if (drift)
+                    PM_CHECK_CUDA(cudaMemcpyAsync(pos_host + 3 * lo(k), dpos + 3 * lo(k), sizeof(double) * 3 * cnt(k),
+                                                  cudaMemcpyDeviceToHost, c->s_d2h));
+            }
+        }
+    }
     if (sum_mom2_host)
         PM_CHECK_CUDA(cudaMemcpyAsync(sum_mom2_host, dsum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     PM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    if (pipelined) PM_CHECK_CUDA(cudaStreamSynchronize(c->s_d2h));
     return PM_OK;
 }
 
