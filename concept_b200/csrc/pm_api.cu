@@ -132,11 +132,19 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
         pm_destroy(c);
         return code;
     };
-    if (cudaMalloc(&c->real, c->real_elems * es) != cudaSuccess) {
-        set_error("pm_create: cannot allocate %zu bytes for the grid", c->real_elems * es);
+    // the hand-written transform (pm_fft.cu) keeps two intermediate copies of the Fourier slab behind the grid
+    size_t alloc_bytes = c->real_elems * es;
+    if (gridsize == 128 || gridsize == 256 || gridsize == 512) {
+        const size_t layout_bytes = (size_t)g.nxl * (gridsize / 2) * gridsize * 2 * es;
+        c->f2_off_a = (alloc_bytes + 255) / 256 * 256;
+        c->f2_off_b = c->f2_off_a + (layout_bytes + 255) / 256 * 256;
+        alloc_bytes = c->f2_off_b + layout_bytes;
+    }
+    if (cudaMalloc(&c->real, alloc_bytes) != cudaSuccess) {
+        set_error("pm_create: cannot allocate %zu bytes for the grid", alloc_bytes);
         return fail(PM_ERR_ALLOC);
     }
-    c->bytes_allocated += c->real_elems * es;
+    c->bytes_allocated += alloc_bytes;
     cudaMemsetAsync(c->real, 0, c->real_elems * es, c->stream);
     if (nranks == 1) {
         c->fourier = c->real;

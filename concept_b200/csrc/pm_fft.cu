@@ -1,20 +1,23 @@
 // pm_fft.cu — hand-written slab transform for the fused Poisson solve (sm_100a, HBM/L2/shared-memory
 // bound; no tensor cores: fp64/fp32 butterflies on the FMA pipes).
 //
-//   fft2d_kernel<DIR=−1>   per x plane: r2c along z (ZFwd tiles), then c2c along y (YPass tiles)
-//   xsolve2_kernel         c2c along x · Green's function · inverse c2c along x, in place, addressing
-//                          every rank's slab through peer pointers (no materialised transpose, fft.c:34-73)
-//   fft2d_kernel<DIR=+1>   per x plane: inverse c2c along y, then c2r along z
+//   fft2d_kernel<DIR=−1>   per x plane: r2c along z (ZFwd tiles: real rows -> A), then c2c along y (YFwd: A -> B)
+//   xsolve2_kernel         c2c along x · Green's function · inverse c2c along x (B of all ranks -> A of all
+//                          ranks through peer pointers; no materialised transpose, fft.c:34-73)
+//   fft2d_kernel<DIR=+1>   per x plane: inverse c2c along y (YInv: A -> real rows), then c2r along z (ZInv)
 //
 // Replaces fft.c's FFTW-MPI plans (fft.c:105-290) + the potential loop (interactions.py:2092-2118) on the
-// default gravity path.  Tile operations and their index math live in pm_fftops.cuh (CPU-checked by
-// tests/test_fftcore_host.py); this file adds the persistent scheduling around them.
+// default gravity path.  Tile operations, layouts and their index math live in pm_fftops.cuh (CPU-checked
+// by tests/test_fftcore_host.py); this file adds the asynchronous tile pipeline around them.
 //
-// Data path of one tile: 128-byte row segments  --ld.global.cg-->  registers  --first radix-8 stage-->
-// ONE shared-memory tile updated in place by the middle stages  --last stage-->  registers  --st.global.
-// (First version staged tiles with cp.async: measured 16 shared-memory wavefronts per 16-byte LDGSTS
-// warp instruction, 4x an STS.128 — 38 % of the shared-memory pipe, which is the scarce resource here.)
-// Several small CTAs per SM instead of one big one: their LDS / FP64 / STS / barrier phases interleave.
+// Data path of one tile: the intermediate layouts A and B make every tile ONE contiguous chunk of global
+// memory, so a single thread moves it with cp.async.bulk (the TMA engine; completion on an mbarrier) into
+// one of the CTA's two 32 KB buffers while the other buffer is being transformed in place; the last stage
+// stores aligned 64-byte segments straight from registers.  No load instruction, register or scoreboard is
+// spent on the input, and three such CTAs per SM interleave their LDS / FP64 / STS / barrier phases.
+// (History, measured on B200: cp.async/LDGSTS staging costs 16 shared-memory wavefronts per 16-byte warp
+// instruction — 38 % of the shared-memory pipe; direct ld.global into registers leaves only ~32 KB per SM
+// in flight and the passes latency-bound at 0.50-0.55 ms each.)
 //
 // Scheduling: persistent CTAs take tiles from a global ticket counter IN ORDER.  In the 2-D kernels the
 // ticket order interleaves the first pass of plane p + lag with the second pass of plane p, and a
@@ -34,16 +37,37 @@ using namespace fftc;
 
 constexpr int kFftThreads = 256;
 constexpr int kFft2dOcc = 3;      // CTAs per SM: independent barrier domains hide each other's LDS/DP/STS phases
-constexpr int kXSolveOcc = 2;
+constexpr int kXSolveOcc = 2;      // measured: 3 (table of Green's-function factors read from global, 85 registers) is 13 % slower
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// the 128-byte lines touched by [p, p + bytes)
-__device__ __forceinline__ void prefetch_l2_span(const void* p, int bytes) {
-    const char* a = reinterpret_cast<const char*>(p);
-    prefetch_l2(a);
-    if ((reinterpret_cast<uintptr_t>(a) & 127) + bytes > 128) prefetch_l2(a + bytes - 1);
+// ---- PTX helpers: mbarrier + bulk asynchronous copy ----------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// orders this CTA's earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) writes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded: a copy that never lands raises the error flag instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity, int* err) {
+    unsigned spins = 0;
+    while (!mbar_test(bar, parity)) {
+        if (++spins > 64) __nanosleep(40);
+        if (spins > (1u << 22)) { atomicExch(err, 2); break; }
+    }
+}
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -51,63 +75,87 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// persistent, ticket-ordered tile loop
+// persistent, ticket-ordered, double-buffered tile loop
 // ---------------------------------------------------------------------------------------------
 // Job interface:
 //   int  decode(unsigned slot)        item (>= 0), −2: empty slot, −1: past the end
 //   const unsigned* dep(int item)     completion counter the item waits for (nullptr: none)
 //   unsigned dep_need()
-//   void process(int item, V* work)   phases with __syncthreads() in between; global loads in the first,
-//                                     global stores in the last
+//   void issue(int item, V* buf, uint64_t* bar)   thread 0: expect_tx + bulk copies of the item's tile
+//   void process(int item, V* buf)    phases with __syncthreads() in between, in place in buf; the last
+//                                     phase stores to global memory from registers
 //   unsigned* signal(int item)        counter to bump once the item's stores are complete (nullptr: none)
-//   void prefetch(int item)           prefetch.global.L2 over the item's input rows
-// Thread 0 always holds the ticket after the current one (its atomic latency hides behind the tile), and
-// the whole CTA prefetches that next tile into L2 while it works on the current one: the direct
-// global->register loads of a tile's first stage then hit L2 (~4x shorter latency), so the few
-// registers a thread can spare for loads in flight are enough to keep HBM busy.
-// A CTA blocks on a dependency only before it starts a tile, dependencies point to strictly lower
-// tickets and first-pass tiles have none, so the CTA with the lowest blocked ticket can always proceed.
+// While tile t is processed in one buffer, thread 0 has already taken the next ticket and — if that
+// tile's dependency is met — started its copy into the other buffer.  A CTA blocks on a dependency only
+// between tiles (holding no unfinished work); dependencies point to strictly lower tickets and first-pass
+// tiles have none, so the CTA with the lowest blocked ticket can always proceed.
 template <class Job, typename V>
-__device__ __forceinline__ void run_tiles(Job& job, unsigned* ticket, V* work, int* err) {
-    __shared__ int s_item, s_ahead;
+__device__ __forceinline__ void run_tiles(Job& job, unsigned* ticket, V* buf0, V* buf1, int* err) {
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ int s_next[2], s_loaded[2];
     const int tid = threadIdx.x;
-    unsigned slot_next = 0;
-    if (tid == 0) slot_next = atomicAdd(ticket, 1u);
-    for (;;) {
-        __syncthreads();                  // the previous tile is done with `work` and s_item
+    auto fetch = [&]() -> int {
+        int item;
+        do { item = job.decode(atomicAdd(ticket, 1u)); } while (item == -2);
+        if (item >= 0 && *reinterpret_cast<volatile int*>(err) != 0) item = -1;   // something already failed: drain
+        return item;
+    };
+    auto ready = [&](int item) -> bool {
+        const unsigned* d = job.dep(item);
+        return d == nullptr || ld_acquire(d) >= job.dep_need();
+    };
+    auto wait_dep = [&](int item) {
+        unsigned spins = 0;
+        while (!ready(item)) {
+            __nanosleep(100);
+            if (++spins > (1u << 24)) { atomicExch(err, 1); break; }   // seconds: give up loudly, never hang
+        }
+    };
+    auto issue = [&](int item, V* buf, uint64_t* bar) {
+        fence_proxy_async();
+        job.issue(item, buf, bar);
+    };
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+        const int item = fetch();
+        if (item >= 0) {
+            wait_dep(item);
+            issue(item, buf0, &mbar[0]);
+        }
+        s_next[1] = item;
+    }
+    __syncthreads();
+    int cur = s_next[1];
+    for (int it = 0; cur >= 0; ++it) {
+        const int b = it & 1;
+        V* bufc = b ? buf1 : buf0;
+        V* bufn = b ? buf0 : buf1;
         if (tid == 0) {
-            int item = job.decode(slot_next);
-            while (item == -2) item = job.decode(atomicAdd(ticket, 1u));
-            int ahead = -1;
-            if (item >= 0) {
-                slot_next = atomicAdd(ticket, 1u);
-                ahead = job.decode(slot_next);
-                const unsigned* d = job.dep(item);
-                if (d != nullptr) {
-                    unsigned spins = 0;
-                    while (ld_acquire(d) < job.dep_need()) {
-                        __nanosleep(100);
-                        if (++spins > (1u << 24)) { atomicExch(err, 1); break; }   // seconds: give up loudly, never hang
-                    }
-                }
+            const int nxt = fetch();
+            int loaded = 0;
+            if (nxt >= 0 && ready(nxt)) {
+                issue(nxt, bufn, &mbar[b ^ 1]);     // bufn: tile it−1 finished before the barrier that ended it
+                loaded = 1;
             }
-            s_item = item;
-            s_ahead = ahead;
+            s_next[b] = nxt;
+            s_loaded[b] = loaded;
         }
-        __syncthreads();
-        const int item = s_item;
-        if (item < 0) break;
-        const int ahead = s_ahead;
-        if (ahead >= 0) job.prefetch(ahead);
-        job.process(item, work);
-        unsigned* sig = job.signal(item);
-        if (sig != nullptr) {             // uniform over the CTA
-            __syncthreads();              // every thread's stores are issued …
-            if (tid == 0) {
-                __threadfence();          // … and made visible device-wide before the counter moves
-                atomicAdd(sig, 1u);
-            }
+        mbar_wait(&mbar[b], (unsigned)(it >> 1) & 1u, err);   // buffer b's (it/2)-th fill
+        job.process(cur, bufc);
+        __syncthreads();                 // end of tile: every thread's stores are issued, bufc is free, s_next[b] visible
+        unsigned* sig = job.signal(cur);
+        if (tid == 0 && sig != nullptr) {
+            __threadfence();             // … and visible device-wide before the counter moves
+            atomicAdd(sig, 1u);
         }
+        const int nxt = s_next[b];
+        if (nxt >= 0 && !s_loaded[b] && tid == 0) {
+            wait_dep(nxt);
+            issue(nxt, bufn, &mbar[b ^ 1]);
+        }
+        cur = nxt;
     }
 }
 
@@ -123,11 +171,42 @@ __device__ __forceinline__ Twiddles<V> load_twiddles(V* smem, const void* gmem, 
     return tw;
 }
 
+template <class Op, typename V, typename T, int NREGS>
+__device__ __forceinline__ void run_phases(const Op& op, V* buf, const Twiddles<V>& tw) {
+    T rg[NREGS];
+#pragma unroll
+    for (int ph = 0; ph < Op::kPhases; ++ph) {
+        op.phase(ph, buf, tw, threadIdx.x, kFftThreads, rg);
+        if (ph + 1 < Op::kPhases) __syncthreads();
+    }
+}
+
+// tiles that are read directly: ask the copy engine to pull the chunk into L2 and complete the phase at once
+template <class Op>
+__device__ __forceinline__ void issue_prefetch(const Op& op, uint64_t* bar) {
+    const TileLoad l = op.load(0);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(l.src)), "r"((unsigned)l.bytes) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <class Op, typename V>
+__device__ __forceinline__ void issue_loads(const Op& op, int nloads, V* buf, uint64_t* bar) {
+    unsigned total = 0;
+    for (int k = 0; k < nloads; ++k) total += (unsigned)op.load(k).bytes;
+    mbar_expect_tx(bar, total);
+    for (int k = 0; k < nloads; ++k) {
+        const TileLoad l = op.load(k);
+        bulk_g2s(reinterpret_cast<char*>(buf) + l.dst_bytes, l.src, (unsigned)l.bytes, bar);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // 2-D (y,z) transforms of the local planes
 // ---------------------------------------------------------------------------------------------
 struct Fft2dParams {
-    void* interior;       // first interior plane
+    void* interior;       // first interior plane of the padded real slab
+    void* a;              // A: V[nxl][NKT][G][CY]
+    void* b;              // B: V[NKT][G][nxl][CY]
     const void* tw;       // B | C | R twiddle tables (pm_fftcore.cuh)
     int nplanes;
     int mode;             // 0: both passes, dependency-ordered (L2-resident); 1: first pass only; 2: second pass only
@@ -139,7 +218,7 @@ struct Fft2dParams {
 
 template <typename T, int G, int DIR>
 struct Fft2dJob {
-    using S = SlabFFT<T, G>;
+    using S = SlabFFT<T, G, kFftThreads>;
     using V = typename S::V;
     // forward: first pass z (kZTilesPerPlane tiles), second y;  inverse: first y, second z
     static constexpr int nA = DIR < 0 ? S::kZTilesPerPlane : S::kYTilesPerPlane;
@@ -170,51 +249,63 @@ struct Fft2dJob {
     __device__ __forceinline__ unsigned* signal(int item) const {
         return (p.mode == 0 && !(item >> 30)) ? p.done + ((item >> 10) & 0xfffff) : nullptr;
     }
-    __device__ __forceinline__ T* plane(int item) const {
-        return reinterpret_cast<T*>(p.interior) + (size_t)((item >> 10) & 0xfffff) * G * S::Gp;
-    }
     __device__ __forceinline__ bool is_z(int item) const { return (DIR < 0) == ((item >> 30) == 0); }
-
-    __device__ __forceinline__ void prefetch(int item) const {
-        if (p.mode == 0 && (item >> 30)) return;     // second pass in one launch: its input was just written, it is in L2
-        const int t = item & 1023;
-        if (is_z(item)) {                            // CZ contiguous rows
-            const char* base = reinterpret_cast<const char*>(plane(item) + (size_t)t * S::CZ * S::Gp);
-            const int bytes = S::CZ * S::Gp * (int)sizeof(T);
-            for (int o = threadIdx.x * 128; o < bytes + 127; o += kFftThreads * 128) prefetch_l2(base + min(o, bytes - 1));
-        } else {                                     // CY·sizeof(V) = 128 bytes of every row
-            const V* col = reinterpret_cast<const V*>(plane(item)) + t * S::CY;
-            for (int j = threadIdx.x; j < G; j += kFftThreads) prefetch_l2_span(col + (size_t)j * S::Gc, S::CY * (int)sizeof(V));
-        }
+    __device__ __forceinline__ int plane_of(int item) const { return (item >> 10) & 0xfffff; }
+    __device__ __forceinline__ T* plane(int item) const {
+        return reinterpret_cast<T*>(p.interior) + (size_t)plane_of(item) * G * S::Gp;
     }
-    template <class Op>
-    __device__ __forceinline__ void run(const Op& op, V* work) const {
-#pragma unroll
-        for (int ph = 0; ph < Op::kPhases; ++ph) {
-            op.phase(ph, work, tw, threadIdx.x, kFftThreads);
-            if (ph + 1 < Op::kPhases) __syncthreads();
-        }
+    __device__ __forceinline__ V* a_plane(int item) const {
+        return reinterpret_cast<V*>(p.a) + (size_t)plane_of(item) * S::NKT * G * S::CY;
     }
-    __device__ __forceinline__ void process(int item, V* work) const {
-        const int t = item & 1023;
+    __device__ __forceinline__ typename S::ZFwd zfwd(int item) const { return typename S::ZFwd{plane(item), a_plane(item), (item & 1023) * S::CZ}; }
+    __device__ __forceinline__ typename S::ZInv zinv(int item) const { return typename S::ZInv{plane(item), (item & 1023) * S::CZ}; }
+    __device__ __forceinline__ typename S::YFwd yfwd(int item) const {
+        const int kt = item & 1023;
+        return typename S::YFwd{a_plane(item) + (size_t)kt * G * S::CY, reinterpret_cast<V*>(p.b), plane_of(item), kt, p.nplanes};
+    }
+    __device__ __forceinline__ typename S::YInv yinv(int item) const {
+        const int kt = item & 1023;
+        return typename S::YInv{a_plane(item) + (size_t)kt * G * S::CY, plane(item), kt};
+    }
+    __device__ __forceinline__ void issue(int item, V* buf, uint64_t* bar) const {
         if (is_z(item)) {
-            if constexpr (DIR < 0) run(typename S::ZFwd{plane(item), t * S::CZ}, work);
-            else run(typename S::ZInv{plane(item), t * S::CZ}, work);
+            if constexpr (DIR < 0) issue_prefetch(zfwd(item), bar);
+            else issue_prefetch(zinv(item), bar);
         } else {
-            run(typename S::template YPass<DIR>{reinterpret_cast<V*>(plane(item)), t * S::CY}, work);
+            if constexpr (DIR < 0) issue_loads(yfwd(item), 1, buf, bar);
+            else issue_loads(yinv(item), 1, buf, bar);
+        }
+    }
+    __device__ __forceinline__ void process(int item, V* buf) const {
+        if (is_z(item)) {
+            if constexpr (DIR < 0) run_phases<typename S::ZFwd, V, T, S::kRegs>(zfwd(item), buf, tw);
+            else run_phases<typename S::ZInv, V, T, S::kRegs>(zinv(item), buf, tw);
+        } else {
+            if constexpr (DIR < 0) {
+                // the A block is in shared memory now and nobody reads it again before the x solve rewrites
+                // it: drop its (dirty) L2 lines instead of letting them be written back to HBM
+                const typename S::YFwd op = yfwd(item);
+                const char* blk = reinterpret_cast<const char*>(op.a_tile);
+                for (int o = threadIdx.x * 128; o < G * S::CY * (int)sizeof(V); o += kFftThreads * 128)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(__cvta_generic_to_global(blk + o)) : "memory");
+                run_phases<typename S::YFwd, V, T, S::kRegs>(op, buf, tw);
+            } else {
+                run_phases<typename S::YInv, V, T, S::kRegs>(yinv(item), buf, tw);
+            }
         }
     }
 };
 
 template <typename T, int G, int DIR>
 __global__ void __launch_bounds__(kFftThreads, kFft2dOcc) fft2d_kernel(const __grid_constant__ Fft2dParams p) {
-    using S = SlabFFT<T, G>;
+    using S = SlabFFT<T, G, kFftThreads>;
     using V = typename S::V;
-    extern __shared__ __align__(16) unsigned char fft_smem[];
-    V* work = reinterpret_cast<V*>(fft_smem);
-    const Twiddles<V> tw = load_twiddles(work + S::kWorkElems, p.tw, G, true);
+    extern __shared__ __align__(128) unsigned char fft_smem[];
+    V* buf0 = reinterpret_cast<V*>(fft_smem);
+    V* buf1 = buf0 + S::kBufElems;
+    const Twiddles<V> tw = load_twiddles(buf1 + S::kBufElems, p.tw, G, true);
     Fft2dJob<T, G, DIR> job(p, tw);
-    run_tiles(job, p.ticket, work, p.err);
+    run_tiles(job, p.ticket, buf0, buf1, p.err);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -222,59 +313,57 @@ __global__ void __launch_bounds__(kFftThreads, kFft2dOcc) fft2d_kernel(const __g
 // ---------------------------------------------------------------------------------------------
 template <typename T, int G>
 struct XSolveKParams {
-    typename SlabFFT<T, G>::XGeom xg;
+    typename SlabFFT<T, G, kFftThreads>::XGeom xg;
     const void* tw;
-    int j0, njl, self_rank;
+    int j0, njl;
     unsigned* ticket;
     int* err;
 };
 
 template <typename T, int G>
 struct XSolveJob {
-    using S = SlabFFT<T, G>;
+    using S = SlabFFT<T, G, kFftThreads>;
     using V = typename S::V;
     const typename S::XGeom* xg;   // in shared memory
     Twiddles<V> tw;
-    int j0, njl, self_rank;
+    int j0, njl;
+    // column tile fastest: consecutive tickets share a j row
     __device__ __forceinline__ int decode(unsigned slot) const {
-        return slot < (unsigned)(njl * S::kYTilesPerPlane) ? (int)slot : -1;
+        return slot < (unsigned)(njl * S::NKT) ? (int)slot : -1;
     }
     __device__ __forceinline__ const unsigned* dep(int) const { return nullptr; }
     __device__ __forceinline__ unsigned dep_need() const { return 0; }
     __device__ __forceinline__ unsigned* signal(int) const { return nullptr; }
-    __device__ __forceinline__ void prefetch(int item) const {
-        const int jl = item / S::kYTilesPerPlane, t = item - jl * S::kYTilesPerPlane;
-        const int nxl = 1 << xg->nxl_shift;
-        for (int il = threadIdx.x; il < nxl; il += kFftThreads)   // peer planes bypass the local L2: own planes only
-            prefetch_l2_span(xg->at(self_rank * nxl + il, j0 + jl, t * S::CY), S::CY * (int)sizeof(V));
+    __device__ __forceinline__ typename S::XSolve op(int item) const {
+        const int jl = item / S::NKT, kt = item - jl * S::NKT;
+        return typename S::XSolve{xg, j0 + jl, kt};
     }
-    __device__ __forceinline__ void process(int item, V* work) const {
-        const int jl = item / S::kYTilesPerPlane, t = item - jl * S::kYTilesPerPlane;
-        const typename S::XSolve o{xg, j0 + jl, t * S::CY};
-#pragma unroll
-        for (int ph = 0; ph < S::XSolve::kPhases; ++ph) {
-            o.phase(ph, work, tw, threadIdx.x, kFftThreads);
-            if (ph + 1 < S::XSolve::kPhases) __syncthreads();
-        }
+    __device__ __forceinline__ void issue(int item, V* buf, uint64_t* bar) const {
+        const typename S::XSolve o = op(item);
+        issue_loads(o, o.nloads(), buf, bar);
+    }
+    __device__ __forceinline__ void process(int item, V* buf) const {
+        run_phases<typename S::XSolve, V, T, S::kRegs>(op(item), buf, tw);
     }
 };
 
 template <typename T, int G>
 __global__ void __launch_bounds__(kFftThreads, kXSolveOcc) xsolve2_kernel(const __grid_constant__ XSolveKParams<T, G> p) {
-    using S = SlabFFT<T, G>;
+    using S = SlabFFT<T, G, kFftThreads>;
     using V = typename S::V;
-    extern __shared__ __align__(16) unsigned char fft_smem[];
-    V* work = reinterpret_cast<V*>(fft_smem);
-    const Twiddles<V> tw = load_twiddles(work + S::kYTileElems, p.tw, G, false);
-    double* sep = reinterpret_cast<double*>(work + S::kYTileElems + 64 + G);
+    extern __shared__ __align__(128) unsigned char fft_smem[];
+    V* buf0 = reinterpret_cast<V*>(fft_smem);
+    V* buf1 = buf0 + S::kYTileElems;
+    const Twiddles<V> tw = load_twiddles(buf1 + S::kYTileElems, p.tw, G, false);
+    double* sep = reinterpret_cast<double*>(buf1 + S::kYTileElems + 64 + G);
     __shared__ typename S::XGeom s_xg;
     for (int m = threadIdx.x; m < G; m += kFftThreads) sep[m] = p.xg.sep[m];
     if (threadIdx.x == 0) {
         s_xg = p.xg;
         s_xg.sep = sep;
     }
-    XSolveJob<T, G> job{&s_xg, tw, p.j0, p.njl, p.self_rank};
-    run_tiles(job, p.ticket, work, p.err);
+    XSolveJob<T, G> job{&s_xg, tw, p.j0, p.njl};
+    run_tiles(job, p.ticket, buf0, buf1, p.err);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -318,6 +407,10 @@ int make_fft2_tables(pm_ctx* c) {
     c->f2_nctr = 4 + 2 * (size_t)c->g.nxl;
     PM_CHECK_CUDA(cudaMalloc(&c->f2_ctr, sizeof(unsigned) * (c->f2_nctr + 1)));
     PM_CHECK_CUDA(cudaMemset(c->f2_ctr, 0, sizeof(unsigned) * (c->f2_nctr + 1)));
+    // the intermediate layouts A and B live behind the real slab in the same allocation (pm_create),
+    // so that one CUDA-IPC handle exposes all three to the peers
+    c->f2_a = reinterpret_cast<char*>(c->real) + c->f2_off_a;
+    c->f2_b = reinterpret_cast<char*>(c->real) + c->f2_off_b;
     c->f2_lag = 10;   // planes; > CTAs in flight / tiles per plane (444 / 96)
     if (const char* e = getenv("PM_FFT_LAG")) c->f2_lag = std::max(1, atoi(e));
     return PM_OK;
@@ -325,20 +418,22 @@ int make_fft2_tables(pm_ctx* c) {
 
 template <typename T, int G>
 static size_t fft2d_smem() {
-    using S = SlabFFT<T, G>;
-    return sizeof(typename S::V) * ((size_t)S::kWorkElems + twiddle_entries<G>());
+    using S = SlabFFT<T, G, kFftThreads>;
+    return sizeof(typename S::V) * ((size_t)2 * S::kBufElems + twiddle_entries<G>());
 }
 template <typename T, int G>
 static size_t xsolve2_smem() {
-    using S = SlabFFT<T, G>;
-    return sizeof(typename S::V) * ((size_t)S::kYTileElems + 64 + G) + sizeof(double) * G;
+    using S = SlabFFT<T, G, kFftThreads>;
+    return sizeof(typename S::V) * ((size_t)2 * S::kYTileElems + 64 + G) + sizeof(double) * G;
 }
 
 template <typename T, int G, int DIR>
 static int launch_fft2d(pm_ctx* c, int mode) {
-    using S = SlabFFT<T, G>;
+    using S = SlabFFT<T, G, kFftThreads>;
     Fft2dParams p;
     p.interior = c->real_interior<T>();
+    p.a = c->f2_a;
+    p.b = c->f2_b;
     p.tw = c->f2_tw;
     p.nplanes = c->g.nxl;
     p.mode = mode;
@@ -358,17 +453,17 @@ static int launch_fft2d(pm_ctx* c, int mode) {
 
 template <typename T, int G>
 static int launch_xsolve2(pm_ctx* c, double prefactor) {
-    using S = SlabFFT<T, G>;
+    using S = SlabFFT<T, G, kFftThreads>;
     using V = typename S::V;
     const Geom& g = c->g;
     XSolveKParams<T, G> p;
-    for (int r = 0; r < kMaxFftPeers; ++r) p.xg.base[r] = nullptr;
-    if (c->nranks == 1) {
-        p.xg.base[0] = reinterpret_cast<V*>(c->real_interior<T>());
-    } else {
-        for (int r = 0; r < c->nranks; ++r)
-            p.xg.base[r] = reinterpret_cast<V*>(reinterpret_cast<T*>(c->peer_real[r]) + (size_t)g.halo * g.G * g.Gp);
+    for (int r = 0; r < kMaxFftPeers; ++r) { p.xg.a[r] = nullptr; p.xg.b[r] = nullptr; }
+    for (int r = 0; r < c->nranks; ++r) {
+        char* base = reinterpret_cast<char*>(c->nranks == 1 ? c->real : c->peer_real[r]);
+        p.xg.a[r] = reinterpret_cast<V*>(base + c->f2_off_a);
+        p.xg.b[r] = reinterpret_cast<const V*>(base + c->f2_off_b);
     }
+    p.xg.nranks = c->nranks;
     p.xg.nxl_shift = 0;
     while ((1 << p.xg.nxl_shift) < g.nxl) ++p.xg.nxl_shift;
     p.xg.sep = c->xs_sep;
@@ -376,12 +471,11 @@ static int launch_xsolve2(pm_ctx* c, double prefactor) {
     p.tw = c->f2_tw;
     p.j0 = g.j0;
     p.njl = g.njl;
-    p.self_rank = c->rank;
     p.ticket = c->f2_ctr + 1;
     p.err = reinterpret_cast<int*>(c->f2_ctr + c->f2_nctr);
     const size_t smem = xsolve2_smem<T, G>();
     PM_CHECK_CUDA(cudaFuncSetAttribute(xsolve2_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t tiles = (int64_t)g.njl * S::kYTilesPerPlane;
+    const int64_t tiles = (int64_t)g.njl * S::NKT;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * kXSolveOcc);
     PM_LAUNCH((xsolve2_kernel<T, G>), grid, kFftThreads, smem, c->stream, p);
     return PM_OK;

@@ -15,14 +15,15 @@
 // needs no reordering pass, and DIT stage C / DIF stage 1 touch the same positions (the x-solve keeps
 // them in registers across the Green's-function multiply).
 //
-// Tile layouts (template policy L):
-//   ColLayout<C>      element (position p, line c) at p·C + c.  C·sizeof(complex) = 128 B, lanes run
-//                     over c first: every quarter-warp access is one contiguous 128 B — conflict-free
-//                     for any position stride.  Used for the y and x passes (lines are strided in
-//                     global memory; 128 B row segments).
-//   RowLayout<N>      element (p, c) at c·PITCH + p + (p>>3) + (p>>6).  Lanes run over positions; the
-//                     padding keeps the stride-8 and stride-64 accesses of the stages conflict-free.
-//                     Used for the z pass (lines are contiguous in global memory).
+// Tile layouts (template policy L).  nat(p, c) is where the bulk copy from global memory leaves element
+// p of line c; idx(p, c) is where the in-place stages keep it (same footprint, swizzled so that the
+// stride-1, stride-8 and stride-64 accesses of the three stages are bank-conflict free):
+//   ColSwz<C>         [position][C] with C·sizeof(complex) = 64 B; lanes run over c first.  Swizzle:
+//                     position p sits in row p ^ bit3(p) ^ bit6(p).  Used for the y and x passes.
+//   RowSwz<M,C,RAW>   [line][M]; lanes run over positions.  nat has row pitch RAW (the padded global
+//                     rows), idx pitch M with the low three position bits XORed with bits 3-5 and 6-7.
+//                     Used for the z pass.
+//   ColLayout / RowLayout: unswizzled reference layouts (CPU tests).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -135,6 +136,23 @@ struct RowLayout {
     static constexpr int C = C_;
     static constexpr int PITCH = N_ + N_ / 8 + N_ / 64 + 1;
     static PM_HD int idx(int p, int c) { return c * PITCH + p + (p >> 3) + (p >> 6); }
+    template <int P> static PM_HD void decode(int b, int& c, int& u) { u = b % P; c = b / P; }
+};
+
+template <int C_>
+struct ColSwz {
+    static constexpr int C = C_;
+    static PM_HD int swz(int p) { return p ^ ((p >> 3) & 1) ^ ((p >> 6) & 1); }
+    static PM_HD int idx(int p, int c) { return swz(p) * C + c; }
+    static PM_HD int nat(int p, int c) { return p * C + c; }
+    template <int P> static PM_HD void decode(int b, int& c, int& u) { c = b % C; u = b / C; }
+};
+
+template <int M_, int C_, int RAWPITCH_>
+struct RowSwz {
+    static constexpr int C = C_;
+    static PM_HD int idx(int p, int c) { return c * M_ + ((p & ~7) | ((p ^ (p >> 3) ^ ((p >> 6) << 1)) & 7)); }
+    static PM_HD int nat(int p, int c) { return c * RAWPITCH_ + p; }
     template <int P> static PM_HD void decode(int b, int& c, int& u) { u = b % P; c = b / P; }
 };
 
@@ -383,6 +401,110 @@ PM_HD void c2r_pre(const Source& src, V* tile, const V* twR, int tid, int nthr) 
         if (k != kp) {
             const int a1 = kp % R1, a2 = (kp / R1) & 7, a3 = kp / (8 * R1);
             tile[L::idx(64 * a1 + 8 * a2 + a3, c)] = zp;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// in-place variants for tiles that a bulk copy left in natural order (L::nat) in the SAME buffer the
+// stages work in (L::idx): everything is read into registers, the caller places a block barrier,
+// then the results are written.
+// ---------------------------------------------------------------------------------------------
+// NBT = ceil(butterflies / NTHR) butterflies per thread, 16 registers each: rg[16·it + a3] real, rg[16·it + 8 + a3] imaginary
+template <class L, typename T, int N, int NTHR, int NBT, typename V>
+PM_HD void dit_stageA_load(const V* tile, int tid, T (&rg)[16 * NBT]) {
+    constexpr int P = N / 8;
+#pragma unroll
+    for (int it = 0; it < NBT; ++it) {
+        const int b = tid + it * NTHR;
+        if (b < P * L::C) {
+            int c, u;
+            L::template decode<P>(b, c, u);
+#pragma unroll
+            for (int a3 = 0; a3 < 8; ++a3) {
+                const V v = tile[L::nat(u + P * a3, c)];
+                rg[16 * it + a3] = v.x; rg[16 * it + 8 + a3] = v.y;
+            }
+        }
+    }
+}
+
+template <class L, typename T, int N, int DIR, int NTHR, int NBT, typename V>
+PM_HD void dit_stageA_store(V* tile, int tid, T (&rg)[16 * NBT]) {
+    constexpr int R1 = N / 64;
+    constexpr int P = N / 8;
+#pragma unroll
+    for (int it = 0; it < NBT; ++it) {
+        const int b = tid + it * NTHR;
+        if (b < P * L::C) {
+            int c, u;
+            L::template decode<P>(b, c, u);
+            const int a1 = u % R1, a2 = u / R1;
+            T r[8], i[8];
+#pragma unroll
+            for (int a3 = 0; a3 < 8; ++a3) { r[a3] = rg[16 * it + a3]; i[a3] = rg[16 * it + 8 + a3]; }
+            dft8<DIR>(r, i);
+            const int p0 = 64 * a1 + 8 * a2;
+#pragma unroll
+            for (int b3 = 0; b3 < 8; ++b3) {
+                V v; v.x = r[b3]; v.y = i[b3];
+                tile[L::idx(p0 + b3, c)] = v;
+            }
+        }
+    }
+}
+
+// c2r_pre in two halves: ITEMS = ceil((M/2+1)·C / NTHR) pairs (Z_k, Z_{M−k}) per thread in rg[4·ITEMS]
+template <class L, typename T, int M, int NTHR, int ITEMS, typename V>
+PM_HD void c2r_pre_load(const V* tile, const V* twR, int tid, T (&rg)[4 * ITEMS]) {
+    constexpr int P = M / 2 + 1;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int b = tid + it * NTHR;
+        if (b < P * L::C) {
+            int c, k;
+            L::template decode<P>(b, c, k);
+            const int kp = (M - k) & (M - 1);
+            V zk, zp;
+            if (k == 0) {
+                const T x0 = tile[L::nat(0, c)].x;
+                zk.x = x0; zk.y = x0;
+                zp = zk;
+            } else {
+                const V xk = tile[L::nat(k, c)];
+                const V xp = tile[L::nat(kp, c)];
+                const T ar = xk.x + xp.x, ai = xk.y - xp.y;
+                T ur = xk.x - xp.x, ui = xk.y + xp.y;
+                cmul<+1>(ur, ui, tw_r<M>(twR, k));
+                zk.x = ar - ui; zk.y = ai + ur;      // A + i·U
+                zp.x = ar + ui; zp.y = -ai + ur;     // conj(A) + i·conj(U)
+            }
+            rg[4 * it + 0] = zk.x; rg[4 * it + 1] = zk.y; rg[4 * it + 2] = zp.x; rg[4 * it + 3] = zp.y;
+        }
+    }
+}
+
+template <class L, typename T, int M, int NTHR, int ITEMS, typename V>
+PM_HD void c2r_pre_store(V* tile, int tid, const T (&rg)[4 * ITEMS]) {
+    constexpr int R1 = M / 64;
+    constexpr int P = M / 2 + 1;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int b = tid + it * NTHR;
+        if (b < P * L::C) {
+            int c, k;
+            L::template decode<P>(b, c, k);
+            const int kp = (M - k) & (M - 1);
+            V zk, zp;
+            zk.x = rg[4 * it + 0]; zk.y = rg[4 * it + 1]; zp.x = rg[4 * it + 2]; zp.y = rg[4 * it + 3];
+            {
+                const int a1 = k % R1, a2 = (k / R1) & 7, a3 = k / (8 * R1);
+                tile[L::idx(64 * a1 + 8 * a2 + a3, c)] = zk;
+            }
+            if (k != kp) {
+                const int a1 = kp % R1, a2 = (kp / R1) & 7, a3 = kp / (8 * R1);
+                tile[L::idx(64 * a1 + 8 * a2 + a3, c)] = zp;
+            }
         }
     }
 }

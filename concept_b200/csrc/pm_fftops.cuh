@@ -1,19 +1,27 @@
 // pm_fftops.cuh — the tile operations of the hand-written slab transform (pm_fft.cu), built from
-// the stages in pm_fftcore.cuh.  Each operation is a sequence of phases separated by a block barrier;
-// phases take (tid, nthr) so the CPU harness (tests/fft_host_harness.cu) can walk through a whole
-// 3-D solve with exactly this code.  Phase 0 reads its inputs straight from global memory
-// (ld.global.cg, 128-byte row segments) into registers; the last phase stores from registers; in
-// between the tile lives in ONE shared-memory buffer that every stage updates in place.
+// the stages in pm_fftcore.cuh.  Each operation names the contiguous global chunks that make up its
+// tile (`loads`; the kernel moves them with cp.async.bulk, the CPU harness with memcpy) and a sequence
+// of phases separated by a block barrier.  Phases take (tid, nthr) and a small per-thread register
+// file that survives the barriers, so tests/fft_host_harness.cu can walk through a whole 3-D solve
+// with exactly this code.  The tile is processed IN PLACE in the buffer the copy filled.
 //
-// Slab layout (per rank): real T[nxl][G][Gp], Gp = G + 2; in place complex V[nxl][G][Gc], Gc = G/2 + 1
-// (what fft.c:124 calls the padded slab).  The kk = G/2 column is never read or transformed: the
-// potential nullifies that Nyquist plane (mesh.py:3615-3622); the forward z pass stores a zero there.
+// Buffers per rank (complex type V, real type T, CY = 64 bytes / sizeof(V) columns per tile,
+// NKT = (G/2)/CY column tiles; the kk = G/2 Nyquist column, which the potential nullifies
+// (mesh.py:3615-3622), is never stored):
+//   real  T[nxl][G][Gp]            padded real slab, Gp = G + 2 (what fft.c:124 allocates)
+//   A     V[nxl][NKT][G][CY]       a (plane, column tile) block = one contiguous y-pass tile
+//   B     V[NKT][G][nxl][CY]       a (column tile, j) block     = one contiguous x-pass tile per rank
+// Every y/x tile is therefore one contiguous chunk (32 KB in fp64 at G = 512; nxl·64 bytes per peer in
+// the x pass) that the copy engine moves, and every store to A or B is an aligned 64-byte segment.  The
+// z tiles read and write whole contiguous rows directly (their `load` only names the chunk to prefetch):
 //
-//   ZFwd   CZ rows of one plane: r2c along z               (contiguous 4 KB rows)
-//   YPass  CY adjacent kk columns of one plane: c2c along y (forward or inverse; 128 B row segments)
-//   XSolve CY adjacent kk columns of one j row, all planes (of all ranks): forward c2c along x,
-//          Green's function (interactions.py:2092-2118, mesh.py:2775-2856, :3585-3622), inverse c2c
-//   ZInv   CZ rows of one plane: c2r along z
+//   ZFwd   8 rows of a plane:    real rows --r2c along z-->  A                (A ← 16-byte pieces, 64 B runs)
+//   YFwd   A block              --c2c along y-->             B
+//   XSolve B blocks of all ranks --c2c along x · Green's function · inverse c2c along x-->  A (of all ranks)
+//          (interactions.py:2092-2118, mesh.py:2775-2856, :3585-3622; the FFTW-MPI transpose of
+//          fft.c:34-73 never materialises)
+//   YInv   A block              --inverse c2c along y-->     real rows (complex view)
+//   ZInv   8 rows of a plane    --c2r along z-->             real rows
 #pragma once
 
 #include "pm_fftcore.cuh"
@@ -23,8 +31,8 @@ namespace fftc {
 
 constexpr int kMaxFftPeers = 16;
 
-// streaming global load: L2 only (the 2-D kernels hand tiles from one SM to another inside a launch,
-// which L1 would not notice; nothing here is re-read anyway)
+// streaming global load: L2 only (the 2-D kernels hand rows from one SM to another inside a launch, which
+// L1 would not notice; nothing here is re-read anyway)
 template <typename V>
 PM_HD V ld_stream(const V* p) {
 #ifdef __CUDA_ARCH__
@@ -34,32 +42,39 @@ PM_HD V ld_stream(const V* p) {
 #endif
 }
 
-template <typename T, int G_>
+struct TileLoad {
+    const void* src;   // global
+    int dst_bytes;     // byte offset inside the tile buffer
+    int bytes;         // multiple of 16; src and dst 16-byte aligned
+};
+
+template <typename T, int G_, int NTHR_>
 struct SlabFFT {
     using V = typename Vec2<T>::type;
     using TW = Twiddles<V>;
     static constexpr int G = G_;
+    static constexpr int NTHR = NTHR_;
     static constexpr int M = G / 2;          // complex points of the packed real transform
     static constexpr int Gc = M + 1;
     static constexpr int Gp = 2 * Gc;
-    static constexpr int CY = 128 / (int)sizeof(V);   // columns per y/x tile (8 in fp64, 16 in fp32)
-    static constexpr int CZ = 8;                      // rows per z tile
-    using LZ = RowLayout<M, CZ>;
-    using LY = ColLayout<CY>;
-    static constexpr int kZTileElems = LZ::PITCH * CZ;
+    static constexpr int CY = 64 / (int)sizeof(V);   // columns per y/x tile: 4 in fp64, 8 in fp32
+    static constexpr int CZ = 8;                     // rows per z tile
+    static constexpr int NKT = M / CY;               // column tiles
+    using LY = ColSwz<CY>;
+    using LZ = RowSwz<M, CZ, Gc>;
     static constexpr int kYTileElems = G * CY;
-    static constexpr int kWorkElems = (kZTileElems > kYTileElems) ? kZTileElems : kYTileElems;
+    static constexpr int kZTileElems = CZ * M;
+    static constexpr int kBufElems = (kZTileElems > kYTileElems) ? kZTileElems : kYTileElems;
     static constexpr int kZTilesPerPlane = G / CZ;
-    static constexpr int kYTilesPerPlane = M / CY;    // kk = 0 … G/2−1
+    static constexpr int kYTilesPerPlane = NKT;
+    static constexpr int kNbtY = ((G / 8) * CY + NTHR - 1) / NTHR;            // first-stage butterflies per thread, y/x tiles
+    static constexpr int kRegs = 16 * kNbtY;
     static_assert(G % 64 == 0 && M % 64 == 0 && G / 64 <= 8, "G must be 128, 256 or 512");
 
-    struct RowSource {     // complex element k of row c
-        const T* plane; int row0;
-        PM_HD V operator()(int c, int k) const {
-            return ld_stream(reinterpret_cast<const V*>(plane + (size_t)(row0 + c) * Gp) + k);
-        }
-    };
-    struct RowSink {
+    static PM_HD size_t a_index(int il, int kt, int j, int c) { return (((size_t)il * NKT + kt) * G + j) * CY + c; }
+    static PM_HD size_t b_index(int kt, int j, int il, int c, int nxl) { return (((size_t)kt * G + j) * nxl + il) * CY + c; }
+
+    struct RowSink {     // complex slot k of row c of a padded real plane
         T* plane; int row0;
         PM_HD void operator()(int c, int k, T r, T i) const {
             V v; v.x = r; v.y = i;
@@ -67,84 +82,130 @@ struct SlabFFT {
         }
     };
 
-    // ------------------------------------------------------------------ z forward (r2c)
+    struct RowSource {     // complex element k of row c, straight from global memory (L2: the rows were prefetched)
+        const T* plane; int row0;
+        PM_HD V operator()(int c, int k) const {
+            return ld_stream(reinterpret_cast<const V*>(plane + (size_t)(row0 + c) * Gp) + k);
+        }
+    };
+
+    // ------------------------------------------------------------------ z forward (r2c): real rows -> A
+    // The rows are read directly (coalesced 512-byte warp loads, contiguous 4 KB rows) — staging them
+    // through the copy engine would cost the z pass an extra shared-memory round trip and barrier.
     struct ZFwd {
-        T* plane;     // first real of the x plane
-        int row0;     // first of the CZ rows
+        const T* plane;   // first real of the x plane
+        V* a_plane;       // A block row of this plane: V[NKT][G][CY]
+        int row0;         // first of the CZ rows
+        static constexpr bool kBulk = false;
+        PM_HD TileLoad load(int) const { return TileLoad{plane + (size_t)row0 * Gp, 0, CZ * Gp * (int)sizeof(T)}; }
         struct ToTile {
             V* tile;
             PM_HD void operator()(int c, int idx, T r, T i) const { V v; v.x = r; v.y = i; tile[LZ::idx(idx, c)] = v; }
         };
+        struct ToA {
+            V* a_plane; int row0;
+            PM_HD void operator()(int c, int k, T r, T i) const {
+                if (k >= M) return;     // the Nyquist column is not stored
+                V v; v.x = r; v.y = i;
+                a_plane[((size_t)(k / CY) * G + row0 + c) * CY + (k % CY)] = v;
+            }
+        };
         static constexpr int kPhases = 4;
-        PM_HD void phase(int ph, V* work, const TW& tw, int tid, int nthr) const {
-            if (ph == 0) dit_stageA<LZ, T, M, -1>(RowSource{plane, row0}, work, tid, nthr);
-            else if (ph == 1) dit_stageB<LZ, T, M, -1>(work, tw.B, tid, nthr);
-            else if (ph == 2) dit_stageC<LZ, T, M, 2, -1>(work, tw.C, tid, nthr, ToTile{work});
-            else r2c_post<LZ, T, M>(work, tw.R, tid, nthr, RowSink{plane, row0});
+        PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int nthr, T (&)[kRegs]) const {
+            if (ph == 0) dit_stageA<LZ, T, M, -1>(RowSource{plane, row0}, tile, tid, nthr);
+            else if (ph == 1) dit_stageB<LZ, T, M, -1>(tile, tw.B, tid, nthr);
+            else if (ph == 2) dit_stageC<LZ, T, M, 2, -1>(tile, tw.C, tid, nthr, ToTile{tile});
+            else r2c_post<LZ, T, M>(tile, tw.R, tid, nthr, ToA{a_plane, row0});
         }
     };
 
-    // ------------------------------------------------------------------ z inverse (c2r)
+    // ------------------------------------------------------------------ z inverse (c2r): real rows in place
     struct ZInv {
         T* plane;
         int row0;
+        static constexpr bool kBulk = false;
+        PM_HD TileLoad load(int) const { return TileLoad{plane + (size_t)row0 * Gp, 0, CZ * Gp * (int)sizeof(T)}; }
         static constexpr int kPhases = 4;
-        PM_HD void phase(int ph, V* work, const TW& tw, int tid, int nthr) const {
-            if (ph == 0) c2r_pre<LZ, T, M>(RowSource{plane, row0}, work, tw.R, tid, nthr);
-            else if (ph == 1) dit_stageA_inplace<LZ, T, M, +1>(work, tid, nthr);
-            else if (ph == 2) dit_stageB<LZ, T, M, +1>(work, tw.B, tid, nthr);
-            else dit_stageC<LZ, T, M, 2, +1>(work, tw.C, tid, nthr, RowSink{plane, row0});   // z_m = x_2m + i·x_2m+1
+        PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int nthr, T (&)[kRegs]) const {
+            if (ph == 0) c2r_pre<LZ, T, M>(RowSource{plane, row0}, tile, tw.R, tid, nthr);
+            else if (ph == 1) dit_stageA_inplace<LZ, T, M, +1>(tile, tid, nthr);
+            else if (ph == 2) dit_stageB<LZ, T, M, +1>(tile, tw.B, tid, nthr);
+            else dit_stageC<LZ, T, M, 2, +1>(tile, tw.C, tid, nthr, RowSink{plane, row0});   // z_m = x_2m + i·x_2m+1
         }
     };
 
-    // ------------------------------------------------------------------ y pass (c2c, either direction)
-    template <int DIR>
-    struct YPass {
-        V* plane;     // complex view of the x plane: [G][Gc]
-        int kk0;      // first of the CY columns
-        struct Source {
-            const V* plane; int kk0;
-            PM_HD V operator()(int c, int j) const { return ld_stream(plane + (size_t)j * Gc + kk0 + c); }
-        };
-        struct ToPlane {
-            V* plane; int kk0;
+    // ------------------------------------------------------------------ y forward: A block -> B
+    struct YFwd {
+        const V* a_tile;  // A block (plane, kt): V[G][CY]
+        V* b;             // this rank's B
+        int il, kt, nxl;
+        static constexpr bool kBulk = true;
+        PM_HD TileLoad load(int) const { return TileLoad{a_tile, 0, G * CY * (int)sizeof(V)}; }
+        struct ToB {
+            V* b; int il, kt, nxl;
             PM_HD void operator()(int c, int j, T r, T i) const {
                 V v; v.x = r; v.y = i;
-                plane[(size_t)j * Gc + kk0 + c] = v;
+                b[b_index(kt, j, il, c, nxl)] = v;
             }
         };
-        static constexpr int kPhases = 3;
-        PM_HD void phase(int ph, V* work, const TW& tw, int tid, int nthr) const {
-            if (ph == 0) dit_stageA<LY, T, G, DIR>(Source{plane, kk0}, work, tid, nthr);
-            else if (ph == 1) dit_stageB<LY, T, G, DIR>(work, tw.B, tid, nthr);
-            else dit_stageC<LY, T, G, 1, DIR>(work, tw.C, tid, nthr, ToPlane{plane, kk0});
+        static constexpr int kPhases = 4;
+        PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int nthr, T (&rg)[kRegs]) const {
+            T(&ra)[16 * kNbtY] = reinterpret_cast<T(&)[16 * kNbtY]>(rg[0]);
+            if (ph == 0) dit_stageA_load<LY, T, G, NTHR, kNbtY>(tile, tid, ra);
+            else if (ph == 1) dit_stageA_store<LY, T, G, -1, NTHR, kNbtY>(tile, tid, ra);
+            else if (ph == 2) dit_stageB<LY, T, G, -1>(tile, tw.B, tid, nthr);
+            else dit_stageC<LY, T, G, 1, -1>(tile, tw.C, tid, nthr, ToB{b, il, kt, nxl});
         }
     };
 
-    // ------------------------------------------------------------------ x solve
-    struct XGeom {
-        V* base[kMaxFftPeers];   // rank r's first interior plane as complex [nxl][G][Gc]
-        int nxl_shift;           // planes per rank = 1 << nxl_shift
-        const double* sep;       // separable factor per axis index l < G: (x_l/sin x_l)^D·exp(−gauss·k_l²)
-        double prefactor;        // −L²·G_N/π
-        PM_HD V* at(int i, int j, int kk) const {
-            const int r = i >> nxl_shift, il = i & ((1 << nxl_shift) - 1);
-            return base[r] + ((size_t)il * G + j) * Gc + kk;
+    // ------------------------------------------------------------------ y inverse: A block -> real rows
+    struct YInv {
+        const V* a_tile;
+        T* plane;         // padded real plane, written through its complex view [G][Gc]
+        int kt;
+        static constexpr bool kBulk = true;
+        PM_HD TileLoad load(int) const { return TileLoad{a_tile, 0, G * CY * (int)sizeof(V)}; }
+        struct ToRows {
+            T* plane; int kt;
+            PM_HD void operator()(int c, int j, T r, T i) const {
+                V v; v.x = r; v.y = i;
+                reinterpret_cast<V*>(plane + (size_t)j * Gp)[kt * CY + c] = v;
+            }
+        };
+        static constexpr int kPhases = 4;
+        PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int nthr, T (&rg)[kRegs]) const {
+            T(&ra)[16 * kNbtY] = reinterpret_cast<T(&)[16 * kNbtY]>(rg[0]);
+            if (ph == 0) dit_stageA_load<LY, T, G, NTHR, kNbtY>(tile, tid, ra);
+            else if (ph == 1) dit_stageA_store<LY, T, G, +1, NTHR, kNbtY>(tile, tid, ra);
+            else if (ph == 2) dit_stageB<LY, T, G, +1>(tile, tw.B, tid, nthr);
+            else dit_stageC<LY, T, G, 1, +1>(tile, tw.C, tid, nthr, ToRows{plane, kt});
         }
+    };
+
+    // ------------------------------------------------------------------ x solve: B (all ranks) -> A (all ranks)
+    struct XGeom {
+        V* a[kMaxFftPeers];          // rank r's A
+        const V* b[kMaxFftPeers];    // rank r's B
+        int nranks;
+        int nxl_shift;               // planes per rank = 1 << nxl_shift
+        const double* sep;           // separable factor per axis index l < G: (x_l/sin x_l)^D·exp(−gauss·k_l²)
+        double prefactor;            // −L²·G_N/π
     };
     struct XSolve {
         const XGeom* g;
         int j;        // global j row
-        int kk0;      // first of the CY columns
-        struct Source {
-            const XGeom* g; int j, kk0;
-            PM_HD V operator()(int c, int i) const { return ld_stream(g->at(i, j, kk0 + c)); }
-        };
-        struct ToSlab {
-            const XGeom* g; int j, kk0;
+        int kt;       // column tile
+        static constexpr bool kBulk = true;
+        PM_HD int nloads() const { return g->nranks; }
+        PM_HD TileLoad load(int r) const {
+            const int nxl = 1 << g->nxl_shift;
+            return TileLoad{g->b[r] + b_index(kt, j, 0, 0, nxl), r * nxl * CY * (int)sizeof(V), nxl * CY * (int)sizeof(V)};
+        }
+        struct ToA {
+            const XGeom* g; int j, kt;
             PM_HD void operator()(int c, int i, T r, T im) const {
                 V v; v.x = r; v.y = im;
-                *g->at(i, j, kk0 + c) = v;
+                g->a[i >> g->nxl_shift][a_index(i & ((1 << g->nxl_shift) - 1), kt, j, c)] = v;
             }
         };
         // per-mode factor in separable form: Π_l sep[l] · prefactor/k²; zero on the Nyquist planes and at
@@ -161,12 +222,14 @@ struct SlabFFT {
             return (g->sep[i] * sep_jk) * (g->prefactor * (1.0 / (double)k2));
 #endif
         }
-        static constexpr int kPhases = 5;
-        PM_HD void phase(int ph, V* work, const TW& tw, int tid, int nthr) const {
+        static constexpr int kPhases = 6;
+        PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int nthr, T (&rg)[kRegs]) const {
             constexpr int R1 = G / 64;
-            if (ph == 0) dit_stageA<LY, T, G, -1>(Source{g, j, kk0}, work, tid, nthr);
-            else if (ph == 1) dit_stageB<LY, T, G, -1>(work, tw.B, tid, nthr);
-            else if (ph == 2) {
+            T(&ra)[16 * kNbtY] = reinterpret_cast<T(&)[16 * kNbtY]>(rg[0]);
+            if (ph == 0) dit_stageA_load<LY, T, G, NTHR, kNbtY>(tile, tid, ra);
+            else if (ph == 1) dit_stageA_store<LY, T, G, -1, NTHR, kNbtY>(tile, tid, ra);
+            else if (ph == 2) dit_stageB<LY, T, G, -1>(tile, tw.B, tid, nthr);
+            else if (ph == 3) {
                 // forward stage C, Green's function, inverse stage 1 — all on the same R1 registers
                 const int kj = j - (j >= M ? G : 0);
                 for (int b = tid; b < 64 * CY; b += nthr) {
@@ -175,12 +238,12 @@ struct SlabFFT {
                     T r[R1], im[R1];
 #pragma unroll
                     for (int a1 = 0; a1 < R1; ++a1) {
-                        const V v = work[LY::idx(64 * a1 + q, c)];
+                        const V v = tile[LY::idx(64 * a1 + q, c)];
                         r[a1] = v.x; im[a1] = v.y;
                         if (a1) cmul<-1>(r[a1], im[a1], tw.C[a1 * 64 + q]);
                     }
                     dftR<R1, -1>(r, im);
-                    const int kk = kk0 + c;
+                    const int kk = kt * CY + c;
                     const double sep_jk = g->sep[j] * g->sep[kk];
                     const int kj2_kk2 = kj * kj + kk * kk;
                     const bool line_nyq = (j == M) || (kk == M);
@@ -189,10 +252,10 @@ struct SlabFFT {
                         const T f = (T)factor(64 * b1 + q, sep_jk, kj2_kk2, line_nyq);
                         r[b1] *= f; im[b1] *= f;
                     }
-                    dif_stage1_regs<LY, T, G, 1, +1>(r, im, work, tw.C, c, q);
+                    dif_stage1_regs<LY, T, G, 1, +1>(r, im, tile, tw.C, c, q);
                 }
-            } else if (ph == 3) dif_stage2<LY, T, G, +1>(work, tw.B, tid, nthr);
-            else dif_stage3<LY, T, G, +1>(work, tid, nthr, ToSlab{g, j, kk0});
+            } else if (ph == 4) dif_stage2<LY, T, G, +1>(tile, tw.B, tid, nthr);
+            else dif_stage3<LY, T, G, +1>(tile, tid, nthr, ToA{g, j, kt});
         }
     };
 };

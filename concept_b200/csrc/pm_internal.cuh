@@ -140,7 +140,10 @@ struct pm_ctx {
     bool fused_solve;         // use the fused path when supported
     int solve_mode;           // PM_SOLVE_* (pmgrav.h): which implementation pm_solve_fused / pm_kick_long use
     // hand-written slab transform (pm_fft.cu)
-    void* f2_tw;              // e^{−2πi m/G} in the grid's precision
+    void* f2_tw;              // twiddle tables B | C | R in the grid's precision
+    void* f2_a;               // intermediate layouts A and B (pm_fftops.cuh), inside the `real` allocation
+    void* f2_b;
+    size_t f2_off_a, f2_off_b; // their byte offsets from `real` (the same on every rank)
     unsigned* f2_ctr;         // tickets, per-plane completion counters, error flag (last entry)
     size_t f2_nctr;
     int f2_lag;

@@ -3,7 +3,9 @@
 // long-double DFT.  Built and run by tests/test_fftcore_host.py (no GPU needed).
 #include <cmath>
 #include <cstdio>
+#include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -195,12 +197,12 @@ static double test_real(int nthr) {
     return err;
 }
 
-// ---- a whole fused solve on the CPU: z/y forward per plane, x solve, y/z inverse ------------------
+// ---- a whole fused solve on the CPU: real -> A -> B -> A -> real, exactly the device tile operations ----
 template <typename T, int G>
 static int solve3d(const char* fin, const char* fsep, const char* fout, double prefactor, int nranks) {
-    using S = SlabFFT<T, G>;
+    constexpr int nthr = 256;
+    using S = SlabFFT<T, G, nthr>;
     using V = typename S::V;
-    const int nthr = 256;
     const int nxl = G / nranks;
     std::vector<double> in((size_t)G * G * G), sep(G);
     FILE* f = fopen(fin, "rb");
@@ -209,37 +211,48 @@ static int solve3d(const char* fin, const char* fsep, const char* fout, double p
     f = fopen(fsep, "rb");
     if (!f || fread(sep.data(), sizeof(double), G, f) != (size_t)G) return 2;
     fclose(f);
-    // one padded slab per "rank"
-    std::vector<std::vector<T>> slab(nranks, std::vector<T>((size_t)nxl * G * S::Gp, (T)7));   // padding holds garbage
+    // per "rank": padded real slab (padding holds garbage), A and B
+    std::vector<std::vector<T>> slab(nranks, std::vector<T>((size_t)nxl * G * S::Gp, (T)7));
+    std::vector<std::vector<V>> A(nranks, std::vector<V>((size_t)nxl * S::M * G)), B(nranks, std::vector<V>((size_t)nxl * S::M * G));
     for (int i = 0; i < G; ++i)
         for (int j = 0; j < G; ++j)
             for (int k = 0; k < G; ++k)
                 slab[i / nxl][((size_t)(i % nxl) * G + j) * S::Gp + k] = (T)in[((size_t)i * G + j) * G + k];
     HostTw<V> ht(G);
-    std::vector<V> work(S::kWorkElems + 16);
-    auto run = [&](auto& op) {
+    std::vector<V> buf(S::kBufElems + 16);
+    std::vector<T> regs((size_t)nthr * S::kRegs);
+    auto run = [&](const auto& op, int nloads) {
+        for (int k = 0; k < nloads && op.kBulk; ++k) {
+            const TileLoad l = op.load(k);
+            if (l.bytes % 16 || l.dst_bytes % 16 || ((uintptr_t)l.src) % 16) { printf("misaligned load\n"); exit(3); }
+            memcpy(reinterpret_cast<char*>(buf.data()) + l.dst_bytes, l.src, l.bytes);
+        }
         for (int ph = 0; ph < op.kPhases; ++ph)
-            for (int t = 0; t < nthr; ++t) op.phase(ph, work.data(), ht.tw, t, nthr);
+            for (int t = 0; t < nthr; ++t)
+                op.phase(ph, buf.data(), ht.tw, t, nthr, reinterpret_cast<T(&)[S::kRegs]>(regs[(size_t)t * S::kRegs]));
     };
     for (int r = 0; r < nranks; ++r)
         for (int p = 0; p < nxl; ++p) {
             T* plane = slab[r].data() + (size_t)p * G * S::Gp;
-            for (int t = 0; t < S::kZTilesPerPlane; ++t) { typename S::ZFwd op{plane, t * S::CZ}; run(op); }
-            for (int t = 0; t < S::kYTilesPerPlane; ++t) { typename S::template YPass<-1> op{reinterpret_cast<V*>(plane), t * S::CY}; run(op); }
+            V* a_plane = A[r].data() + (size_t)p * S::NKT * G * S::CY;
+            for (int t = 0; t < S::kZTilesPerPlane; ++t) run(typename S::ZFwd{plane, a_plane, t * S::CZ}, 1);
+            for (int kt = 0; kt < S::NKT; ++kt) run(typename S::YFwd{a_plane + (size_t)kt * G * S::CY, B[r].data(), p, kt, nxl}, 1);
         }
     typename S::XGeom xg;
-    for (int r = 0; r < kMaxFftPeers; ++r) xg.base[r] = r < nranks ? reinterpret_cast<V*>(slab[r].data()) : nullptr;
+    for (int r = 0; r < kMaxFftPeers; ++r) { xg.a[r] = r < nranks ? A[r].data() : nullptr; xg.b[r] = r < nranks ? B[r].data() : nullptr; }
+    xg.nranks = nranks;
     xg.nxl_shift = 0;
     while ((1 << xg.nxl_shift) < nxl) ++xg.nxl_shift;
     xg.sep = sep.data();
     xg.prefactor = prefactor;
     for (int j = 0; j < G; ++j)
-        for (int t = 0; t < S::kYTilesPerPlane; ++t) { typename S::XSolve op{&xg, j, t * S::CY}; run(op); }
+        for (int kt = 0; kt < S::NKT; ++kt) run(typename S::XSolve{&xg, j, kt}, nranks);
     for (int r = 0; r < nranks; ++r)
         for (int p = 0; p < nxl; ++p) {
             T* plane = slab[r].data() + (size_t)p * G * S::Gp;
-            for (int t = 0; t < S::kYTilesPerPlane; ++t) { typename S::template YPass<+1> op{reinterpret_cast<V*>(plane), t * S::CY}; run(op); }
-            for (int t = 0; t < S::kZTilesPerPlane; ++t) { typename S::ZInv op{plane, t * S::CZ}; run(op); }
+            V* a_plane = A[r].data() + (size_t)p * S::NKT * G * S::CY;
+            for (int kt = 0; kt < S::NKT; ++kt) run(typename S::YInv{a_plane + (size_t)kt * G * S::CY, plane, kt}, 1);
+            for (int t = 0; t < S::kZTilesPerPlane; ++t) run(typename S::ZInv{plane, t * S::CZ}, 1);
         }
     std::vector<double> out((size_t)G * G * G);
     for (int i = 0; i < G; ++i)
@@ -254,11 +267,13 @@ static int solve3d(const char* fin, const char* fsep, const char* fout, double p
 
 int main(int argc, char** argv) {
     if (argc >= 8 && std::string(argv[1]) == "solve3d") {
-        // solve3d <f64|f32> <in.bin> <sep.bin> <out.bin> <prefactor> <nranks>     (G = 128)
+        // solve3d <f64|f32> <in.bin> <sep.bin> <out.bin> <prefactor> <nranks> [G = 128 | 256]
         const double pre = atof(argv[6]);
         const int nr = atoi(argv[7]);
-        return std::string(argv[2]) == "f64" ? solve3d<double, 128>(argv[3], argv[4], argv[5], pre, nr)
-                                             : solve3d<float, 128>(argv[3], argv[4], argv[5], pre, nr);
+        const int G = argc >= 9 ? atoi(argv[8]) : 128;
+        const bool f64 = std::string(argv[2]) == "f64";
+        if (G == 256) return f64 ? solve3d<double, 256>(argv[3], argv[4], argv[5], pre, nr) : solve3d<float, 256>(argv[3], argv[4], argv[5], pre, nr);
+        return f64 ? solve3d<double, 128>(argv[3], argv[4], argv[5], pre, nr) : solve3d<float, 128>(argv[3], argv[4], argv[5], pre, nr);
     }
     int fails = 0;
     auto report = [&](const char* name, double err, double tol) {

@@ -38,11 +38,10 @@ def _sep_table(G, deconv, gauss):
     return (x/np.sin(x))**deconv*np.exp(-gauss*k*k), k
 
 
-@pytest.mark.parametrize('dtype,nranks,tol', [('f64', 1, 1e-12), ('f64', 4, 1e-12), ('f32', 2, 2e-5)])
-def test_whole_solve_against_numpy(harness, dtype, nranks, tol):
+@pytest.mark.parametrize('dtype,nranks,tol,G', [('f64', 1, 1e-12, 128), ('f64', 4, 1e-12, 128), ('f32', 2, 2e-5, 128), ('f64', 2, 1e-12, 256)])
+def test_whole_solve_against_numpy(harness, dtype, nranks, tol, G):
     """z/y forward, x solve with the Green's function, y/z inverse — vs rfftn · factor · irfftn."""
     exe, d = harness
-    G = 128
     rng = np.random.default_rng(5)
     rho = rng.standard_normal((G, G, G))
     sep, k = _sep_table(G, 4, 0.0)
@@ -50,7 +49,7 @@ def test_whole_solve_against_numpy(harness, dtype, nranks, tol):
     fin, fsep, fout = (os.path.join(d, n) for n in ('in.bin', 'sep.bin', 'out.bin'))
     rho.tofile(fin)
     sep.tofile(fsep)
-    r = subprocess.run([exe, 'solve3d', dtype, fin, fsep, fout, repr(pre), str(nranks)], capture_output=True, text=True)
+    r = subprocess.run([exe, 'solve3d', dtype, fin, fsep, fout, repr(pre), str(nranks), str(G)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     got = np.fromfile(fout).reshape(G, G, G)
     # reference: Nyquist planes and origin nullified, separable factor · prefactor/k²
