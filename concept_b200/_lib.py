@@ -59,6 +59,7 @@ SIGNATURES = {
     'pm_fused_solve_available': (c_int, [c_void_p]),
     'pm_set_fused_solve': (c_int, [c_void_p, c_int]),
     'pm_check_async_error': (c_int, [c_void_p]),
+    'pm_power_k2': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'pm_slab_save': (c_int, [c_void_p]),
     'pm_slab_accumulate': (c_int, [c_void_p]),
     'pm_slab_restore': (c_int, [c_void_p]),

@@ -328,6 +328,11 @@ int pm_check_async_error(pm_ctx* c) {
     return fft2_check_error(c);
 }
 
+int pm_power_k2(pm_ctx* c, int k2_max, double* power, unsigned long long* count) {
+    PM_REQUIRE(c != nullptr, "pm_power_k2: NULL context");
+    return launch_power_k2(c, k2_max, power, count);
+}
+
 int pm_slab_save(pm_ctx* c) { PM_REQUIRE(c != nullptr, "NULL context"); return slab_copy(c, 0); }
 int pm_slab_accumulate(pm_ctx* c) { PM_REQUIRE(c != nullptr, "NULL context"); return slab_copy(c, 1); }
 int pm_slab_restore(pm_ctx* c) { PM_REQUIRE(c != nullptr, "NULL context"); return slab_copy(c, 2); }

@@ -143,6 +143,52 @@ int launch_kspace(pm_ctx* c, double prefactor, int deconv_order, double gauss, d
 }
 
 // ---------------------------------------------------------------------------
+// power per integer k² (compute_powerspec, analysis.py:500-547)
+// ---------------------------------------------------------------------------
+// Visits the modes of fourier_loop(gridsize, sparse=True, skip_origin=True, k2_max) (mesh.py:2615-2890):
+// Nyquist planes and the origin excluded; on the kk = 0 plane only one point of every complex-conjugate
+// pair (ki > 0 and (ki = 0, kj > 0) skipped, mesh.py:2813-2826); k² ≤ k2_max.  power[k²] += re² + im²,
+// count[k²] += 1 (the multiplicity get_powerspec_bins tallies on the host, analysis.py:303-312).
+template <typename T>
+__global__ void __launch_bounds__(256)
+power_k2_kernel(const typename Cplx<T>::type* __restrict__ slab, Geom g, int k2_max,
+                double* __restrict__ power, unsigned long long* __restrict__ count) {
+    const int nyq = g.G / 2;
+    const int64_t total = (int64_t)g.G * g.njl * g.Gc;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / g.Gc;
+        const int kk = (int)(idx - row * g.Gc);
+        const int i = (int)(row / g.njl);
+        const int j = g.j0 + (int)(row - (int64_t)i * g.njl);
+        if (i == nyq || j == nyq || kk == nyq) continue;
+        const int ki = i - (i >= nyq ? g.G : 0);
+        const int kj = j - (j >= nyq ? g.G : 0);
+        if (kk == 0 && (ki > 0 || (ki == 0 && kj >= 0))) continue;   // conjugate pairs and the origin
+        const int k2 = (kj * kj + ki * ki) + kk * kk;
+        if (k2 > k2_max) continue;
+        const typename Cplx<T>::type v = slab[idx];
+        const double re = (double)v.x, im = (double)v.y;
+        atomicAdd(power + k2, re * re + im * im);
+        if (count != nullptr) atomicAdd(count + k2, 1ULL);
+    }
+}
+
+int launch_power_k2(pm_ctx* c, int k2_max, double* power, unsigned long long* count) {
+    PM_REQUIRE(c->space_fourier, "pm_power_k2: the slab holds real-space data (call pm_fft_forward)");
+    PM_REQUIRE(k2_max >= 1 && power != nullptr, "pm_power_k2: bad argument");
+    const int grid = kNumSMs * 8;
+    if (c->dtype == PM_GRID_F64) {
+        PM_LAUNCH((power_k2_kernel<double>), grid, 256, 0, c->stream, reinterpret_cast<const double2*>(c->fourier), c->g,
+                  k2_max, power, count);
+    } else {
+        PM_LAUNCH((power_k2_kernel<float>), grid, 256, 0, c->stream, reinterpret_cast<const float2*>(c->fourier), c->g,
+                  k2_max, power, count);
+    }
+    return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
 // slab save / accumulate / restore
 // ---------------------------------------------------------------------------
 template <typename T>

@@ -187,6 +187,7 @@ int fft_backward(pm_ctx* c);
 int launch_kspace(pm_ctx* c, double prefactor, int deconv_order, double gauss, double scale,
                   const double* shift, int diff_dim, bool from_saved, bool potential);
 int slab_copy(pm_ctx* c, int mode);  // 0 save, 1 accumulate, 2 restore
+int launch_power_k2(pm_ctx* c, int k2_max, double* power, unsigned long long* count);
 // implemented in pm_particles.cu
 int launch_drift(pm_ctx* c, double* pos, const double* mom, int64_t n, double dt_over_mass);
 int launch_sum_mom2(pm_ctx* c, const double* mom, int64_t n, double* out);

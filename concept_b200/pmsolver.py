@@ -158,6 +158,11 @@ class PMContext:
     def fourier_operate(self, deconv_order=0, shift=None, scale=1.0, diff_dim=-1, from_saved=False):
         check(self.lib.pm_fourier_operate(self._h, int(deconv_order), vec3(shift), float(scale), int(diff_dim), int(from_saved)))
 
+    def power_k2(self, k2_max, power, count=None):
+        """power[k²] += |mode|² (and count[k²] += 1) over the sparse half-space; device tensors of k2_max + 1 entries
+        (float64 / int64)."""
+        check(self.lib.pm_power_k2(self._h, int(k2_max), _ptr(power), _ptr(count)))
+
     def slab_save(self):
         check(self.lib.pm_slab_save(self._h))
 

@@ -144,6 +144,12 @@ int pm_set_fused_solve(pm_ctx* ctx, int mode);
 /* Host-synchronising check of the asynchronous give-up flag of the dependency-ordered kernels
  * (a tile dependency that was not satisfied within seconds); PM_ERR_ARG with a message if set. */
 int pm_check_async_error(pm_ctx* ctx);
+/* The mode loop of compute_powerspec (analysis.py:500-547) on the Fourier slab: for every mode of
+ * fourier_loop(gridsize, sparse=True, skip_origin=True, k2_max) (mesh.py:2615-2890)
+ *   power[k²] += re² + im²   and, if count != NULL,   count[k²] += 1
+ * (device arrays of k2_max + 1 entries, not zeroed here; k² in grid units).  With several ranks every
+ * rank adds its part of the slab; the host code sums over ranks (Reduce, analysis.py:549-553). */
+int pm_power_k2(pm_ctx* ctx, int k2_max, double* power, unsigned long long* count);
 int pm_slab_save(pm_ctx* ctx);      /* slab_updownstream_subgroup[...] = slab (interactions.py:2256) */
 int pm_slab_accumulate(pm_ctx* ctx);/* saved += working slab (copy_modes '+=' for interlacing) */
 int pm_slab_restore(pm_ctx* ctx);   /* working slab = saved */

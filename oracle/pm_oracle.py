@@ -387,3 +387,45 @@ def get_rung(acc, current, rung_factor, n_rungs):
 def rung_factor(dt, fac_softening, softening_length):
     """Component.get_rung_factor (species.py:2362-2370)"""
     return 0.5*np.log2(dt**2/(2*fac_softening*softening_length))
+
+
+# --------------------------------------------------------------------------
+# power spectrum (§8f rank 1): analysis.py:235-579
+# --------------------------------------------------------------------------
+def sparse_mode_mask(G, k2_max):
+    """Modes visited by fourier_loop(G, sparse=True, skip_origin=True, k2_max) (mesh.py:2615-2890): no
+    Nyquist planes, no origin, one point of each conjugate pair on the kk = 0 plane (ki > 0 and
+    (ki = 0, kj > 0) skipped, mesh.py:2813-2826), k² ≤ k2_max.  Natural layout [i, j, kk]."""
+    ki = signed_wavenumbers(G)
+    m = mode_mask(G) & (k2_grid(G) <= k2_max)
+    skip0 = (ki[:, None] > 0) | ((ki[:, None] == 0) & (ki[None, :] >= 0))
+    m[:, :, 0] &= ~skip0
+    return m
+
+
+def density_fourier(pos, mass, a, boxsize, gridsize, order, deconvolve=True, interlace=True, w_eff=0.0):
+    """interpolate_upstream(components, …, 'ρ', order, deconvolve, interlace, output_space='Fourier')
+    (mesh.py:492-616) for one particle component: for every lattice deposit ρ with the G⁻³ FFT factor,
+    forward FFT, nullify Nyquist, deconvolve^order and rotate by the lattice phase, each /n_lattices."""
+    G = int(gridsize)
+    contribution = a**(-3*(1 + w_eff))*mass
+    contribution *= float(G)**(-3)*(G/boxsize)**3
+    shifts = [(0.0, 0.0, 0.0), (-0.5, -0.5, -0.5)] if interlace else [(0.0, 0.0, 0.0)]
+    slab = np.zeros((G, G, G//2 + 1), dtype=np.complex128)
+    for shift in shifts:
+        s = forward_fft(deposit(pos, boxsize, G, order, contribution, shift))
+        s[~mode_mask(G)] = 0
+        s = s*(deconv_factor(G, order*bool(deconvolve))*(1/len(shifts)))
+        if any(shift):
+            s = s*interlace_phase(G, shift)
+        slab += s
+    return slab
+
+
+def power_by_k2(slab, k2_max):
+    """The mode loop of compute_powerspec before binning: Σ|δ̂|² and multiplicity per integer k²."""
+    G = slab.shape[0]
+    m = sparse_mode_mask(G, k2_max)
+    k2 = k2_grid(G)[m]
+    p = (slab.real**2 + slab.imag**2)[m]
+    return np.bincount(k2, weights=p, minlength=k2_max + 1), np.bincount(k2, minlength=k2_max + 1)
