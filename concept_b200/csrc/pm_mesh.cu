@@ -393,8 +393,11 @@ int launch_gather(pm_ctx* c, int which, const double* pos, double* mom, int64_t 
 // reassociation (last-bit differences; the stated kick tolerance is 1e-9).
 constexpr int kGkChunkTiles = 16;  // 2048 consecutive particles per ticket
 
+// CIC with a 2-point difference: cap the kernel at 80 registers (6 CTAs = 24 warps per SM).  The kernel waits on
+// L1/L2 gathers 78 % of the time (ncu), so warps in flight matter more than the 50 bytes of spills: measured
+// 0.88 -> 0.77 ms; a cap of 64 registers (8 CTAs) spills too much (0.92 ms).  The wider stencils keep their registers.
 template <int ORDER, int REACH, typename T, bool DRIFT>
-__global__ void __launch_bounds__(kGkBlock)
+__global__ void __launch_bounds__(kGkBlock, (ORDER <= 2 && REACH == 1) ? 6 : 1)
 gather_kick_kernel(const T* __restrict__ phi, double* __restrict__ pos,
                    double* __restrict__ mom, int64_t n, Geom g, Coord co, FD fd, double factor,
                    double* __restrict__ sum_mom2, unsigned long long* __restrict__ tile_counter,

@@ -10,6 +10,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from concept_b200 import _lib  # noqa: E402
+if os.environ.get('PM_LIB_PATH'):      # experiment builds of the library (development only)
+    _lib.LIB_PATH = os.environ['PM_LIB_PATH']
 from concept_b200.pmsolver import PMContext, make_kick_params  # noqa: E402
 from concept_b200.synthetic import zeldovich_particles  # noqa: E402
 
