@@ -352,9 +352,15 @@ def run_gpu(args):
                  'gather_kick_drift': 'gather_kick_kernel<2,1,double,drift> (fused gradient + CIC gather + kick + sum mom^2 + drift)',
                  'deposit': 'deposit_kernel<2,double> (CIC scatter, red.global.add.f64)', 'grid_zero': 'cudaMemsetAsync'}
         dom = max((k for k in alg if k in names), key=lambda k: kernels[k]['ms'])
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+                traffic = json.load(f)['dram_bytes_per_launch'].get(dom) if world == 1 else None
+        except Exception:
+            traffic = None
         b_alg = 120*n_total + 48*GRID**3
         roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': kernels[dom]['achieved_GBps'], 'peak': peak, 'unit': 'GB/s',
-                    'frac': kernels[dom]['achieved_GBps']/peak, 'traffic': None,
+                    'frac': kernels[dom]['achieved_GBps']/peak, 'traffic': traffic,
                     'peak_source': peak_src, 'kernel_ms': kernels[dom]['ms'], 'algorithmic_bytes_per_launch': alg[dom],
                     'kernels': kernels,
                     'cycle': {'algorithmic_bytes': b_alg, 'achieved_GBps_per_gpu': b_alg/world/(ms_step*1e-3)/1e9,
