@@ -29,6 +29,14 @@ int ensure_force(pm_ctx* c) {
     return PM_OK;
 }
 
+int ensure_in_real(pm_ctx* c) {
+    if (!c->grid_in_phi) return PM_OK;
+    PM_CHECK_CUDA(cudaMemcpyAsync(c->real, c->phi, c->real_elems * c->elem_size(), cudaMemcpyDeviceToDevice, c->stream));
+    c->grid_in_phi = false;
+    c->real_is_zero = false;
+    return PM_OK;
+}
+
 static int halo_for_gather(int order, int diff_order, int interlace, int* lo, int* hi) {
     // planes touched along x beyond the slab: interpolation reach + difference reach; the
     // half-cell lattice shift of interlacing moves the footprint by up to one more plane
@@ -55,7 +63,7 @@ static int get_grid_t(pm_ctx* c, int which, double* host_out) {
         for (size_t i = 0; i < n; ++i) host_out[i] = (double)tmp[i];
         return PM_OK;
     }
-    const T* src = reinterpret_cast<const T*>(which == PM_TAP_FORCE ? c->force : c->real) +
+    const T* src = reinterpret_cast<const T*>(which == PM_TAP_FORCE ? c->force : c->grid_read()) +
                    (size_t)g.halo * g.G * g.Gp;
     const size_t n = (size_t)g.nxl * g.G * g.Gp;
     std::vector<T> tmp(n);
@@ -74,6 +82,8 @@ static int set_grid_t(pm_ctx* c, const double* host_in) {
         for (int k = 0; k < g.G; ++k) tmp[r * g.Gp + k] = (T)host_in[r * g.G + k];
     T* dst = reinterpret_cast<T*>(c->real) + (size_t)g.halo * g.G * g.Gp;
     PM_CHECK_CUDA(cudaMemcpy(dst, tmp.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+    c->grid_in_phi = false;
+    c->real_is_zero = false;
     return PM_OK;
 }
 
@@ -146,6 +156,7 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
     }
     c->bytes_allocated += alloc_bytes;
     cudaMemsetAsync(c->real, 0, c->real_elems * es, c->stream);
+    c->real_is_zero = true;
     if (nranks == 1) {
         c->fourier = c->real;
     } else {
@@ -209,6 +220,7 @@ int pm_destroy(pm_ctx* c) {
     cudaFree(c->sr_tmp);
     if (c->fourier && c->fourier != c->real) cudaFree(c->fourier);
     cudaFree(c->real);
+    cudaFree(c->phi);
     cudaFree(c->saved);
     cudaFree(c->force);
     cudaFree(c->sendbuf);
@@ -261,7 +273,10 @@ int64_t pm_device_bytes(const pm_ctx* c) { return c ? c->bytes_allocated : 0; }
 // ---- mesh operators ---------------------------------------------------------
 int pm_grid_zero(pm_ctx* c) {
     PM_REQUIRE(c != nullptr, "pm_grid_zero: NULL context");
-    PM_CHECK_CUDA(cudaMemsetAsync(c->real, 0, c->real_elems * c->elem_size(), c->stream));
+    // (after a fused solve on one rank the forward transform has already nullified the grid)
+    if (!c->real_is_zero) PM_CHECK_CUDA(cudaMemsetAsync(c->real, 0, c->real_elems * c->elem_size(), c->stream));
+    c->real_is_zero = true;
+    c->grid_in_phi = false;
     c->space_fourier = false;
     return PM_OK;
 }
@@ -269,6 +284,9 @@ int pm_grid_zero(pm_ctx* c) {
 int pm_deposit(pm_ctx* c, const double* pos, int64_t n, int order, double contribution, const double* shift) {
     PM_REQUIRE(c != nullptr && (pos != nullptr || n == 0) && n >= 0, "pm_deposit: bad argument");
     PM_REQUIRE(!c->space_fourier, "pm_deposit: the slab holds Fourier data (call pm_grid_zero)");
+    if (c->grid_in_phi && !c->real_is_zero) PM_TRY(ensure_in_real(c));
+    c->grid_in_phi = false;       // the density grid is `real`
+    if (n > 0) c->real_is_zero = false;
     return launch_deposit(c, pos, n, order, contribution, shift);
 }
 

@@ -204,7 +204,8 @@ __device__ __forceinline__ void issue_loads(const Op& op, int nloads, V* buf, ui
 // 2-D (y,z) transforms of the local planes
 // ---------------------------------------------------------------------------------------------
 struct Fft2dParams {
-    void* interior;       // first interior plane of the padded real slab
+    void* interior;       // first interior plane of the padded real slab (forward: input; inverse: output)
+    int clear_input;      // forward: nullify the real rows once read
     void* a;              // A: V[nxl][NKT][G][CY]
     void* b;              // B: V[NKT][G][nxl][CY]
     const void* tw;       // B | C | R twiddle tables (pm_fftcore.cuh)
@@ -257,7 +258,7 @@ struct Fft2dJob {
     __device__ __forceinline__ V* a_plane(int item) const {
         return reinterpret_cast<V*>(p.a) + (size_t)plane_of(item) * S::NKT * G * S::CY;
     }
-    __device__ __forceinline__ typename S::ZFwd zfwd(int item) const { return typename S::ZFwd{plane(item), a_plane(item), (item & 1023) * S::CZ}; }
+    __device__ __forceinline__ typename S::ZFwd zfwd(int item) const { return typename S::ZFwd{plane(item), a_plane(item), (item & 1023) * S::CZ, p.clear_input != 0}; }
     __device__ __forceinline__ typename S::ZInv zinv(int item) const { return typename S::ZInv{plane(item), (item & 1023) * S::CZ}; }
     __device__ __forceinline__ typename S::YFwd yfwd(int item) const {
         const int kt = item & 1023;
@@ -278,6 +279,8 @@ struct Fft2dJob {
     }
     __device__ __forceinline__ void process(int item, V* buf) const {
         if (is_z(item)) {
+            // (self-cleaning density grid: the forward z tiles nullify the rows they have consumed — plain stores;
+            // bulk stores from a block of zeros in shared memory were measured slower, 1.01 vs 0.97 ms)
             if constexpr (DIR < 0) run_phases<typename S::ZFwd, V, T, S::kRegs>(zfwd(item), buf, tw);
             else run_phases<typename S::ZInv, V, T, S::kRegs>(zinv(item), buf, tw);
         } else {
@@ -431,7 +434,10 @@ template <typename T, int G, int DIR>
 static int launch_fft2d(pm_ctx* c, int mode) {
     using S = SlabFFT<T, G, kFftThreads>;
     Fft2dParams p;
-    p.interior = c->real_interior<T>();
+    // one rank: the density grid cleans itself and the potential goes to `phi` (pm_internal.cuh)
+    const bool self_clean = c->nranks == 1 && c->phi != nullptr;
+    p.interior = (DIR > 0 && self_clean) ? c->phi : static_cast<void*>(c->real_interior<T>());
+    p.clear_input = (DIR < 0 && self_clean) ? 1 : 0;
     p.a = c->f2_a;
     p.b = c->f2_b;
     p.tw = c->f2_tw;
@@ -516,11 +522,24 @@ int solve_fft2(pm_ctx* c, double prefactor, int deconv_order, double gauss, bool
     PM_REQUIRE(fft2_supported(c) && c->f2_tw != nullptr, "hand-written FFT path not available for this grid size / rank layout");
     PM_TRY(update_sep_table(c, deconv_order, gauss));
     const bool f64 = c->dtype == PM_GRID_F64;
+    if (c->nranks == 1) {
+        if (stage == 0 || stage == 1) PM_TRY(ensure_in_real(c));     // the input is the density in `real`
+        if (c->phi == nullptr && getenv("PM_NO_SELF_CLEAN") == nullptr) {
+            if (cudaMalloc(&c->phi, c->real_elems * c->elem_size()) == cudaSuccess) c->bytes_allocated += c->real_elems * c->elem_size();
+            else { c->phi = nullptr; cudaGetLastError(); }           // no room: keep the in-place scheme
+        }
+    }
     int s;
     switch (c->g.G) {
         case 128: s = f64 ? solve_fft2_tg<double, 128>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 128>(c, prefactor, l2_fused, stage); break;
         case 256: s = f64 ? solve_fft2_tg<double, 256>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 256>(c, prefactor, l2_fused, stage); break;
         default:  s = f64 ? solve_fft2_tg<double, 512>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 512>(c, prefactor, l2_fused, stage); break;
+    }
+    if (s == PM_OK && c->nranks == 1 && c->phi != nullptr) {
+        if (stage == 0 || stage == 1) c->real_is_zero = true;     // the forward z pass has nullified what it read
+        if (stage == 0 || stage == 3) c->grid_in_phi = true;      // the potential is in `phi`
+    } else if (s == PM_OK && (stage == 0 || stage == 1)) {
+        c->real_is_zero = false;
     }
     return s;
 }

@@ -93,9 +93,10 @@ struct SlabFFT {
     // The rows are read directly (coalesced 512-byte warp loads, contiguous 4 KB rows) — staging them
     // through the copy engine would cost the z pass an extra shared-memory round trip and barrier.
     struct ZFwd {
-        const T* plane;   // first real of the x plane
+        T* plane;         // first real of the x plane
         V* a_plane;       // A block row of this plane: V[NKT][G][CY]
         int row0;         // first of the CZ rows
+        bool clear;       // nullify the rows once they are read (self-cleaning density grid)
         static constexpr bool kBulk = false;
         PM_HD TileLoad load(int) const { return TileLoad{plane + (size_t)row0 * Gp, 0, CZ * Gp * (int)sizeof(T)}; }
         struct ToTile {
@@ -113,7 +114,14 @@ struct SlabFFT {
         static constexpr int kPhases = 4;
         PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int nthr, T (&)[kRegs]) const {
             if (ph == 0) dit_stageA<LZ, T, M, -1>(RowSource{plane, row0}, tile, tid, nthr);
-            else if (ph == 1) dit_stageB<LZ, T, M, -1>(tile, tw.B, tid, nthr);
+            else if (ph == 1) {
+                if (clear) {     // every thread of the tile has consumed its rows by now
+                    V zero; zero.x = 0; zero.y = 0;
+                    V* rows = reinterpret_cast<V*>(plane + (size_t)row0 * Gp);
+                    for (int e = tid; e < CZ * Gc; e += nthr) rows[e] = zero;
+                }
+                dit_stageB<LZ, T, M, -1>(tile, tw.B, tid, nthr);
+            }
             else if (ph == 2) dit_stageC<LZ, T, M, 2, -1>(tile, tw.C, tid, nthr, ToTile{tile});
             else r2c_post<LZ, T, M>(tile, tw.R, tid, nthr, ToA{a_plane, row0});
         }

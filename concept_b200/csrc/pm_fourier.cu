@@ -316,6 +316,8 @@ void destroy_plans(pm_ctx* c) {
 
 int fft_forward(pm_ctx* c) {
     PM_REQUIRE(!c->space_fourier, "pm_fft_forward: slab already holds Fourier data");
+    PM_TRY(ensure_in_real(c));
+    c->real_is_zero = false;
     const bool f64 = c->dtype == PM_GRID_F64;
     if (f64) {
         double* r = c->real_interior<double>();
@@ -374,6 +376,8 @@ int solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss, int
         return solve_fft2(c, prefactor, deconv_order, gauss, mode == PM_SOLVE_FFT2_L2, stage);
     PM_REQUIRE(stage == 0, "pm_solve_fused_stage: staged execution needs the hand-written transforms");
     PM_REQUIRE(xsolve_supported(c), "pm_solve_fused: not available for this grid size / rank layout");
+    PM_TRY(ensure_in_real(c));
+    c->real_is_zero = false;
     const bool f64 = c->dtype == PM_GRID_F64;
     const size_t plane = (size_t)c->g.G * c->g.Gp;
     const int nchunks = c->g.nxl / c->fft_chunk;

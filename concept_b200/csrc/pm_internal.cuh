@@ -158,10 +158,18 @@ struct pm_ctx {
     cudaStream_t s_h2d, s_d2h;
     cudaEvent_t ev_pipe[3 * 16];
     bool pipe_ready;
+    // Self-cleaning density grid (one rank, hand-written transform): the forward z pass zeroes the rows of
+    // `real` it has consumed and the inverse transforms deliver the potential into `phi`, so the next deposit
+    // finds `real` already nullified and the 1 GB memset of get_buffer(nullify=True) disappears from the cycle.
+    void* phi;                // lazily allocated, same shape as `real`
+    bool real_is_zero;        // `real` is known to hold zeros
+    bool grid_in_phi;         // the current real-space grid (what gathers and taps read) is `phi`
     // state flags
     bool space_fourier;       // working slab currently holds Fourier data
 
     size_t elem_size() const { return dtype == PM_GRID_F64 ? 8 : 4; }
+    // the buffer that currently holds the real-space grid for readers (gather, diff, taps)
+    void* grid_read() const { return grid_in_phi ? phi : real; }
     template <typename T> T* real_interior() const {
         return reinterpret_cast<T*>(real) + (size_t)g.halo * g.G * g.Gp;
     }
@@ -214,5 +222,6 @@ int solve_fused(pm_ctx* c, double prefactor, int deconv_order, double gauss, int
 
 int ensure_saved(pm_ctx* c);
 int ensure_force(pm_ctx* c);
+int ensure_in_real(pm_ctx* c);   // un-fused operators work on `real`: bring the grid back from `phi` if needed
 
 }  // namespace pm

@@ -282,7 +282,7 @@ int launch_diff(pm_ctx* c, int dim, int order) {
     PM_TRY(ensure_force(c));
     const int grid = kNumSMs * 8;
 #define PM_DIFF_CASE(R, T)                                                                       \
-    PM_LAUNCH((diff_kernel<R, T>), grid, 256, 0, c->stream, reinterpret_cast<const T*>(c->real), \
+    PM_LAUNCH((diff_kernel<R, T>), grid, 256, 0, c->stream, reinterpret_cast<const T*>(c->grid_read()), \
               reinterpret_cast<T*>(c->force), c->g, fd, dim)
     if (c->dtype == PM_GRID_F64) {
         switch (fd.reach) {
@@ -359,7 +359,7 @@ int launch_gather(pm_ctx* c, int which, const double* pos, double* mom, int64_t 
     const Coord co = make_coord(c, shift, true);
     const int64_t ntiles = (n + kGatBlock - 1) / kGatBlock;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * 16);
-    const void* src = which == PM_TAP_REAL ? c->real : c->force;
+    const void* src = which == PM_TAP_REAL ? c->grid_read() : c->force;
 #define PM_GATHER_CASE(O, T)                                                                           \
     PM_LAUNCH((gather_kernel<O, T>), grid, kGatBlock, 0, c->stream, reinterpret_cast<const T*>(src),  \
               pos, mom, n, c->g, co, dim, factor)
@@ -536,7 +536,7 @@ static int gather_kick_dispatch(pm_ctx* c, double* pos, double* mom, int64_t n, 
                                 bool drift, double drift_dt) {
     const int64_t nchunks = (n + (int64_t)kGkBlock * kGkChunkTiles - 1) / ((int64_t)kGkBlock * kGkChunkTiles);
     const int grid = (int)std::min<int64_t>(nchunks, (int64_t)kNumSMs * 8);
-    const T* phi = reinterpret_cast<const T*>(c->real);
+    const T* phi = reinterpret_cast<const T*>(c->grid_read());
     unsigned long long* ctr = c->d_tilectr + 1;
     PM_CHECK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), c->stream));
 #define PM_GK(O, R)                                                                                     \

@@ -235,7 +235,7 @@ static int solve3d(const char* fin, const char* fsep, const char* fout, double p
         for (int p = 0; p < nxl; ++p) {
             T* plane = slab[r].data() + (size_t)p * G * S::Gp;
             V* a_plane = A[r].data() + (size_t)p * S::NKT * G * S::CY;
-            for (int t = 0; t < S::kZTilesPerPlane; ++t) run(typename S::ZFwd{plane, a_plane, t * S::CZ}, 1);
+            for (int t = 0; t < S::kZTilesPerPlane; ++t) run(typename S::ZFwd{plane, a_plane, t * S::CZ, false}, 1);
             for (int kt = 0; kt < S::NKT; ++kt) run(typename S::YFwd{a_plane + (size_t)kt * G * S::CY, B[r].data(), p, kt, nxl}, 1);
         }
     typename S::XGeom xg;
