@@ -69,6 +69,7 @@ SIGNATURES = {
     'pm_gather_kick_drift': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_double, POINTER(c_double), c_void_p, c_double]),
     'pm_drift': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double]),
     'pm_sum_mom2': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    'pm_sort_particles': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
     'pm_exchange': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64]),
     'pm_shortrange': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, POINTER(c_double), c_int, c_double,
                               c_void_p, c_int, c_double, c_void_p]),

@@ -199,6 +199,11 @@ class PMContext:
         check(self.lib.pm_sum_mom2(self._h, _particles(mom), mom.shape[0], _ptr(acc)))
         return float(acc.item()) if out is None else None
 
+    def sort_particles(self, pos, mom, ids=None, n=None):
+        """Stable reorder of the first n particles by grid cell (tile_sort analogue)."""
+        n = pos.shape[0] if n is None else int(n)
+        check(self.lib.pm_sort_particles(self._h, _particles(pos), _particles(mom), _ptr(ids), n))
+
     def exchange(self, pos, mom, ids, n):
         """Slab migration.  pos/mom(/ids) are capacity-sized buffers; returns the new local count."""
         n_io = ctypes.c_int64(int(n))

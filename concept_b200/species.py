@@ -164,6 +164,12 @@ class Component:
             self._ϱ_bar = self.N*self.mass/p.boxsize**3
         return self._ϱ_bar
 
+    def cell_sort(self, gridsize=None):
+        """Reorder the local particles by grid cell (the tile_sort analogue, species.py:2657-2780): keeps the
+        deposit/gather locality that lattice-ordered particles lose over many steps."""
+        ctx = self._pm_context() if gridsize is None else mesh.get_context(gridsize)
+        ctx.sort_particles(self.pos, self.mom, self.ids, self.N_local)
+
     def _pm_context(self):
         method = self.forces.get('gravity', 'pm')
         method = method if method in ('pm', 'p3m') else 'pm'

@@ -178,6 +178,11 @@ int pm_gather_kick_drift(pm_ctx* ctx, double* pos, double* mom, int64_t n, int o
 int pm_drift(pm_ctx* ctx, double* pos, const double* mom, int64_t n, double dt_over_mass);
 /* measure(component,'v_rms') reduction: *out += Σ mom² (device double) */
 int pm_sum_mom2(pm_ctx* ctx, const double* mom, int64_t n, double* out);
+/* Reorder the local particles by grid cell (x plane, y row, z; stable) — the analogue of
+ * Component.tile_sort (species.py:2657-2780): deposit and gather rely on consecutive particles touching
+ * neighbouring grid rows.  Lattice-ordered initial conditions have that order; call this every few
+ * hundred steps (or after loading unordered particles).  ids may be NULL. */
+int pm_sort_particles(pm_ctx* ctx, double* pos, double* mom, int64_t* ids, int64_t n);
 /* exchange(component) (communication.py:135-517) for the x-slab decomposition: particles
  * whose owner floor(x/L·P) differs from this rank are sent to their owner.  pos/mom/ids are
  * device arrays with room for `capacity` particles; *n_inout is updated (host int64).

@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--nofuse', action='store_true', help='three-call solve (cuFFT 3-D + k-space kernel) instead of the fused x-solve')
     ap.add_argument('--solve-mode', default='auto', help='auto | fft2_l2 | fft2_split | cufft2d (see PMContext.SOLVE_MODES)')
     ap.add_argument('--nodriftfuse', action='store_true', help='separate gather_kick and drift kernels')
+    ap.add_argument('--sort', action='store_true', help='pm_sort_particles before timing (after --shuffle: restores locality); its time is reported')
     ap.add_argument('--shuffle', action='store_true', help='random particle order (worst-case locality)')
     a = ap.parse_args()
     L = 512.0
@@ -39,6 +40,15 @@ def main():
     N = pos.shape[0]
     ctx = PMContext(a.grid, L, dtype=a.dtype)
     ctx.set_fused_solve(a.solve_mode)
+    sort_ms = None
+    if a.sort:
+        ctx.sort_particles(pos, mom)     # warm-up: scratch allocation
+        if a.shuffle:
+            perm = torch.randperm(pos.shape[0], device='cuda')
+            pos, mom = pos[perm].contiguous(), mom[perm].contiguous()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ctx.sort_particles(pos, mom); e1.record(); torch.cuda.synchronize()
+        sort_ms = e0.elapsed_time(e1)
     p = make_kick_params(mass=1.0, boxsize=L, gridsize=a.grid, order=a.order, G_Newton=4.4985024439973154e-05,
                          dt_rho_over_dt1=2.0, dt_kick=1e-3, diff_order=a.diff)
     s = torch.zeros(1, dtype=torch.float64, device='cuda')
@@ -73,7 +83,7 @@ def main():
     alg = {'grid_zero': es*G3, 'deposit': 24*N + es*G3, 'fft_forward': 2*es*G3, 'kspace': 2*es*G3, 'fft_backward': 2*es*G3, 'solve_fused': 4*es*G3,
            'gather_kick': 72*N + es*G3, 'drift': 72*N, 'gather_kick_drift': 96*N + es*G3}
     ctx.check_async_error()
-    out = {'N': N, 'grid': a.grid, 'solve_mode': a.solve_mode, 'order': a.order, 'dtype': a.dtype, 'sigma': a.sigma, 'shuffle': a.shuffle,
+    out = {'N': N, 'grid': a.grid, 'sort_ms': sort_ms, 'solve_mode': a.solve_mode, 'order': a.order, 'dtype': a.dtype, 'sigma': a.sigma, 'shuffle': a.shuffle,
            'device_bytes': ctx.device_bytes, 'stages_ms': {}, 'stages_GBps': {}}
     for k in times:
         t = sorted(times[k])[len(times[k])//2]
