@@ -280,6 +280,7 @@ def run_gpu(args):
     e1.record()
     barrier()
     launches = lib.pm_launch_count() - launches0
+    ctx.check_async_error()      # a tile dependency that timed out would have invalidated the run: fail loudly
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     stage_ms = [sum(e[k].elapsed_time(e[k + 1]) for e in evs)/len(evs) for k in range(len(STAGES))]
