@@ -122,7 +122,10 @@ __device__ __forceinline__ void stage_particles(const double* __restrict__ src, 
 // DRAM.)  One block-wide atomic per chunk, not per tile: with a ticket per 256-particle tile 64 % of the
 // deposit's warp stalls were the barrier around the ticket (ncu, r01).  Inside a chunk the warps run
 // free; consecutive tiles of a chunk share grid rows, which the SM's L1 keeps for the gather.
-constexpr int kChunkTiles = 8;
+#ifndef PM_DEP_CHUNK_TILES
+#define PM_DEP_CHUNK_TILES 4
+#endif
+constexpr int kChunkTiles = PM_DEP_CHUNK_TILES;
 
 __device__ __forceinline__ int64_t next_chunk(unsigned long long* counter, int64_t* s_slot) {
     __syncthreads();
@@ -391,7 +394,10 @@ int launch_gather(pm_ctx* c, int which, const double* pos, double* mom, int64_t 
 // independently (no shared-memory staging, no barrier inside a chunk).  x and y sums run over their
 // line index innermost, so their summation order differs from the reference's (a, b, c) nest by a
 // reassociation (last-bit differences; the stated kick tolerance is 1e-9).
-constexpr int kGkChunkTiles = 16;  // 2048 consecutive particles per ticket
+#ifndef PM_GK_CHUNK_TILES
+#define PM_GK_CHUNK_TILES 8
+#endif
+constexpr int kGkChunkTiles = PM_GK_CHUNK_TILES;  // 1024 consecutive particles per ticket (measured: 512…8192 → 1024 best)
 
 // CIC with a 2-point difference: cap the kernel at 80 registers (6 CTAs = 24 warps per SM).  The kernel waits on
 // L1/L2 gathers 78 % of the time (ncu), so warps in flight matter more than the 50 bytes of spills: measured
