@@ -127,6 +127,13 @@ template <int C_>
 struct ColLayout {
     static constexpr int C = C_;
     static PM_HD int idx(int p, int c) { return p * C + c; }
+    // strided accessors used by the stages (k is a compile-time constant after unrolling):
+    //   idx_s8 (p0, k, c) = idx(p0 + 8·k, c)   with p0 = 64·x + y, y < 8
+    //   idx_s64(q,  k, c) = idx(64·k + q, c)   with q < 64
+    //   idx_s1 (p0, k, c) = idx(p0 + k, c)     with p0 a multiple of 8, k < 8
+    static PM_HD int idx_s8(int p0, int k, int c) { return idx(p0 + 8 * k, c); }
+    static PM_HD int idx_s64(int q, int k, int c) { return idx(64 * k + q, c); }
+    static PM_HD int idx_s1(int p0, int k, int c) { return idx(p0 + k, c); }
     // butterfly b of a stage with P butterflies per line  ->  (line, butterfly-in-line)
     template <int P> static PM_HD void decode(int b, int& c, int& u) { c = b % C; u = b / C; }
 };
@@ -136,6 +143,13 @@ struct RowLayout {
     static constexpr int C = C_;
     static constexpr int PITCH = N_ + N_ / 8 + N_ / 64 + 1;
     static PM_HD int idx(int p, int c) { return c * PITCH + p + (p >> 3) + (p >> 6); }
+    // strided accessors used by the stages (k is a compile-time constant after unrolling):
+    //   idx_s8 (p0, k, c) = idx(p0 + 8·k, c)   with p0 = 64·x + y, y < 8
+    //   idx_s64(q,  k, c) = idx(64·k + q, c)   with q < 64
+    //   idx_s1 (p0, k, c) = idx(p0 + k, c)     with p0 a multiple of 8, k < 8
+    static PM_HD int idx_s8(int p0, int k, int c) { return idx(p0 + 8 * k, c); }
+    static PM_HD int idx_s64(int q, int k, int c) { return idx(64 * k + q, c); }
+    static PM_HD int idx_s1(int p0, int k, int c) { return idx(p0 + k, c); }
     template <int P> static PM_HD void decode(int b, int& c, int& u) { u = b % P; c = b / P; }
 };
 
@@ -144,6 +158,18 @@ struct ColSwz {
     static constexpr int C = C_;
     static PM_HD int swz(int p) { return p ^ ((p >> 3) & 1) ^ ((p >> 6) & 1); }
     static PM_HD int idx(int p, int c) { return swz(p) * C + c; }
+    // The strided accessors (see ColLayout) written so that, with k a compile-time constant, every access is
+    // one of TWO per-thread base addresses plus an immediate offset — the plain idx() costs two to three
+    // integer instructions and an address register per access, and these kernels are issue-bound.
+    //   p0 + 8k: bit 3 = k & 1 (p0's own bit 3 is clear), bit 6 = bit 6 of p0
+    static PM_HD int idx_s8(int p0, int k, int c) { return ((p0 ^ (((p0 >> 6) ^ k) & 1)) + 8 * k) * C + c; }
+    //   64k + q: bit 3 = bit 3 of q, bit 6 = k & 1
+    static PM_HD int idx_s64(int q, int k, int c) { return ((q ^ (((q >> 3) ^ k) & 1)) + 64 * k) * C + c; }
+    //   p0 + k: the swizzle bit s is a property of p0; k ^ s = k + s for even k, k − s for odd k
+    static PM_HD int idx_s1(int p0, int k, int c) {
+        const int s = ((p0 >> 3) ^ (p0 >> 6)) & 1;
+        return (p0 + k + ((k & 1) ? -s : s)) * C + c;
+    }
     static PM_HD int nat(int p, int c) { return p * C + c; }
     template <int P> static PM_HD void decode(int b, int& c, int& u) { c = b % C; u = b / C; }
 };
@@ -152,6 +178,13 @@ template <int M_, int C_, int RAWPITCH_>
 struct RowSwz {
     static constexpr int C = C_;
     static PM_HD int idx(int p, int c) { return c * M_ + ((p & ~7) | ((p ^ (p >> 3) ^ ((p >> 6) << 1)) & 7)); }
+    // strided accessors used by the stages (k is a compile-time constant after unrolling):
+    //   idx_s8 (p0, k, c) = idx(p0 + 8·k, c)   with p0 = 64·x + y, y < 8
+    //   idx_s64(q,  k, c) = idx(64·k + q, c)   with q < 64
+    //   idx_s1 (p0, k, c) = idx(p0 + k, c)     with p0 a multiple of 8, k < 8
+    static PM_HD int idx_s8(int p0, int k, int c) { return idx(p0 + 8 * k, c); }
+    static PM_HD int idx_s64(int q, int k, int c) { return idx(64 * k + q, c); }
+    static PM_HD int idx_s1(int p0, int k, int c) { return idx(p0 + k, c); }
     static PM_HD int nat(int p, int c) { return c * RAWPITCH_ + p; }
     template <int P> static PM_HD void decode(int b, int& c, int& u) { u = b % P; c = b / P; }
 };
@@ -203,7 +236,7 @@ PM_HD void dit_stageA(const Source& src, V* dst, int tid, int nthr) {
 #pragma unroll
         for (int b3 = 0; b3 < 8; ++b3) {
             V v; v.x = r[b3]; v.y = i[b3];
-            dst[L::idx(p0 + b3, c)] = v;
+            dst[L::idx_s1(p0, b3, c)] = v;
         }
     }
 }
@@ -218,14 +251,14 @@ PM_HD void dit_stageA_inplace(V* tile, int tid, int nthr) {
         T r[8], i[8];
 #pragma unroll
         for (int a3 = 0; a3 < 8; ++a3) {
-            const V v = tile[L::idx(8 * u + a3, c)];
+            const V v = tile[L::idx_s1(8 * u, a3, c)];
             r[a3] = v.x; i[a3] = v.y;
         }
         dft8<DIR>(r, i);
 #pragma unroll
         for (int b3 = 0; b3 < 8; ++b3) {
             V v; v.x = r[b3]; v.y = i[b3];
-            tile[L::idx(8 * u + b3, c)] = v;
+            tile[L::idx_s1(8 * u, b3, c)] = v;
         }
     }
 }
@@ -242,7 +275,7 @@ PM_HD void dit_stageB(V* tile, const V* twB, int tid, int nthr) {
         T r[8], i[8];
 #pragma unroll
         for (int a2 = 0; a2 < 8; ++a2) {
-            const V v = tile[L::idx(p0 + 8 * a2, c)];
+            const V v = tile[L::idx_s8(p0, a2, c)];
             r[a2] = v.x; i[a2] = v.y;
             if (a2) cmul<DIR>(r[a2], i[a2], twB[a2 * 8 + b3]);
         }
@@ -250,7 +283,7 @@ PM_HD void dit_stageB(V* tile, const V* twB, int tid, int nthr) {
 #pragma unroll
         for (int b2 = 0; b2 < 8; ++b2) {
             V v; v.x = r[b2]; v.y = i[b2];
-            tile[L::idx(p0 + 8 * b2, c)] = v;
+            tile[L::idx_s8(p0, b2, c)] = v;
         }
     }
 }
@@ -266,7 +299,7 @@ PM_HD void dit_stageC(const V* tile, const V* twC, int tid, int nthr, const Sink
         T r[R1], i[R1];
 #pragma unroll
         for (int a1 = 0; a1 < R1; ++a1) {
-            const V v = tile[L::idx(64 * a1 + q, c)];
+            const V v = tile[L::idx_s64(q, a1, c)];
             r[a1] = v.x; i[a1] = v.y;
             if (a1) cmul<DIR>(r[a1], i[a1], twC[(a1 * TWS) * 64 + q]);
         }
@@ -289,7 +322,7 @@ PM_HD void dif_stage1_regs(T (&r)[N / 64], T (&i)[N / 64], V* tile, const V* twC
     for (int b1 = 0; b1 < R1; ++b1) {
         if (b1) cmul<DIR>(r[b1], i[b1], twC[(b1 * TWS) * 64 + q]);
         V v; v.x = r[b1]; v.y = i[b1];
-        tile[L::idx(64 * b1 + q, c)] = v;
+        tile[L::idx_s64(q, b1, c)] = v;
     }
 }
 
@@ -305,7 +338,7 @@ PM_HD void dif_stage2(V* tile, const V* twB, int tid, int nthr) {
         T r[8], i[8];
 #pragma unroll
         for (int a2 = 0; a2 < 8; ++a2) {
-            const V v = tile[L::idx(p0 + 8 * a2, c)];
+            const V v = tile[L::idx_s8(p0, a2, c)];
             r[a2] = v.x; i[a2] = v.y;
         }
         dft8<DIR>(r, i);
@@ -313,7 +346,7 @@ PM_HD void dif_stage2(V* tile, const V* twB, int tid, int nthr) {
         for (int b2 = 0; b2 < 8; ++b2) {
             if (b2) cmul<DIR>(r[b2], i[b2], twB[b2 * 8 + a3]);
             V v; v.x = r[b2]; v.y = i[b2];
-            tile[L::idx(p0 + 8 * b2, c)] = v;
+            tile[L::idx_s8(p0, b2, c)] = v;
         }
     }
 }
@@ -331,7 +364,7 @@ PM_HD void dif_stage3(const V* tile, int tid, int nthr, const Sink& sink) {
         T r[8], i[8];
 #pragma unroll
         for (int a3 = 0; a3 < 8; ++a3) {
-            const V v = tile[L::idx(8 * u + a3, c)];
+            const V v = tile[L::idx_s1(8 * u, a3, c)];
             r[a3] = v.x; i[a3] = v.y;
         }
         dft8<DIR>(r, i);
@@ -448,7 +481,7 @@ PM_HD void dit_stageA_store(V* tile, int tid, T (&rg)[16 * NBT]) {
 #pragma unroll
             for (int b3 = 0; b3 < 8; ++b3) {
                 V v; v.x = r[b3]; v.y = i[b3];
-                tile[L::idx(p0 + b3, c)] = v;
+                tile[L::idx_s1(p0, b3, c)] = v;
             }
         }
     }

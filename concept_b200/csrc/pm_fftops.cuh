@@ -246,7 +246,7 @@ struct SlabFFT {
                     T r[R1], im[R1];
 #pragma unroll
                     for (int a1 = 0; a1 < R1; ++a1) {
-                        const V v = tile[LY::idx(64 * a1 + q, c)];
+                        const V v = tile[LY::idx_s64(q, a1, c)];
                         r[a1] = v.x; im[a1] = v.y;
                         if (a1) cmul<-1>(r[a1], im[a1], tw.C[a1 * 64 + q]);
                     }
