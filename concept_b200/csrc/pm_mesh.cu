@@ -123,7 +123,7 @@ __device__ __forceinline__ void stage_particles(const double* __restrict__ src, 
 // deposit's warp stalls were the barrier around the ticket (ncu, r01).  Inside a chunk the warps run
 // free; consecutive tiles of a chunk share grid rows, which the SM's L1 keeps for the gather.
 #ifndef PM_DEP_CHUNK_TILES
-#define PM_DEP_CHUNK_TILES 4
+#define PM_DEP_CHUNK_TILES 2   /* 512 particles per ticket (measured 256 … 8192: 0.78, 0.62, 0.64, 0.68, 0.71, 0.74 ms) */
 #endif
 constexpr int kChunkTiles = PM_DEP_CHUNK_TILES;
 
@@ -395,9 +395,9 @@ int launch_gather(pm_ctx* c, int which, const double* pos, double* mom, int64_t 
 // line index innermost, so their summation order differs from the reference's (a, b, c) nest by a
 // reassociation (last-bit differences; the stated kick tolerance is 1e-9).
 #ifndef PM_GK_CHUNK_TILES
-#define PM_GK_CHUNK_TILES 8
+#define PM_GK_CHUNK_TILES 4
 #endif
-constexpr int kGkChunkTiles = PM_GK_CHUNK_TILES;  // 1024 consecutive particles per ticket (measured: 512…8192 → 1024 best)
+constexpr int kGkChunkTiles = PM_GK_CHUNK_TILES;  // 512 consecutive particles per ticket (measured 512 … 8192: 0.73, 0.75, 0.77, 0.77, 0.87 ms)
 
 // CIC with a 2-point difference: cap the kernel at 80 registers (6 CTAs = 24 warps per SM).  The kernel waits on
 // L1/L2 gathers 78 % of the time (ncu), so warps in flight matter more than the 50 bytes of spills: measured
