@@ -10,11 +10,15 @@
 // default gravity path.  Tile operations, layouts and their index math live in pm_fftops.cuh (CPU-checked
 // by tests/test_fftcore_host.py); this file adds the asynchronous tile pipeline around them.
 //
-// Data path of one tile: the intermediate layouts A and B make every tile ONE contiguous chunk of global
-// memory, so a single thread moves it with cp.async.bulk (the TMA engine; completion on an mbarrier) into
-// one of the CTA's two 32 KB buffers while the other buffer is being transformed in place; the last stage
-// stores aligned 64-byte segments straight from registers.  No load instruction, register or scoreboard is
-// spent on the input, and three such CTAs per SM interleave their LDS / FP64 / STS / barrier phases.
+// Data path of a y or x tile: the intermediate layouts A and B make the tile ONE contiguous chunk of global
+// memory (per rank), so a single thread moves it with cp.async.bulk (the TMA engine; completion on an
+// mbarrier) into one of the CTA's two 32 KB buffers while the other buffer is being transformed in place; the
+// last stage stores aligned 64-byte segments straight from registers.  No load instruction, register or
+// scoreboard is spent on the input, and three such CTAs per SM interleave their LDS / FP64 / STS / barrier
+// phases.  z tiles read and write whole contiguous rows directly; their "load" is a cp.async.bulk.prefetch.L2
+// of the next tile's rows.  A blocks that a forward y tile has consumed are dropped from L2
+// (discard.global.L2) instead of being written back, and on one rank the forward z tiles nullify the density
+// rows they have consumed (self-cleaning grid, pm_internal.cuh).
 // (History, measured on B200: cp.async/LDGSTS staging costs 16 shared-memory wavefronts per 16-byte warp
 // instruction — 38 % of the shared-memory pipe; direct ld.global into registers leaves only ~32 KB per SM
 // in flight and the passes latency-bound at 0.50-0.55 ms each.)
