@@ -184,3 +184,30 @@ def test_kick_long_host_pipelined_matches_device_path():
     assert np.max(np.abs(mh - m1.cpu().numpy())) < 1e-11*dm + 2e-15
     assert np.array_equal(ph, O.drift(pos_h, mh, dtm, L))
     assert abs(s2 - s1.item()) < 1e-9*abs(s2)
+
+
+def test_empty_and_single_particle_on_the_hand_written_path():
+    """Edge cases through pm_kick_drift at G = 128: no particles (a no-op that still leaves a clean grid),
+    and a single particle (its self-force through the mesh, against the oracle)."""
+    from concept_b200.pmsolver import make_kick_params
+    from oracle import pm_oracle as O
+    G, L = 128, 64.0
+    kw = dict(mass=1.0, boxsize=L, gridsize=G, order=2, G_Newton=G_NEWTON, dt_rho_over_dt1=1.0, dt_kick=0.5, diff_order=2)
+    params = make_kick_params(**kw)
+    ctx = _ctx(G, L)
+    pos = torch.zeros((0, 3), dtype=torch.float64, device='cuda')
+    mom = torch.zeros((0, 3), dtype=torch.float64, device='cuda')
+    ctx.kick_drift(pos, mom, params, 0.1)
+    ctx.sort_particles(pos, mom)
+    ctx.check_async_error()
+    assert np.all(ctx.get_grid() == 0)
+    pos_h = np.array([[L - 1e-9, 0.3*L, 17.123]])
+    mom_h = np.array([[0.1, -0.2, 0.3]])
+    pos, mom = torch.as_tensor(pos_h, device='cuda'), torch.as_tensor(mom_h, device='cuda')
+    ctx.kick_drift(pos, mom, params, 0.1)
+    ctx.check_async_error()
+    ref = O.pm_kick(pos_h, mom_h, **kw)
+    scale = max(np.max(np.abs(ref - mom_h)), 1e-30)
+    assert np.max(np.abs(mom.cpu().numpy() - ref)) < 1e-9*scale + 1e-15
+    assert np.array_equal(pos.cpu().numpy(), O.drift(pos_h, mom.cpu().numpy(), 0.1, L))
+    ctx.close()
