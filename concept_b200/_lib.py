@@ -78,6 +78,13 @@ SIGNATURES = {
     'pm_flag_rung_jumps': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_double, c_double,
                                    POINTER(c_double), c_int, POINTER(c_int)]),
     'pm_apply_rung_jumps': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, POINTER(c_int64)]),
+    'pm_ic_lattice': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int64, c_int64, POINTER(c_int64)]),
+    'pm_ic_potential': (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(c_double), c_double]),
+    'pm_ic_displace': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_double]),
+    'pm_ic_wrap': (c_int, [c_void_p, c_void_p, c_int64]),
+    'pm_real_export': (c_int, [c_void_p, c_void_p]),
+    'pm_ic_2lpt_source': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'pm_fourier_resize': (c_int, [c_void_p, c_void_p]),
     'pm_kick_long': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(KickParams), c_void_p]),
     'pm_kick_drift': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(KickParams), c_double, c_void_p]),
     'pm_kick_long_host': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(KickParams), c_double, POINTER(c_double)]),

@@ -207,7 +207,46 @@ def load_params(path_or_text='', extra='', **overrides):
     p.initial_conditions = up.get('initial_conditions', None)
     p.output_times = up.get('output_times', {})
     p.output_dirs = up.get('output_dirs', {})
-    p.random_seeds = up.get('random_seeds', {})
+    # initial conditions (commons.py:3640-3658, :3742-3830, :3895-3925)
+    p.random_seeds = {'general': 0, 'primordial amplitudes': 1_000, 'primordial phases': 2_000}
+    for key, val in dict(up.get('random_seeds', {})).items():
+        if key not in p.random_seeds:
+            abort(f'Key {key} in random_seeds not understood')
+        p.random_seeds[key] = int(val)
+    p.random_generator = str(up.get('random_generator', 'PCG64DXSM'))
+    p.primordial_noise_imprinting = str(up.get('primordial_noise_imprinting', 'distributed')).lower()
+    if p.primordial_noise_imprinting not in {'simple', 'distributed'}:
+        abort(f'primordial_noise_imprinting = "{p.primordial_noise_imprinting}" ∉ {{"simple", "distributed"}}')
+    p.primordial_amplitude_fixed = bool(up.get('primordial_amplitude_fixed', False))
+    p.primordial_phase_shift = float(np.mod(float(up.get('primordial_phase_shift', 0)), τ))
+    ps = {}
+    for key, val in dict(up.get('primordial_spectrum', {})).items():
+        k = str(key).lower()
+        for ch in '_sk':
+            k = k.replace(ch, '')
+        k = k.replace('alpha', 'α')
+        full = {'a': 'A_s', 'n': 'n_s', 'α': 'α_s', 'pivot': 'pivot'}.get(k)
+        if full is None:
+            masterwarn(f'Could not understand primordial spectrum parameter "{key}"')
+        else:
+            ps[full] = val
+    p.primordial_spectrum = {key: float(ps.get(key, val))
+                             for key, val in {'A_s': 2.1e-9, 'n_s': 0.96, 'α_s': 0, 'pivot': 0.05/units.Mpc}.items()}
+    ro = {}
+    for key, val in dict(up.get('realization_options', {})).items():
+        k = str(key).lower().replace('-', '').replace('_', '').replace(' ', '')
+        if isinstance(val, dict):     # per-component dicts: only the 'default'/'all'/'particles' entry is used here
+            val = next((val[q] for q in ('default', 'all', 'particles', 'matter') if q in val), None)
+        ro[k] = val
+    p.realization_options = {
+        'backscale': bool(ro.get('backscale', False) or False),
+        'lpt': int(round(ro.get('lpt', 1) or 1)),
+        'dealias': bool(ro.get('dealias', False) or False),
+        'nongaussianity': float(next((ro[q] for q in ('nongauss', 'nongaussian', 'nongaussianity') if ro.get(q)), 0.0)),
+        'structure': 'primordial',
+    }
+    if p.realization_options['lpt'] not in {1, 2, 3}:
+        abort(f"{p.realization_options['lpt']}LPT not implemented")
     p.N_rungs = int(up.get('N_rungs', 8))
     p.Δt_base_background_factor = float(up.get('Δt_base_background_factor', 1))
     p.Δt_base_nonlinear_factor = float(up.get('Δt_base_nonlinear_factor', 1))

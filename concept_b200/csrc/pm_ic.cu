@@ -1,0 +1,279 @@
+// pm_ic.cu — device side of the particle initial-condition generator.
+//
+// Reference (all under src/): ic.py:1199-1399 realize_particles, :670-782 realize_grid, :1447-1589
+// carryout_1lpt / carryout_2lpt, :2138-2247 preinitialize_particles, :2249-2283 displace_particles;
+// mesh.py:3422-3437 laplacian_inverse, :3470-3510 fourier_diff, mesh.py resize_grid (dealiasing).
+//
+// The primordial noise itself is drawn on the host (sequential NumPy bit streams, ic.py:928-1163);
+// everything downstream of it runs here.  All kernels are streaming, HBM-bound passes over a G³ grid
+// or over the particle arrays; grids are fp64 (PM_GRID_F64 contexts only).
+#include "pm_internal.cuh"
+
+namespace pm {
+
+// pos at lattice points, mom = 0, ids by lattice point (preinitialize_particles, ic.py:2197-2243)
+__global__ void __launch_bounds__(256)
+ic_lattice_kernel(double* __restrict__ pos, double* __restrict__ mom, int64_t* __restrict__ ids, int n, int nxl,
+                  double bx, double by, double bz, double cell, int64_t index_bgn, int64_t id_bgn, int64_t id_plane0) {
+    const int64_t total = (int64_t)nxl * n * n;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(p % n);
+        const int64_t r = p / n;
+        const int j = (int)(r % n);
+        const int i = (int)(r / n);
+        double* q = pos + 3 * (index_bgn + p);
+        q[0] = (bx + i) * cell;
+        q[1] = (by + j) * cell;
+        q[2] = (bz + k) * cell;
+        double* m = mom + 3 * (index_bgn + p);
+        m[0] = 0; m[1] = 0; m[2] = 0;
+        if (ids != nullptr) ids[index_bgn + p] = id_bgn + id_plane0 + p;
+    }
+}
+
+// realize_grid (scalar, Fourier output) + laplacian_inverse in one pass:
+//   slab[k] = amplitudes[k²]·noise[k]·e^{iθ} · (−lap_factor/k_f²)/k²,  θ = −2π/G·k·shift';  origin and Nyquist planes 0
+__global__ void __launch_bounds__(256)
+ic_potential_kernel(const double2* __restrict__ noise, double2* __restrict__ dst, Geom g,
+                    const double* __restrict__ amplitudes, int k2_max, double th0, double th1, double th2, int rotate,
+                    double lap) {
+    const int nyq = g.G / 2;
+    const int64_t total = (int64_t)g.G * g.njl * g.Gc;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / g.Gc;
+        const int kk = (int)(idx - row * g.Gc);
+        const int i = (int)(row / g.njl);
+        const int j = g.j0 + (int)(row - (int64_t)i * g.njl);
+        double2 out = make_double2(0.0, 0.0);
+        if (i != nyq && j != nyq && kk != nyq) {
+            const int ki = i - (i >= nyq ? g.G : 0);
+            const int kj = j - (j >= nyq ? g.G : 0);
+            const int k2 = (kj * kj + ki * ki) + kk * kk;
+            if (k2 != 0 && k2 <= k2_max) {
+                const double2 v = noise[idx];
+                double re = v.x, im = v.y;
+                if (rotate) {
+                    const double theta = (ki * th0 + kj * th1) + kk * th2;
+                    double sn, cs;
+                    sincos(theta, &sn, &cs);
+                    const double r2 = re * cs - im * sn;
+                    const double i2 = re * sn + im * cs;
+                    re = r2; im = i2;
+                }
+                const double amplitude = amplitudes[k2];
+                const double inv = lap / k2;
+                out.x = (amplitude * re) * inv;
+                out.y = (amplitude * im) * inv;
+            }
+        }
+        dst[idx] = out;
+    }
+}
+
+// displace_particles (ic.py:2249-2283): lattice particle p = (i·G + j)·G + k reads grid point (i, j, k)
+__global__ void __launch_bounds__(256)
+ic_displace_kernel(double* __restrict__ pos, double* __restrict__ mom, const double* __restrict__ grid, int G, int Gp,
+                   int nxl, int64_t index_bgn, int dim, double pos_factor, double mom_factor) {
+    const int64_t total = (int64_t)nxl * G * G;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(p % G);
+        const int64_t row = p / G;
+        const double psi = __ldcs(grid + row * Gp + k);
+        const int64_t q = 3 * (index_bgn + p) + dim;
+        if (pos != nullptr) pos[q] += pos_factor * psi;
+        if (mom != nullptr) mom[q] += mom_factor * psi;
+    }
+}
+
+__device__ __forceinline__ double ic_mod_box(double x, double L) {
+    double r = fmod(x, L);
+    if (r < 0) r += L;
+    if (r == L) r = 0;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) ic_wrap_kernel(double* __restrict__ pos, int64_t n3, double L) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x)
+        pos[i] = ic_mod_box(pos[i], L);
+}
+
+// real grid (padded rows) → compact [nxl][G][G]
+__global__ void __launch_bounds__(256)
+real_export_kernel(const double* __restrict__ grid, double* __restrict__ out, int G, int Gp, int64_t total) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(p % G);
+        out[p] = __ldcs(grid + (p / G) * Gp + k);
+    }
+}
+
+// source of the 2LPT potential (carryout_2lpt, ic.py:1553-1575), accumulated in the reference's order
+__global__ void __launch_bounds__(256)
+ic_2lpt_source_kernel(double* __restrict__ grid, const double* __restrict__ d00, const double* __restrict__ d11,
+                      const double* __restrict__ d22, const double* __restrict__ d01, const double* __restrict__ d12,
+                      const double* __restrict__ d02, int G, int Gp, int64_t total) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(p % G);
+        const double a = d00[p], b = d11[p], c = d22[p], e = d01[p], f = d12[p], h = d02[p];
+        double v = -(a * b);
+        v -= b * c;
+        v -= c * a;
+        v += e * e;
+        v += f * f;
+        v += h * h;
+        grid[(p / G) * Gp + k] = v;
+    }
+}
+
+// resize_grid(…, 'fourier') as the LPT code uses it: dst[k] = src[k] for |k_i|, |k_j| < n and kk < n with
+// n = min(G_src, G_dst)/2, zero elsewhere
+__global__ void __launch_bounds__(256)
+fourier_resize_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int Gs, int Gd) {
+    const int Gcd = Gd / 2 + 1, Gcs = Gs / 2 + 1;
+    const int n = (Gs < Gd ? Gs : Gd) / 2;
+    const int nyqd = Gd / 2;
+    const int64_t total = (int64_t)Gd * Gd * Gcd;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / Gcd;
+        const int kk = (int)(idx - row * Gcd);
+        const int i = (int)(row / Gd);
+        const int j = (int)(row - (int64_t)i * Gd);
+        const int ki = i - (i >= nyqd ? Gd : 0);
+        const int kj = j - (j >= nyqd ? Gd : 0);
+        double2 v = make_double2(0.0, 0.0);
+        if (ki > -n && ki < n && kj > -n && kj < n && kk < n) {
+            const int is = ki < 0 ? ki + Gs : ki;
+            const int js = kj < 0 ? kj + Gs : kj;
+            v = src[((int64_t)is * Gs + js) * Gcs + kk];
+        }
+        dst[idx] = v;
+    }
+}
+
+}  // namespace pm
+
+using namespace pm;
+
+static int ic_check(pm_ctx* c, const char* who) {
+    PM_REQUIRE(c != nullptr, "%s: NULL context", who);
+    PM_REQUIRE(c->dtype == PM_GRID_F64, "%s: initial conditions need a PM_GRID_F64 context", who);
+    return PM_OK;
+}
+
+extern "C" {
+
+int pm_ic_lattice(pm_ctx* c, double* pos, double* mom, int64_t* ids, const double* shift, int64_t index_bgn,
+                  int64_t id_bgn, int64_t* n_local_out) {
+    PM_TRY(ic_check(c, "pm_ic_lattice"));
+    PM_REQUIRE(pos != nullptr && mom != nullptr && index_bgn >= 0, "pm_ic_lattice: bad argument");
+    const Geom& g = c->g;
+    const int64_t total = (int64_t)g.nxl * g.G * g.G;
+    const double s0 = shift ? shift[0] : 0.0, s1 = shift ? shift[1] : 0.0, s2 = shift ? shift[2] : 0.0;
+    // ℝ[domain_bgn + 0.5*cell_centered + lattice.shift] (ic.py:2206-2216); cell-centred grids only
+    PM_LAUNCH(ic_lattice_kernel, kNumSMs * 4, 256, 0, c->stream, pos, mom, ids, g.G, g.nxl, g.x0 + 0.5 + s0, 0 + 0.5 + s1,
+              0 + 0.5 + s2, c->boxsize / g.G, index_bgn, id_bgn, (int64_t)g.x0 * g.G * g.G);
+    if (n_local_out) *n_local_out = total;
+    return PM_OK;
+}
+
+int pm_ic_potential(pm_ctx* c, const double* noise, const double* amplitudes, int k2_max, const double* shift,
+                    double lap_factor) {
+    PM_TRY(ic_check(c, "pm_ic_potential"));
+    PM_REQUIRE(noise != nullptr && amplitudes != nullptr && k2_max >= 1, "pm_ic_potential: bad argument");
+    const Geom& g = c->g;
+    PM_REQUIRE(k2_max >= 3 * (g.G / 2 - 1) * (g.G / 2 - 1), "pm_ic_potential: amplitude table too short (k2_max = %d)", k2_max);
+    const double kf = 2 * M_PI / c->boxsize;
+    double th[3];
+    int rotate = 0;
+    for (int d = 0; d < 3; ++d) {
+        // realize_grid negates the particle shift (ic.py:692-695); fourier_loop: θ = −2π/G·k·shift' (mesh.py:2873-2888)
+        const double s = shift ? -shift[d] : 0.0;
+        th[d] = -2 * M_PI / g.G * s;
+        if (s != 0.0) rotate = 1;
+    }
+    PM_LAUNCH(ic_potential_kernel, kNumSMs * 8, 256, 0, c->stream, reinterpret_cast<const double2*>(noise),
+              reinterpret_cast<double2*>(c->fourier), g, amplitudes, k2_max, th[0], th[1], th[2], rotate,
+              -lap_factor / (kf * kf));
+    c->space_fourier = true;
+    c->grid_in_phi = false;
+    c->real_is_zero = false;
+    return PM_OK;
+}
+
+int pm_ic_displace(pm_ctx* c, double* pos, double* mom, int64_t index_bgn, int dim, double pos_factor,
+                   double mom_factor) {
+    PM_TRY(ic_check(c, "pm_ic_displace"));
+    PM_REQUIRE(dim >= 0 && dim < 3 && index_bgn >= 0, "pm_ic_displace: bad argument");
+    PM_REQUIRE(!c->space_fourier, "pm_ic_displace: the slab holds Fourier data (call pm_fft_backward)");
+    const Geom& g = c->g;
+    PM_LAUNCH(ic_displace_kernel, kNumSMs * 8, 256, 0, c->stream, pos, mom,
+              reinterpret_cast<const double*>(c->grid_read()) + (size_t)g.halo * g.G * g.Gp, g.G, g.Gp, g.nxl, index_bgn,
+              dim, pos_factor, mom_factor);
+    return PM_OK;
+}
+
+int pm_ic_wrap(pm_ctx* c, double* pos, int64_t n) {
+    PM_REQUIRE(c != nullptr && n >= 0 && (pos != nullptr || n == 0), "pm_ic_wrap: bad argument");
+    if (n == 0) return PM_OK;
+    PM_LAUNCH(ic_wrap_kernel, kNumSMs * 8, 256, 0, c->stream, pos, 3 * n, c->boxsize);
+    return PM_OK;
+}
+
+int pm_real_export(pm_ctx* c, double* dev_out) {
+    PM_TRY(ic_check(c, "pm_real_export"));
+    PM_REQUIRE(dev_out != nullptr, "pm_real_export: NULL output");
+    PM_REQUIRE(!c->space_fourier, "pm_real_export: the slab holds Fourier data");
+    const Geom& g = c->g;
+    const int64_t total = (int64_t)g.nxl * g.G * g.G;
+    PM_LAUNCH(real_export_kernel, kNumSMs * 8, 256, 0, c->stream,
+              reinterpret_cast<const double*>(c->grid_read()) + (size_t)g.halo * g.G * g.Gp, dev_out, g.G, g.Gp, total);
+    return PM_OK;
+}
+
+int pm_ic_2lpt_source(pm_ctx* c, const double* d00, const double* d11, const double* d22, const double* d01,
+                      const double* d12, const double* d02) {
+    PM_TRY(ic_check(c, "pm_ic_2lpt_source"));
+    PM_REQUIRE(d00 && d11 && d22 && d01 && d12 && d02, "pm_ic_2lpt_source: NULL input");
+    const Geom& g = c->g;
+    const int64_t total = (int64_t)g.nxl * g.G * g.G;
+    PM_LAUNCH(ic_2lpt_source_kernel, kNumSMs * 8, 256, 0, c->stream, c->real_interior<double>(), d00, d11, d22, d01, d12,
+              d02, g.G, g.Gp, total);
+    c->space_fourier = false;
+    c->grid_in_phi = false;
+    c->real_is_zero = false;
+    return PM_OK;
+}
+
+int pm_fourier_resize(pm_ctx* src, pm_ctx* dst) {
+    PM_TRY(ic_check(src, "pm_fourier_resize"));
+    PM_TRY(ic_check(dst, "pm_fourier_resize"));
+    PM_REQUIRE(src != dst, "pm_fourier_resize: source and destination are the same context");
+    PM_REQUIRE(src->nranks == 1 && dst->nranks == 1, "pm_fourier_resize: single-rank contexts only");
+    PM_REQUIRE(src->space_fourier, "pm_fourier_resize: the source slab holds real-space data");
+    PM_REQUIRE(src->device == dst->device, "pm_fourier_resize: contexts live on different devices");
+    // order the two contexts' streams: dst waits for everything queued on src
+    if (src->stream != dst->stream) {
+        cudaEvent_t ev;
+        PM_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        PM_CHECK_CUDA(cudaEventRecord(ev, src->stream));
+        PM_CHECK_CUDA(cudaStreamWaitEvent(dst->stream, ev, 0));
+        PM_CHECK_CUDA(cudaEventDestroy(ev));
+    }
+    PM_LAUNCH(fourier_resize_kernel, kNumSMs * 8, 256, 0, dst->stream, reinterpret_cast<const double2*>(src->fourier),
+              reinterpret_cast<double2*>(dst->fourier), src->g.G, dst->g.G);
+    if (src->stream != dst->stream) {
+        // and src must not overwrite its slab before dst has read it
+        cudaEvent_t ev;
+        PM_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        PM_CHECK_CUDA(cudaEventRecord(ev, dst->stream));
+        PM_CHECK_CUDA(cudaStreamWaitEvent(src->stream, ev, 0));
+        PM_CHECK_CUDA(cudaEventDestroy(ev));
+    }
+    dst->space_fourier = true;
+    dst->grid_in_phi = false;
+    dst->real_is_zero = false;
+    return PM_OK;
+}
+
+}  // extern "C"

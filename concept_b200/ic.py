@@ -1,0 +1,393 @@
+"""Initial-condition generator of the host mirror: particle realisations from
+primordial noise with 1LPT / 2LPT (optionally back-scaled, optionally dealiased).
+
+Reference (ic.py): PseudoRandomNumberGenerator :67-232, get_amplitudes :542-627, realize_grid :670-782,
+generate_primordial_noise :928-1163, realize_particles :1199-1399, carryout_1lpt :1447-1509,
+carryout_2lpt :1539-1589, handle_lpt_term :1895-2057, diff_ifft :2093-2108, preinitialize_particles
+:2138-2247, displace_particles :2249-2283; mesh.py: fourier_curve_loop / fourier_curve_slice_loop
+:2909-3044, get_fourier_curve_coords :3109-3160, laplacian_inverse :3422-3437, fourier_diff :3470-3510.
+
+Division of labour: the primordial noise is drawn on the host — it is defined by sequential NumPy bit
+streams (one per kj slice), so it cannot be generated out of order — but vectorised: one draw per
+stream and slice instead of one Python call per mode.  Everything downstream (amplitudes × noise,
+lattice phase, inverse Laplacian, Fourier differentiation, inverse FFT, displacement of the lattice
+particles, 2LPT source, dealiasing resize, periodic wrap) runs in libpmgrav.so (csrc/pm_ic.cu); torch is
+used for device memory only.
+
+Not built: 3LPT, non-Gaussianity (f_NL), fluid realisations, the non-linear ("structure":
+"non-linear") realisations — each aborts with a message.
+"""
+import collections
+import math
+
+import numpy as np
+import torch
+
+from . import commons, communication, linear, mesh
+from .commons import abort, masterprint, masterwarn, universals, π
+from .integration import hubble
+
+
+# ------------------------------------------------------------------------------------------ random numbers
+class PseudoRandomNumberGenerator:
+    """ic.py:67-232.  Same seeding (salt for integer seeds), same child streams (spawn) and the same
+    sequences; draws are served from cached batches like the reference's, or as whole arrays (`*_array`)."""
+    streams = {name: attr for name, attr in vars(np.random).items()
+               if isinstance(attr, type) and issubclass(attr, np.random.BitGenerator) and attr is not np.random.BitGenerator}
+
+    def __init__(self, seed=None, stream=None, cache_size=2**12, salt=True):
+        stream = stream or commons.params.random_generator
+        if salt and isinstance(seed, (int, np.integer)) and not isinstance(seed, bool):
+            seed = int(seed) + int(π*1e+8) + 137           # magic number + lucky_seed_offset, ic.py:108-116
+        if not isinstance(seed, np.random.SeedSequence):
+            seed = np.random.SeedSequence(seed)
+        self.seed, self.stream, self.cache_size = seed, stream, int(cache_size)
+        bit_generator = self.streams.get(stream)
+        if bit_generator is None and stream == 'PCG64DXSM':
+            masterwarn(f'Pseudo-random bit generator "{stream}" not available in NumPy. Falling back to "PCG64".')
+            stream = 'PCG64'
+            bit_generator = self.streams.get(stream)
+        if bit_generator is None:
+            abort(f'Pseudo-random bit generator "{stream}" not available in NumPy. '
+                  f'The available ones are {", ".join(self.streams)}.')
+        self.bit_generator = bit_generator(self.seed)
+        self.generator = np.random.Generator(self.bit_generator)
+        self._cache = {'uniform': None, 'gaussian': None, 'rayleigh': None}
+        self._index = dict.fromkeys(self._cache, self.cache_size - 1)
+
+    def spawn(self, spawn_key=0):
+        spawn_key = tuple(int(k) for k in (spawn_key if isinstance(spawn_key, (tuple, list)) else (spawn_key, )))
+        seed = np.random.SeedSequence(self.seed.entropy, spawn_key=(self.seed.spawn_key + spawn_key))
+        return type(self)(seed, self.stream, self.cache_size)
+
+    def _draw(self, kind, size):
+        if kind == 'uniform':
+            return self.generator.uniform(0, 1, size=size)
+        if kind == 'gaussian':
+            return self.generator.normal(0, 1, size=size)
+        return self.generator.rayleigh(1, size=size)
+
+    def _next(self, kind):
+        self._index[kind] += 1
+        if self._index[kind] == self.cache_size:
+            self._index[kind] = 0
+            self._cache[kind] = self._draw(kind, self.cache_size)
+        return self._cache[kind][self._index[kind]]
+
+    def uniform(self, low=0, high=1):
+        return low + self._next('uniform')*(high - low)
+
+    def gaussian(self, scale=1):
+        return self._next('gaussian')*scale
+
+    def rayleigh(self, scale=1):
+        return self._next('rayleigh')*scale
+
+    # whole-array forms: the next `size` numbers of the same sequences (fresh generators only)
+    def uniform_array(self, size, low=0, high=1):
+        return low + self._draw('uniform', size)*(high - low)
+
+    def rayleigh_array(self, size, scale=1):
+        return self._draw('rayleigh', size)*scale
+
+
+# ---------------------------------------------------------------------------- Fourier space-filling curve
+def _icbrt(x):
+    r = np.rint(np.cbrt(x.astype(np.float64))).astype(np.int64)
+    r -= r**3 > x
+    r += (r + 1)**3 <= x
+    return r
+
+
+def get_fourier_curve_coords(key):
+    """mesh.py:3109-3160 for an int64 array of keys → (ki, kj, kk)"""
+    key = np.asarray(key, dtype=np.int64).copy()
+    g = _icbrt(2*key)
+    g += g & 1
+    g += np.where(g**2*(g//2 + 1) <= key, 2, 0)
+    s = g//2
+    key -= (g - 2)**2*s
+    s_safe = np.maximum(s, 1)
+    f0 = 2*s**2 - s
+    f1 = 2*s**2 - 2*s + f0
+    f2 = f0 + f1
+    f3 = 2*s**2 + f2
+    ki, kj, kk = np.zeros_like(key), np.zeros_like(key), np.zeros_like(key)
+    done = np.zeros(key.shape, dtype=bool)
+
+    def face(mask, k, a, b, c):
+        m = mask & ~done
+        ki[m], kj[m], kk[m] = a(k, s, s_safe)[m], b(k, s, s_safe)[m], c(k, s, s_safe)[m]
+        done[m] = True
+    face(key < f0, key, lambda k, s, q: s - 1, lambda k, s, q: -s + 1 + k//q, lambda k, s, q: k % q)
+    face(key < f1, key - f0, lambda k, s, q: -s + 1 + k//q, lambda k, s, q: s - 1, lambda k, s, q: k % q)
+    face(key < f2, key - f1, lambda k, s, q: -s, lambda k, s, q: -s + 1 + k//q, lambda k, s, q: k % q)
+    face(key < f3, key - f2, lambda k, s, q: -s + k//q, lambda k, s, q: -s, lambda k, s, q: k % q)
+    face(np.ones(key.shape, dtype=bool), key - f3, lambda k, s, q: -s + k//(2*q), lambda k, s, q: -s + k % (2*q),
+         lambda k, s, q: s)
+    return ki, kj, kk
+
+
+def fourier_curve_slice_order(gridsize):
+    """The (ki, kk) visited by fourier_curve_slice_loop (mesh.py:2984-3044), in order; identical for every
+    j slice.  All points except those on Nyquist planes, origin included."""
+    nyquist = gridsize//2
+    keys = []
+    for s in range(nyquist):
+        for f in range(1 + (2 if s < nyquist - 1 else 0)):
+            key_bgn = f**2 + (f == 2) + (1 + 6*f - (f == 1))*s + (5 + 4*f - (f == 2))*s**2 + 4*s**3
+            num = (s + 1)*(1 + (f == 2))
+            step = 1 + ((num - 1) if f == 2 else 0)
+            keys.append(key_bgn + step*np.arange(num, dtype=np.int64))
+    ki, kj, kk = get_fourier_curve_coords(np.concatenate(keys))
+    assert not kj.any()
+    return ki, kk
+
+
+def generate_primordial_noise(gridsize, fixed_amplitude=False, phase_shift=0):
+    """ic.py:928-1163 on the host.  Returns the noise as a complex array in the reference's transposed
+    Fourier layout [j][i][kk], kk = 0 … gridsize/2: origin nullified, Nyquist planes zero (the reference
+    leaves them untouched and nullifies them in realize_grid)."""
+    p = commons.params
+    G, nyquist = int(gridsize), int(gridsize)//2
+    slab = np.zeros((G, G, nyquist + 1), dtype=np.complex128)
+    prng_amplitudes_common = PseudoRandomNumberGenerator(p.random_seeds['primordial amplitudes'])
+    prng_phases_common = PseudoRandomNumberGenerator(p.random_seeds['primordial phases'])
+    scale = 1/math.sqrt(2)
+
+    def polar(r, θ):
+        if phase_shift:
+            θ = θ + phase_shift
+        return r*np.cos(θ) + 1j*(r*np.sin(θ))
+
+    if p.primordial_noise_imprinting == 'simple':
+        n_total = G*G*(nyquist + 1)
+        n_nyquist = G**2 + nyquist*(2*G - 1)
+        ki, kj, kk = get_fourier_curve_coords(np.arange(n_total - n_nyquist, dtype=np.int64))
+        n = len(ki)
+        r = np.ones(n) if fixed_amplitude else prng_amplitudes_common.rayleigh_array(n, scale)
+        θ = prng_phases_common.uniform_array(n, -π, π)
+        value = polar(r, θ)
+        lower = (ki < 0) | ((ki == 0) & (kj < 0))
+        direct = (kk != 0) | lower
+        slab[kj[direct] % G, ki[direct] % G, kk[direct]] = value[direct]
+        conj = (kk == 0) & lower
+        slab[(-kj[conj]) % G, (-ki[conj]) % G, 0] = np.conj(value[conj])
+    elif p.primordial_noise_imprinting == 'distributed':
+        spawn_key_offset = 2**32
+        ki, kk = fourier_curve_slice_order(G)
+        n = len(ki)
+        i_direct, i_conj = ki % G, (-ki) % G
+        for j in range(G):
+            kj = j - (G if j >= nyquist else 0)
+            if kj == -nyquist:
+                continue
+            streams = [common.spawn(spawn_key_offset + sign*kj) for common in (prng_amplitudes_common, prng_phases_common)
+                       for sign in (+1, -1)]
+            if fixed_amplitude:
+                r = r_conj = np.ones(n)
+            else:
+                r, r_conj = streams[0].rayleigh_array(n, scale), streams[1].rayleigh_array(n, scale)
+            θ, θ_conj = streams[2].uniform_array(n, -π, π), streams[3].uniform_array(n, -π, π)
+            direct = (kk != 0) | (ki < 0) | ((ki == 0) & (kj < 0))
+            slab[j, i_direct[direct], kk[direct]] = polar(r, θ)[direct]
+            conj = (kk == 0) & ((ki < 0) | ((ki == 0) & (kj >= 0)))
+            slab[j, i_conj[conj], 0] = np.conj(polar(r_conj, θ_conj)[conj])
+    else:
+        abort(f'primordial_noise_imprinting = "{p.primordial_noise_imprinting}" not implemented')
+    slab[0, 0, 0] = 0
+    return slab
+
+
+# ------------------------------------------------------------------------------------------------ amplitudes
+def get_primordial_curvature_perturbation(k):
+    """linear.py:3329-3341: ζ(k) = π·√(2A_s)·k^(−3/2)·(k/pivot)^((n_s−1)/2)·exp(α_s/4·ln(k/pivot)²)"""
+    ps = commons.params.primordial_spectrum
+    return (π*math.sqrt(2*ps['A_s'])/ps['pivot']**((ps['n_s'] - 1)/2))*k**(ps['n_s']/2 - 2)*np.exp(
+        ps['α_s']/4*(np.log(k) - math.log(ps['pivot']))**2)
+
+
+# The two look-ups the realisation makes into linear theory (CLASS in the reference, linear.py:2587, :2730).
+# They are module attributes so that a caller (or a test) can install tabulated CLASS output instead of the
+# analytic stand-ins of concept_b200.linear.
+compute_transfer = linear.compute_transfer
+compute_cosmo = linear.compute_cosmo
+
+
+def get_amplitudes(gridsize, component, a, a_next=-1, variable=-1, multi_index=None, factor=1):
+    """ic.py:542-627 for the primordial structure: table over integer k² of T(a, k)·ζ(k)·L^(−3/2)·factor"""
+    if variable not in (0, 1):
+        abort(f'get_amplitudes() called with variable = {variable}')
+    options = component.realization_options
+    transfer_spline, _ = compute_transfer(component, variable, gridsize, multi_index, a, a_next, options.get('gauge', 'nbody'),
+                                          weight=None, backscale=options['backscale']*(variable == 0))
+    nyquist = gridsize//2
+    k2_max = 3*(nyquist - 1)**2
+    amplitudes = np.zeros(k2_max + 1)
+    normalization = commons.params.boxsize**(-1.5)*factor
+    k_magnitude = (2*π/commons.params.boxsize)*np.sqrt(np.arange(1, k2_max + 1))
+    transfer = np.array([transfer_spline.eval(k) for k in k_magnitude]) if not hasattr(transfer_spline, 'eval_array') \
+        else transfer_spline.eval_array(k_magnitude)
+    amplitudes[1:] = transfer*get_primordial_curvature_perturbation(k_magnitude)*normalization
+    return amplitudes
+
+
+# ----------------------------------------------------------------------------------------------- realisation
+LATTICE_SHIFTS = {   # Lattice.shifts_all, mesh.py:85-100 (cell-centred grids: shift_amount = −½)
+    'sc': [(0, 0, 0)],
+    'bcc': [(0, 0, 0), (-.5, -.5, -.5)],
+    'fcc': [(0, 0, 0), (0, -.5, -.5), (-.5, 0, -.5), (-.5, -.5, 0)],
+}
+n_particles_realized = {'components_tally': 0, 'components_total': 0, 'particles_tally': 0}
+
+
+def _icbrt_int(n):
+    r = round(n**(1/3))
+    return r if r**3 == n else -1
+
+
+def preic_lattice(N):
+    """species.py:1106-1117"""
+    if _icbrt_int(N) > 0:
+        return 'sc'
+    if N % 2 == 0 and _icbrt_int(N//2) > 0:
+        return 'bcc'
+    if N % 4 == 0 and _icbrt_int(N//4) > 0:
+        return 'fcc'
+    return ''
+
+
+def _device_noise(ctx, noise):
+    """Reference layout [j][i][kk] → the context's slab layout [i][j_local][kk] as device doubles."""
+    local = noise[ctx.j_start:ctx.j_start + ctx.nj_local].transpose(1, 0, 2)
+    return torch.from_numpy(np.ascontiguousarray(local).view(np.float64)).to(ctx.torch_device)
+
+
+def realize_particles(component, a, components_all=None):
+    """ic.py:1199-1399"""
+    p = commons.params
+    options = dict(p.realization_options)
+    options.update(getattr(component, 'realization_options', None) or {})
+    component.realization_options = options
+    if options['lpt'] == 3:
+        abort('3LPT is not implemented in concept_b200 (1LPT and 2LPT are)')
+    if options['lpt'] not in {1, 2}:
+        abort(f'realize_particles() called with attempted {options["lpt"]}LPT')
+    if options.get('nongaussianity'):
+        abort('Non-Gaussian initial conditions are not implemented in concept_b200')
+    if component.representation != 'particles':
+        abort(f'realize_particles() called with non-particle component {component.name}')
+    if communication.nprocs != 1:
+        abort('concept_b200 realises initial conditions on one GPU (load a snapshot for multi-GPU runs)')
+    kind = preic_lattice(component.N)
+    if not kind:
+        abort(f'Cannot initialize particle component {component.name} with N = {component.N} on a lattice, '
+              f'as neither of {{N, N/2, N/4}} is a cubic number')
+    gridsize = _icbrt_int(component.N//{'sc': 1, 'bcc': 2, 'fcc': 4}[kind])
+    if gridsize % 2:
+        abort(f'The particle lattice of {component.name} has an odd size {gridsize}; the FFT grids must be even')
+    shifts = LATTICE_SHIFTS[kind]
+    if n_particles_realized['components_tally'] == 0:
+        others = [c for c in (components_all or [component]) if c.representation == 'particles' and c.mass == -1]
+        n_particles_realized['components_total'] = max(len(others), 1)
+    if kind == 'sc':
+        total, tally = n_particles_realized['components_total'], n_particles_realized['components_tally']
+        if total == 2:
+            shifts = [LATTICE_SHIFTS['bcc'][tally % 2]]
+        elif total == 4:
+            shifts = [LATTICE_SHIFTS['fcc'][tally % 4]]
+        elif total != 1:
+            masterwarn(f'{total} ∉ {{1, 2, 4}} particle components are to be initialized on simple cubic lattices. '
+                       f'This leads to anisotropies in the initial conditions.')
+    if component.mass == -1:
+        component.mass = component.ϱ_bar*p.boxsize**3/component.N
+    masterprint(f'Realising {len(shifts)}×{gridsize}³ particles of {component.name} ...')
+    growth_factors = dict.fromkeys(('D1', 'f1', 'D2', 'f2'), float('nan'))
+    if options['backscale'] or options['lpt'] > 1:
+        cosmoresults = compute_cosmo(class_call_reason='in order to get growth factors')
+        for key in growth_factors:
+            growth_factors[key] = float(getattr(cosmoresults, f'growth_fac_{key}')(a))
+    ctx = mesh.get_context(gridsize, 'f64')
+    ctx_dealias = ctx
+    if options['dealias'] and options['lpt'] > 1:
+        gridsize_dealias = (gridsize*3)//2
+        gridsize_dealias += gridsize_dealias & 1
+        ctx_dealias = mesh.get_context(gridsize_dealias, 'f64')
+    component.N_local = 0
+    component.resize(component.N)
+    component.N_local = component.N
+    noise = _device_noise(ctx, generate_primordial_noise(gridsize, p.primordial_amplitude_fixed, p.primordial_phase_shift))
+    n_particles = gridsize**3
+    index_bgn = 0
+    id_bgn = n_particles_realized['particles_tally']
+    for shift in shifts:
+        n_local = ctx.ic_lattice(component.pos, component.mom, component.ids, shift, index_bgn, id_bgn)
+        carryout_1lpt(component, ctx, noise, shift, gridsize, options, a, growth_factors, index_bgn)
+        if options['lpt'] >= 2:
+            carryout_2lpt(component, ctx, ctx_dealias, a, growth_factors, index_bgn)
+        id_bgn += n_particles
+        index_bgn += n_local
+    n_particles_realized['particles_tally'] = id_bgn
+    n_particles_realized['components_tally'] += 1
+    ctx.ic_wrap(component.pos, component.N_local)      # ic.py:1396-1398
+    component._ids_set = True
+    component.exchange()
+    masterprint('done')
+
+
+def _mom_factor(component, a):
+    """displace_particles (ic.py:2265-2271): mom = a·m(a)·u"""
+    return a*(a**(-3*component.w_eff(a=a))*component.mass)
+
+
+def _displace_from_saved(component, ctx, index_bgn, pos_factor, mom_factor):
+    """Ψᵢ = ℱ⁻¹[i·kᵢ·Φ] for i = 0, 1, 2 (diff_ifft, ic.py:2093-2108) from the saved potential, applied to the
+    lattice particles (displace_particles).  A factor of None leaves that array untouched."""
+    for dim in range(3):
+        ctx.fourier_operate(diff_dim=dim, from_saved=True)
+        ctx.fft_backward()
+        ctx.ic_displace(None if pos_factor is None else component.pos, None if mom_factor is None else component.mom,
+                        index_bgn, dim, pos_factor or 0.0, mom_factor or 0.0)
+
+
+def carryout_1lpt(component, ctx, noise, shift, gridsize, options, a, growth_factors, index_bgn):
+    """ic.py:1447-1509: ∇²Φ⁽¹⁾ = −δ.  Leaves Φ⁽¹⁾ (from δ) in the context's saved Fourier slab."""
+    velocity_factor = a*hubble(a)*growth_factors['f1']
+    for variable in range(1 - options['backscale'], -1, -1):      # first θ, then δ
+        amplitudes = get_amplitudes(gridsize, component, a, variable=variable)
+        amplitudes_dev = torch.from_numpy(amplitudes).to(noise.device)
+        ctx.ic_potential(noise, amplitudes_dev, len(amplitudes) - 1, shift, lap_factor=2*variable - 1)
+        ctx.slab_save()
+        if variable == 1:
+            _displace_from_saved(component, ctx, index_bgn, None, _mom_factor(component, a))
+        elif options['backscale']:
+            _displace_from_saved(component, ctx, index_bgn, 1.0, velocity_factor*_mom_factor(component, a))
+        else:
+            _displace_from_saved(component, ctx, index_bgn, 1.0, None)
+
+
+def carryout_2lpt(component, ctx, ctx_dealias, a, growth_factors, index_bgn):
+    """ic.py:1539-1589 with handle_lpt_term (:1895-2057) and diff_ifft (:2093-2108):
+    ∇²Φ⁽²⁾ = D⁽²⁾/(D⁽¹⁾)²·(−Φ,₀₀Φ,₁₁ − Φ,₁₁Φ,₂₂ − Φ,₂₂Φ,₀₀ + Φ,₀₁² + Φ,₁₂² + Φ,₂₀²), the products formed in real
+    space — on a grid enlarged by 3/2 (Orszag) when dealiasing."""
+    dealias = ctx_dealias is not ctx
+    fft_factor = float(ctx_dealias.gridsize)**(-3)
+    potential_factor = fft_factor*growth_factors['D2']/growth_factors['D1']**2
+    velocity_factor = a*hubble(a)*growth_factors['f2']
+    second = {}
+    for i, j in ((0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)):
+        ctx.fourier_operate(diff_dim=i, from_saved=True)
+        ctx.fourier_operate(diff_dim=j)
+        if dealias:
+            ctx.fourier_resize_into(ctx_dealias)
+        ctx_dealias.fft_backward()
+        second[i, j] = ctx_dealias.real_export()
+    ctx_dealias.ic_2lpt_source(*(second[ij] for ij in ((0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2))))
+    del second
+    ctx_dealias.fft_forward()
+    if dealias:
+        ctx_dealias.fourier_resize_into(ctx)
+    # laplacian_inverse(Φ2, potential_factor): ×(−potential_factor/k_f²)/k² (mesh.py:3422-3437)
+    ctx.kspace_potential(-potential_factor*(commons.params.boxsize/(2*π))**2, 0)
+    ctx.slab_save()
+    _displace_from_saved(component, ctx, index_bgn, 1.0, velocity_factor*_mom_factor(component, a))

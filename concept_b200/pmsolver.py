@@ -37,6 +37,7 @@ class PMContext:
         if device is None:
             device = torch.cuda.current_device()
         self.device = int(device)
+        self.torch_device = torch.device('cuda', self.device)
         self.gridsize = int(gridsize)
         self.boxsize = float(boxsize)
         self.dtype = {'f64': PM_GRID_F64, 'f32': PM_GRID_F32, 'float64': PM_GRID_F64, 'float32': PM_GRID_F32}[str(dtype)]
@@ -209,6 +210,47 @@ class PMContext:
         n_io = ctypes.c_int64(int(n))
         check(self.lib.pm_exchange(self._h, _particles(pos), _particles(mom), _ptr(ids), ctypes.byref(n_io), pos.shape[0]))
         return n_io.value
+
+    # -- initial conditions (csrc/pm_ic.cu) ------------------------------------------------
+    def ic_lattice(self, pos, mom, ids, shift, index_bgn, id_bgn):
+        """preinitialize_particles for this rank's slab of the gridsize³ lattice; returns the local count."""
+        n_local = ctypes.c_int64(0)
+        check(self.lib.pm_ic_lattice(self._h, _particles(pos), _particles(mom), _ptr(ids), vec3(shift), int(index_bgn),
+                                     int(id_bgn), ctypes.byref(n_local)))
+        return n_local.value
+
+    def ic_potential(self, noise, amplitudes, k2_max, shift=None, lap_factor=1.0):
+        """working slab = amplitudes[k²]·noise·phase(shift)·(−lap_factor/k_f²)/k²  (realize_grid + laplacian_inverse)"""
+        if noise.dtype != torch.float64 or noise.numel() != 2*self.gridsize*self.nj_local*(self.gridsize//2 + 1):
+            raise TypeError('noise must hold the float64 (re, im) pairs of the local Fourier slab')
+        if amplitudes.dtype != torch.float64 or amplitudes.numel() < k2_max + 1:
+            raise TypeError('amplitudes must be a float64 table with k2_max + 1 entries')
+        check(self.lib.pm_ic_potential(self._h, _ptr(noise), _ptr(amplitudes), int(k2_max), vec3(shift), float(lap_factor)))
+
+    def ic_displace(self, pos, mom, index_bgn, dim, pos_factor=1.0, mom_factor=0.0):
+        check(self.lib.pm_ic_displace(self._h, None if pos is None else _particles(pos), None if mom is None else _particles(mom),
+                                      int(index_bgn), int(dim), float(pos_factor), float(mom_factor)))
+
+    def ic_wrap(self, pos, n):
+        check(self.lib.pm_ic_wrap(self._h, _particles(pos), int(n)))
+
+    def real_export(self, out=None):
+        """The real-space grid without padding as a device tensor (nx_local, G, G)."""
+        if out is None:
+            out = torch.empty((self.nx_local, self.gridsize, self.gridsize), dtype=torch.float64, device=self.torch_device)
+        check(self.lib.pm_real_export(self._h, _ptr(out)))
+        return out
+
+    def ic_2lpt_source(self, d00, d11, d22, d01, d12, d02):
+        n = self.nx_local*self.gridsize**2
+        for t in (d00, d11, d22, d01, d12, d02):
+            if t.dtype != torch.float64 or t.numel() != n:
+                raise TypeError('second-derivative grids must be float64 of shape (nx_local, G, G)')
+        check(self.lib.pm_ic_2lpt_source(self._h, *(_ptr(t) for t in (d00, d11, d22, d01, d12, d02))))
+
+    def fourier_resize_into(self, other):
+        """Copy this context's Fourier slab into `other`'s (another grid size): modes |k| < min(G, G')/2."""
+        check(self.lib.pm_fourier_resize(self._h, other._h))
 
     # -- whole kick -------------------------------------------------------------------
     def kick_long(self, pos, mom, params, sum_mom2=None):

@@ -217,6 +217,38 @@ int pm_flag_rung_jumps(pm_ctx* ctx, const double* acc, int64_t n, const signed c
 int pm_apply_rung_jumps(pm_ctx* ctx, int64_t n, signed char* rung, signed char* rung_jumped, int n_rungs,
                         int64_t* rungs_N_host);
 
+/* ---- initial conditions (PM_GRID_F64 contexts, lattice size == gridsize) ------- */
+/* preinitialize_particles (ic.py:2138-2247): the rank's x-slab of the n³ lattice (n = gridsize), cell-centred,
+ * pos = ((x_start + ½ + shift) + i)·L/n …, mom = 0, ids (may be NULL) = id_bgn + ((i·n + j)·n + k).
+ * Particles index_bgn … index_bgn + n_local − 1 of the device arrays are written; shift[3] is the
+ * lattice shift in grid units (mesh.py:85-100), NULL = (0,0,0). */
+int pm_ic_lattice(pm_ctx* ctx, double* pos, double* mom, int64_t* ids, const double* shift, int64_t index_bgn,
+                  int64_t id_bgn, int64_t* n_local_out);
+/* realize_grid (ic.py:670-782; scalar, output_space='Fourier', then nullify_modes origin + nyquist) fused with
+ * laplacian_inverse (mesh.py:3422-3437) into the working slab:
+ *   slab[k] = amplitudes[k²]·noise[k]·e^{iθ(k, −shift)} · (−lap_factor/k_f²)/k²
+ * noise: device doubles (re, im) in the slab layout of PM_TAP_FOURIER (the primordial noise of
+ * generate_primordial_noise, ic.py:928-1163, drawn by the host code); amplitudes: device table over integer k²
+ * with k2_max + 1 entries (get_amplitudes, ic.py:542-627). */
+int pm_ic_potential(pm_ctx* ctx, const double* noise, const double* amplitudes, int k2_max, const double* shift,
+                    double lap_factor);
+/* displace_particles (ic.py:2249-2283) from the real-space grid: lattice particle (i, j, k) gets
+ *   pos[dim] += pos_factor·ψ[i][j][k],  mom[dim] += mom_factor·ψ[i][j][k]      (either array may be NULL) */
+int pm_ic_displace(pm_ctx* ctx, double* pos, double* mom, int64_t index_bgn, int dim, double pos_factor,
+                   double mom_factor);
+/* pos = mod(pos, L) (ic.py:1396-1398) */
+int pm_ic_wrap(pm_ctx* ctx, double* pos, int64_t n);
+/* copy the real-space grid, padding stripped, into a device buffer of nx_local·G·G doubles */
+int pm_real_export(pm_ctx* ctx, double* dev_out);
+/* source of the 2LPT potential (carryout_2lpt, ic.py:1553-1575) into the real-space grid:
+ *   −Φ,₀₀Φ,₁₁ − Φ,₁₁Φ,₂₂ − Φ,₂₂Φ,₀₀ + Φ,₀₁² + Φ,₁₂² + Φ,₂₀²   from six exported second-derivative grids */
+int pm_ic_2lpt_source(pm_ctx* ctx, const double* d00, const double* d11, const double* d22, const double* d01,
+                      const double* d12, const double* d02);
+/* resize_grid(…, 'fourier') as the dealiased LPT terms use it (ic.py:2093-2108, :2027-2034): the working
+ * Fourier slab of `src` is copied into the one of `dst` (another grid size, same device, one rank each) for the
+ * modes |k| < min(G_src, G_dst)/2; every other mode of `dst` is nullified. */
+int pm_fourier_resize(pm_ctx* src, pm_ctx* dst);
+
 /* ---- whole-path entry points --------------------------------------------- */
 typedef struct {
     int order;            /* interpolation order 1..4 */

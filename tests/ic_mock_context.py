@@ -1,0 +1,123 @@
+"""TEST INFRASTRUCTURE ONLY — a numpy model of the libpmgrav entry points that concept_b200.ic calls
+(include/pmgrav.h: pm_ic_lattice, pm_ic_potential, pm_slab_save, pm_fourier_operate, pm_fft_forward /
+pm_fft_backward, pm_kspace_potential, pm_ic_displace, pm_real_export, pm_ic_2lpt_source, pm_fourier_resize,
+pm_ic_wrap), one rank, fp64.  It lets the CPU suite run the *orchestration* of concept_b200/ic.py — the
+order of operations, factors and signs the host hands to the kernels — against the reference's golden
+vectors without a GPU.  The kernels themselves are checked by the `-m gpu` tests of tests/test_ic.py.
+
+Slab layout as on the device with one rank: complex [i][j][kk] (PM_TAP_FOURIER), real [i][j][k].
+"""
+import numpy as np
+import torch
+
+
+class MockContext:
+    torch_device = torch.device('cpu')
+    device = 0
+
+    def __init__(self, gridsize, boxsize):
+        self.gridsize, self.boxsize = int(gridsize), float(boxsize)
+        G = self.gridsize
+        self.nx_local = self.nj_local = G
+        self.x_start = self.j_start = 0
+        self.fourier = None
+        self.real = None
+        self.saved = None
+        i = np.fft.fftfreq(G, 1/G).astype(np.int64)
+        self.k = (i[:, None, None], i[None, :, None], np.arange(G//2 + 1, dtype=np.int64)[None, None, :])
+        nyq = G//2
+        self.live = np.broadcast_to((np.abs(self.k[0]) < nyq) & (np.abs(self.k[1]) < nyq) & (self.k[2] < nyq),
+                                    (G, G, nyq + 1)).copy()
+        self.live_nonzero = self.live.copy()
+        self.live_nonzero[0, 0, 0] = False
+        self.k2 = self.k[0]**2 + self.k[1]**2 + self.k[2]**2
+
+    # -- pm_ic_lattice
+    def ic_lattice(self, pos, mom, ids, shift, index_bgn, id_bgn):
+        G = self.gridsize
+        shift = shift or (0, 0, 0)
+        cell = self.boxsize/G
+        ax = [((0.5 + shift[d]) + np.arange(G))*cell for d in range(3)]
+        X, Y, Z = np.meshgrid(*ax, indexing='ij')
+        n = G**3
+        pos[index_bgn:index_bgn + n] = torch.from_numpy(np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1))
+        mom[index_bgn:index_bgn + n] = 0
+        if ids is not None:
+            ids[index_bgn:index_bgn + n] = id_bgn + torch.arange(n)
+        return n
+
+    # -- pm_ic_potential
+    def ic_potential(self, noise, amplitudes, k2_max, shift=None, lap_factor=1.0):
+        G = self.gridsize
+        noise = noise.numpy().view(np.complex128).reshape(G, G, G//2 + 1)
+        amplitudes = amplitudes.numpy()
+        v = noise.copy()
+        if shift is not None and tuple(shift) != (0, 0, 0):
+            θ = sum(self.k[d]*(-2*np.pi/G*(-shift[d])) for d in range(3))
+            v = v*(np.cos(θ) + 1j*np.sin(θ))
+        kf = 2*np.pi/self.boxsize
+        k2 = np.where(self.live_nonzero, self.k2, 1)
+        v = amplitudes[np.minimum(k2, k2_max)]*v*((-lap_factor/kf**2)/k2)
+        self.fourier = np.where(self.live_nonzero, v, 0)
+        self.real = None
+
+    def slab_save(self):
+        self.saved = self.fourier.copy()
+
+    # -- pm_fourier_operate (deconv_order 0, no shift)
+    def fourier_operate(self, deconv_order=0, shift=None, scale=1.0, diff_dim=-1, from_saved=False):
+        assert deconv_order == 0 and shift is None
+        src = self.saved if from_saved else self.fourier
+        assert src is not None
+        v = src*scale
+        if diff_dim >= 0:
+            v = v*1j*(2*np.pi/self.boxsize)*self.k[diff_dim]
+        self.fourier = np.where(self.live, v, 0)
+        self.real = None
+
+    # -- pm_kspace_potential (deconv_order 0, gauss 0)
+    def kspace_potential(self, prefactor, deconv_order, gauss=0.0, scale=1.0):
+        assert deconv_order == 0 and gauss == 0 and self.fourier is not None
+        k2 = np.where(self.live_nonzero, self.k2, 1)
+        self.fourier = np.where(self.live_nonzero, self.fourier*(scale*prefactor/k2), 0)
+
+    def fft_backward(self):
+        G = self.gridsize
+        assert self.fourier is not None
+        self.real = np.fft.irfftn(self.fourier, s=(G, G, G), axes=(0, 1, 2))*float(G)**3
+        self.fourier = None
+
+    def fft_forward(self):
+        assert self.real is not None
+        self.fourier = np.fft.rfftn(self.real, axes=(0, 1, 2))
+        self.real = None
+
+    # -- pm_ic_displace
+    def ic_displace(self, pos, mom, index_bgn, dim, pos_factor=1.0, mom_factor=0.0):
+        assert self.real is not None
+        ψ = torch.from_numpy(self.real.ravel().copy())
+        n = ψ.numel()
+        if pos is not None:
+            pos[index_bgn:index_bgn + n, dim] += pos_factor*ψ
+        if mom is not None:
+            mom[index_bgn:index_bgn + n, dim] += mom_factor*ψ
+
+    def ic_wrap(self, pos, n):
+        pos[:n] = torch.from_numpy(np.mod(pos[:n].numpy(), self.boxsize))
+
+    def real_export(self, out=None):
+        return torch.from_numpy(self.real.copy())
+
+    def ic_2lpt_source(self, d00, d11, d22, d01, d12, d02):
+        a, b, c, e, f, h = (t.numpy() for t in (d00, d11, d22, d01, d12, d02))
+        self.real = -(a*b) - b*c - c*a + e*e + f*f + h*h
+        self.fourier = None
+
+    def fourier_resize_into(self, other):
+        Gs, Gd = self.gridsize, other.gridsize
+        n = min(Gs, Gd)//2
+        out = np.zeros((Gd, Gd, Gd//2 + 1), dtype=complex)
+        idx = np.arange(-n + 1, n)
+        out[np.ix_(idx % Gd, idx % Gd, np.arange(n))] = self.fourier[np.ix_(idx % Gs, idx % Gs, np.arange(n))]
+        other.fourier = out
+        other.real = None
