@@ -8,8 +8,11 @@
 // everything downstream of it runs here.  All kernels are streaming, HBM-bound passes over a G³ grid
 // or over the particle arrays; grids are fp64 (PM_GRID_F64 contexts only).
 #include "pm_internal.cuh"
+#include "pm_ic_ops.cuh"
 
 namespace pm {
+
+using icops::Slab;
 
 // pos at lattice points, mom = 0, ids by lattice point (preinitialize_particles, ic.py:2197-2243)
 __global__ void __launch_bounds__(256)
@@ -17,58 +20,22 @@ ic_lattice_kernel(double* __restrict__ pos, double* __restrict__ mom, int64_t* _
                   double bx, double by, double bz, double cell, int64_t index_bgn, int64_t id_bgn, int64_t id_plane0) {
     const int64_t total = (int64_t)nxl * n * n;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(p % n);
-        const int64_t r = p / n;
-        const int j = (int)(r % n);
-        const int i = (int)(r / n);
-        double* q = pos + 3 * (index_bgn + p);
-        q[0] = (bx + i) * cell;
-        q[1] = (by + j) * cell;
-        q[2] = (bz + k) * cell;
+        icops::lattice_point(p, n, bx, by, bz, cell, pos + 3 * (index_bgn + p));
         double* m = mom + 3 * (index_bgn + p);
         m[0] = 0; m[1] = 0; m[2] = 0;
         if (ids != nullptr) ids[index_bgn + p] = id_bgn + id_plane0 + p;
     }
 }
 
-// realize_grid (scalar, Fourier output) + laplacian_inverse in one pass:
-//   slab[k] = amplitudes[k²]·noise[k]·e^{iθ} · (−lap_factor/k_f²)/k²,  θ = −2π/G·k·shift';  origin and Nyquist planes 0
+// realize_grid (scalar, Fourier output) + laplacian_inverse in one pass over the local slab
 __global__ void __launch_bounds__(256)
-ic_potential_kernel(const double2* __restrict__ noise, double2* __restrict__ dst, Geom g,
+ic_potential_kernel(const double2* __restrict__ noise, double2* __restrict__ dst, Slab s,
                     const double* __restrict__ amplitudes, int k2_max, double th0, double th1, double th2, int rotate,
                     double lap) {
-    const int nyq = g.G / 2;
-    const int64_t total = (int64_t)g.G * g.njl * g.Gc;
+    const int64_t total = (int64_t)s.G * s.njl * (s.G / 2 + 1);
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = idx / g.Gc;
-        const int kk = (int)(idx - row * g.Gc);
-        const int i = (int)(row / g.njl);
-        const int j = g.j0 + (int)(row - (int64_t)i * g.njl);
-        double2 out = make_double2(0.0, 0.0);
-        if (i != nyq && j != nyq && kk != nyq) {
-            const int ki = i - (i >= nyq ? g.G : 0);
-            const int kj = j - (j >= nyq ? g.G : 0);
-            const int k2 = (kj * kj + ki * ki) + kk * kk;
-            if (k2 != 0 && k2 <= k2_max) {
-                const double2 v = noise[idx];
-                double re = v.x, im = v.y;
-                if (rotate) {
-                    const double theta = (ki * th0 + kj * th1) + kk * th2;
-                    double sn, cs;
-                    sincos(theta, &sn, &cs);
-                    const double r2 = re * cs - im * sn;
-                    const double i2 = re * sn + im * cs;
-                    re = r2; im = i2;
-                }
-                const double amplitude = amplitudes[k2];
-                const double inv = lap / k2;
-                out.x = (amplitude * re) * inv;
-                out.y = (amplitude * im) * inv;
-            }
-        }
-        dst[idx] = out;
-    }
+         idx += (int64_t)gridDim.x * blockDim.x)
+        dst[idx] = icops::potential_mode(idx, s, noise, amplitudes, k2_max, th0, th1, th2, rotate, lap);
 }
 
 // displace_particles (ic.py:2249-2283): lattice particle p = (i·G + j)·G + k reads grid point (i, j, k)
@@ -77,78 +44,41 @@ ic_displace_kernel(double* __restrict__ pos, double* __restrict__ mom, const dou
                    int nxl, int64_t index_bgn, int dim, double pos_factor, double mom_factor) {
     const int64_t total = (int64_t)nxl * G * G;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(p % G);
-        const int64_t row = p / G;
-        const double psi = __ldcs(grid + row * Gp + k);
+        const double psi = __ldcs(grid + icops::real_index(p, G, Gp));
         const int64_t q = 3 * (index_bgn + p) + dim;
         if (pos != nullptr) pos[q] += pos_factor * psi;
         if (mom != nullptr) mom[q] += mom_factor * psi;
     }
 }
 
-__device__ __forceinline__ double ic_mod_box(double x, double L) {
-    double r = fmod(x, L);
-    if (r < 0) r += L;
-    if (r == L) r = 0;
-    return r;
-}
-
 __global__ void __launch_bounds__(256) ic_wrap_kernel(double* __restrict__ pos, int64_t n3, double L) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x)
-        pos[i] = ic_mod_box(pos[i], L);
+        pos[i] = icops::mod_box(pos[i], L);
 }
 
 // real grid (padded rows) → compact [nxl][G][G]
 __global__ void __launch_bounds__(256)
 real_export_kernel(const double* __restrict__ grid, double* __restrict__ out, int G, int Gp, int64_t total) {
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(p % G);
-        out[p] = __ldcs(grid + (p / G) * Gp + k);
-    }
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x)
+        out[p] = __ldcs(grid + icops::real_index(p, G, Gp));
 }
 
-// source of the 2LPT potential (carryout_2lpt, ic.py:1553-1575), accumulated in the reference's order
+// source of the 2LPT potential (carryout_2lpt, ic.py:1553-1575)
 __global__ void __launch_bounds__(256)
 ic_2lpt_source_kernel(double* __restrict__ grid, const double* __restrict__ d00, const double* __restrict__ d11,
                       const double* __restrict__ d22, const double* __restrict__ d01, const double* __restrict__ d12,
                       const double* __restrict__ d02, int G, int Gp, int64_t total) {
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(p % G);
-        const double a = d00[p], b = d11[p], c = d22[p], e = d01[p], f = d12[p], h = d02[p];
-        double v = -(a * b);
-        v -= b * c;
-        v -= c * a;
-        v += e * e;
-        v += f * f;
-        v += h * h;
-        grid[(p / G) * Gp + k] = v;
-    }
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x)
+        grid[icops::real_index(p, G, Gp)] = icops::lpt2_source(d00[p], d11[p], d22[p], d01[p], d12[p], d02[p]);
 }
 
-// resize_grid(…, 'fourier') as the LPT code uses it: dst[k] = src[k] for |k_i|, |k_j| < n and kk < n with
-// n = min(G_src, G_dst)/2, zero elsewhere
+// resize_grid(…, 'fourier'): dst[k] = src[k] for |k| < min(G_src, G_dst)/2, zero elsewhere
 __global__ void __launch_bounds__(256)
 fourier_resize_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int Gs, int Gd) {
-    const int Gcd = Gd / 2 + 1, Gcs = Gs / 2 + 1;
-    const int n = (Gs < Gd ? Gs : Gd) / 2;
-    const int nyqd = Gd / 2;
-    const int64_t total = (int64_t)Gd * Gd * Gcd;
+    const int64_t total = (int64_t)Gd * Gd * (Gd / 2 + 1);
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = idx / Gcd;
-        const int kk = (int)(idx - row * Gcd);
-        const int i = (int)(row / Gd);
-        const int j = (int)(row - (int64_t)i * Gd);
-        const int ki = i - (i >= nyqd ? Gd : 0);
-        const int kj = j - (j >= nyqd ? Gd : 0);
-        double2 v = make_double2(0.0, 0.0);
-        if (ki > -n && ki < n && kj > -n && kj < n && kk < n) {
-            const int is = ki < 0 ? ki + Gs : ki;
-            const int js = kj < 0 ? kj + Gs : kj;
-            v = src[((int64_t)is * Gs + js) * Gcs + kk];
-        }
-        dst[idx] = v;
-    }
+         idx += (int64_t)gridDim.x * blockDim.x)
+        dst[idx] = icops::resize_mode(idx, src, Gs, Gd);
 }
 
 }  // namespace pm
@@ -193,7 +123,7 @@ int pm_ic_potential(pm_ctx* c, const double* noise, const double* amplitudes, in
         if (s != 0.0) rotate = 1;
     }
     PM_LAUNCH(ic_potential_kernel, kNumSMs * 8, 256, 0, c->stream, reinterpret_cast<const double2*>(noise),
-              reinterpret_cast<double2*>(c->fourier), g, amplitudes, k2_max, th[0], th[1], th[2], rotate,
+              reinterpret_cast<double2*>(c->fourier), Slab{g.G, g.njl, g.j0}, amplitudes, k2_max, th[0], th[1], th[2], rotate,
               -lap_factor / (kf * kf));
     c->space_fourier = true;
     c->grid_in_phi = false;

@@ -231,13 +231,53 @@ def _dump_times():
     return [DumpTime(a) for a in sorted(values) if a >= universals.a]
 
 
+def _output_dir(kind):
+    od = commons.params.output_dirs
+    if isinstance(od, str):      # one directory for everything (param/example_basic)
+        return od
+    return od.get(kind, od.get('default')) if isinstance(od, dict) else None
+
+
+def _wanted(kind, dump_time):
+    val = commons.params.output_times.get(kind)
+    if val is None:
+        return False
+    if isinstance(val, dict):
+        val = [x for v in val.values() for x in np.ravel(v).tolist()]
+    return any(float(x) == dump_time.a for x in np.ravel(val).tolist())
+
+
+def dump_powerspec(components, dump_time):
+    """analysis.powerspec + save_powerspec (analysis.py:500-579, :796-836) with the defaults of powerspec_options
+    (commons.py:3354-3385: PCS, deconvolution, bcc interlacing, k_max = Nyquist, grid 2·∛N).  Columns as in the
+    reference's text files: k, number of modes, P(k)."""
+    out_dir = _output_dir('powerspec')
+    particle_components = [c for c in components if c.representation == 'particles']
+    if not particle_components:
+        return None
+    gridsize = max(2*round(c.N**(1/3)) for c in particle_components)
+    gridsize += gridsize & 1
+    k, power, n_modes = analysis.powerspec(particle_components, gridsize)
+    if out_dir and communication.master:
+        os.makedirs(out_dir, exist_ok=True)
+        filename = os.path.join(out_dir, f'powerspec_a={dump_time.a:.2f}')
+        names = ', '.join(c.name for c in particle_components)
+        header = (f'Power spectrum of {names} at a = {universals.a:.8g}, t = {universals.t:.8g} {commons.unit_time}, '
+                  f'grid size {gridsize} (concept_b200)\n'
+                  f'k [{commons.unit_length}^-1]\tmodes\tpower [{commons.unit_length}^3]')
+        np.savetxt(filename, np.column_stack([k, n_modes, power]), fmt=('%.8e', '%d', '%.8e'), delimiter='\t', header=header)
+    return k, power, n_modes
+
+
 def dump(components, dump_time, on_dump=None):
-    """main.py:1676-1712: snapshots are written as .npz (HDF5 is unavailable); `on_dump` is the hook the
-    tests use to capture the state."""
+    """main.py:1676-1712: snapshots are written as .npz (HDF5 is unavailable), power spectra as text files;
+    `on_dump` is the hook the tests use to capture the state."""
     if on_dump is not None:
         on_dump(components, dump_time)
-    out_dir = commons.params.output_dirs.get('snapshot') if isinstance(commons.params.output_dirs, dict) else None
-    wants_snapshot = 'snapshot' in commons.params.output_times
+    if _wanted('powerspec', dump_time):
+        dump_powerspec(components, dump_time)
+    out_dir = _output_dir('snapshot')
+    wants_snapshot = _wanted('snapshot', dump_time)
     if out_dir and wants_snapshot:
         for c in components:
             pos, mom = c.gather_global()
@@ -353,3 +393,40 @@ def timeloop(components, on_dump=None, on_step=None, max_steps=None):
                     recompute_Δt_max = False
                     continue
     return time_step
+
+
+def get_initial_conditions(initial_conditions_touse=None, do_realization=True):
+    """snapshot.get_initial_conditions (snapshot.py:3425-3474): each entry of the `initial_conditions` parameter
+    is a path to a snapshot (GADGET-2 here) or a dict describing a component to be realised (ic.realize_particles)."""
+    from . import ic, snapshot
+    from .species import Component
+    spec = commons.params.initial_conditions if initial_conditions_touse is None else initial_conditions_touse
+    if not spec:
+        return []
+    entries = [spec] if isinstance(spec, (str, dict)) else list(spec)
+    components, to_realize = [], []
+    for entry in entries:
+        if isinstance(entry, str):
+            components.append(snapshot.load(entry))
+        elif isinstance(entry, dict):
+            entry = dict(entry)
+            species = str(entry.pop('species', None))
+            name = str(entry.pop('name', species))
+            to_realize.append(Component(name, species, **{key.replace(' ', '_'): value for key, value in entry.items()}))
+        else:
+            abort(f'Error parsing initial_conditions of type {type(entry)}')
+    if do_realization and to_realize:
+        ic.n_particles_realized.update(components_tally=0, components_total=0, particles_tally=0)
+        for component in to_realize:
+            ic.realize_particles(component, universals.a, components_all=to_realize)
+    return components + to_realize
+
+
+def run(param, extra='', on_dump=None, on_step=None, max_steps=None):
+    """What `concept -p param` does for a particle-only run (main.py:2437-2470): load the parameter file, set up
+    the background, obtain the initial conditions and run the time loop.  Returns the components."""
+    commons.load_params(param, extra)
+    init_time()
+    components = get_initial_conditions()
+    timeloop(components, on_dump=on_dump, on_step=on_step, max_steps=max_steps)
+    return components

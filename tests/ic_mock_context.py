@@ -121,3 +121,99 @@ class MockContext:
         out[np.ix_(idx % Gd, idx % Gd, np.arange(n))] = self.fourier[np.ix_(idx % Gs, idx % Gs, np.arange(n))]
         other.fourier = out
         other.real = None
+
+
+class HostKernelContext(MockContext):
+    """MockContext with the operations of csrc/pm_ic.cu executed by the *device code itself*, compiled for the CPU
+    (tests/ic_host_harness.cu over csrc/pm_ic_ops.cuh), on buffers laid out as on the device: one allocation of
+    G·G·(G+2) doubles that holds the padded real grid [i][j][G+2] or, in place, the Fourier slab [i][j][G/2+1].
+    The FFTs and the pre-existing k-space kernels (pm_fourier_operate, pm_kspace_potential; GPU-tested elsewhere)
+    stay numpy."""
+    lib = None
+
+    def __init__(self, gridsize, boxsize):
+        super().__init__(gridsize, boxsize)
+        G = self.gridsize
+        self.buf = np.zeros(G*G*(G + 2))
+
+    # views of the in-place buffer
+    def _real_view(self):
+        G = self.gridsize
+        return self.buf.reshape(G, G, G + 2)
+
+    def _fourier_view(self):
+        G = self.gridsize
+        return self.buf.view(np.complex128).reshape(G, G, G//2 + 1)
+
+    def _sync_from_buf(self, fourier):
+        if fourier:
+            self.fourier, self.real = self._fourier_view().copy(), None
+        else:
+            self.real, self.fourier = self._real_view()[:, :, :self.gridsize].copy(), None
+
+    def _sync_to_buf(self):
+        if self.fourier is not None:
+            self._fourier_view()[...] = self.fourier
+        else:
+            self.buf[:] = np.nan          # padding is garbage on the device too
+            self._real_view()[:, :, :self.gridsize] = self.real
+
+    @staticmethod
+    def _p(a):
+        import ctypes
+        return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+    def ic_lattice(self, pos, mom, ids, shift, index_bgn, id_bgn):
+        import ctypes
+        G = self.gridsize
+        shift = shift or (0, 0, 0)
+        n = G**3
+        host = pos.numpy()
+        assert host.flags.c_contiguous
+        self.lib.h_lattice(self._p(host), G, G, ctypes.c_double(0 + 0.5 + shift[0]), ctypes.c_double(0 + 0.5 + shift[1]),
+                           ctypes.c_double(0 + 0.5 + shift[2]), ctypes.c_double(self.boxsize/G), ctypes.c_int64(index_bgn))
+        mom[index_bgn:index_bgn + n] = 0
+        ids[index_bgn:index_bgn + n] = id_bgn + torch.arange(n)
+        return n
+
+    def ic_potential(self, noise, amplitudes, k2_max, shift=None, lap_factor=1.0):
+        import ctypes
+        G = self.gridsize
+        kf = 2*np.pi/self.boxsize
+        th = np.array([-2*np.pi/G*(-(shift[d] if shift is not None else 0.0)) for d in range(3)])
+        rotate = int(shift is not None and any(s != 0 for s in shift))
+        self.buf[:] = np.nan
+        self.lib.h_potential(self._p(noise.numpy()), self._p(self.buf), G, G, 0, self._p(amplitudes.numpy()), int(k2_max),
+                             self._p(th), rotate, ctypes.c_double(-lap_factor/(kf*kf)))
+        self._sync_from_buf(fourier=True)
+
+    def ic_displace(self, pos, mom, index_bgn, dim, pos_factor=1.0, mom_factor=0.0):
+        import ctypes
+        G = self.gridsize
+        self._sync_to_buf()
+        self.lib.h_displace(self._p(None if pos is None else pos.numpy()), self._p(None if mom is None else mom.numpy()),
+                            self._p(self.buf), G, G + 2, G, ctypes.c_int64(index_bgn), int(dim), ctypes.c_double(pos_factor),
+                            ctypes.c_double(mom_factor))
+
+    def ic_wrap(self, pos, n):
+        import ctypes
+        self.lib.h_wrap(self._p(pos.numpy()), ctypes.c_int64(3*n), ctypes.c_double(self.boxsize))
+
+    def real_export(self, out=None):
+        G = self.gridsize
+        self._sync_to_buf()
+        out = np.empty((G, G, G))
+        self.lib.h_export(self._p(self.buf), self._p(out), G, G + 2, G)
+        return torch.from_numpy(out)
+
+    def ic_2lpt_source(self, d00, d11, d22, d01, d12, d02):
+        G = self.gridsize
+        self.buf[:] = np.nan
+        self.lib.h_source(self._p(self.buf), *(self._p(t.numpy()) for t in (d00, d11, d22, d01, d12, d02)), G, G + 2, G)
+        self._sync_from_buf(fourier=False)
+
+    def fourier_resize_into(self, other):
+        self._sync_to_buf()
+        other.buf[:] = np.nan
+        self.lib.h_resize(self._p(self.buf), self._p(other.buf), self.gridsize, other.gridsize)
+        other._sync_from_buf(fourier=True)

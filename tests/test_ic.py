@@ -180,13 +180,36 @@ def test_amplitudes_match_reference(path, monkeypatch):
             assert np.allclose(table, d[f'amplitudes{variable}'], rtol=1e-14, atol=0)
 
 
+@pytest.fixture(scope='module')
+def host_kernels():
+    """csrc/pm_ic_ops.cuh compiled for the CPU (tests/ic_host_harness.cu) as a ctypes library"""
+    import ctypes
+    import subprocess
+    import tempfile
+    root = os.path.dirname(HERE)
+    d = tempfile.mkdtemp(prefix='ic_harness_')
+    src = os.path.join(d, 'ic_host_harness.cpp')
+    with open(os.path.join(HERE, 'ic_host_harness.cu')) as f, open(src, 'w') as g:
+        g.write(f.read())
+    lib = os.path.join(d, 'libic_harness.so')
+    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-I', '/usr/local/cuda/include',
+                    '-I', os.path.join(root, 'concept_b200', 'csrc'), src, '-o', lib], check=True)
+    return ctypes.CDLL(lib)
+
+
+@pytest.mark.parametrize('kernels', ['numpy-model', 'device-code-on-cpu'])
 @pytest.mark.parametrize('path', CASES, ids=IDS)
-def test_orchestration_through_kernel_model(path, monkeypatch):
-    """concept_b200.ic.realize_particles with the kernels replaced by their numpy model (tests/ic_mock_context.py)"""
+def test_orchestration_through_kernel_model(path, kernels, monkeypatch, host_kernels):
+    """concept_b200.ic.realize_particles with the kernels replaced by their numpy model, and by the device code
+    itself compiled for the CPU (tests/ic_mock_context.py)"""
     import torch
     from concept_b200 import commons, ic, integration, mesh
     from concept_b200.species import Component
-    from ic_mock_context import MockContext
+    import ic_mock_context
+    MockContext = ic_mock_context.MockContext
+    if kernels == 'device-code-on-cpu':
+        MockContext = ic_mock_context.HostKernelContext
+        monkeypatch.setattr(MockContext, 'lib', host_kernels)
     d = np.load(path)
     commons.load_params(_param_text(d))
     integration.init_time()
@@ -321,3 +344,85 @@ realization_options = {{'lpt': {lpt}, 'dealias': {dealias}, 'backscale': {lpt ==
     disp -= p.boxsize*np.rint(disp/p.boxsize)
     rms = np.sqrt((disp**2).sum(axis=1).mean())/cell
     assert 0.005 < rms < 0.2
+
+
+EXAMPLE_BASIC = '''
+initial_conditions = {
+    'species': 'matter',
+    'N'      : 64**3,
+}
+output_dirs = '%s'
+output_times = {'powerspec': 1.0}
+boxsize = 256*Mpc/h
+potential_options = 128
+H0 = 67*km/(s*Mpc)
+Ωb = 0.049
+Ωcdm = 0.27
+a_begin = 0.02
+primordial_spectrum = {
+    'A_s': 2.1e-9,
+    'n_s': 0.96,
+}
+'''   # the settings of param/example_basic
+
+
+def test_get_initial_conditions_realises_the_component_dict(monkeypatch, tmp_path):
+    """main.get_initial_conditions (snapshot.py:3425-3474) for param/example_basic's `initial_conditions` dict,
+    kernels replaced by their numpy model: a 64³ lattice displaced by a few per cent of the spacing."""
+    import torch
+    from concept_b200 import commons, ic, integration, main, mesh
+    from concept_b200.species import Component
+    from ic_mock_context import MockContext
+    p = commons.load_params(EXAMPLE_BASIC % tmp_path)
+    integration.init_time()
+    contexts = {}
+    monkeypatch.setattr(mesh, 'get_context', lambda gridsize, dtype=None: contexts.setdefault(
+        int(gridsize), MockContext(gridsize, commons.params.boxsize)))
+    monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
+    components = main.get_initial_conditions()
+    assert [c.name for c in components] == ['matter'] and list(contexts) == [64]
+    c = components[0]
+    assert c.N == c.N_local == 64**3 and c.forces == {'gravity': 'p3m'}
+    assert c.mass == pytest.approx(c.ϱ_bar*p.boxsize**3/c.N, rel=1e-14)
+    pos, mom = c.pos[:c.N].numpy(), c.mom[:c.N].numpy()
+    assert pos.min() >= 0 and pos.max() < p.boxsize
+    cell = p.boxsize/64
+    lattice = (np.stack(np.meshgrid(*[np.arange(64)]*3, indexing='ij'), axis=-1).reshape(-1, 3) + 0.5)*cell
+    disp = pos - lattice
+    disp -= p.boxsize*np.rint(disp/p.boxsize)
+    assert 0.03 < np.sqrt((disp**2).sum(axis=1).mean())/cell < 0.1
+    # Zel'dovich: mom = a·m·u with u = a·H·f·ψ up to the difference between the θ and δ transfer functions (none
+    # in the analytic stand-in): the two fields are proportional
+    a = commons.universals.a
+    cosmo = ic.compute_cosmo()
+    expected = a*c.mass*a*integration.hubble(a)*cosmo.growth_fac_f1(a)*disp
+    assert np.abs(mom - expected).max() < 1e-9*np.abs(expected).max()
+
+
+@pytest.mark.gpu
+def test_gpu_example_basic_initial_conditions_and_powerspec(tmp_path):
+    """param/example_basic up to its first steps on the GPU: realise the 64³ component, measure P(k) of the
+    initial conditions with the estimator (PCS, interlaced, deconvolved, grid 128) — it must reproduce the
+    linear-theory input below the particle Nyquist frequency — then take two P³M base steps."""
+    pytest.importorskip('torch')
+    from concept_b200 import commons, ic, integration, linear, main, mesh
+    p = commons.load_params(EXAMPLE_BASIC % tmp_path)
+    integration.init_time()
+    components = main.get_initial_conditions()
+    c = components[0]
+    assert c.N_local == 64**3
+    dump_time = main.DumpTime(commons.universals.a)
+    k, power, n_modes = main.dump_powerspec(components, dump_time)
+    table = np.loadtxt(os.path.join(str(tmp_path), f'powerspec_a={dump_time.a:.2f}'))
+    assert table.shape == (len(k), 3) and np.allclose(table[:, 2], power, rtol=1e-7)
+    T, _ = linear.compute_transfer(c, 0, 64, a=commons.universals.a)
+    linear_power = (T.eval_array(k)*ic.get_primordial_curvature_perturbation(k))**2
+    k_nyquist = np.pi*64/p.boxsize
+    good = (n_modes >= 100) & (k < 0.9*k_nyquist)
+    assert good.sum() >= 8
+    assert np.abs(power[good]/linear_power[good] - 1).max() < 0.1
+    steps = main.timeloop(components, max_steps=2)
+    assert steps == 2 and commons.universals.a > p.a_begin
+    pos = c.pos_local.cpu().numpy()
+    assert np.isfinite(pos).all() and pos.min() >= 0 and pos.max() < p.boxsize
+    mesh.free_contexts()
