@@ -1,0 +1,29 @@
+"""`python -m concept_b200 -p <parameter file> [-c "name = value" ...]` — the particle-only counterpart of the
+reference's `concept -p param` launcher (the bash launcher/installer themselves are out of scope):
+load the parameter file, realise or load the initial conditions, run the time loop, write the requested outputs.
+Under torchrun one process drives one GPU (x-slab decomposition)."""
+import argparse
+import sys
+
+from . import commons, communication, main, mesh
+
+
+def cli(argv=None):
+    parser = argparse.ArgumentParser(prog='python -m concept_b200', description=__doc__)
+    parser.add_argument('-p', '--params', required=True, help='CO*N*CEPT parameter file')
+    parser.add_argument('-c', '--command-line-params', action='append', default=[],
+                        help='extra parameter assignments, executed after the file (repeatable)')
+    parser.add_argument('--max-steps', type=int, default=None, help='stop after this many base time steps')
+    args = parser.parse_args(argv)
+    communication.init()
+    commons.verbose = True
+    try:
+        components = main.run(args.params, '\n'.join(args.command_line_params), max_steps=args.max_steps)
+    finally:
+        mesh.free_contexts()
+    commons.masterprint(f'concept_b200 run finished: {len(components)} component(s), a = {commons.universals.a:.6g}')
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(cli())

@@ -14,6 +14,9 @@ lattice phase, inverse Laplacian, Fourier differentiation, inverse FFT, displace
 particles, 2LPT source, dealiasing resize, periodic wrap) runs in libpmgrav.so (csrc/pm_ic.cu); torch is
 used for device memory only.
 
+On several GPUs the realisation is replicated (every rank realises the deterministic particle set on a
+private one-rank context and keeps its x-slab), see _get_context.
+
 Not built: 3LPT, non-Gaussianity (f_NL), fluid realisations, the non-linear ("structure":
 "non-linear") realisations — each aborts with a message.
 """
@@ -257,6 +260,31 @@ def preic_lattice(N):
     return ''
 
 
+_private_contexts = {}
+
+
+def _get_context(gridsize):
+    """The fp64 context the realisation works on.  On one rank it is the cached context of mesh.get_context (shared
+    with the PM solver when the grid sizes coincide).  On several ranks the realisation is *replicated*: the slab
+    FFT of a multi-rank context would need the reference's distributed noise/lattice bookkeeping, while the
+    realisation is a deterministic, one-off, G³-sized job — so every rank runs it on a private single-rank context
+    and keeps its own slab of particles afterwards."""
+    if communication.nprocs == 1:
+        return mesh.get_context(gridsize, 'f64')
+    ctx = _private_contexts.get(int(gridsize))
+    if ctx is None:
+        from .pmsolver import PMContext
+        ctx = _private_contexts[int(gridsize)] = PMContext(gridsize, commons.params.boxsize, dtype='f64', rank=0, nranks=1,
+                                                           device=communication.local_rank)
+    return ctx
+
+
+def _free_private_contexts():
+    for ctx in _private_contexts.values():
+        ctx.close()
+    _private_contexts.clear()
+
+
 def _device_noise(ctx, noise):
     """Reference layout [j][i][kk] → the context's slab layout [i][j_local][kk] as device doubles."""
     local = noise[ctx.j_start:ctx.j_start + ctx.nj_local].transpose(1, 0, 2)
@@ -277,8 +305,6 @@ def realize_particles(component, a, components_all=None):
         abort('Non-Gaussian initial conditions are not implemented in concept_b200')
     if component.representation != 'particles':
         abort(f'realize_particles() called with non-particle component {component.name}')
-    if communication.nprocs != 1:
-        abort('concept_b200 realises initial conditions on one GPU (load a snapshot for multi-GPU runs)')
     kind = preic_lattice(component.N)
     if not kind:
         abort(f'Cannot initialize particle component {component.name} with N = {component.N} on a lattice, '
@@ -307,12 +333,12 @@ def realize_particles(component, a, components_all=None):
         cosmoresults = compute_cosmo(class_call_reason='in order to get growth factors')
         for key in growth_factors:
             growth_factors[key] = float(getattr(cosmoresults, f'growth_fac_{key}')(a))
-    ctx = mesh.get_context(gridsize, 'f64')
+    ctx = _get_context(gridsize)
     ctx_dealias = ctx
     if options['dealias'] and options['lpt'] > 1:
         gridsize_dealias = (gridsize*3)//2
         gridsize_dealias += gridsize_dealias & 1
-        ctx_dealias = mesh.get_context(gridsize_dealias, 'f64')
+        ctx_dealias = _get_context(gridsize_dealias)
     component.N_local = 0
     component.resize(component.N)
     component.N_local = component.N
@@ -331,7 +357,15 @@ def realize_particles(component, a, components_all=None):
     n_particles_realized['components_tally'] += 1
     ctx.ic_wrap(component.pos, component.N_local)      # ic.py:1396-1398
     component._ids_set = True
-    component.exchange()
+    if communication.nprocs > 1:
+        # exchange(component) (ic.py:1399): every rank has realised the whole (deterministic) particle set on its
+        # own GPU; keep the particles of this rank's x-slab and release the rest
+        pos, mom, ids = component.pos[:component.N], component.mom[:component.N], component.ids[:component.N]
+        component.pos = component.mom = component.ids = None
+        component.N_allocated = component.N_local = 0
+        component.set_particles(pos, mom, ids, distribute=True)
+        del pos, mom, ids
+        _free_private_contexts()
     masterprint('done')
 
 

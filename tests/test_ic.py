@@ -426,3 +426,35 @@ def test_gpu_example_basic_initial_conditions_and_powerspec(tmp_path):
     pos = c.pos_local.cpu().numpy()
     assert np.isfinite(pos).all() and pos.min() >= 0 and pos.max() < p.boxsize
     mesh.free_contexts()
+
+
+@pytest.mark.parametrize('rank', [0, 1])
+def test_replicated_realisation_keeps_the_rank_slab(rank, monkeypatch):
+    """Two ranks (host logic only, kernels replaced by their numpy model): every rank realises the whole set and
+    keeps the particles of its own x-slab — together exactly the single-rank realisation, ids global."""
+    import torch
+    from concept_b200 import commons, communication, ic, integration, mesh
+    from concept_b200.species import Component
+    from ic_mock_context import MockContext
+    d = np.load(os.path.join(HERE, 'golden', 'ic_1lpt_sc_G8.npz'))
+    commons.load_params(_param_text(d) + "potential_options = {'gridsize': {'gravity': {'pm': 8}}}\nselect_forces = {'matter': {'gravity': 'pm'}}\n")
+    integration.init_time()
+    _install_golden_linear_theory(monkeypatch, d)
+    monkeypatch.setattr(communication, 'rank', rank)
+    monkeypatch.setattr(communication, 'nprocs', 2)
+    monkeypatch.setattr(communication, 'master', rank == 0)
+    made = []
+    monkeypatch.setattr(ic, '_get_context', lambda gridsize: made.append(gridsize) or MockContext(gridsize, commons.params.boxsize))
+    monkeypatch.setattr(mesh, 'get_context', lambda *a, **k: pytest.fail('the shared multi-rank context must not be used'))
+    monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
+    c = Component('matter', 'matter', N=8**3)
+    ic.realize_particles(c, float(d['a']))
+    assert made == [8]
+    L = float(d['boxsize'])
+    mine = np.clip((d['pos'][:, 0]*(8/L)).astype(np.int64), 0, 7)//4 == rank
+    assert c.N == 512 and c.N_local == mine.sum() and 0 < c.N_local < 512
+    ids = c.ids[:c.N_local].numpy()
+    assert np.array_equal(ids, np.nonzero(mine)[0])
+    assert np.abs(c.pos[:c.N_local].numpy() - d['pos'][mine]).max() < 1e-11
+    assert np.abs(c.mom[:c.N_local].numpy() - d['mom'][mine]).max() < 1e-11*np.abs(d['mom']).max()
+    assert c.N_allocated >= c.N_local
