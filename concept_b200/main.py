@@ -112,7 +112,121 @@ def get_base_timestep_size(components, static_timestepping_func=None):
             Δt_max, bottleneck = Δt_p3m, f'the P³M method of the gravity force for {c.name}'
     if t in initial_fac_times:
         Δt_max *= Δt_initial_fac
+    # Record static time-stepping to disk (main.py:897-912)
+    if communication.master and isinstance(p.static_timestepping, str):
+        if t + Δt_max < cosmic_time(1):
+            Δa_max = scale_factor(t + Δt_max) - a
+            n = int(math.ceil(math.log10(1/Δt_reltol) + 0.5))
+            with open(p.static_timestepping, mode='a', encoding='utf-8') as f:
+                if f.tell() == 0:
+                    header = ['Time-stepping recorded by concept_b200', '', '{}a{}Δa'.format(' '*((n + 3)//2), ' '*(n + 5))]
+                    f.write('\n'.join(f'# {line}' for line in header) + '\n')
+                f.write(f'{{:.{n}e}} {{:.{n}e}}\n'.format(a, Δa_max))
     return Δt_max, bottleneck
+
+
+def _remove_doppelgängers(x, y, rel_tol):
+    """integration.py:403-500: drop consecutive (nearly) equal x, scanning from the right"""
+    size = len(x)
+    if size < 2:
+        return x.copy(), y.copy()
+    if np.any(np.diff(x) < 0):
+        abort('The values in the x array passed to remove_doppelgängers() are not in increasing order')
+    accepted = [size - 1, size - 2]
+    x_prev = x[size - 2]
+    xdiff_prev = x[size - 1] - x_prev
+    for i in range(size - 3, -1, -1):
+        xdiff = x_prev - x[i]
+        if xdiff > rel_tol*xdiff_prev:
+            accepted.append(i)
+            x_prev, xdiff_prev = x[i], xdiff
+    accepted = accepted[::-1]
+    return x[accepted].copy(), y[accepted].copy()
+
+
+def prepare_static_timestepping():
+    """main.py:499-656.  `static_timestepping` is None, a callable a ↦ Δa, or a path: an existing file of
+    (a, Δa) records is replayed (log–log interpolation within each stretch of growing Δa, exact look-up at the
+    recorded scale factors), otherwise the run records its own time-stepping to that path (see
+    get_base_timestep_size).  Every rank evaluates the same function of the same numbers: no broadcast needed."""
+    static_timestepping = commons.params.static_timestepping
+    if static_timestepping is None:
+        return None
+    if isinstance(static_timestepping, str):
+        if not os.path.exists(static_timestepping):
+            static_timestepping_dir = os.path.dirname(static_timestepping)
+            if static_timestepping_dir and communication.master:
+                os.makedirs(static_timestepping_dir, exist_ok=True)
+            masterprint(f'Static time-stepping information will be written to "{static_timestepping}"')
+            return None
+        if os.path.isdir(static_timestepping):
+            abort(f'Supplied static_timestepping = "{static_timestepping}" is a directory, not a file')
+        import collections
+        import scipy.interpolate
+        table_a, table_Δa = (arr.copy() for arr in np.loadtxt(static_timestepping, unpack=True, ndmin=2))
+        data = collections.defaultdict(list)
+        for a, Δa in zip(table_a, table_Δa):
+            data[float(a)].append(float(Δa))
+        for Δa_list in data.values():
+            Δa_list.reverse()
+        table_a, table_Δa = _remove_doppelgängers(table_a, table_Δa, Δt_reltol)
+        mask = np.diff(table_Δa) < 0
+        for index in range(1, len(mask)):
+            mask[index] &= not mask[index - 1]
+        if len(mask):
+            mask[-1] = False
+        interval_indices = list(np.where(mask)[0] + 1)
+        a_intervals, a_right = [], 0
+        for index in interval_indices:
+            a_left, a_right = a_right, table_a[index]
+            a_intervals.append((a_left, a_right))
+        interval_indices.append(table_a.shape[0])
+        a_intervals.append((a_right, ထ))
+        interps, index_left = [], 0
+        for index_right in interval_indices:
+            xs, ys = np.log(table_a[index_left:index_right]), np.log(table_Δa[index_left:index_right])
+            if len(xs) == 1:
+                interps.append(lambda a, *, y=ys[0]: math.exp(float(y)))
+            else:
+                interps.append(lambda a, *, f=scipy.interpolate.interp1d(xs, ys, 'linear', fill_value='extrapolate'):
+                               math.exp(float(f(math.log(a)))))
+            index_left = index_right
+        n = int(math.ceil(math.log10(1/Δt_reltol) + 0.5))
+
+        def static_timestepping_func(a=-1):
+            if a == -1:
+                a, t = universals.a, universals.t
+            else:
+                t = cosmic_time(a)
+            Δa_list = data.get(float(f'{{:.{n}e}}'.format(a)))
+            if Δa_list:
+                Δa = Δa_list.pop()
+            else:
+                for (a_left, a_right), interp in zip(a_intervals, interps):
+                    if a_right != ထ and math.isclose(float(a), float(a_right)):
+                        continue
+                    if math.isclose(float(a), float(a_left + machine_ϵ)):
+                        a = a_left
+                    if a_left <= a < a_right:
+                        break
+                else:
+                    abort(f'static_timestepping_func(): a = {a} not in any interval')
+                Δa = interp(a)
+            a_next = a + Δa
+            return cosmic_time(a_next) - t if a_next <= 1 else ထ
+        masterprint(f'Static time-stepping information will be read from "{static_timestepping}"')
+        return static_timestepping_func
+    if callable(static_timestepping):
+        def static_timestepping_func(a=-1):
+            if a == -1:
+                a, t = universals.a, universals.t
+            else:
+                t = cosmic_time(a)
+            a_next = a + static_timestepping(a)
+            return cosmic_time(a_next) - t if a_next <= 1 else ထ
+        masterprint('Static time-stepping configured using supplied function')
+        return static_timestepping_func
+    abort(f'Could not interpret static_timestepping = {static_timestepping} of type {type(static_timestepping)}')
 
 
 def update_base_timestep_size(Δt, Δt_min, Δt_max, bottleneck, time_step=-1, time_step_last_sync=-1,
@@ -302,8 +416,9 @@ def timeloop(components, on_dump=None, on_step=None, max_steps=None):
         dump_times.pop(0)
         if not dump_times:
             return 0
+    static_timestepping_func = prepare_static_timestepping()
     initial_fac_times.add(universals.t)
-    Δt_max, bottleneck = get_base_timestep_size(components)
+    Δt_max, bottleneck = get_base_timestep_size(components, static_timestepping_func)
     Δt_begin = Δt_max
     if Δt_begin > dump_times[0].t - universals.t:
         Δt_begin = dump_times[0].t - universals.t
@@ -335,7 +450,7 @@ def timeloop(components, on_dump=None, on_step=None, max_steps=None):
                 if dump_time.t - universals.t <= 1.5*Δt:
                     sync_time = dump_time.t
                     continue
-                Δt_max, bottleneck = get_base_timestep_size(components)
+                Δt_max, bottleneck = get_base_timestep_size(components, static_timestepping_func)
                 if Δt > Δt_max:
                     sync_time = universals.t + 0.5*Δt
                     recompute_Δt_max = False
@@ -361,9 +476,10 @@ def timeloop(components, on_dump=None, on_step=None, max_steps=None):
                             Δt = Δt_backup
                         Δt_backup = -1
                     if recompute_Δt_max:
-                        Δt_max, bottleneck = get_base_timestep_size(components)
+                        Δt_max, bottleneck = get_base_timestep_size(components, static_timestepping_func)
                     recompute_Δt_max = True
-                    Δt, bottleneck = update_base_timestep_size(Δt, Δt_min, Δt_max, bottleneck, time_step, time_step_last_sync)
+                    Δt, bottleneck = update_base_timestep_size(Δt, Δt_min, Δt_max, bottleneck, time_step, time_step_last_sync,
+                                                               tolerate_danger=(bottleneck == bottleneck_static_timestepping))
                     time_step += 1
                     time_step_last_sync = time_step
                     if universals.t == dump_time.t:
@@ -383,7 +499,7 @@ def timeloop(components, on_dump=None, on_step=None, max_steps=None):
                 if dump_time.t - universals.t <= 1.5*Δt:
                     sync_time = dump_time.t
                     continue
-                Δt_max, bottleneck = get_base_timestep_size(components)
+                Δt_max, bottleneck = get_base_timestep_size(components, static_timestepping_func)
                 if Δt > Δt_max:
                     sync_time = universals.t + Δt
                     recompute_Δt_max = False

@@ -111,3 +111,53 @@ def test_spline_matches_scipy_natural():
     assert s.integrate(3, 1) == -s.integrate(1, 3)
     with pytest.raises(SystemExit):
         s.eval(10.0)     # outside the tabulated interval: abort, like the reference
+
+
+def test_static_timestepping_callable_file_replay_and_recording(tmp_path):
+    """main.prepare_static_timestepping (reference main.py:499-656) and the recording in get_base_timestep_size
+    (:897-912): Δt follows Δa(a) from a callable; a recorded file is replayed exactly at its recorded scale
+    factors and log–log interpolated in between, stretch by stretch."""
+    from concept_b200 import main
+    from concept_b200.commons import universals
+    from concept_b200.integration import cosmic_time, init_time, scale_factor
+    commons.load_params(PM8, static_timestepping=lambda a: 0.01*a)
+    init_time()
+    f = main.prepare_static_timestepping()
+    Δt, bottleneck = main.get_base_timestep_size([], f)
+    assert bottleneck == main.bottleneck_static_timestepping
+    assert Δt == pytest.approx(cosmic_time(0.02*1.01) - universals.t, rel=1e-12)
+    assert f(0.995) == commons.ထ                                     # a + Δa beyond a = 1
+    # recording: no file yet ⇒ the controller runs as usual and appends "a Δa" lines
+    path = str(tmp_path/'sub'/'timestepping')
+    commons.load_params(PM8, static_timestepping=path)
+    init_time()
+    assert main.prepare_static_timestepping() is None and os.path.isdir(os.path.dirname(path))
+
+    class Matter:
+        name, representation, forces, ϱ_bar = 'matter', 'particles', {}, commons.params.Ωm*commons.params.ρ_crit
+
+        def w_eff(self, a=-1):
+            return 0.0
+    recorded = []
+    for a in (0.02, 0.03, 0.05):
+        universals.a, universals.t = a, cosmic_time(a)
+        Δt, _ = main.get_base_timestep_size([Matter()])
+        recorded.append((a, scale_factor(universals.t + Δt) - a))
+    lines = open(path, encoding='utf-8').read().split('\n')
+    assert lines[0].startswith('# Time-stepping recorded by') and lines[2].split() == ['#', 'a', 'Δa']
+    table = np.loadtxt(path)
+    assert np.allclose(table, np.array(recorded), rtol=1e-9)
+    # replay
+    commons.load_params(PM8, static_timestepping=path)
+    init_time()
+    f = main.prepare_static_timestepping()
+    assert callable(f)
+    for a, Δa in recorded:
+        universals.a, universals.t = a, cosmic_time(a)
+        assert f() == pytest.approx(cosmic_time(a + Δa) - universals.t, rel=1e-8)
+    a_mid = 0.04
+    Δa_mid = np.exp(np.interp(np.log(a_mid), np.log(table[:, 0]), np.log(table[:, 1])))
+    assert f(a_mid) == pytest.approx(cosmic_time(a_mid + Δa_mid) - cosmic_time(a_mid), rel=1e-9)
+    with pytest.raises(commons.ConceptAbort):
+        commons.load_params(PM8, static_timestepping=str(tmp_path))
+        main.prepare_static_timestepping()
