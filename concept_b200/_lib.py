@@ -85,6 +85,7 @@ SIGNATURES = {
     'pm_real_export': (c_int, [c_void_p, c_void_p]),
     'pm_ic_2lpt_source': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'pm_fourier_resize': (c_int, [c_void_p, c_void_p]),
+    'pm_fourier_copy_modes': (c_int, [c_void_p, c_void_p, c_int, POINTER(c_double), c_double, c_int, c_int, c_int]),
     'pm_kick_long': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(KickParams), c_void_p]),
     'pm_kick_drift': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(KickParams), c_double, c_void_p]),
     'pm_kick_long_host': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(KickParams), c_double, POINTER(c_double)]),

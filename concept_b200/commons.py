@@ -324,6 +324,48 @@ def gridsize_for(method, N):
     return g + (g & 1)
 
 
+def _method_value(spec, method):
+    """{'gravity': {'pm': x}} / {'gravity': x} / {'pm': x} / x  →  x for this method (None if absent)"""
+    if isinstance(spec, dict):
+        spec = _lower_keys(spec)
+        if 'gravity' in spec:
+            return _method_value(spec['gravity'], method)
+        if 'pm' in spec or 'p3m' in spec:
+            return spec.get(method)
+        return None
+    return spec
+
+
+def component_gridsizes(name, species, method, N):
+    """(upstream, downstream) potential grid sizes of one component (commons.py:2958-3237,
+    doc/parameters/numerics.rst `potential_options`): an entry of potential_options['gridsize'] keyed by the
+    component's name or species — an int or an (upstream, downstream) pair — else the default for all components."""
+    spec = params.potential_options_raw.get('gridsize') if isinstance(params.potential_options_raw, dict) else None
+    if isinstance(spec, dict):
+        for key in (name, species, 'particles', 'all', 'default'):
+            for k, v in spec.items():
+                if str(k).lower() == str(key).lower() and str(k).lower() not in ('global', 'gravity', 'pm', 'p3m'):
+                    g = _method_value(v, method)
+                    if g is not None:
+                        g = tuple(g) if isinstance(g, (tuple, list)) else (g, g)
+                        return tuple(int(x) + (int(x) & 1) for x in g)
+    g = gridsize_for(method, N)
+    return (g, g)
+
+
+def global_gridsize(method, components):
+    """Global grid size of a potential: potential_options['gridsize']['global'] if given, else the largest
+    upstream/downstream grid size in use (doc/parameters/numerics.rst:300-310)."""
+    spec = params.potential_options_raw.get('gridsize') if isinstance(params.potential_options_raw, dict) else None
+    if isinstance(spec, dict):
+        for k, v in spec.items():
+            if str(k).lower() == 'global':
+                g = _method_value(v, method)
+                if g is not None and g != -1:
+                    return int(g) + (int(g) & 1)
+    return max(max(c.potential_gridsizes['gravity'][method]) for c in components)
+
+
 def shortrange_scale(gridsize):
     """shortrange_params['gravity']['scale'] = 1.25·boxsize/gridsize (commons.py:3254-3269)"""
     sp = user_params.get('shortrange_params', {})

@@ -74,12 +74,9 @@ def find_interactions(components, interaction_type='any', instantaneous='both'):
 def get_potential_specs(force, method, receivers, suppliers):
     """interactions.py:2786-2821"""
     p = commons.params
-    gridsizes = {c.potential_gridsizes[force][method][0] for c in list(receivers) + list(suppliers)}
-    if len(gridsizes) != 1:
-        abort('concept_b200 requires all components of one PM interaction to share a grid size '
-              f'(got {sorted(gridsizes)}); up/down-scaling between grids is out of scope')
-    return PotentialSpecs(gridsizes.pop(), p.interpolation_order[method], UpDown(*p.deconvolve[method]),
-                          UpDown(*p.interlace[method]))
+    components = list(dict.fromkeys(list(receivers) + list(suppliers)))
+    return PotentialSpecs(commons.global_gridsize(method, components), p.interpolation_order[method],
+                          UpDown(*p.deconvolve[method]), UpDown(*p.interlace[method]))
 
 
 def gravity(method, receivers, suppliers, ᔑdt, interaction_type, printout=True):
@@ -119,8 +116,14 @@ def particle_mesh(receivers, suppliers, gridsize_global, quantity, force, method
         abort('concept_b200 supports interlacing only when enabled both upstream and downstream')
     p = commons.params
     L, G = p.boxsize, int(gridsize_global)
-    ctx = mesh.get_context(G)
     order = int(interpolation_order)
+    gridsizes_upstream = [c.potential_gridsizes[force][method][0] for c in suppliers]
+    gridsizes_downstream = [c.potential_gridsizes[force][method][1] for c in receivers]
+    if any(g != G for g in gridsizes_upstream + gridsizes_downstream):
+        return _particle_mesh_mixed_gridsizes(receivers, suppliers, gridsizes_upstream, gridsizes_downstream, G, quantity,
+                                              force, method, potential, order, deconvolve_upstream, deconvolve_downstream,
+                                              interlace_upstream, ᔑdt, ᔑdt_key)
+    ctx = mesh.get_context(G)
     # both deconvolutions are promoted to the global slab (interactions.py:2069-2080)
     deconv_order_global = order*(int(bool(deconvolve_upstream)) + int(bool(deconvolve_downstream)))
     prefactor = -L**2*commons.G_Newton/math.pi
@@ -174,3 +177,83 @@ def particle_mesh(receivers, suppliers, gridsize_global, quantity, force, method
                 for c in group:
                     ctx.gather_kick(c.pos_local, c.mom_local, order, diff_order, c.mass*(-ᔑdt[ᔑdt_key[0], c.name]), shift)
             first = False
+
+
+def _particle_mesh_mixed_gridsizes(receivers, suppliers, gridsizes_upstream, gridsizes_downstream, G, quantity, force, method,
+                                   potential, order, deconvolve_upstream, deconvolve_downstream, interlace, ᔑdt, ᔑdt_key):
+    """particle_mesh (interactions.py:1985-2335) when components bring their own upstream / downstream grid sizes:
+    suppliers are deposited group by group onto upstream grids, transformed, Nyquist-nullified and *copied* — with the
+    upstream deconvolution, the interlacing phase and the half-cell phase between grids — into the global slab
+    (interpolate_upstream, mesh.py:492-616; add_upstream_to_global_slabs :618-710; copy_modes :980-1322); the global
+    potential is copied to every downstream grid size in use, where the downstream deconvolution, differentiation and
+    interpolation happen.  A deconvolution is promoted to the global slab only if all grids on its side have the global
+    size (interactions.py:2069-2080).  The accumulating global slab and the finished potential live in the saved
+    slabs of the contexts (pm_slab_save), the working slabs being transformed in place."""
+    from . import communication
+    p = commons.params
+    if communication.nprocs > 1:
+        abort('Component-specific upstream/downstream grid sizes need the cross-rank mode exchange of copy_modes '
+              '(mesh.py:1105-1230), which concept_b200 does not provide: use one grid size per potential on several GPUs')
+    if str(p.grid_dtype) not in ('f64', 'float64'):
+        abort('Component-specific upstream/downstream grid sizes are available for fp64 grids only')
+    L = p.boxsize
+    all_upstream_global = all(g == G for g in gridsizes_upstream)
+    all_downstream_global = all(g == G for g in gridsizes_downstream)
+    deconv_order_upstream = order*int(bool(deconvolve_upstream) and not all_upstream_global)
+    deconv_order_downstream = order*int(bool(deconvolve_downstream) and not all_downstream_global)
+    deconv_order_global = order*(int(bool(deconvolve_upstream) and all_upstream_global)
+                                 + int(bool(deconvolve_downstream) and all_downstream_global))
+    prefactor = -L**2*commons.G_Newton/math.pi
+    gauss = (2*math.pi/L*commons.shortrange_scale(G))**2 if potential == 'gravity long-range' else 0.0
+    shifts = [None, BCC_SHIFT] if interlace else [None]
+    nl = len(shifts)
+    ctx_global = mesh.get_context(G, 'f64')
+
+    def global_first(gridsize):
+        return (gridsize != G, gridsize)
+    # upstream: Σ over groups and lattices into the saved slab of the global context
+    first = True
+    for gridsize_upstream in sorted(set(gridsizes_upstream), key=global_first):
+        ctx = ctx_global if gridsize_upstream == G else mesh.get_context(gridsize_upstream, 'f64')
+        group = [c for c, g in zip(suppliers, gridsizes_upstream) if g == gridsize_upstream]
+        for shift in shifts:
+            ctx.grid_zero()
+            for c in group:
+                mesh.interpolate_particles(c, gridsize_upstream, ctx, quantity, order, ᔑdt, shift, float(gridsize_upstream)**(-3))
+            ctx.halo_add()
+            ctx.fft_forward()
+            if ctx is ctx_global:
+                ctx.fourier_operate(deconv_order_upstream, shift, 1.0/nl, -1, False)      # also nullifies the Nyquist planes
+                ctx.slab_save() if first else ctx.slab_accumulate()
+            else:
+                ctx.fourier_copy_modes_into(ctx_global, deconv_order_upstream, shift, 1.0/nl, src_saved=False, dst_saved=True,
+                                            accumulate=not first)
+            first = False
+    ctx_global.fourier_operate(0, None, 1.0, -1, True)          # working slab = accumulated global slab
+    ctx_global.kspace_potential(prefactor, deconv_order_global, gauss, 1.0)
+    ctx_global.slab_save()
+    # downstream
+    for gridsize_downstream in sorted(set(gridsizes_downstream), key=global_first):
+        if gridsize_downstream == G:
+            ctx = ctx_global
+        else:
+            ctx = mesh.get_context(gridsize_downstream, 'f64')
+            ctx_global.fourier_copy_modes_into(ctx, 0, None, 1.0, src_saved=True, dst_saved=True, accumulate=False)
+        group_downstream = [c for c, g in zip(receivers, gridsizes_downstream) if g == gridsize_downstream]
+        diff_orders = {c.potential_differentiations[force][method] for c in group_downstream}
+        for diff_order in sorted(diff_orders, reverse=True):
+            group = [c for c in group_downstream if c.potential_differentiations[force][method] == diff_order]
+            for shift in shifts:
+                if diff_order == 0:
+                    for dim in range(3):
+                        ctx.fourier_operate(deconv_order_downstream, shift, 1.0/nl, dim, True)
+                        ctx.fft_backward()
+                        ctx.halo_fill()
+                        for c in group:
+                            ctx.gather(0, c.pos_local, c.mom_local, order, dim, c.mass*(-ᔑdt[ᔑdt_key[0], c.name]), shift)
+                else:
+                    ctx.fourier_operate(deconv_order_downstream, shift, 1.0/nl, -1, True)
+                    ctx.fft_backward()
+                    ctx.halo_fill()
+                    for c in group:
+                        ctx.gather_kick(c.pos_local, c.mom_local, order, diff_order, c.mass*(-ᔑdt[ᔑdt_key[0], c.name]), shift)

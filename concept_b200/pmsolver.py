@@ -252,6 +252,12 @@ class PMContext:
         """Copy this context's Fourier slab into `other`'s (another grid size): modes |k| < min(G, G')/2."""
         check(self.lib.pm_fourier_resize(self._h, other._h))
 
+    def fourier_copy_modes_into(self, other, deconv_order=0, shift=None, scale=1.0, src_saved=False, dst_saved=False,
+                                accumulate=False):
+        """copy_modes onto a context of another grid size (see pm_fourier_copy_modes in include/pmgrav.h)"""
+        check(self.lib.pm_fourier_copy_modes(self._h, other._h, int(deconv_order), vec3(shift), float(scale), int(src_saved),
+                                             int(dst_saved), int(accumulate)))
+
     # -- whole kick -------------------------------------------------------------------
     def kick_long(self, pos, mom, params, sum_mom2=None):
         check(self.lib.pm_kick_long(self._h, _particles(pos), _particles(mom), pos.shape[0], ctypes.byref(params), _ptr(sum_mom2)))

@@ -35,8 +35,8 @@ class Component:
         self.potential_gridsizes = {'gravity': {}}
         self.potential_differentiations = {'gravity': {}}
         for method in ('pm', 'p3m'):
-            g = commons.gridsize_for(method, self.N) if self.N > 0 else None
-            self.potential_gridsizes['gravity'][method] = (g, g)
+            self.potential_gridsizes['gravity'][method] = (
+                commons.component_gridsizes(self.name, self.species, method, self.N) if self.N > 0 else (None, None))
             self.potential_differentiations['gravity'][method] = p.differentiation[method]
         # softening_length default 0.025·L/∛N (commons.py:3862-3873)
         self.softening_length = 0.025*p.boxsize/max(self.N, 1)**(1/3)

@@ -249,6 +249,16 @@ int pm_ic_2lpt_source(pm_ctx* ctx, const double* d00, const double* d11, const d
  * modes |k| < min(G_src, G_dst)/2; every other mode of `dst` is nullified. */
 int pm_fourier_resize(pm_ctx* src, pm_ctx* dst);
 
+/* copy_modes(slab_from, slab_onto, deconv_order, lattice, '=' | '+=') between grids of DIFFERENT size
+ * (mesh.py:980-1322), as used for component-specific upstream/downstream grids (add_upstream_to_global_slabs,
+ * mesh.py:618-710; interactions.py:2120-2140).  For every mode inside the cube |k| < min(G_src, G_dst)/2:
+ *   dst (+)= scale·[Π x_l/sin x_l]^deconv_order·e^{i(θ_cell + θ_shift)}·src
+ * deconvolution and θ_shift = −2π/G_src·k·shift evaluated for the SOURCE grid, θ_cell = (π/G_dst − π/G_src)·(ki+kj+kk)
+ * the half-cell offset between cell-centred grids.  '=' (accumulate == 0) nullifies every other mode of dst.
+ * src_saved / dst_saved select the saved copy (pm_slab_save) instead of the working slab.  One rank per context. */
+int pm_fourier_copy_modes(pm_ctx* src, pm_ctx* dst, int deconv_order, const double* shift, double scale,
+                          int src_saved, int dst_saved, int accumulate);
+
 /* ---- whole-path entry points --------------------------------------------- */
 typedef struct {
     int order;            /* interpolation order 1..4 */

@@ -429,3 +429,91 @@ def power_by_k2(slab, k2_max):
     k2 = k2_grid(G)[m]
     p = (slab.real**2 + slab.imag**2)[m]
     return np.bincount(k2, weights=p, minlength=k2_max + 1), np.bincount(k2, minlength=k2_max + 1)
+
+
+# --------------------------------------------------------------------------
+# Component-specific upstream / downstream grid sizes (a5 / a10 / a16)
+# --------------------------------------------------------------------------
+def copy_modes(slab_from, G_onto, deconv_order=0, shift=None, n_lattices=1):
+    """copy_modes(slab_from, slab_onto, deconv_order, lattice, '=') (mesh.py:980-1322) onto a nullified slab of
+    grid size G_onto; natural layout [i, j, kk].  Deconvolution and interlacing are evaluated for the grid the
+    modes come from (fourier_loop(gridsize_small, gridsize_from, …), :1245-1250).  Between different grid sizes
+    only the modes strictly inside the smaller grid's Nyquist cube are copied (:1134-1135), and every mode gets
+    the phase (π/G_onto − π/G_from)·(ki + kj + kk) of the half-cell offset between two cell-centred grids (:1302)."""
+    G_from = slab_from.shape[0]
+    ki = signed_wavenumbers(G_from).astype(np.float64)
+    kk = np.arange(G_from//2 + 1, dtype=np.float64)
+    value = slab_from*(deconv_factor(G_from, deconv_order)*(1/n_lattices))
+    theta = None
+    if G_from != G_onto:
+        theta = (np.pi/G_onto - np.pi/G_from)*((ki[:, None, None] + ki[None, :, None]) + kk[None, None, :])
+    if shift is not None and tuple(shift) != (0, 0, 0):
+        lattice = ((ki*(-2*np.pi/G_from*shift[0]))[:, None, None] + (ki*(-2*np.pi/G_from*shift[1]))[None, :, None]) \
+            + (kk*(-2*np.pi/G_from*shift[2]))[None, None, :]
+        theta = lattice if theta is None else theta + lattice
+    if theta is not None:
+        value = value*(np.cos(theta) + 1j*np.sin(theta))
+    if G_from == G_onto:
+        value[~mode_mask(G_from)] = 0
+        return value
+    n = min(G_from, G_onto)//2
+    out = np.zeros((G_onto, G_onto, G_onto//2 + 1), dtype=complex)
+    idx = np.arange(-n + 1, n)
+    out[np.ix_(idx % G_onto, idx % G_onto, np.arange(n))] = value[np.ix_(idx % G_from, idx % G_from, np.arange(n))]
+    return out
+
+
+def pm_kick_multigrid(components, *, boxsize, gridsize_global, order, G_Newton, dt1, deconvolve=True, interlace=False,
+                      r_scale=0.0):
+    """interactions.gravity('pm'|'p3m', components, components, ᔑdt, 'long-range') for particle components with
+    their own (upstream, downstream) grid sizes (particle_mesh, interactions.py:1985-2335; interpolate_upstream,
+    mesh.py:492-616; add_upstream_to_global_slabs :618-710).
+    components: list of dicts with pos, mom, mass, upstream, downstream, dt_rho (= ᔑdt['a**(-3*w_eff-1)', name]),
+    dt_kick (= ᔑdt['a**(-3*w_eff)', name]) and diff_order.  Returns the list of new momenta."""
+    Gg = int(gridsize_global)
+    shifts = [(0.0, 0.0, 0.0)] + ([(BCC_SHIFT,)*3] if interlace else [])
+    nl = len(shifts)
+    # which deconvolutions are promoted to the global slab (interactions.py:2069-2080)
+    all_up_global = all(c['upstream'] == Gg for c in components)
+    all_down_global = all(c['downstream'] == Gg for c in components)
+    deconv_up = order*int(deconvolve and not all_up_global)
+    deconv_down = order*int(deconvolve and not all_down_global)
+    deconv_global = order*(int(deconvolve and all_up_global) + int(deconvolve and all_down_global))
+    # upstream
+    slab_global = np.zeros((Gg, Gg, Gg//2 + 1), dtype=complex)
+    for G_up in sorted({c['upstream'] for c in components}, key=lambda g: (g != Gg, g)):
+        for s in shifts:
+            rho = np.zeros((G_up, G_up, G_up))
+            for c in components:
+                if c['upstream'] != G_up:
+                    continue
+                contribution = c['dt_rho']/dt1
+                contribution *= c['mass']
+                contribution *= float(G_up)**(-3)*(G_up/boxsize)**3
+                rho += deposit(c['pos'], boxsize, G_up, order, contribution, s)
+            f = forward_fft(rho)
+            f[~mode_mask(G_up)] = 0
+            slab_global = slab_global + copy_modes(f, Gg, deconv_up, s, nl)
+    slab_global = slab_global*potential_factor(Gg, boxsize, G_Newton, deconv_global, r_scale)
+    # downstream
+    out = [np.array(c['mom'], dtype=np.float64, copy=True) for c in components]
+    for G_down in sorted({c['downstream'] for c in components}, key=lambda g: (g != Gg, g)):
+        slab_down = slab_global if G_down == Gg else copy_modes(slab_global, G_down)
+        h = boxsize/G_down
+        ki = signed_wavenumbers(G_down).astype(np.float64)
+        kvec = [ki[:, None, None], ki[None, :, None], np.arange(G_down//2 + 1, dtype=np.float64)[None, None, :]]
+        for q, c in enumerate(components):
+            if c['downstream'] != G_down:
+                continue
+            kick_factor = c['mass']*(-c['dt_kick'])
+            for s in shifts:
+                f = copy_modes(slab_down, G_down, deconv_down, s, nl)     # fourier_operate (mesh.py:3327-3400)
+                if c['diff_order'] == 0:
+                    for dim in range(3):
+                        force = backward_fft(1j*(2*np.pi/boxsize)*kvec[dim]*f, G_down)
+                        out[q][:, dim] += gather(force, c['pos'], boxsize, order, s)*kick_factor
+                else:
+                    phi = backward_fft(f, G_down)
+                    for dim in range(3):
+                        out[q][:, dim] += gather(diff_grid(phi, dim, c['diff_order'], h), c['pos'], boxsize, order, s)*kick_factor
+    return out

@@ -3,6 +3,7 @@
 // g++ into a shared library and driven through ctypes by tests/test_ic.py (no GPU needed).
 #include <cstdint>
 
+#include "pm_copy_ops.cuh"
 #include "pm_ic_ops.cuh"
 
 using namespace pm::icops;
@@ -50,6 +51,22 @@ void h_resize(const double* src, double* dst, int Gs, int Gd) {
 
 void h_wrap(double* pos, int64_t n3, double L) {
     for (int64_t i = 0; i < n3; ++i) pos[i] = mod_box(pos[i], L);
+}
+
+// pm_fourier_copy_modes (csrc/pm_copymodes.cu): '=' or '+=' of slab [Gs][Gs][Gs/2+1] onto [Gd][Gd][Gd/2+1]
+void h_copy_modes(const double* src, double* dst, int Gs, int Gd, int deconv_order, const double* th, int rotate,
+                  double cell_phase, double scale, const double* tab_x, const double* tab_sin, int accumulate) {
+    pm::copyops::CopyParams p;
+    p.Gs = Gs; p.Gd = Gd; p.deconv_order = deconv_order; p.rotate = rotate;
+    p.th[0] = th[0]; p.th[1] = th[1]; p.th[2] = th[2];
+    p.cell_phase = cell_phase; p.scale = scale;
+    double2* out = reinterpret_cast<double2*>(dst);
+    for (int64_t idx = 0; idx < (int64_t)Gd * Gd * (Gd / 2 + 1); ++idx) {
+        double2 v;
+        const bool shared = pm::copyops::copy_mode(idx, reinterpret_cast<const double2*>(src), p, tab_x, tab_sin, &v);
+        if (!accumulate) out[idx] = v;
+        else if (shared) { out[idx].x += v.x; out[idx].y += v.y; }
+    }
 }
 
 }  // extern "C"

@@ -217,3 +217,90 @@ class HostKernelContext(MockContext):
         other.buf[:] = np.nan
         self.lib.h_resize(self._p(self.buf), self._p(other.buf), self.gridsize, other.gridsize)
         other._sync_from_buf(fourier=True)
+
+
+class MeshMockContext(HostKernelContext):
+    """HostKernelContext plus a numpy model (built from oracle/pm_oracle.py) of the mesh entry points that
+    concept_b200.interactions.particle_mesh sequences — pm_grid_zero, pm_deposit, pm_fourier_operate with deconvolution
+    and lattice phase, pm_kspace_potential, pm_slab_accumulate, pm_gather, pm_gather_kick — and pm_fourier_copy_modes
+    executed by the device code compiled for the CPU.  Used to check the host orchestration of component-specific
+    grid sizes against the reference's golden vectors without a GPU."""
+
+    def __init__(self, gridsize, boxsize):
+        super().__init__(gridsize, boxsize)
+        G = self.gridsize
+        k = np.where(np.arange(G) >= G//2, np.arange(G) - G, np.arange(G))
+        self.tab_x = k*(np.pi/G) + 2.220446049250313e-16
+        self.tab_sin = np.sin(self.tab_x)
+
+    def grid_zero(self):
+        G = self.gridsize
+        self.real, self.fourier = np.zeros((G, G, G)), None
+
+    def deposit(self, pos, order, contribution, shift=None):
+        from oracle import pm_oracle as O
+        assert self.real is not None
+        self.real = self.real + O.deposit(pos.numpy(), self.boxsize, self.gridsize, order, contribution, shift or (0.0, 0.0, 0.0))
+
+    def halo_add(self):
+        pass
+
+    def halo_fill(self):
+        pass
+
+    def slab_accumulate(self):
+        self.saved = self.saved + self.fourier
+
+    def fourier_operate(self, deconv_order=0, shift=None, scale=1.0, diff_dim=-1, from_saved=False):
+        from oracle import pm_oracle as O
+        G = self.gridsize
+        src = self.saved if from_saved else self.fourier
+        assert src is not None
+        v = src*(O.deconv_factor(G, deconv_order)*scale)
+        if shift is not None and tuple(shift) != (0, 0, 0):
+            v = v*O.interlace_phase(G, shift)
+        if diff_dim >= 0:
+            v = v*1j*(2*np.pi/self.boxsize)*self.k[diff_dim]
+        self.fourier, self.real = np.where(self.live, v, 0), None
+
+    def kspace_potential(self, prefactor, deconv_order, gauss=0.0, scale=1.0):
+        from oracle import pm_oracle as O
+        G = self.gridsize
+        assert self.fourier is not None
+        k2 = np.where(self.live_nonzero, self.k2, 1).astype(np.float64)
+        factor = O.deconv_factor(G, deconv_order)*scale*(prefactor/k2)
+        if gauss:
+            factor = factor*np.exp(k2*(-gauss))
+        self.fourier = np.where(self.live_nonzero, self.fourier*factor, 0)
+
+    def gather(self, which, pos, mom, order, dim, factor, shift=None):
+        from oracle import pm_oracle as O
+        assert which == 0 and self.real is not None
+        mom[:, dim] += torch.from_numpy(O.gather(self.real, pos.numpy(), self.boxsize, order, shift or (0.0, 0.0, 0.0))*factor)
+
+    def gather_kick(self, pos, mom, order, diff_order, factor, shift=None, sum_mom2=None):
+        from oracle import pm_oracle as O
+        assert self.real is not None
+        for dim in range(3):
+            force = O.diff_grid(self.real, dim, diff_order, self.boxsize/self.gridsize)
+            mom[:, dim] += torch.from_numpy(O.gather(force, pos.numpy(), self.boxsize, order, shift or (0.0, 0.0, 0.0))*factor)
+
+    def fourier_copy_modes_into(self, other, deconv_order=0, shift=None, scale=1.0, src_saved=False, dst_saved=False,
+                                accumulate=False):
+        import ctypes
+        Gs, Gd = self.gridsize, other.gridsize
+        assert Gs != Gd
+        src = np.ascontiguousarray(self.saved if src_saved else self.fourier)
+        if accumulate:
+            dst = np.ascontiguousarray(other.saved if dst_saved else other.fourier).copy()
+        else:
+            dst = np.full((Gd, Gd, Gd//2 + 1), np.nan + 0j)
+        th = np.array([-2*np.pi/Gs*(shift[d] if shift is not None else 0.0) for d in range(3)])
+        rotate = int(shift is not None and any(s != 0 for s in shift))
+        self.lib.h_copy_modes(self._p(src), self._p(dst), Gs, Gd, int(deconv_order), self._p(th), rotate,
+                              ctypes.c_double(np.pi/Gd - np.pi/Gs), ctypes.c_double(scale), self._p(self.tab_x),
+                              self._p(self.tab_sin), int(accumulate))
+        if dst_saved:
+            other.saved = dst
+        else:
+            other.fourier, other.real = dst, None

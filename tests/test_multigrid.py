@@ -1,0 +1,155 @@
+"""PM / P³M long-range kicks with component-specific upstream and downstream grid sizes (SURVEY §8 a5/a10/a16;
+reference particle_mesh interactions.py:1985-2335, interpolate_upstream mesh.py:492-616,
+add_upstream_to_global_slabs :618-710, copy_modes :980-1322) against golden vectors made by the unmodified reference
+(tests/golden/gen_golden_multigrid.py): two particle components, upstream/downstream grids smaller and larger than
+the global one, CIC/TSC/PCS, finite-difference and Fourier differentiation, interlacing, the Gaussian-split P³M
+potential, with and without deconvolution.
+
+CPU: the oracle restatement (oracle/pm_oracle.py::pm_kick_multigrid) and the host orchestration of
+concept_b200.interactions with the kernels replaced by a numpy model (copy_modes: the device code on the CPU).
+GPU: interactions.gravity through libpmgrav.so.
+
+Tolerance: Δmom to 1e-9 of max|Δmom| (the kicks are ~1e-4 of the momenta, so Δmom itself carries ~1e-12)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = sorted(glob.glob(os.path.join(HERE, 'golden', 'multigrid_*.npz')))
+IDS = [os.path.basename(p)[:-4] for p in CASES]
+ORDER_NAME = {1: 'NGP', 2: 'CIC', 3: 'TSC', 4: 'PCS'}
+SPECIES = {'cdm': 'cold dark matter', 'baryons': 'baryons'}
+
+
+def _param_text(d):
+    m = str(d['method'])
+    diff = 'fourier' if int(d['diff_order']) == 0 else int(d['diff_order'])
+    grids = ''.join(f"        '{name}': {{'gravity': {{'{m}': {tuple(int(x) for x in d[f'grids_{name}'])}}}}},\n"
+                    for name in d['names'].tolist())
+    return f'''
+boxsize = {float(d['boxsize'])}*Mpc
+potential_options = {{
+    'gridsize': {{
+        'global': {{'gravity': {{'{m}': {int(d['gridsize_global'])}}}}},
+{grids}    }},
+    'interpolation': {{'gravity': {{'{m}': '{ORDER_NAME[int(d['order'])]}'}}}},
+    'deconvolve': {{'gravity': {{'{m}': ({bool(d['deconvolve'])}, {bool(d['deconvolve'])})}}}},
+    'interlace': {{'gravity': {{'{m}': ({bool(d['interlace'])}, {bool(d['interlace'])})}}}},
+    'differentiation': {{'default': {{'gravity': {{'pm': {diff!r}, 'p3m': {diff!r}}}}}}},
+}}
+select_forces = {{'all': {{'gravity': '{m}'}}}}
+H0 = 70*km/s/Mpc
+Ωcdm = 0.25
+Ωb = 0.05
+a_begin = 0.02
+'''
+
+
+def _assert_kicks(d, moms):
+    for name, mom in zip(d['names'].tolist(), moms):
+        kick_ref = d[f'mom_out_{name}'] - d[f'mom_{name}']
+        assert np.abs((mom - d[f'mom_{name}']) - kick_ref).max() < 1e-9*np.abs(kick_ref).max(), name
+
+
+@pytest.mark.parametrize('path', CASES, ids=IDS)
+def test_oracle_matches_reference(path):
+    from oracle import pm_oracle as O
+    d = np.load(path)
+    comps = []
+    for name in d['names'].tolist():
+        up, down = (int(x) for x in d[f'grids_{name}'])
+        comps.append(dict(pos=d[f'pos_{name}'], mom=d[f'mom_{name}'], mass=float(d[f'mass_{name}']), upstream=up, downstream=down,
+                          dt_rho=float(d[f'dt_rho_{name}']), dt_kick=float(d[f'dt_kick_{name}']), diff_order=int(d['diff_order'])))
+    moms = O.pm_kick_multigrid(comps, boxsize=float(d['boxsize']), gridsize_global=int(d['gridsize_global']), order=int(d['order']),
+                               G_Newton=float(d['G_Newton']), dt1=float(d['dt1']), deconvolve=bool(d['deconvolve']),
+                               interlace=bool(d['interlace']), r_scale=float(d['r_scale']))
+    _assert_kicks(d, moms)
+
+
+def test_oracle_copy_modes_properties():
+    """Between equal grids copy_modes is fourier_operate; up- then down-scaling returns the modes inside the small
+    grid's Nyquist cube unchanged (the two half-cell phases cancel)."""
+    from oracle import pm_oracle as O
+    rng = np.random.default_rng(3)
+    slab = O.forward_fft(rng.standard_normal((8, 8, 8)))
+    same = O.copy_modes(slab, 8, 2, (-.5, -.5, -.5), 2)
+    expect = slab*O.deconv_factor(8, 2)*0.5*O.interlace_phase(8, (-.5, -.5, -.5))
+    expect[~O.mode_mask(8)] = 0
+    assert np.allclose(same, expect, rtol=1e-14, atol=0)
+    back = O.copy_modes(O.copy_modes(slab, 12), 8)
+    inside = slab.copy()
+    inside[~O.mode_mask(8)] = 0
+    assert np.allclose(back, inside, rtol=1e-13, atol=1e-13)
+
+
+def _components(d):
+    from concept_b200 import commons
+    from concept_b200.species import Component
+    comps, ᔑdt = [], {'1': float(d['dt1'])}
+    for name in d['names'].tolist():
+        c = Component(name, SPECIES[name], N=len(d[f'pos_{name}']), mass=float(d[f'mass_{name}']))
+        c.set_particles(d[f'pos_{name}'], d[f'mom_{name}'])
+        assert c.potential_gridsizes['gravity'][str(d['method'])] == tuple(int(x) for x in d[f'grids_{name}'])
+        ᔑdt['a**(-3*w_eff-1)', name] = float(d[f'dt_rho_{name}'])
+        ᔑdt['a**(-3*w_eff)', name] = float(d[f'dt_kick_{name}'])
+        comps.append(c)
+    commons.universals.a = float(d['a'])
+    return comps, ᔑdt
+
+
+@pytest.mark.parametrize('path', CASES, ids=IDS)
+def test_orchestration_through_kernel_model(path, monkeypatch):
+    import ctypes
+    import subprocess
+    import tempfile
+    import torch
+    from concept_b200 import commons, interactions, mesh
+    from concept_b200.species import Component
+    import ic_mock_context
+    root = os.path.dirname(HERE)
+    tmp = tempfile.mkdtemp(prefix='mg_harness_')
+    src = os.path.join(tmp, 'ic_host_harness.cpp')
+    with open(os.path.join(HERE, 'ic_host_harness.cu')) as f, open(src, 'w') as g:
+        g.write(f.read())
+    lib = os.path.join(tmp, 'libic_harness.so')
+    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-I', '/usr/local/cuda/include',
+                    '-I', os.path.join(root, 'concept_b200', 'csrc'), src, '-o', lib], check=True)
+    monkeypatch.setattr(ic_mock_context.MeshMockContext, 'lib', ctypes.CDLL(lib))
+    d = np.load(path)
+    commons.load_params(_param_text(d))
+    assert commons.shortrange_scale(int(d['gridsize_global'])) == pytest.approx(float(d['r_scale'])) or str(d['method']) == 'pm'
+    contexts = {}
+    monkeypatch.setattr(mesh, 'get_context', lambda gridsize, dtype=None: contexts.setdefault(
+        int(gridsize), ic_mock_context.MeshMockContext(gridsize, commons.params.boxsize)))
+    monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
+    comps, ᔑdt = _components(d)
+    interactions.gravity(str(d['method']), comps, comps, ᔑdt, 'long-range', False)
+    used = {int(x) for name in d['names'].tolist() for x in d[f'grids_{name}']} | {int(d['gridsize_global'])}
+    assert set(contexts) == used
+    _assert_kicks(d, [c.mom_local.numpy() for c in comps])
+
+
+def test_mixed_gridsizes_need_one_rank(monkeypatch):
+    from concept_b200 import commons, communication, interactions
+    d = np.load(CASES[0])
+    commons.load_params(_param_text(d))
+    monkeypatch.setattr(communication, 'nprocs', 2)
+    with pytest.raises(commons.ConceptAbort):
+        interactions._particle_mesh_mixed_gridsizes([], [], [8], [8], 12, 'a²ρ', 'gravity', 'pm', 'gravity', 2, True, True,
+                                                    False, {}, ('a**(-3*w_eff)', 'component'))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('path', CASES, ids=IDS)
+def test_gpu_mixed_gridsizes_match_reference(path):
+    pytest.importorskip('torch')
+    from concept_b200 import commons, interactions, mesh
+    d = np.load(path)
+    commons.load_params(_param_text(d))
+    comps, ᔑdt = _components(d)
+    interactions.gravity(str(d['method']), comps, comps, ᔑdt, 'long-range', False)
+    moms = [c.mom_local.cpu().numpy() for c in comps]
+    mesh.free_contexts()
+    _assert_kicks(d, moms)
