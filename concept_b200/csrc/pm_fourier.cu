@@ -139,6 +139,10 @@ int launch_kspace(pm_ctx* c, double prefactor, int deconv_order, double gauss, d
                   c->tab_x, c->tab_sin);
     }
     c->space_fourier = true;
+    // the working slab (the interior of `real`) now holds this Fourier data whatever the context held before —
+    // in particular a potential that a fused solve had left in `phi` is no longer the current grid
+    c->grid_in_phi = false;
+    c->real_is_zero = false;
     return PM_OK;
 }
 
