@@ -80,6 +80,7 @@ SIGNATURES = {
     'pm_apply_rung_jumps': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, POINTER(c_int64)]),
     'pm_ic_lattice': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int64, c_int64, POINTER(c_int64)]),
     'pm_ic_potential': (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(c_double), c_double]),
+    'pm_ic_nongaussianity': (c_int, [c_void_p, c_double]),
     'pm_ic_displace': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_double]),
     'pm_ic_wrap': (c_int, [c_void_p, c_void_p, c_int64]),
     'pm_real_export': (c_int, [c_void_p, c_void_p]),

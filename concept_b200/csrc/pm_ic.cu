@@ -56,6 +56,15 @@ __global__ void __launch_bounds__(256) ic_wrap_kernel(double* __restrict__ pos, 
         pos[i] = icops::mod_box(pos[i], L);
 }
 
+// local non-Gaussianity on the real-space grid: x += f·x²
+__global__ void __launch_bounds__(256)
+ic_nongaussianity_kernel(double* __restrict__ grid, int G, int Gp, int64_t total, double f) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = icops::real_index(p, G, Gp);
+        grid[q] = icops::nongaussian_point(grid[q], f);
+    }
+}
+
 // real grid (padded rows) → compact [nxl][G][G]
 __global__ void __launch_bounds__(256)
 real_export_kernel(const double* __restrict__ grid, double* __restrict__ out, int G, int Gp, int64_t total) {
@@ -147,6 +156,17 @@ int pm_ic_wrap(pm_ctx* c, double* pos, int64_t n) {
     PM_REQUIRE(c != nullptr && n >= 0 && (pos != nullptr || n == 0), "pm_ic_wrap: bad argument");
     if (n == 0) return PM_OK;
     PM_LAUNCH(ic_wrap_kernel, kNumSMs * 8, 256, 0, c->stream, pos, 3 * n, c->boxsize);
+    return PM_OK;
+}
+
+int pm_ic_nongaussianity(pm_ctx* c, double f_nl) {
+    PM_TRY(ic_check(c, "pm_ic_nongaussianity"));
+    PM_REQUIRE(!c->space_fourier, "pm_ic_nongaussianity: the slab holds Fourier data (call pm_fft_backward)");
+    PM_TRY(ensure_in_real(c));
+    const Geom& g = c->g;
+    PM_LAUNCH(ic_nongaussianity_kernel, kNumSMs * 8, 256, 0, c->stream, c->real_interior<double>(), g.G, g.Gp,
+              (int64_t)g.nxl * g.G * g.G, f_nl);
+    c->real_is_zero = false;
     return PM_OK;
 }
 

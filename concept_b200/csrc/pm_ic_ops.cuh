@@ -65,11 +65,19 @@ PM_HD double2 potential_mode(int64_t idx, Slab s, const double2* noise, const do
         re = r2; im = i2;
     }
     const double amplitude = amplitudes[k2];
+    if (lap == 0.0) {          // realize_grid on its own (the non-Gaussian path transforms before the inverse Laplacian)
+        out.x = amplitude * re;
+        out.y = amplitude * im;
+        return out;
+    }
     const double inv = lap / k2;
     out.x = (amplitude * re) * inv;
     out.y = (amplitude * im) * inv;
     return out;
 }
+
+// local non-Gaussianity (realize_grid, ic.py:766-771): x += f·x²
+PM_HD double nongaussian_point(double x, double f) { return x + f * (x * x); }
 
 // lattice particle p = (i·G + j)·G + k  →  element of the padded real grid [nxl][G][Gp]
 PM_HD int64_t real_index(int64_t p, int G, int Gp) { return (p / G) * Gp + (p % G); }

@@ -1,5 +1,5 @@
 """Initial-condition generator of the host mirror: particle realisations from
-primordial noise with 1LPT / 2LPT (optionally back-scaled, optionally dealiased).
+primordial noise with 1LPT / 2LPT (optionally back-scaled, dealiased, with local non-Gaussianity).
 
 Reference (ic.py): PseudoRandomNumberGenerator :67-232, get_amplitudes :542-627, realize_grid :670-782,
 generate_primordial_noise :928-1163, realize_particles :1199-1399, carryout_1lpt :1447-1509,
@@ -17,8 +17,8 @@ used for device memory only.
 On several GPUs the realisation is replicated (every rank realises the deterministic particle set on a
 private one-rank context and keeps its x-slab), see _get_context.
 
-Not built: 3LPT, non-Gaussianity (f_NL), fluid realisations, the non-linear ("structure":
-"non-linear") realisations — each aborts with a message.
+Not built: 3LPT, fluid realisations, the non-linear ("structure": "non-linear") realisations — each
+aborts with a message.
 """
 import collections
 import math
@@ -301,8 +301,6 @@ def realize_particles(component, a, components_all=None):
         abort('3LPT is not implemented in concept_b200 (1LPT and 2LPT are)')
     if options['lpt'] not in {1, 2}:
         abort(f'realize_particles() called with attempted {options["lpt"]}LPT')
-    if options.get('nongaussianity'):
-        abort('Non-Gaussian initial conditions are not implemented in concept_b200')
     if component.representation != 'particles':
         abort(f'realize_particles() called with non-particle component {component.name}')
     kind = preic_lattice(component.N)
@@ -390,7 +388,17 @@ def carryout_1lpt(component, ctx, noise, shift, gridsize, options, a, growth_fac
     for variable in range(1 - options['backscale'], -1, -1):      # first θ, then δ
         amplitudes = get_amplitudes(gridsize, component, a, variable=variable)
         amplitudes_dev = torch.from_numpy(amplitudes).to(noise.device)
-        ctx.ic_potential(noise, amplitudes_dev, len(amplitudes) - 1, shift, lap_factor=2*variable - 1)
+        nongaussianity = options.get('nongaussianity', 0)*(variable == 0)      # velocities are unaffected (ic.py:1488-1490)
+        if nongaussianity:
+            # realize_grid (ic.py:766-776): to real space, x += f·x², back with the forward normalisation G⁻³ — folded,
+            # with laplacian_inverse(…, 2·variable − 1), into the prefactor of pm_kspace_potential
+            ctx.ic_potential(noise, amplitudes_dev, len(amplitudes) - 1, shift, lap_factor=0.0)
+            ctx.fft_backward()
+            ctx.ic_nongaussianity(nongaussianity)
+            ctx.fft_forward()
+            ctx.kspace_potential(-(2*variable - 1)*float(gridsize)**(-3)*(commons.params.boxsize/(2*π))**2, 0)
+        else:
+            ctx.ic_potential(noise, amplitudes_dev, len(amplitudes) - 1, shift, lap_factor=2*variable - 1)
         ctx.slab_save()
         if variable == 1:
             _displace_from_saved(component, ctx, index_bgn, None, _mom_factor(component, a))

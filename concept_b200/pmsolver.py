@@ -227,6 +227,10 @@ class PMContext:
             raise TypeError('amplitudes must be a float64 table with k2_max + 1 entries')
         check(self.lib.pm_ic_potential(self._h, _ptr(noise), _ptr(amplitudes), int(k2_max), vec3(shift), float(lap_factor)))
 
+    def ic_nongaussianity(self, f_nl):
+        """real-space grid: x += f_nl·x²  (realize_grid, ic.py:766-771)"""
+        check(self.lib.pm_ic_nongaussianity(self._h, float(f_nl)))
+
     def ic_displace(self, pos, mom, index_bgn, dim, pos_factor=1.0, mom_factor=0.0):
         check(self.lib.pm_ic_displace(self._h, None if pos is None else _particles(pos), None if mom is None else _particles(mom),
                                       int(index_bgn), int(dim), float(pos_factor), float(mom_factor)))

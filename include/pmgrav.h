@@ -229,9 +229,14 @@ int pm_ic_lattice(pm_ctx* ctx, double* pos, double* mom, int64_t* ids, const dou
  *   slab[k] = amplitudes[k²]·noise[k]·e^{iθ(k, −shift)} · (−lap_factor/k_f²)/k²
  * noise: device doubles (re, im) in the slab layout of PM_TAP_FOURIER (the primordial noise of
  * generate_primordial_noise, ic.py:928-1163, drawn by the host code); amplitudes: device table over integer k²
- * with k2_max + 1 entries (get_amplitudes, ic.py:542-627). */
+ * with k2_max + 1 entries (get_amplitudes, ic.py:542-627).  lap_factor == 0 leaves the inverse Laplacian out
+ * (plain realize_grid). */
 int pm_ic_potential(pm_ctx* ctx, const double* noise, const double* amplitudes, int k2_max, const double* shift,
                     double lap_factor);
+/* Local non-Gaussianity of realize_grid (ic.py:766-771) on the real-space grid: x += f_nl·x².  The caller
+ * realises with lap_factor = 0, transforms back, calls this, transforms forward and applies the inverse Laplacian
+ * and the forward normalisation G⁻³ with pm_kspace_potential. */
+int pm_ic_nongaussianity(pm_ctx* ctx, double f_nl);
 /* displace_particles (ic.py:2249-2283) from the real-space grid: lattice particle (i, j, k) gets
  *   pos[dim] += pos_factor·ψ[i][j][k],  mom[dim] += mom_factor·ψ[i][j][k]      (either array may be NULL) */
 int pm_ic_displace(pm_ctx* ctx, double* pos, double* mom, int64_t index_bgn, int dim, double pos_factor,

@@ -9,7 +9,7 @@ Follows (all under /root/reference/src/):
   ic.py:928-1163    generate_primordial_noise ('distributed' and 'simple' imprinting)
   mesh.py:2909-3044 fourier_curve_loop / fourier_curve_slice_loop, :3109-3160 get_fourier_curve_coords
   ic.py:542-627     get_amplitudes;  linear.py:3329-3341 get_primordial_curvature_perturbation
-  ic.py:670-782     realize_grid (scalar realisations, lattice phase shift)
+  ic.py:670-782     realize_grid (scalar realisations, lattice phase shift, local non-Gaussianity)
   mesh.py:3422-3437 laplacian_inverse, :3470-3510 fourier_diff, :3591-3622 nullify_modes
   ic.py:1447-1509   carryout_1lpt, :1539-1589 carryout_2lpt, :1895-2057 handle_lpt_term (incl. dealiasing)
   ic.py:2138-2247   preinitialize_particles, :2249-2283 displace_particles, :1396-1398 wrap
@@ -279,7 +279,7 @@ LATTICE_SHIFTS = {   # mesh.py:85-100 with cell_centered = True ⇒ shift_amount
 
 
 def realize_particles(n, lattices, boxsize, a, H, mass, w_eff, noise, transfer_delta, transfer_theta, primordial,
-                      backscale=False, lpt=1, dealias=False, growth=None):
+                      backscale=False, lpt=1, dealias=False, growth=None, nongaussianity=0.0):
     """ic.py:1199-1399.  noise: complex [j][i][kk] from primordial_noise(n, …).  Returns pos, mom [N][3]."""
     G = n
     N1 = n**3
@@ -300,7 +300,13 @@ def realize_particles(n, lattices, boxsize, a, H, mass, w_eff, noise, transfer_d
         # carryout_1lpt (ic.py:1447-1509)
         for variable in range(1 - backscale, -1, -1):
             amplitudes = get_amplitudes(G, boxsize, transfer_theta if variable == 1 else transfer_delta, primordial)
-            Φ1 = laplacian_inverse(realize_grid(noise, amplitudes, shift), boxsize, factor=2*variable - 1)
+            slab = realize_grid(noise, amplitudes, shift)
+            if nongaussianity and variable == 0:
+                # realize_grid, ic.py:766-776: x += f·x² in real space, back with the forward normalisation G⁻³
+                real = backward(slab)
+                real = real + nongaussianity*real**2
+                slab = forward(real)*float(G)**(-3)
+            Φ1 = laplacian_inverse(slab, boxsize, factor=2*variable - 1)
             for d in range(3):
                 ψ = backward(fourier_diff(Φ1, boxsize, d)).ravel()
                 if variable == 0:

@@ -28,6 +28,8 @@ CASES = {
     'ic_2lpt_sc_G12': dict(n=12, lattices=1, boxsize=100.0, lpt=2),
     'ic_2lpt_sc_G8_dealias': dict(n=8, lattices=1, boxsize=64.0, lpt=2, dealias=True),
     'ic_1lpt_sc_G16_seeds': dict(n=16, lattices=1, boxsize=128.0, seeds=(11, 22)),
+    'ic_1lpt_sc_G8_nongauss': dict(n=8, lattices=1, boxsize=64.0, nongauss=0.6),
+    'ic_2lpt_sc_G10_nongauss_backscale': dict(n=10, lattices=1, boxsize=80.0, nongauss=-0.4, backscale=True, lpt=2),
 }
 
 # analytic stand-ins for the CLASS transfer functions: T_δ(k, a) = −A_δ·a·k²/(1 + (k/k0)²)^1.1,
@@ -50,6 +52,7 @@ realization_options = {{
     'backscale': {bool(c.get('backscale', False))},
     'lpt': {c.get('lpt', 1)},
     'dealias': {bool(c.get('dealias', False))},
+    'nongaussianity': {c.get('nongauss', 0)},
 }}
 primordial_amplitude_fixed = {bool(c.get('fixed', False))}
 primordial_phase_shift = {c.get('phase_shift', 0)}
@@ -116,7 +119,7 @@ def worker(name):
     out = dict(n=n, lattices=nl, boxsize=float(boxsize), a=a, H=float(hubble(a)), mass=float(comp.mass),
                varrho_bar=float(comp.ϱ_bar), w_eff=float(comp.w_eff(a=a)),
                backscale=bool(c.get('backscale', False)), lpt=int(c.get('lpt', 1)), dealias=bool(c.get('dealias', False)),
-               fixed=bool(c.get('fixed', False)), phase_shift=float(comp.realization_options['phaseshift']),
+               nongaussianity=float(c.get('nongauss', 0)), fixed=bool(c.get('fixed', False)), phase_shift=float(comp.realization_options['phaseshift']),
                imprinting=str(c.get('imprinting', 'distributed')),
                seeds=np.array([commons.random_seeds['primordial amplitudes'], commons.random_seeds['primordial phases']]),
                noise=noise, pos=pos, mom=mom,

@@ -49,6 +49,13 @@ void h_resize(const double* src, double* dst, int Gs, int Gd) {
         out[idx] = resize_mode(idx, reinterpret_cast<const double2*>(src), Gs, Gd);
 }
 
+void h_nongaussianity(double* grid, int G, int Gp, int nxl, double f) {
+    for (int64_t p = 0; p < (int64_t)nxl * G * G; ++p) {
+        const int64_t q = real_index(p, G, Gp);
+        grid[q] = nongaussian_point(grid[q], f);
+    }
+}
+
 void h_wrap(double* pos, int64_t n3, double L) {
     for (int64_t i = 0; i < n3; ++i) pos[i] = mod_box(pos[i], L);
 }

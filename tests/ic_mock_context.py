@@ -57,9 +57,15 @@ class MockContext:
             v = v*(np.cos(θ) + 1j*np.sin(θ))
         kf = 2*np.pi/self.boxsize
         k2 = np.where(self.live_nonzero, self.k2, 1)
-        v = amplitudes[np.minimum(k2, k2_max)]*v*((-lap_factor/kf**2)/k2)
+        v = amplitudes[np.minimum(k2, k2_max)]*v
+        if lap_factor != 0:
+            v = v*((-lap_factor/kf**2)/k2)
         self.fourier = np.where(self.live_nonzero, v, 0)
         self.real = None
+
+    def ic_nongaussianity(self, f_nl):
+        assert self.real is not None
+        self.real = self.real + f_nl*self.real**2
 
     def slab_save(self):
         self.saved = self.fourier.copy()
@@ -194,6 +200,13 @@ class HostKernelContext(MockContext):
         self.lib.h_displace(self._p(None if pos is None else pos.numpy()), self._p(None if mom is None else mom.numpy()),
                             self._p(self.buf), G, G + 2, G, ctypes.c_int64(index_bgn), int(dim), ctypes.c_double(pos_factor),
                             ctypes.c_double(mom_factor))
+
+    def ic_nongaussianity(self, f_nl):
+        import ctypes
+        G = self.gridsize
+        self._sync_to_buf()
+        self.lib.h_nongaussianity(self._p(self.buf), G, G + 2, G, ctypes.c_double(f_nl))
+        self._sync_from_buf(fourier=False)
 
     def ic_wrap(self, pos, n):
         import ctypes

@@ -1,8 +1,8 @@
 """Initial-condition generator (reference ic.py:928-1399, :1447-1589, :2138-2283) against
 golden vectors made by the unmodified reference (tests/golden/gen_golden_ic.py): primordial noise slab,
 amplitude tables and the realised particles for sc / bcc / fcc lattices, 1LPT with and without
-back-scaling, 2LPT with and without dealiasing, fixed amplitudes + phase shift, both noise imprinting
-schemes and non-default seeds.
+back-scaling, 2LPT with and without dealiasing, local non-Gaussianity, fixed amplitudes + phase shift, both
+noise imprinting schemes and non-default seeds.
 
 CPU: the oracle restatement (oracle/ic_oracle.py), the product's host side (vectorised noise, amplitudes,
 linear-theory stand-in) and the orchestration of concept_b200.ic through a numpy model of the kernels.
@@ -46,7 +46,7 @@ def _param_text(d):
             f"random_seeds = {{'primordial amplitudes': {int(d['seeds'][0])}, 'primordial phases': {int(d['seeds'][1])}}}\n"
             f"primordial_noise_imprinting = '{str(d['imprinting'])}'\n"
             f"primordial_amplitude_fixed = {bool(d['fixed'])}\nprimordial_phase_shift = {float(d['phase_shift'])!r}\n"
-            f"realization_options = {{'backscale': {bool(d['backscale'])}, 'lpt': {int(d['lpt'])}, 'dealias': {bool(d['dealias'])}}}\n")
+            f"realization_options = {{'backscale': {bool(d['backscale'])}, 'lpt': {int(d['lpt'])}, 'dealias': {bool(d['dealias'])}, 'nongaussianity': {float(d['nongaussianity']) if 'nongaussianity' in d else 0.0}}}\n")
 
 
 def _assert_particles(pos, mom, d):
@@ -73,7 +73,7 @@ def test_oracle_matches_reference(path):
             assert np.allclose(O.get_amplitudes(n, float(d['boxsize']), T, prim), d[f'amplitudes{variable}'], rtol=1e-14, atol=0)
     pos, mom = O.realize_particles(n, int(d['lattices']), float(d['boxsize']), float(d['a']), float(d['H']), float(d['mass']),
                                    float(d['w_eff']), noise, Td, Tt, prim, bool(d['backscale']), int(d['lpt']),
-                                   bool(d['dealias']), _growth(d))
+                                   bool(d['dealias']), _growth(d), float(d['nongaussianity']) if 'nongaussianity' in d else 0.0)
     _assert_particles(pos, mom, d)
 
 
@@ -82,6 +82,7 @@ def test_cases_cover_the_options():
             for d in map(np.load, CASES)}
     assert {s[0] for s in seen} == {1, 2, 4} and {s[2] for s in seen} == {1, 2}
     assert any(s[1] for s in seen) and any(s[3] for s in seen) and any(s[4] for s in seen)
+    assert any('nongaussianity' in d and float(d['nongaussianity']) for d in map(np.load, CASES))
     assert {s[5] for s in seen} == {'simple', 'distributed'}
 
 
