@@ -2,7 +2,7 @@
 //
 // Everything here is __host__ __device__ and free of CUDA-only types beyond double2, so that
 // tests/ic_host_harness.cu can compile the very same code with g++ and run it on the CPU against the
-// reference's golden vectors (tests/test_ic.py) — like pm_fftcore.cuh does for the transform stages.
+// reference's golden vectors (tests/test_widen_ic.py) — like pm_fftcore.cuh does for the transform stages.
 #pragma once
 
 #include <cuda_runtime.h>

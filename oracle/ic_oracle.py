@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — CPU restatement (numpy / plain Python loops) of the reference's particle
 initial-condition generator, pinned to golden vectors made by the unmodified reference
-(tests/golden/gen_golden_ic.py → tests/golden/ic_*.npz; tests/test_ic.py).  Parity PINNED.
+(tests/golden/gen_golden_ic.py → tests/golden/ic_*.npz; tests/test_widen_ic.py).  Parity PINNED.
 
 Nothing here is imported by the product (concept_b200/); only tests/ use it as the checker.
 

@@ -1,6 +1,6 @@
 // CPU build of the per-element code of the initial-condition kernels (concept_b200/csrc/pm_ic_ops.cuh):
 // the same __host__ __device__ functions pm_ic.cu's kernels call, looped over sequentially.  Compiled with
-// g++ into a shared library and driven through ctypes by tests/test_ic.py (no GPU needed).
+// g++ into a shared library and driven through ctypes by tests/test_widen_ic.py (no GPU needed).
 #include <cstdint>
 
 #include "pm_copy_ops.cuh"

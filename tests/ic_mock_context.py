@@ -3,7 +3,7 @@
 pm_fft_backward, pm_kspace_potential, pm_ic_displace, pm_real_export, pm_ic_2lpt_source, pm_fourier_resize,
 pm_ic_wrap), one rank, fp64.  It lets the CPU suite run the *orchestration* of concept_b200/ic.py — the
 order of operations, factors and signs the host hands to the kernels — against the reference's golden
-vectors without a GPU.  The kernels themselves are checked by the `-m gpu` tests of tests/test_ic.py.
+vectors without a GPU.  The kernels themselves are checked by the `-m gpu` tests of tests/test_widen_ic.py.
 
 Slab layout as on the device with one rank: complex [i][j][kk] (PM_TAP_FOURIER), real [i][j][k].
 """
