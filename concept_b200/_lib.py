@@ -85,6 +85,8 @@ SIGNATURES = {
     'pm_ic_wrap': (c_int, [c_void_p, c_void_p, c_int64]),
     'pm_real_export': (c_int, [c_void_p, c_void_p]),
     'pm_ic_2lpt_source': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'pm_lpt_accumulate': (c_int, [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_int]),
+    'pm_real_import': (c_int, [c_void_p, c_void_p]),
     'pm_fourier_resize': (c_int, [c_void_p, c_void_p]),
     'pm_fourier_copy_modes': (c_int, [c_void_p, c_void_p, c_int, POINTER(c_double), c_double, c_int, c_int, c_int]),
     'pm_kick_long': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(KickParams), c_void_p]),

@@ -81,6 +81,23 @@ ic_2lpt_source_kernel(double* __restrict__ grid, const double* __restrict__ d00,
         grid[icops::real_index(p, G, Gp)] = icops::lpt2_source(d00[p], d11[p], d22[p], d01[p], d12[p], d02[p]);
 }
 
+// one term of an LPT source (handle_lpt_term, ic.py:1895-2057) on compact grids: acc (=|+=) factor·a·b[·c]
+__global__ void __launch_bounds__(256)
+lpt_accumulate_kernel(double* __restrict__ acc, int64_t n, double factor, const double* __restrict__ a,
+                      const double* __restrict__ b, const double* __restrict__ c, int assign) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const double v = factor * icops::lpt_product(a[p], b[p], c != nullptr ? c[p] : 1.0, c != nullptr);
+        acc[p] = assign ? v : acc[p] + v;
+    }
+}
+
+// compact [nxl][G][G] → real grid (padded rows)
+__global__ void __launch_bounds__(256)
+real_import_kernel(double* __restrict__ grid, const double* __restrict__ in, int G, int Gp, int64_t total) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x)
+        grid[icops::real_index(p, G, Gp)] = in[p];
+}
+
 // resize_grid(…, 'fourier'): dst[k] = src[k] for |k| < min(G_src, G_dst)/2, zero elsewhere
 __global__ void __launch_bounds__(256)
 fourier_resize_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int Gs, int Gd) {
@@ -189,6 +206,26 @@ int pm_ic_2lpt_source(pm_ctx* c, const double* d00, const double* d11, const dou
     const int64_t total = (int64_t)g.nxl * g.G * g.G;
     PM_LAUNCH(ic_2lpt_source_kernel, kNumSMs * 8, 256, 0, c->stream, c->real_interior<double>(), d00, d11, d22, d01, d12,
               d02, g.G, g.Gp, total);
+    c->space_fourier = false;
+    c->grid_in_phi = false;
+    c->real_is_zero = false;
+    return PM_OK;
+}
+
+int pm_lpt_accumulate(pm_ctx* c, double* acc, int64_t n, double factor, const double* a, const double* b,
+                      const double* third, int assign) {
+    PM_REQUIRE(c != nullptr && acc != nullptr && a != nullptr && b != nullptr && n >= 0, "pm_lpt_accumulate: bad argument");
+    if (n == 0) return PM_OK;
+    PM_LAUNCH(lpt_accumulate_kernel, kNumSMs * 8, 256, 0, c->stream, acc, n, factor, a, b, third, assign ? 1 : 0);
+    return PM_OK;
+}
+
+int pm_real_import(pm_ctx* c, const double* dev_in) {
+    PM_TRY(ic_check(c, "pm_real_import"));
+    PM_REQUIRE(dev_in != nullptr, "pm_real_import: NULL input");
+    const Geom& g = c->g;
+    PM_LAUNCH(real_import_kernel, kNumSMs * 8, 256, 0, c->stream, c->real_interior<double>(), dev_in, g.G, g.Gp,
+              (int64_t)g.nxl * g.G * g.G);
     c->space_fourier = false;
     c->grid_in_phi = false;
     c->real_is_zero = false;

@@ -93,6 +93,13 @@ PM_HD double lpt2_source(double d00, double d11, double d22, double d01, double 
     return v;
 }
 
+// one product of handle_lpt_term (ic.py:2003-2021): the grids are multiplied into the base grid one after the other
+PM_HD double lpt_product(double a, double b, double c, int has_c) {
+    double v = a * b;
+    if (has_c) v *= c;
+    return v;
+}
+
 // resize_grid(…, 'fourier') as the LPT code uses it, one rank: mode idx of the destination slab [Gd][Gd][Gd/2+1]
 PM_HD double2 resize_mode(int64_t idx, const double2* src, int Gs, int Gd) {
     const int Gcd = Gd / 2 + 1, Gcs = Gs / 2 + 1;

@@ -1,9 +1,9 @@
 """Initial-condition generator of the host mirror: particle realisations from
-primordial noise with 1LPT / 2LPT (optionally back-scaled, dealiased, with local non-Gaussianity).
+primordial noise with 1LPT / 2LPT / 3LPT (optionally back-scaled, dealiased, with local non-Gaussianity).
 
 Reference (ic.py): PseudoRandomNumberGenerator :67-232, get_amplitudes :542-627, realize_grid :670-782,
 generate_primordial_noise :928-1163, realize_particles :1199-1399, carryout_1lpt :1447-1509,
-carryout_2lpt :1539-1589, handle_lpt_term :1895-2057, diff_ifft :2093-2108, preinitialize_particles
+carryout_2lpt :1539-1589, carryout_3lpt_a/b/c :1619-1893, handle_lpt_term :1895-2057, diff_ifft :2093-2108, preinitialize_particles
 :2138-2247, displace_particles :2249-2283; mesh.py: fourier_curve_loop / fourier_curve_slice_loop
 :2909-3044, get_fourier_curve_coords :3109-3160, laplacian_inverse :3422-3437, fourier_diff :3470-3510.
 
@@ -17,8 +17,7 @@ used for device memory only.
 On several GPUs the realisation is replicated (every rank realises the deterministic particle set on a
 private one-rank context and keeps its x-slab), see _get_context.
 
-Not built: 3LPT, fluid realisations, the non-linear ("structure": "non-linear") realisations — each
-aborts with a message.
+Not built: fluid realisations and the non-linear ("structure": "non-linear") realisations.
 """
 import collections
 import math
@@ -297,9 +296,7 @@ def realize_particles(component, a, components_all=None):
     options = dict(p.realization_options)
     options.update(getattr(component, 'realization_options', None) or {})
     component.realization_options = options
-    if options['lpt'] == 3:
-        abort('3LPT is not implemented in concept_b200 (1LPT and 2LPT are)')
-    if options['lpt'] not in {1, 2}:
+    if options['lpt'] not in {1, 2, 3}:
         abort(f'realize_particles() called with attempted {options["lpt"]}LPT')
     if component.representation != 'particles':
         abort(f'realize_particles() called with non-particle component {component.name}')
@@ -326,7 +323,8 @@ def realize_particles(component, a, components_all=None):
     if component.mass == -1:
         component.mass = component.ϱ_bar*p.boxsize**3/component.N
     masterprint(f'Realising {len(shifts)}×{gridsize}³ particles of {component.name} ...')
-    growth_factors = dict.fromkeys(('D1', 'f1', 'D2', 'f2'), float('nan'))
+    growth_factors = dict.fromkeys(('D1', 'f1', 'D2', 'f2') + (('D3a', 'f3a', 'D3b', 'f3b', 'D3c', 'f3c') if options['lpt'] >= 3 else ()),
+                                   float('nan'))
     if options['backscale'] or options['lpt'] > 1:
         cosmoresults = compute_cosmo(class_call_reason='in order to get growth factors')
         for key in growth_factors:
@@ -348,7 +346,10 @@ def realize_particles(component, a, components_all=None):
         n_local = ctx.ic_lattice(component.pos, component.mom, component.ids, shift, index_bgn, id_bgn)
         carryout_1lpt(component, ctx, noise, shift, gridsize, options, a, growth_factors, index_bgn)
         if options['lpt'] >= 2:
-            carryout_2lpt(component, ctx, ctx_dealias, a, growth_factors, index_bgn)
+            second1 = carryout_2lpt(component, ctx, ctx_dealias, a, growth_factors, index_bgn)
+            if options['lpt'] >= 3:
+                carryout_3lpt(component, ctx, ctx_dealias, a, growth_factors, index_bgn, second1)
+            del second1
         id_bgn += n_particles
         index_bgn += n_local
     n_particles_realized['particles_tally'] = id_bgn
@@ -372,14 +373,15 @@ def _mom_factor(component, a):
     return a*(a**(-3*component.w_eff(a=a))*component.mass)
 
 
-def _displace_from_saved(component, ctx, index_bgn, pos_factor, mom_factor):
-    """Ψᵢ = ℱ⁻¹[i·kᵢ·Φ] for i = 0, 1, 2 (diff_ifft, ic.py:2093-2108) from the saved potential, applied to the
-    lattice particles (displace_particles).  A factor of None leaves that array untouched."""
-    for dim in range(3):
-        ctx.fourier_operate(diff_dim=dim, from_saved=True)
+def _displace_from_saved(component, ctx, index_bgn, pos_factor, mom_factor, dims=((0, 0, 1), (1, 1, 1), (2, 2, 1))):
+    """Ψ = sign·ℱ⁻¹[i·k_along·Φ] (diff_ifft, ic.py:2093-2108) from the saved potential, added to component `target` of
+    the lattice particles (displace_particles), for every (target, along, sign) of `dims` — the gradient by
+    default.  A factor of None leaves that array untouched."""
+    for target, along, sign in dims:
+        ctx.fourier_operate(scale=sign, diff_dim=along, from_saved=True)
         ctx.fft_backward()
         ctx.ic_displace(None if pos_factor is None else component.pos, None if mom_factor is None else component.mom,
-                        index_bgn, dim, pos_factor or 0.0, mom_factor or 0.0)
+                        index_bgn, target, pos_factor or 0.0, mom_factor or 0.0)
 
 
 def carryout_1lpt(component, ctx, noise, shift, gridsize, options, a, growth_factors, index_bgn):
@@ -416,16 +418,8 @@ def carryout_2lpt(component, ctx, ctx_dealias, a, growth_factors, index_bgn):
     fft_factor = float(ctx_dealias.gridsize)**(-3)
     potential_factor = fft_factor*growth_factors['D2']/growth_factors['D1']**2
     velocity_factor = a*hubble(a)*growth_factors['f2']
-    second = {}
-    for i, j in ((0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)):
-        ctx.fourier_operate(diff_dim=i, from_saved=True)
-        ctx.fourier_operate(diff_dim=j)
-        if dealias:
-            ctx.fourier_resize_into(ctx_dealias)
-        ctx_dealias.fft_backward()
-        second[i, j] = ctx_dealias.real_export()
+    second = _second_derivatives(ctx, ctx_dealias)
     ctx_dealias.ic_2lpt_source(*(second[ij] for ij in ((0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2))))
-    del second
     ctx_dealias.fft_forward()
     if dealias:
         ctx_dealias.fourier_resize_into(ctx)
@@ -433,3 +427,88 @@ def carryout_2lpt(component, ctx, ctx_dealias, a, growth_factors, index_bgn):
     ctx.kspace_potential(-potential_factor*(commons.params.boxsize/(2*π))**2, 0)
     ctx.slab_save()
     _displace_from_saved(component, ctx, index_bgn, 1.0, velocity_factor*_mom_factor(component, a))
+    return second
+
+
+def _second_derivatives(ctx, ctx_dealias):
+    """Φ,ᵢⱼ in real space for the potential in ctx's saved Fourier slab (fourier_diff twice + diff_ifft,
+    mesh.py:3470-3510, ic.py:2093-2108), on the dealiasing grid if there is one; keyed by (i, j) both ways."""
+    second = {}
+    for i, j in ((0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)):
+        ctx.fourier_operate(diff_dim=i, from_saved=True)
+        ctx.fourier_operate(diff_dim=j)
+        if ctx_dealias is not ctx:
+            ctx.fourier_resize_into(ctx_dealias)
+        ctx_dealias.fft_backward()
+        second[i, j] = second[j, i] = ctx_dealias.real_export()
+    return second
+
+
+def _lpt_potential(ctx, ctx_dealias, terms, potential_factor):
+    """handle_lpt_term (ic.py:1895-2057) for a list of (factor, [grid, grid(, grid)]) terms, then the forward
+    transform and laplacian_inverse(…, potential_factor): the potential ends up in ctx's saved Fourier slab.
+    Products are formed pairwise in the order written; with dealiasing an intermediate product is cut back to
+    the cube |k| < G/2 before the next factor (forward, shrink, enlarge, backward: the two unnormalised
+    transforms cost Gd⁻³, folded into the term's factor)."""
+    dealias = ctx_dealias is not ctx
+    fft_factor = float(ctx_dealias.gridsize)**(-3)
+    acc = torch.empty((ctx_dealias.nx_local, ctx_dealias.gridsize, ctx_dealias.gridsize), dtype=torch.float64,
+                      device=ctx_dealias.torch_device)
+    tmp = torch.empty_like(acc) if dealias else None
+    for n, (factor, grids) in enumerate(terms):
+        if len(grids) == 2:
+            ctx_dealias.lpt_accumulate(acc, factor, grids[0], grids[1], None, assign=(n == 0))
+        elif not dealias:
+            ctx_dealias.lpt_accumulate(acc, factor, grids[0], grids[1], grids[2], assign=(n == 0))
+        else:
+            ctx_dealias.lpt_accumulate(tmp, 1.0, grids[0], grids[1], None, assign=True)
+            ctx_dealias.real_import(tmp)
+            ctx_dealias.fft_forward()
+            ctx_dealias.fourier_resize_into(ctx)
+            ctx.fourier_resize_into(ctx_dealias)
+            ctx_dealias.fft_backward()
+            ctx_dealias.real_export(tmp)
+            ctx_dealias.lpt_accumulate(acc, factor*fft_factor, tmp, grids[2], None, assign=(n == 0))
+    ctx_dealias.real_import(acc)
+    ctx_dealias.fft_forward()
+    if dealias:
+        ctx_dealias.fourier_resize_into(ctx)
+    ctx.kspace_potential(-potential_factor*(commons.params.boxsize/(2*π))**2, 0)
+    ctx.slab_save()
+
+
+def carryout_3lpt(component, ctx, ctx_dealias, a, growth_factors, index_bgn, P1):
+    """carryout_3lpt_a, _b and _c (ic.py:1619-1893).  P1: the second derivatives of Φ⁽¹⁾ (from carryout_2lpt);
+    ctx's saved slab holds Φ⁽²⁾ on entry."""
+    g = growth_factors
+    fft_factor = float(ctx_dealias.gridsize)**(-3)
+    mom_factor = _mom_factor(component, a)
+    aH = a*hubble(a)
+    P2 = _second_derivatives(ctx, ctx_dealias)
+    # 'a' term: the determinant of the Hessian of Φ⁽¹⁾
+    _lpt_potential(ctx, ctx_dealias, [
+        (+1, [P1[0, 2], P1[0, 2], P1[1, 1]]), (-1, [P1[1, 1], P1[2, 2], P1[0, 0]]), (+1, [P1[0, 0], P1[1, 2], P1[1, 2]]),
+        (-2, [P1[1, 2], P1[0, 2], P1[0, 1]]), (+1, [P1[0, 1], P1[0, 1], P1[2, 2]]),
+    ], fft_factor*g['D3a']/g['D1']**3)
+    _displace_from_saved(component, ctx, index_bgn, 1.0, aH*g['f3a']*mom_factor)
+    # 'b' term
+    _lpt_potential(ctx, ctx_dealias, [
+        (-.5, [P1[2, 2], P2[0, 0]]), (-.5, [P2[0, 0], P1[1, 1]]), (-.5, [P1[1, 1], P2[2, 2]]), (-.5, [P2[2, 2], P1[0, 0]]),
+        (-.5, [P1[0, 0], P2[1, 1]]), (-.5, [P2[1, 1], P1[2, 2]]),
+        (+1, [P2[0, 2], P1[0, 2]]), (+1, [P2[0, 1], P1[0, 1]]), (+1, [P2[1, 2], P1[1, 2]]),
+    ], fft_factor*g['D3b']/(g['D1']*g['D2']))
+    _displace_from_saved(component, ctx, index_bgn, 1.0, aH*g['f3b']*mom_factor)
+    # 'c' term: the transverse displacement, the curl of the vector potential A⁽³ᶜ⁾
+    for i in range(3):
+        j, k = (i + 1) % 3, (i + 2) % 3
+        _lpt_potential(ctx, ctx_dealias, [
+            (+1, [P2[j, j], P1[j, k]]), (-1, [P1[j, k], P2[k, k]]), (-1, [P1[i, j], P2[i, k]]),
+            (-1, [P1[j, j], P2[j, k]]), (+1, [P2[j, k], P1[k, k]]), (+1, [P2[i, j], P1[i, k]]),
+        ], fft_factor*g['D3c']/(g['D1']*g['D2']))
+        dims = []
+        for target in range(3):
+            if target == i:
+                continue
+            along = ({0, 1, 2} - {i, target}).pop()
+            dims.append((target, along, 2*(along == (target + 1) % 3) - 1))
+        _displace_from_saved(component, ctx, index_bgn, 1.0, aH*g['f3c']*mom_factor, dims)

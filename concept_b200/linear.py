@@ -9,7 +9,8 @@ by an analytic stand-in for a flat matter + Λ universe — the same background 
     with the Eisenstein & Hu (1998) no-wiggle fit T_EH and D1 → a in the matter era; the sign follows
     CLASS (δ < 0 for positive curvature perturbation);
   * θ transfer function  T_θ = −a·H(a)·f1(a)·T_δ        (continuity equation, N-body gauge);
-  * growth factors D1, f1 = dlnD1/dlna, D2 (> 0, → 3/7·D1²), f2 from the linear growth ODEs.
+  * growth factors and rates D1, f1, D2, f2, D3a, f3a, D3b, f3b, D3c, f3c from the growth ODEs the reference
+    itself integrates when CLASS backgrounds are off (integration.py:1104-1290): D1(a = 1) = 1, all taken positive.
 
 Tabulated CLASS output can be installed instead with `install_transfer(k, delta, theta)` (or by
 assigning `concept_b200.ic.compute_transfer` / `.compute_cosmo`, which is what the parity tests do).
@@ -74,42 +75,79 @@ def eisenstein_hu_nowiggle(k):
 
 
 class CosmoResults:
-    """growth_fac_D1(a), growth_fac_f1(a), growth_fac_D2(a), growth_fac_f2(a) for flat matter + Λ."""
+    """Growth factors and rates of flat matter + Λ: growth_fac_D1 / f1 / D2 / f2 / D3a / f3a / D3b / f3b / D3c / f3c.
+    The same ODE system, matter-era initial conditions and normalisation D1(a = 1) = 1 (D2 ∝ D1², D3 ∝ D1³; all
+    taken positive) that the reference integrates itself when CLASS backgrounds are disabled
+    (integration.py:1104-1148, dgrowth_da :1190-1290)."""
+    keys = ('D1', 'D2', 'D3a', 'D3b', 'D3c')
 
     def __init__(self):
         p = commons.params
         self.key = (p.H0, p.Ωm)
-        x0, x1 = math.log(1e-4), math.log(1.0) + 1e-9
         Ωm = p.Ωm
 
-        def rhs(x, y):
-            a = math.exp(x)
+        def rhs(a, y):
             E2 = Ωm*a**-3 + 1 - Ωm
-            Ωma = Ωm*a**-3/E2
-            dlnH = -1.5*Ωma
-            D1, dD1, D2, dD2 = y
-            return [dD1, -(2 + dlnH)*dD1 + 1.5*Ωma*D1,
-                    dD2, -(2 + dlnH)*dD2 + 1.5*Ωma*(D2 + D1**2)]
-        a0 = math.exp(x0)
-        y0 = [a0, a0, 3/7*a0**2, 6/7*a0**2]
-        self.sol = scipy.integrate.solve_ivp(rhs, (x0, x1), y0, method='DOP853', rtol=1e-10, atol=0, dense_output=True)
+            dH_da_over_H = -1.5*Ωm/E2/a**4
+            D, dD, D2, dD2, D3a, dD3a, D3b, dD3b, D3c, dD3c = y
+            damping = 3/a + dH_da_over_H
+            source = -dH_da_over_H/a
+            return [dD, -damping*dD + source*D,
+                    dD2, -damping*dD2 + source*(D2 + D**2),
+                    dD3a, -damping*dD3a + source*(D3a + 2*D**3),
+                    dD3b, -damping*dD3b + source*(D3b + 2*D*D2 + 2*D**3),
+                    dD3c, -damping*dD3c + source*D**3]
+        a0 = 1e-5
+        y0 = [a0, 1, 3/7*a0**2, 6/7*a0, 1/3*a0**3, a0**2, 10/21*a0**3, 10/7*a0**2, 1/7*a0**3, 3/7*a0**2]
+        self.a_min = a0
+        self.sol = scipy.integrate.solve_ivp(rhs, (a0, 1.0 + 1e-9), y0, method='DOP853', rtol=1e-11, atol=0, dense_output=True)
+        self.normalization = 1/float(self.sol.sol(1.0)[0])
 
     def _y(self, a):
-        return self.sol.sol(math.log(a))
+        if not self.a_min <= a <= 1.0 + 1e-9:
+            commons.abort(f'growth factors requested at a = {a} outside [{self.a_min}, 1]')
+        return self.sol.sol(a)
 
-    def growth_fac_D1(self, a):
+    def growth_unnormalised(self, a):
+        """D1 normalised to D1 → a in the matter era (what relates ζ to δ)"""
         return float(self._y(a)[0])
 
-    def growth_fac_f1(self, a):
+    def _D(self, a, index, power):
+        return float(self._y(a)[2*index])*self.normalization**power
+
+    def _f(self, a, index):
         y = self._y(a)
-        return float(y[1]/y[0])
+        return float(a*y[2*index + 1]/y[2*index])
+
+    def growth_fac_D1(self, a):
+        return self._D(a, 0, 1)
+
+    def growth_fac_f1(self, a):
+        return self._f(a, 0)
 
     def growth_fac_D2(self, a):
-        return float(self._y(a)[2])
+        return self._D(a, 1, 2)
 
     def growth_fac_f2(self, a):
-        y = self._y(a)
-        return float(y[3]/y[2])
+        return self._f(a, 1)
+
+    def growth_fac_D3a(self, a):
+        return self._D(a, 2, 3)
+
+    def growth_fac_f3a(self, a):
+        return self._f(a, 2)
+
+    def growth_fac_D3b(self, a):
+        return self._D(a, 3, 3)
+
+    def growth_fac_f3b(self, a):
+        return self._f(a, 3)
+
+    def growth_fac_D3c(self, a):
+        return self._D(a, 4, 3)
+
+    def growth_fac_f3c(self, a):
+        return self._f(a, 4)
 
 
 _cosmoresults = None
@@ -134,7 +172,7 @@ def compute_transfer(component, variable, gridsize_or_k_magnitudes, specific_mul
     if a == -1:
         a = commons.universals.a
     p = commons.params
-    D1, f1 = cosmo.growth_fac_D1(a), cosmo.growth_fac_f1(a)
+    D1, f1 = cosmo.growth_unnormalised(a), cosmo.growth_fac_f1(a)
     norm = -(2/5)*commons.light_speed**2/(p.Ωm*p.H0**2)*D1
     if variable == 1:
         norm *= -a*hubble(a)*f1

@@ -252,6 +252,19 @@ class PMContext:
                 raise TypeError('second-derivative grids must be float64 of shape (nx_local, G, G)')
         check(self.lib.pm_ic_2lpt_source(self._h, *(_ptr(t) for t in (d00, d11, d22, d01, d12, d02))))
 
+    def lpt_accumulate(self, acc, factor, a, b, third=None, assign=False):
+        """acc (= | +=) factor·a·b[·third] on compact device grids (one term of an LPT source)"""
+        n = acc.numel()
+        for t in (acc, a, b) + ((third, ) if third is not None else ()):
+            if t.dtype != torch.float64 or t.numel() != n:
+                raise TypeError('LPT grids must be float64 tensors of equal size')
+        check(self.lib.pm_lpt_accumulate(self._h, _ptr(acc), n, float(factor), _ptr(a), _ptr(b), _ptr(third), int(assign)))
+
+    def real_import(self, grid):
+        if grid.dtype != torch.float64 or grid.numel() != self.nx_local*self.gridsize**2:
+            raise TypeError('expected a float64 device grid of shape (nx_local, G, G)')
+        check(self.lib.pm_real_import(self._h, _ptr(grid)))
+
     def fourier_resize_into(self, other):
         """Copy this context's Fourier slab into `other`'s (another grid size): modes |k| < min(G, G')/2."""
         check(self.lib.pm_fourier_resize(self._h, other._h))

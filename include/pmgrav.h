@@ -249,6 +249,13 @@ int pm_real_export(pm_ctx* ctx, double* dev_out);
  *   −Φ,₀₀Φ,₁₁ − Φ,₁₁Φ,₂₂ − Φ,₂₂Φ,₀₀ + Φ,₀₁² + Φ,₁₂² + Φ,₂₀²   from six exported second-derivative grids */
 int pm_ic_2lpt_source(pm_ctx* ctx, const double* d00, const double* d11, const double* d22, const double* d01,
                       const double* d12, const double* d02);
+/* One term of an LPT source (handle_lpt_term, ic.py:1895-2057; the 3LPT potentials of carryout_3lpt_a/b/c,
+ * :1619-1893) on compact device grids of n doubles: acc (= | +=) factor·a·b[·third]   (third may be NULL).
+ * `ctx` only supplies the stream. */
+int pm_lpt_accumulate(pm_ctx* ctx, double* acc, int64_t n, double factor, const double* a, const double* b,
+                      const double* third, int assign);
+/* the inverse of pm_real_export: a compact device grid of nx_local·G·G doubles becomes the real-space grid */
+int pm_real_import(pm_ctx* ctx, const double* dev_in);
 /* resize_grid(…, 'fourier') as the dealiased LPT terms use it (ic.py:2093-2108, :2027-2034): the working
  * Fourier slab of `src` is copied into the one of `dst` (another grid size, same device, one rank each) for the
  * modes |k| < min(G_src, G_dst)/2; every other mode of `dst` is nullified. */

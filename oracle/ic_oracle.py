@@ -11,7 +11,8 @@ Follows (all under /root/reference/src/):
   ic.py:542-627     get_amplitudes;  linear.py:3329-3341 get_primordial_curvature_perturbation
   ic.py:670-782     realize_grid (scalar realisations, lattice phase shift, local non-Gaussianity)
   mesh.py:3422-3437 laplacian_inverse, :3470-3510 fourier_diff, :3591-3622 nullify_modes
-  ic.py:1447-1509   carryout_1lpt, :1539-1589 carryout_2lpt, :1895-2057 handle_lpt_term (incl. dealiasing)
+  ic.py:1447-1509   carryout_1lpt, :1539-1589 carryout_2lpt, :1619-1893 carryout_3lpt_a/b/c,
+                    :1895-2057 handle_lpt_term (incl. dealiasing)
   ic.py:2138-2247   preinitialize_particles, :2249-2283 displace_particles, :1396-1398 wrap
 
 Fourier slabs are complex arrays in the reference's transposed layout [j][i][kk], kk = 0 … G/2.
@@ -338,5 +339,60 @@ def realize_particles(n, lattices, boxsize, a, H, mass, w_eff, noise, transfer_d
                 ψ = backward(fourier_diff(Φ2, boxsize, d)).ravel()
                 pos[sl, d] += ψ
                 mom[sl, d] += (velocity_factor*mom_factor)*ψ
+        if lpt >= 3:
+            # carryout_3lpt_a / _b / _c (ic.py:1619-1893) through handle_lpt_term (:1895-2057): products are formed
+            # pairwise in the order written; with dealiasing every intermediate product is cut back to the cube
+            # |k| < G/2 (forward, nullify, backward — the two unnormalised transforms cost the factor Gd⁻³).
+            def dd2(i, j):
+                s = fourier_diff(Φ2, boxsize, i, j)
+                return backward(resize_fourier(s, Gd) if dealias else s)
+
+            def cut(prod):
+                if not dealias:
+                    return prod
+                return backward(resize_fourier(resize_fourier(forward(prod), G), Gd))*fft_factor
+
+            def potential(terms, potential_factor):
+                total = 0
+                for factor, grids in terms:
+                    prod = grids[0]*grids[1]
+                    for g in grids[2:]:
+                        prod = cut(prod)*g
+                    total = total + factor*(resize_fourier(forward(prod), G) if dealias else prod)
+                if not dealias:
+                    total = forward(total)
+                return laplacian_inverse(total, boxsize, potential_factor)
+
+            def displace(Φ, velocity_factor, dims=((0, 0, 1), (1, 1, 1), (2, 2, 1))):
+                for target, along, sign in dims:
+                    ψ = backward(fourier_diff(Φ, boxsize, along, factor=sign)).ravel()
+                    pos[sl, target] += ψ
+                    mom[sl, target] += (velocity_factor*mom_factor)*ψ
+
+            P1 = {ij: dd(*ij) for ij in ((0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2))}
+            P2 = {ij: dd2(*ij) for ij in ((0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2))}
+            P1.update({(j, i): v for (i, j), v in list(P1.items())})
+            P2.update({(j, i): v for (i, j), v in list(P2.items())})
+            Φ3a = potential([(+1, [P1[0, 2], P1[0, 2], P1[1, 1]]), (-1, [P1[1, 1], P1[2, 2], P1[0, 0]]),
+                             (+1, [P1[0, 0], P1[1, 2], P1[1, 2]]), (-2, [P1[1, 2], P1[0, 2], P1[0, 1]]),
+                             (+1, [P1[0, 1], P1[0, 1], P1[2, 2]])], fft_factor*growth['D3a']/growth['D1']**3)
+            displace(Φ3a, a*H*growth['f3a'])
+            Φ3b = potential([(-.5, [P1[2, 2], P2[0, 0]]), (-.5, [P2[0, 0], P1[1, 1]]), (-.5, [P1[1, 1], P2[2, 2]]),
+                             (-.5, [P2[2, 2], P1[0, 0]]), (-.5, [P1[0, 0], P2[1, 1]]), (-.5, [P2[1, 1], P1[2, 2]]),
+                             (+1, [P2[0, 2], P1[0, 2]]), (+1, [P2[0, 1], P1[0, 1]]), (+1, [P2[1, 2], P1[1, 2]])],
+                            fft_factor*growth['D3b']/(growth['D1']*growth['D2']))
+            displace(Φ3b, a*H*growth['f3b'])
+            for i in range(3):
+                j, k = (i + 1) % 3, (i + 2) % 3
+                A3c = potential([(+1, [P2[j, j], P1[j, k]]), (-1, [P1[j, k], P2[k, k]]), (-1, [P1[i, j], P2[i, k]]),
+                                 (-1, [P1[j, j], P2[j, k]]), (+1, [P2[j, k], P1[k, k]]), (+1, [P2[i, j], P1[i, k]])],
+                                fft_factor*growth['D3c']/(growth['D1']*growth['D2']))
+                dims = []
+                for jj in range(3):
+                    if jj == i:
+                        continue
+                    kk = ({0, 1, 2} - {i, jj}).pop()
+                    dims.append((jj, kk, 2*(kk == (jj + 1) % 3) - 1))
+                displace(A3c, a*H*growth['f3c'], dims)
     pos = np.mod(pos, boxsize)
     return pos, mom

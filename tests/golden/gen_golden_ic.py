@@ -28,6 +28,8 @@ CASES = {
     'ic_2lpt_sc_G12': dict(n=12, lattices=1, boxsize=100.0, lpt=2),
     'ic_2lpt_sc_G8_dealias': dict(n=8, lattices=1, boxsize=64.0, lpt=2, dealias=True),
     'ic_1lpt_sc_G16_seeds': dict(n=16, lattices=1, boxsize=128.0, seeds=(11, 22)),
+    'ic_3lpt_sc_G8': dict(n=8, lattices=1, boxsize=64.0, lpt=3),
+    'ic_3lpt_sc_G8_dealias_backscale': dict(n=8, lattices=1, boxsize=64.0, lpt=3, dealias=True, backscale=True),
     'ic_1lpt_sc_G8_nongauss': dict(n=8, lattices=1, boxsize=64.0, nongauss=0.6),
     'ic_2lpt_sc_G10_nongauss_backscale': dict(n=10, lattices=1, boxsize=80.0, nongauss=-0.4, backscale=True, lpt=2),
 }
@@ -35,7 +37,7 @@ CASES = {
 # analytic stand-ins for the CLASS transfer functions: T_δ(k, a) = −A_δ·a·k²/(1 + (k/k0)²)^1.1,
 # T_θ(k, a) = +A_θ·a^½·k²/(1 + (k/k0)²)^1.1 — the shape only has to be smooth and k-dependent
 TRANSFER = dict(A_delta=1.5e8, A_theta=0.7e8, k0=0.07)
-GROWTH = dict(D1=0.0251, f1=0.993, D2=-2.7e-4, f2=1.98, D3a=1e-6, f3a=3.0, D3b=1e-6, f3b=3.0, D3c=1e-6, f3c=3.0)
+GROWTH = dict(D1=0.0251, f1=0.993, D2=-2.7e-4, f2=1.98, D3a=5.3e-6, f3a=2.97, D3b=3.2e-6, f3b=2.96, D3c=1.1e-6, f3c=2.95)
 
 
 def param_text(c):

@@ -56,6 +56,17 @@ void h_nongaussianity(double* grid, int G, int Gp, int nxl, double f) {
     }
 }
 
+void h_lpt_accumulate(double* acc, int64_t n, double factor, const double* a, const double* b, const double* c, int assign) {
+    for (int64_t p = 0; p < n; ++p) {
+        const double v = factor * lpt_product(a[p], b[p], c ? c[p] : 1.0, c != nullptr);
+        acc[p] = assign ? v : acc[p] + v;
+    }
+}
+
+void h_import(double* grid, const double* in, int G, int Gp, int nxl) {
+    for (int64_t p = 0; p < (int64_t)nxl * G * G; ++p) grid[real_index(p, G, Gp)] = in[p];
+}
+
 void h_wrap(double* pos, int64_t n3, double L) {
     for (int64_t i = 0; i < n3; ++i) pos[i] = mod_box(pos[i], L);
 }

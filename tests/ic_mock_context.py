@@ -112,12 +112,25 @@ class MockContext:
         pos[:n] = torch.from_numpy(np.mod(pos[:n].numpy(), self.boxsize))
 
     def real_export(self, out=None):
-        return torch.from_numpy(self.real.copy())
+        if out is None:
+            return torch.from_numpy(self.real.copy())
+        out.copy_(torch.from_numpy(self.real))
+        return out
 
     def ic_2lpt_source(self, d00, d11, d22, d01, d12, d02):
         a, b, c, e, f, h = (t.numpy() for t in (d00, d11, d22, d01, d12, d02))
         self.real = -(a*b) - b*c - c*a + e*e + f*f + h*h
         self.fourier = None
+
+    def lpt_accumulate(self, acc, factor, a, b, third=None, assign=False):
+        v = a*b if third is None else (a*b)*third
+        if assign:
+            acc.copy_(factor*v)
+        else:
+            acc += factor*v
+
+    def real_import(self, grid):
+        self.real, self.fourier = grid.numpy().copy(), None
 
     def fourier_resize_into(self, other):
         Gs, Gd = self.gridsize, other.gridsize
@@ -212,18 +225,30 @@ class HostKernelContext(MockContext):
         import ctypes
         self.lib.h_wrap(self._p(pos.numpy()), ctypes.c_int64(3*n), ctypes.c_double(self.boxsize))
 
-    def real_export(self, out=None):
-        G = self.gridsize
-        self._sync_to_buf()
-        out = np.empty((G, G, G))
-        self.lib.h_export(self._p(self.buf), self._p(out), G, G + 2, G)
-        return torch.from_numpy(out)
-
     def ic_2lpt_source(self, d00, d11, d22, d01, d12, d02):
         G = self.gridsize
         self.buf[:] = np.nan
         self.lib.h_source(self._p(self.buf), *(self._p(t.numpy()) for t in (d00, d11, d22, d01, d12, d02)), G, G + 2, G)
         self._sync_from_buf(fourier=False)
+
+    def lpt_accumulate(self, acc, factor, a, b, third=None, assign=False):
+        import ctypes
+        self.lib.h_lpt_accumulate(self._p(acc.numpy()), ctypes.c_int64(acc.numel()), ctypes.c_double(factor), self._p(a.numpy()),
+                                  self._p(b.numpy()), self._p(None if third is None else third.numpy()), int(assign))
+
+    def real_import(self, grid):
+        G = self.gridsize
+        self.buf[:] = np.nan
+        self.lib.h_import(self._p(self.buf), self._p(grid.numpy()), G, G + 2, G)
+        self._sync_from_buf(fourier=False)
+
+    def real_export(self, out=None):
+        G = self.gridsize
+        self._sync_to_buf()
+        if out is None:
+            out = torch.empty((G, G, G), dtype=torch.float64)
+        self.lib.h_export(self._p(self.buf), self._p(out.numpy()), G, G + 2, G)
+        return out
 
     def fourier_resize_into(self, other):
         self._sync_to_buf()

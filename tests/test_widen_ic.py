@@ -1,7 +1,7 @@
 """Initial-condition generator (reference ic.py:928-1399, :1447-1589, :2138-2283) against
 golden vectors made by the unmodified reference (tests/golden/gen_golden_ic.py): primordial noise slab,
 amplitude tables and the realised particles for sc / bcc / fcc lattices, 1LPT with and without
-back-scaling, 2LPT with and without dealiasing, local non-Gaussianity, fixed amplitudes + phase shift, both
+back-scaling, 2LPT and 3LPT with and without dealiasing, local non-Gaussianity, fixed amplitudes + phase shift, both
 noise imprinting schemes and non-default seeds.
 
 CPU: the oracle restatement (oracle/ic_oracle.py), the product's host side (vectorised noise, amplitudes,
@@ -80,7 +80,7 @@ def test_oracle_matches_reference(path):
 def test_cases_cover_the_options():
     seen = {(int(d['lattices']), bool(d['backscale']), int(d['lpt']), bool(d['dealias']), bool(d['fixed']), str(d['imprinting']))
             for d in map(np.load, CASES)}
-    assert {s[0] for s in seen} == {1, 2, 4} and {s[2] for s in seen} == {1, 2}
+    assert {s[0] for s in seen} == {1, 2, 4} and {s[2] for s in seen} == {1, 2, 3}
     assert any(s[1] for s in seen) and any(s[3] for s in seen) and any(s[4] for s in seen)
     assert any('nongaussianity' in d and float(d['nongaussianity']) for d in map(np.load, CASES))
     assert {s[5] for s in seen} == {'simple', 'distributed'}
@@ -235,14 +235,18 @@ def test_linear_theory_stand_in():
     p = commons.load_params('boxsize = 512*Mpc\nH0 = 67*km/(s*Mpc)\nΩb = 0.049\nΩcdm = 0.27\n')
     cosmo = linear.compute_cosmo()
     a = 1e-3
-    assert cosmo.growth_fac_D1(a) == pytest.approx(a, rel=1e-3)
+    assert cosmo.growth_unnormalised(a) == pytest.approx(a, rel=1e-3)
+    assert cosmo.growth_fac_D1(1.0) == pytest.approx(1, rel=1e-12)        # normalised like integration.py:1140-1148
+    assert cosmo.growth_fac_D1(a) == pytest.approx(a/cosmo.growth_unnormalised(1.0), rel=1e-3)
     assert cosmo.growth_fac_f1(a) == pytest.approx(1, rel=1e-3)
-    assert cosmo.growth_fac_D2(a)/cosmo.growth_fac_D1(a)**2 == pytest.approx(3/7, rel=1e-3)
     assert cosmo.growth_fac_f2(a) == pytest.approx(2, rel=1e-3)
+    for key, ratio, power in (('D2', 3/7, 2), ('D3a', 1/3, 3), ('D3b', 10/21, 3), ('D3c', 1/7, 3)):
+        assert getattr(cosmo, f'growth_fac_{key}')(a)/cosmo.growth_fac_D1(a)**power == pytest.approx(ratio, rel=1e-3)
+        assert getattr(cosmo, f'growth_fac_f{key[1:]}')(a) == pytest.approx(power, rel=1e-3)
     Ωm1 = p.Ωm
     assert cosmo.growth_fac_f1(1.0) == pytest.approx(Ωm1**0.55, rel=2e-2)
     assert cosmo.growth_fac_f2(1.0) == pytest.approx(2*Ωm1**(6/11), rel=2e-2)
-    assert 0.75 < cosmo.growth_fac_D1(1.0) < 0.82          # Λ suppression of growth for Ωm = 0.319
+    assert 0.75 < cosmo.growth_unnormalised(1.0) < 0.82          # Λ suppression of growth for Ωm = 0.319
     assert linear.eisenstein_hu_nowiggle(1e-6) == pytest.approx(1, abs=1e-4)
     k = np.logspace(-4, 1.5, 4000)                       # 1/Mpc
     T, _ = linear.compute_transfer(None, 0, 0, a=1.0)
@@ -272,9 +276,6 @@ def test_unsupported_options_abort():
     from concept_b200.species import Component
     with pytest.raises(commons.ConceptAbort):
         commons.load_params('boxsize = 8*Mpc\nrealization_options = {"lpt": 4}\n')
-    commons.load_params('boxsize = 8*Mpc\nrealization_options = {"lpt": 3}\n')
-    with pytest.raises(commons.ConceptAbort):
-        ic.realize_particles(Component('matter', 'matter', N=8**3), 0.02)
     commons.load_params('boxsize = 8*Mpc\n')
     with pytest.raises(commons.ConceptAbort):
         ic.realize_particles(Component('matter', 'matter', N=8**3 + 1), 0.02)      # not on a lattice
@@ -302,7 +303,7 @@ def test_gpu_realize_particles_matches_reference(path, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('lpt,dealias', [(1, False), (2, False), (2, True)])
+@pytest.mark.parametrize('lpt,dealias', [(1, False), (2, False), (2, True), (3, True)])
 def test_gpu_realize_64cubed_against_oracle(lpt, dealias):
     """example_basic's particle load (64³ on a 256 Mpc/h box) with the analytic linear-theory stand-in,
     GPU vs the oracle fed with the same transfer functions and growth factors."""
@@ -317,7 +318,7 @@ H0 = 67*km/(s*Mpc)
 Ωb = 0.049
 Ωcdm = 0.27
 a_begin = {a}
-realization_options = {{'lpt': {lpt}, 'dealias': {dealias}, 'backscale': {lpt == 2}}}
+realization_options = {{'lpt': {lpt}, 'dealias': {dealias}, 'backscale': {lpt >= 2}}}
 ''')
     integration.init_time()
     ic.n_particles_realized.update(components_tally=0, particles_tally=0)
@@ -326,13 +327,13 @@ realization_options = {{'lpt': {lpt}, 'dealias': {dealias}, 'backscale': {lpt ==
     pos, mom = c.pos_local.cpu().numpy(), c.mom_local.cpu().numpy()
     mesh.free_contexts()
     cosmo = linear.compute_cosmo()
-    growth = {key: getattr(cosmo, f'growth_fac_{key}')(a) for key in ('D1', 'f1', 'D2', 'f2')}
+    growth = {key: getattr(cosmo, f'growth_fac_{key}')(a) for key in ('D1', 'f1', 'D2', 'f2', 'D3a', 'f3a', 'D3b', 'f3b', 'D3c', 'f3c')}
     Td, Tt = linear.compute_transfer(c, 0, n, a=a)[0], linear.compute_transfer(c, 1, n, a=a)[0]
     ps = p.primordial_spectrum
     prim = dict(A_s=ps['A_s'], n_s=ps['n_s'], alpha_s=ps['α_s'], pivot=ps['pivot'])
     noise = ic.generate_primordial_noise(n)          # pinned to the reference by the CPU tests above
     pos_o, mom_o = O.realize_particles(n, 1, p.boxsize, a, integration.hubble(a), c.mass, 0.0, noise, Td.eval_array,
-                                       Tt.eval_array, prim, lpt == 2, lpt, dealias, growth)
+                                       Tt.eval_array, prim, lpt >= 2, lpt, dealias, growth)
     cell = p.boxsize/n
     dp = np.abs(pos - pos_o)
     dp = np.minimum(dp, p.boxsize - dp)
