@@ -460,3 +460,17 @@ def test_replicated_realisation_keeps_the_rank_slab(rank, monkeypatch):
     assert np.abs(c.pos[:c.N_local].numpy() - d['pos'][mine]).max() < 1e-11
     assert np.abs(c.mom[:c.N_local].numpy() - d['mom'][mine]).max() < 1e-11*np.abs(d['mom']).max()
     assert c.N_allocated >= c.N_local
+
+
+def test_growth_factors_match_the_reference_background():
+    """linear.CosmoResults against the unmodified reference's own matter + Λ growth factors (integration.py:1104-1290
+    through its temporal splines; tests/golden/gen_golden_growth.py).  The reference tabulates on ~4600 points and
+    evaluates log–log splines; agreement is at the 1e-4 level of that tabulation."""
+    from concept_b200 import commons, linear
+    d = np.load(os.path.join(HERE, 'golden', 'growth_factors.npz'))
+    commons.load_params('boxsize = 64*Mpc\nH0 = 67*km/(s*Mpc)\nΩb = 0.049\nΩcdm = 0.27\na_begin = 0.02\n')
+    assert commons.params.H0 == pytest.approx(float(d['H0']), rel=1e-14) and commons.params.Ωm == pytest.approx(float(d['Om']), rel=1e-14)
+    cosmo = linear.compute_cosmo()
+    for key in ('D', 'f', 'D2', 'f2', 'D3a', 'f3a', 'D3b', 'f3b', 'D3c', 'f3c'):
+        ours = np.array([getattr(cosmo, 'growth_fac_' + {'D': 'D1', 'f': 'f1'}.get(key, key))(a) for a in d['a']])
+        assert np.abs(ours/d[key] - 1).max() < 3e-4, key
