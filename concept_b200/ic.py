@@ -19,7 +19,6 @@ private one-rank context and keeps its x-slab), see _get_context.
 
 Not built: fluid realisations and the non-linear ("structure": "non-linear") realisations.
 """
-import collections
 import math
 
 import numpy as np
