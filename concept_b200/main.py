@@ -329,20 +329,44 @@ def _assign_rungs(components, Δt):
 
 
 class DumpTime:
-    def __init__(self, a):
-        self.time_param, self.a, self.t = 'a', float(a), cosmic_time(float(a))
+    def __init__(self, a=None, t=None):
+        if a is not None:
+            self.time_param, self.a, self.t = 'a', float(a), cosmic_time(float(a))
+        else:
+            self.time_param, self.t, self.a = 't', float(t), scale_factor(float(t))
+
+
+def _output_times_flat():
+    """output_times as {time_param: {kind: [values]}} (commons.py:2800-2870): the parameter is either
+    {kind: values} (scale factors) or {'a': {kind: values}, 't': {kind: values}}; None means no output."""
+    ot = commons.params.output_times or {}
+    nested = {'a': {}, 't': {}}
+    for key, val in ot.items():
+        if key in ('a', 't') and isinstance(val, dict):
+            for kind, v in val.items():
+                nested[key][kind] = v
+        else:
+            nested['a'][key] = val
+    flat = {'a': {}, 't': {}}
+    for time_param, kinds in nested.items():
+        for kind, v in kinds.items():
+            values = [float(x) for x in np.ravel(v).tolist() if x is not None] if v is not None else []
+            if values:
+                flat[time_param][kind] = values
+    return flat
 
 
 def _dump_times():
-    ot = commons.params.output_times
-    values = set()
-    for kind, val in ot.items():
-        if isinstance(val, dict):      # {'a': {...}} / {'t': {...}} forms are not used by the hot-path configs
-            for v in val.values():
-                values.update(np.ravel(v).tolist())
-        else:
-            values.update(np.ravel(val).tolist())
-    return [DumpTime(a) for a in sorted(values) if a >= universals.a]
+    flat = _output_times_flat()
+    times = {}
+    for a in {x for values in flat['a'].values() for x in values}:
+        if a >= universals.a:
+            d = DumpTime(a=a)
+            times[d.t] = d
+    for t in {x for values in flat['t'].values() for x in values}:
+        if t >= universals.t:
+            times.setdefault(t, DumpTime(t=t))
+    return [times[t] for t in sorted(times)]
 
 
 def _output_dir(kind):
@@ -353,12 +377,9 @@ def _output_dir(kind):
 
 
 def _wanted(kind, dump_time):
-    val = commons.params.output_times.get(kind)
-    if val is None:
-        return False
-    if isinstance(val, dict):
-        val = [x for v in val.values() for x in np.ravel(v).tolist()]
-    return any(float(x) == dump_time.a for x in np.ravel(val).tolist())
+    flat = _output_times_flat()
+    return (any(x == dump_time.a for x in flat['a'].get(kind, ())) and dump_time.time_param == 'a') or \
+           (any(x == dump_time.t for x in flat['t'].get(kind, ())) and dump_time.time_param == 't')
 
 
 def dump_powerspec(components, dump_time):

@@ -161,3 +161,22 @@ def test_static_timestepping_callable_file_replay_and_recording(tmp_path):
     with pytest.raises(commons.ConceptAbort):
         commons.load_params(PM8, static_timestepping=str(tmp_path))
         main.prepare_static_timestepping()
+
+
+def test_output_times_forms():
+    """output_times as {kind: scale factors} and as {'a': {...}, 't': {...}} with None entries (param/example_explanatory)"""
+    from concept_b200 import main
+    from concept_b200.integration import cosmic_time, init_time
+    commons.load_params(PM8, output_times={'snapshot': (0.1, 0.5, 1), 'powerspec': 0.5})
+    init_time()
+    times = main._dump_times()
+    assert [d.a for d in times] == [0.1, 0.5, 1.0] and all(d.time_param == 'a' for d in times)
+    assert main._wanted('powerspec', times[1]) and not main._wanted('powerspec', times[0]) and main._wanted('snapshot', times[2])
+    t_half = cosmic_time(0.25)
+    commons.load_params(PM8, output_times={'a': {'snapshot': [0.5, 1.0], 'powerspec': None, 'render2D': 1},
+                                           't': {'snapshot': None, 'powerspec': t_half}})
+    init_time()
+    times = main._dump_times()
+    assert [d.time_param for d in times] == ['t', 'a', 'a']
+    assert times[0].a == pytest.approx(0.25, rel=1e-9) and main._wanted('powerspec', times[0]) and not main._wanted('snapshot', times[0])
+    assert main._wanted('snapshot', times[1]) and not main._wanted('powerspec', times[1])
