@@ -55,3 +55,59 @@ def test_two_rank_host_logic_over_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert sorted(out.get(timeout=5) for _ in range(2)) == [(0, 'ok'), (1, 'ok')]
+
+
+def _ic_worker(rank, world, port, out):
+    """Replicated initial-condition realisation on two ranks (concept_b200.ic._get_context): the kernels are the
+    numpy model of tests/ic_mock_context.py, everything else — parameters, noise, orchestration, slab ownership,
+    all-gather of the result — is the product's host code over a real gloo process group."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    from concept_b200 import commons, communication, ic, integration
+    from concept_b200.species import Component
+    from ic_mock_context import MockContext
+    communication.init(backend='gloo')
+    d = np.load(os.path.join(here, 'golden', 'ic_1lpt_sc_G8.npz'))
+    commons.load_params(f"boxsize = {float(d['boxsize'])}*Mpc\nH0 = 70*km/s/Mpc\nΩcdm = 0.25\nΩb = 0.05\na_begin = {float(d['a'])}\n"
+                        f"primordial_spectrum = {{'A_s': {float(d['A_s'])}, 'n_s': {float(d['n_s'])}, 'α_s': {float(d['alpha_s'])}, "
+                        f"'pivot': {float(d['pivot'])}/Mpc}}\n"
+                        "potential_options = {'gridsize': {'gravity': {'pm': 8}}}\nselect_forces = {'matter': {'gravity': 'pm'}}\n")
+    integration.init_time()
+    A_d, A_t, k0 = (float(x) for x in d['transfer'])
+    a = float(d['a'])
+
+    class Spline:
+        def __init__(self, f):
+            self.eval = f
+    ic.compute_transfer = lambda component, variable, *args, **kw: (
+        Spline((lambda k: -A_d*a*k**2/(1 + (k/k0)**2)**1.1) if variable == 0 else (lambda k: A_t*a**0.5*k**2/(1 + (k/k0)**2)**1.1)), None)
+    ic._get_context = lambda gridsize: MockContext(gridsize, commons.params.boxsize)
+    Component.device = property(lambda self: torch.device('cpu'))
+    c = Component('matter', 'matter', N=8**3)
+    ic.realize_particles(c, a)
+    counts = communication.allgather(c.N_local)
+    assert sum(counts) == 512 and all(n > 0 for n in counts)
+    pos, mom = c.gather_global()          # all ranks' particles ordered by id
+    L = float(d['boxsize'])
+    dp = np.abs(pos - d['pos'])
+    assert np.minimum(dp, L - dp).max() < 1e-11 and np.abs(mom - d['mom']).max() < 1e-11*np.abs(d['mom']).max()
+    x = c.pos[:c.N_local, 0].numpy()
+    assert np.all(communication.slab_owner(x, L, 8) == rank)
+    communication.barrier()
+    torch.distributed.destroy_process_group()
+    out.put((rank, 'ok'))
+
+
+def test_two_rank_replicated_initial_conditions_over_gloo():
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ic_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert sorted(out.get(timeout=5) for _ in range(2)) == [(0, 'ok'), (1, 'ok')]
