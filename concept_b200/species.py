@@ -164,6 +164,13 @@ class Component:
             self._ϱ_bar = self.N*self.mass/p.boxsize**3
         return self._ϱ_bar
 
+    def realize(self, a=-1, a_next=-1, variables=None, multi_indices=None, use_gridˣ=False):
+        """species.py:2094-2098 → ic.realize (ic.py:297-398): for a particle component the full realisation"""
+        if not self.is_active(a):
+            return
+        from . import ic
+        ic.realize_particles(self, commons.universals.a if a == -1 else a)
+
     def cell_sort(self, gridsize=None):
         """Reorder the local particles by grid cell (the tile_sort analogue, species.py:2657-2780): keeps the
         deposit/gather locality that lattice-ordered particles lose over many steps."""
