@@ -142,7 +142,7 @@ def get_powerspec_bins(gridsize, k_max='nyquist', bins_per_decade=None, n_modes_
 
 
 def powerspec(components, gridsize, interpolation=None, deconvolve=None, interlace=None, k_max=None,
-              bins_per_decade=None):
+              bins_per_decade=None, gridsizes_upstream=None):
     """compute_powerspec (analysis.py:500-579) of a group of particle components on the GPU:
     PCS (default) deposit of ρ onto one or two interlaced lattices, forward FFT, Nyquist nullification,
     deconvolution and interlacing phase (interpolate_upstream(…, output_space='Fourier'), mesh.py:492-616),
@@ -162,6 +162,10 @@ def powerspec(components, gridsize, interpolation=None, deconvolve=None, interla
     shifts = [None, (-0.5, -0.5, -0.5)] if interlace in (True, 'bcc') else [None]
     nl = len(shifts)
     fft_factor = float(gridsize)**(-3)
+    if gridsizes_upstream is not None and any(int(g) != int(gridsize) for g in gridsizes_upstream):
+        _upstream_to_global_mixed(components, [int(g) for g in gridsizes_upstream], int(gridsize), ctx, order,
+                                  int(bool(deconvolve))*order, shifts)
+        shifts = []
     for l, shift in enumerate(shifts):
         ctx.grid_zero()
         for component in components:
@@ -171,9 +175,9 @@ def powerspec(components, gridsize, interpolation=None, deconvolve=None, interla
         ctx.fourier_operate(deconv_order=int(bool(deconvolve))*order, shift=shift, scale=1.0/nl)
         if nl > 1:
             ctx.slab_save() if l == 0 else ctx.slab_accumulate()
-    if nl > 1:
+    if nl > 1 and shifts:
         ctx.slab_restore()
-    dev = f'cuda:{ctx.device}'
+    dev = ctx.torch_device
     power_k2 = torch.zeros(k2_max + 1, dtype=torch.float64, device=dev)
     count_k2 = torch.zeros(k2_max + 1, dtype=torch.int64, device=dev)
     ctx.power_k2(k2_max, power_k2, count_k2)
@@ -191,3 +195,33 @@ def powerspec(components, gridsize, interpolation=None, deconvolve=None, interla
     normalization = sum(a**(-3*(1 + c.w_eff(a=a)))*c.ϱ_bar for c in components)**(-2)*float(commons.params.boxsize)**3
     power *= normalization/n_modes
     return k_bin_centers, power, n_modes
+
+
+def _upstream_to_global_mixed(components, gridsizes_upstream, gridsize, ctx_global, order, deconv_order, shifts):
+    """interpolate_upstream (mesh.py:492-616) for components with their own upstream grid sizes: every group is
+    deposited on its own grid, transformed, and copied — with its deconvolution, interlacing phase and the half-cell
+    phase between grids — into the global slab (add_upstream_to_global_slabs :618-710, copy_modes :980-1322), which
+    ends up in ctx_global's working slab.  One rank (see pm_fourier_copy_modes)."""
+    from . import communication, mesh
+    if communication.nprocs > 1:
+        commons.abort('Power spectra with component-specific upstream grid sizes need one rank '
+                      '(the cross-rank mode exchange of copy_modes, mesh.py:1105-1230, is not provided)')
+    nl = len(shifts)
+    first = True
+    for gridsize_upstream in sorted(set(gridsizes_upstream), key=lambda g: (g != gridsize, g)):
+        ctx = ctx_global if gridsize_upstream == gridsize else mesh.get_context(gridsize_upstream, 'f64')
+        group = [c for c, g in zip(components, gridsizes_upstream) if g == gridsize_upstream]
+        for shift in shifts:
+            ctx.grid_zero()
+            for component in group:
+                mesh.interpolate_particles(component, gridsize_upstream, ctx, 'ρ', order, None, shift, float(gridsize_upstream)**(-3))
+            ctx.halo_add()
+            ctx.fft_forward()
+            if ctx is ctx_global:
+                ctx.fourier_operate(deconv_order=deconv_order, shift=shift, scale=1.0/nl)
+                ctx.slab_save() if first else ctx.slab_accumulate()
+            else:
+                ctx.fourier_copy_modes_into(ctx_global, deconv_order, shift, 1.0/nl, src_saved=False, dst_saved=True,
+                                            accumulate=not first)
+            first = False
+    ctx_global.fourier_operate(from_saved=True)          # working slab = accumulated global slab

@@ -390,9 +390,11 @@ def dump_powerspec(components, dump_time):
     particle_components = [c for c in components if c.representation == 'particles']
     if not particle_components:
         return None
-    gridsize = max(2*round(c.N**(1/3)) for c in particle_components)
-    gridsize += gridsize & 1
-    k, power, n_modes = analysis.powerspec(particle_components, gridsize)
+    # powerspec_options defaults: upstream grid size 2·∛N per particle component, global = the largest upstream size
+    gridsizes_upstream = [2*round(c.N**(1/3)) for c in particle_components]
+    gridsizes_upstream = [g + (g & 1) for g in gridsizes_upstream]
+    gridsize = max(gridsizes_upstream)
+    k, power, n_modes = analysis.powerspec(particle_components, gridsize, gridsizes_upstream=gridsizes_upstream)
     if out_dir and communication.master:
         os.makedirs(out_dir, exist_ok=True)
         filename = os.path.join(out_dir, f'powerspec_a={dump_time.a:.2f}')

@@ -517,3 +517,23 @@ def pm_kick_multigrid(components, *, boxsize, gridsize_global, order, G_Newton, 
                     for dim in range(3):
                         out[q][:, dim] += gather(diff_grid(phi, dim, c['diff_order'], h), c['pos'], boxsize, order, s)*kick_factor
     return out
+
+
+def density_fourier_group(components, a, boxsize, gridsize_global, order, deconvolve=True, interlace=True):
+    """interpolate_upstream(components, gridsizes_upstream, gridsize_global, 'ρ', order, deconvolve, interlace,
+    output_space='Fourier') (mesh.py:492-616) for particle components with their own upstream grid sizes:
+    components is a list of dicts with pos, mass, w_eff and upstream.  Natural layout [i, j, kk]."""
+    G = int(gridsize_global)
+    shifts = [(0.0, 0.0, 0.0)] + ([(BCC_SHIFT,)*3] if interlace else [])
+    slab = np.zeros((G, G, G//2 + 1), dtype=complex)
+    for G_up in sorted({c['upstream'] for c in components}, key=lambda g: (g != G, g)):
+        for s in shifts:
+            rho = np.zeros((G_up, G_up, G_up))
+            for c in components:
+                if c['upstream'] == G_up:
+                    contribution = a**(-3*(1 + c['w_eff']))*c['mass']*(float(G_up)**(-3)*(G_up/boxsize)**3)
+                    rho += deposit(c['pos'], boxsize, G_up, order, contribution, s)
+            f = forward_fft(rho)
+            f[~mode_mask(G_up)] = 0
+            slab += copy_modes(f, G, order*int(bool(deconvolve)), s, len(shifts))
+    return slab

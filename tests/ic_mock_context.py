@@ -311,6 +311,14 @@ class MeshMockContext(HostKernelContext):
             factor = factor*np.exp(k2*(-gauss))
         self.fourier = np.where(self.live_nonzero, self.fourier*factor, 0)
 
+    def power_k2(self, k2_max, power, count=None):
+        from oracle import pm_oracle as O
+        assert self.fourier is not None
+        p2, c2 = O.power_by_k2(self.fourier, k2_max)
+        power += torch.from_numpy(p2)
+        if count is not None:
+            count += torch.from_numpy(c2.astype(np.int64))
+
     def gather(self, which, pos, mom, order, dim, factor, shift=None):
         from oracle import pm_oracle as O
         assert which == 0 and self.real is not None
