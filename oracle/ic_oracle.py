@@ -280,8 +280,10 @@ LATTICE_SHIFTS = {   # mesh.py:85-100 with cell_centered = True ⇒ shift_amount
 
 
 def realize_particles(n, lattices, boxsize, a, H, mass, w_eff, noise, transfer_delta, transfer_theta, primordial,
-                      backscale=False, lpt=1, dealias=False, growth=None, nongaussianity=0.0):
-    """ic.py:1199-1399.  noise: complex [j][i][kk] from primordial_noise(n, …).  Returns pos, mom [N][3]."""
+                      backscale=False, lpt=1, dealias=False, growth=None, nongaussianity=0.0, shifts=None):
+    """ic.py:1199-1399.  noise: complex [j][i][kk] from primordial_noise(n, …).  Returns pos, mom [N][3].
+    shifts: the primitive lattices to realise (default: all of the sc / bcc / fcc lattice); a simple-cubic component
+    that shares the box with one or three others gets a single primitive lattice of bcc / fcc (ic.py:1248-1253)."""
     G = n
     N1 = n**3
     pos = np.zeros((lattices*N1, 3))
@@ -292,7 +294,7 @@ def realize_particles(n, lattices, boxsize, a, H, mass, w_eff, noise, transfer_d
     if dealias:
         Gd = (G*3)//2
         Gd += Gd & 1
-    for l, shift in enumerate(LATTICE_SHIFTS[lattices]):
+    for l, shift in enumerate(LATTICE_SHIFTS[lattices] if shifts is None else shifts):
         sl = slice(l*N1, (l + 1)*N1)
         # preinitialize_particles (ic.py:2138-2247), cell-centred
         ax = [(0.5 + shift[d] + np.arange(G))*cell for d in range(3)]

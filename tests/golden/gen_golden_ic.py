@@ -30,6 +30,7 @@ CASES = {
     'ic_1lpt_sc_G16_seeds': dict(n=16, lattices=1, boxsize=128.0, seeds=(11, 22)),
     'ic_3lpt_sc_G8': dict(n=8, lattices=1, boxsize=64.0, lpt=3),
     'ic_3lpt_sc_G8_dealias_backscale': dict(n=8, lattices=1, boxsize=64.0, lpt=3, dealias=True, backscale=True),
+    'ic_1lpt_two_components_G6': dict(n=6, lattices=1, boxsize=48.0, components=2),
     'ic_1lpt_sc_G8_nongauss': dict(n=8, lattices=1, boxsize=64.0, nongauss=0.6),
     'ic_2lpt_sc_G10_nongauss_backscale': dict(n=10, lattices=1, boxsize=80.0, nongauss=-0.4, backscale=True, lpt=2),
 }
@@ -110,9 +111,23 @@ def worker(name):
     n, nl = c['n'], c['lattices']
     a = float(a_begin)
     universals.a = a
-    comp = species.Component('matter', 'matter', N=nl*n**3)
-    assert comp.preic_lattice == {1: 'sc', 2: 'bcc', 4: 'fcc'}[nl]
-    ic.realize_particles(comp, a)
+    extra = {}
+    if c.get('components', 1) == 2:
+        # two simple-cubic components are interleaved into one bcc lattice (ic.py:1248-1251); ids continue
+        comps = [species.Component('cdm', 'cold dark matter', N=n**3), species.Component('baryons', 'baryons', N=n**3)]
+        for other in comps:
+            ic.realize_particles(other, a)
+        comp = comps[0]
+        for q, other in enumerate(comps):
+            extra[f'pos_{q}'] = np.asarray(other.pos_mv).copy().reshape(-1, 3)
+            extra[f'mom_{q}'] = np.asarray(other.mom_mv).copy().reshape(-1, 3)
+            extra[f'mass_{q}'] = float(other.mass)
+        extra['component_names'] = np.array(['cdm', 'baryons'])
+        extra['component_species'] = np.array(['cold dark matter', 'baryons'])
+    else:
+        comp = species.Component('matter', 'matter', N=nl*n**3)
+        assert comp.preic_lattice == {1: 'sc', 2: 'bcc', 4: 'fcc'}[nl]
+        ic.realize_particles(comp, a)
     pos = np.asarray(comp.pos_mv).copy().reshape(-1, 3)
     mom = np.asarray(comp.mom_mv).copy().reshape(-1, 3)
     # the primordial noise on its own, in the reference's transposed Fourier layout [j][i][2·kk(+1)]
@@ -131,6 +146,7 @@ def worker(name):
                transfer_calls=np.array(calls))
     for variable, table in amplitudes.items():
         out[f'amplitudes{variable}'] = table
+    out.update(extra)
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
     print(name, 'ok: N', len(pos), 'pos[0]', pos[0], 'mom[0]', mom[0], 'calls', calls)
 

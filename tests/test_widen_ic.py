@@ -49,12 +49,26 @@ def _param_text(d):
             f"realization_options = {{'backscale': {bool(d['backscale'])}, 'lpt': {int(d['lpt'])}, 'dealias': {bool(d['dealias'])}, 'nongaussianity': {float(d['nongaussianity']) if 'nongaussianity' in d else 0.0}}}\n")
 
 
-def _assert_particles(pos, mom, d):
+def _expected(d):
+    """[(name, species, N, lattice shifts or None, pos, mom, mass)] per realised component of a golden case"""
+    n = int(d['n'])
+    if 'component_names' in d.files:
+        from oracle import ic_oracle as O
+        total = len(d['component_names'])
+        kind = {2: 2, 4: 4}[total]
+        return [(str(name), str(species), n**3, [O.LATTICE_SHIFTS[kind][q]], d[f'pos_{q}'], d[f'mom_{q}'], float(d[f'mass_{q}']))
+                for q, (name, species) in enumerate(zip(d['component_names'].tolist(), d['component_species'].tolist()))]
+    return [('matter', 'matter', int(d['lattices'])*n**3, None, d['pos'], d['mom'], float(d['mass']))]
+
+
+def _assert_particles(pos, mom, d, pos_ref=None, mom_ref=None):
     L, n = float(d['boxsize']), int(d['n'])
-    dp = np.abs(pos - d['pos'])
+    pos_ref = d['pos'] if pos_ref is None else pos_ref
+    mom_ref = d['mom'] if mom_ref is None else mom_ref
+    dp = np.abs(pos - pos_ref)
     dp = np.minimum(dp, L - dp)          # a particle within rounding of the box edge may wrap either way
     assert dp.max() < 1e-11*L/n
-    assert np.abs(mom - d['mom']).max() < 1e-11*np.abs(d['mom']).max()
+    assert np.abs(mom - mom_ref).max() < 1e-11*np.abs(mom_ref).max()
 
 
 # --------------------------------------------------------------------------------------------- oracle (CPU)
@@ -71,10 +85,12 @@ def test_oracle_matches_reference(path):
     for variable, T in ((0, Td), (1, Tt)):
         if f'amplitudes{variable}' in d:
             assert np.allclose(O.get_amplitudes(n, float(d['boxsize']), T, prim), d[f'amplitudes{variable}'], rtol=1e-14, atol=0)
-    pos, mom = O.realize_particles(n, int(d['lattices']), float(d['boxsize']), float(d['a']), float(d['H']), float(d['mass']),
-                                   float(d['w_eff']), noise, Td, Tt, prim, bool(d['backscale']), int(d['lpt']),
-                                   bool(d['dealias']), _growth(d), float(d['nongaussianity']) if 'nongaussianity' in d else 0.0)
-    _assert_particles(pos, mom, d)
+    for name, species, N, shifts, pos_ref, mom_ref, mass in _expected(d):
+        pos, mom = O.realize_particles(n, int(d['lattices']), float(d['boxsize']), float(d['a']), float(d['H']), mass,
+                                       float(d['w_eff']), noise, Td, Tt, prim, bool(d['backscale']), int(d['lpt']),
+                                       bool(d['dealias']), _growth(d), float(d['nongaussianity']) if 'nongaussianity' in d else 0.0,
+                                       shifts)
+        _assert_particles(pos, mom, d, pos_ref, mom_ref)
 
 
 def test_cases_cover_the_options():
@@ -220,12 +236,16 @@ def test_orchestration_through_kernel_model(path, kernels, monkeypatch, host_ker
     monkeypatch.setattr(mesh, 'get_context', lambda gridsize, dtype=None: contexts.setdefault(
         int(gridsize), MockContext(gridsize, commons.params.boxsize)))
     monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
-    c = Component('matter', 'matter', N=int(d['lattices'])*int(d['n'])**3)
-    ic.realize_particles(c, float(d['a']))
-    assert c.mass == pytest.approx(float(d['mass']), rel=1e-13)
-    assert c.N_local == c.N == len(d['pos'])
-    assert np.array_equal(c.ids[:c.N].numpy(), np.arange(c.N))
-    _assert_particles(c.pos[:c.N].numpy(), c.mom[:c.N].numpy(), d)
+    expected = _expected(d)
+    comps = [Component(name, species, N=N) for name, species, N, *_ in expected]
+    id_bgn = 0
+    for c, (_, _, N, _, pos_ref, mom_ref, mass) in zip(comps, expected):
+        ic.realize_particles(c, float(d['a']), components_all=comps)
+        assert c.mass == pytest.approx(mass, rel=1e-13)
+        assert c.N_local == c.N == len(pos_ref)
+        assert np.array_equal(c.ids[:c.N].numpy(), id_bgn + np.arange(c.N))
+        _assert_particles(c.pos[:c.N].numpy(), c.mom[:c.N].numpy(), d, pos_ref, mom_ref)
+        id_bgn += N
 
 
 def test_linear_theory_stand_in():
@@ -293,13 +313,19 @@ def test_gpu_realize_particles_matches_reference(path, monkeypatch):
     d = np.load(path)
     commons.load_params(_param_text(d))
     _install_golden_linear_theory(monkeypatch, d)
-    c = Component('matter', 'matter', N=int(d['lattices'])*int(d['n'])**3)
-    ic.realize_particles(c, float(d['a']))
-    pos, mom, ids = c.pos_local.cpu().numpy(), c.mom_local.cpu().numpy(), c.ids[:c.N_local].cpu().numpy()
+    expected = _expected(d)
+    comps = [Component(name, species, N=N) for name, species, N, *_ in expected]
+    results = []
+    for c in comps:
+        ic.realize_particles(c, float(d['a']), components_all=comps)
+        results.append((c.pos_local.cpu().numpy(), c.mom_local.cpu().numpy(), c.ids[:c.N_local].cpu().numpy()))
     mesh.free_contexts()
-    assert np.array_equal(ids, np.arange(c.N))
-    assert c.mass == pytest.approx(float(d['mass']), rel=1e-13)
-    _assert_particles(pos, mom, d)
+    id_bgn = 0
+    for c, (pos, mom, ids), (_, _, N, _, pos_ref, mom_ref, mass) in zip(comps, results, expected):
+        assert np.array_equal(ids, id_bgn + np.arange(c.N))
+        assert c.mass == pytest.approx(mass, rel=1e-13)
+        _assert_particles(pos, mom, d, pos_ref, mom_ref)
+        id_bgn += N
 
 
 @pytest.mark.gpu
