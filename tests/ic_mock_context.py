@@ -350,3 +350,46 @@ class MeshMockContext(HostKernelContext):
             other.saved = dst
         else:
             other.fourier, other.real = dst, None
+
+
+class PMKickMockContext(MeshMockContext):
+    """MeshMockContext plus a numpy model of the whole-kick and particle entry points the PM time loop uses
+    (pm_kick_long with the scalars of struct pm_kick_params, pm_drift, pm_sum_mom2), so that concept_b200.main.timeloop —
+    the time-step controller, the kick/drift sequencing, dumps, static time-stepping — runs on the CPU."""
+
+    def kick_long(self, pos, mom, params, sum_mom2=None):
+        from oracle import pm_oracle as O
+        G, L = self.gridsize, self.boxsize
+        x = pos.numpy()
+        shifts = [(0.0, 0.0, 0.0)] + ([(O.BCC_SHIFT,)*3] if params.interlace else [])
+        nl = len(shifts)
+        slab = 0
+        for s in shifts:
+            f = O.forward_fft(O.deposit(x, L, G, params.order, params.contribution, s))
+            f[~O.mode_mask(G)] = 0
+            slab = slab + (f*(1/nl)*O.interlace_phase(G, s) if nl > 1 else f)
+        k2 = np.where(self.live_nonzero, self.k2, 1).astype(np.float64)
+        factor = O.deconv_factor(G, params.deconv_order)*(params.prefactor/k2)
+        if params.gauss:
+            factor = factor*np.exp(k2*(-params.gauss))
+        slab = np.where(self.live_nonzero, slab*factor, 0)
+        kick = np.zeros_like(x)
+        for s in shifts:
+            f = slab*(1/nl)*O.interlace_phase(G, s) if nl > 1 else slab
+            if params.diff_order == 0:
+                for dim in range(3):
+                    force = O.backward_fft(1j*(2*np.pi/L)*self.k[dim]*f, G)
+                    kick[:, dim] += O.gather(force, x, L, params.order, s)*params.kick_factor
+            else:
+                phi = O.backward_fft(f, G)
+                for dim in range(3):
+                    kick[:, dim] += O.gather(O.diff_grid(phi, dim, params.diff_order, L/G), x, L, params.order, s)*params.kick_factor
+        mom += torch.from_numpy(kick)
+
+    def drift(self, pos, mom, dt_over_mass):
+        from oracle import pm_oracle as O
+        pos.copy_(torch.from_numpy(O.drift(pos.numpy(), mom.numpy(), dt_over_mass, self.boxsize)))
+
+    def sum_mom2(self, mom, out=None):
+        from oracle import pm_oracle as O
+        return O.sum_mom2(mom.numpy())
