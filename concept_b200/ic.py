@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import commons, communication, linear, mesh
-from .commons import abort, masterprint, masterwarn, universals, π
+from .commons import abort, masterprint, masterwarn, π
 from .integration import hubble
 
 
