@@ -289,6 +289,9 @@ class MeshMockContext(HostKernelContext):
     def slab_accumulate(self):
         self.saved = self.saved + self.fourier
 
+    def slab_restore(self):
+        self.fourier, self.real = self.saved.copy(), None
+
     def fourier_operate(self, deconv_order=0, shift=None, scale=1.0, diff_dim=-1, from_saved=False):
         from oracle import pm_oracle as O
         G = self.gridsize
