@@ -396,3 +396,97 @@ class PMKickMockContext(MeshMockContext):
     def sum_mom2(self, mom, out=None):
         from oracle import pm_oracle as O
         return O.sum_mom2(mom.numpy())
+
+
+class ShortRangeFakeLib:
+    """TEST INFRASTRUCTURE — a numpy model of the P³M entry points that concept_b200.shortrange calls straight on
+    `ctx.lib` with raw pointers (pm_shortrange, pm_apply_dmom, pm_assign_rungs, pm_flag_rung_jumps,
+    pm_apply_rung_jumps; csrc/pm_shortrange.cu).  The tensors live in host memory here, so the pointers are mapped
+    back to numpy arrays.  Everything else is forwarded to the CPU build of the device code (`harness`)."""
+
+    def __init__(self, harness, boxsize):
+        self._harness, self._boxsize = harness, boxsize
+
+    def __getattr__(self, name):
+        return getattr(self._harness, name)
+
+    @staticmethod
+    def _arr(ptr, n, ctype):
+        import ctypes
+        if isinstance(ptr, int):
+            return np.ctypeslib.as_array((ctype*n).from_address(ptr))
+        return np.ctypeslib.as_array(ptr, shape=(n,)) if not isinstance(ptr, ctypes.Array) else np.ctypeslib.as_array(ptr)
+
+    @staticmethod
+    def _get_rung(acc, current, rung_factor, n_rungs):
+        acc2 = (acc**2).sum(axis=1)
+        with np.errstate(divide='ignore'):
+            rf = rung_factor + 0.25*np.log2(np.where(acc2 == 0, 1.0, acc2))
+        rung = np.where(rf < 0, 0, np.where(rf > n_rungs - 1, n_rungs - 1, 1 + np.trunc(np.clip(rf, 0, n_rungs)).astype(np.int64)))
+        return np.where(acc2 == 0, current, rung).astype(np.int8)
+
+    def pm_shortrange(self, h, pos, n, rung, rung_jumped, lowest_active_rung, factors, nfactors, rng, table, tablesize, maxr2, dmom):
+        import ctypes
+        from oracle import pm_oracle as O
+        x = self._arr(pos, 3*n, ctypes.c_double).reshape(n, 3)
+        r = self._arr(rung, n, ctypes.c_int8)
+        rj = self._arr(rung_jumped, n, ctypes.c_int8)
+        f = self._arr(factors, nfactors, ctypes.c_double)
+        tab = self._arr(table, tablesize, ctypes.c_double)
+        out = self._arr(dmom, 3*n, ctypes.c_double).reshape(n, 3)
+        active = r >= lowest_active_rung
+        S = O.shortrange_sums(x, self._boxsize, rng, tab, maxr2, active)
+        out[active] = S[active]*f[rj[active]][:, None]
+        return 0
+
+    def pm_apply_dmom(self, h, mom, dmom, n, rung, rung_jumped, lowest_active_rung, conv, nconv, apply):
+        import ctypes
+        m = self._arr(mom, 3*n, ctypes.c_double).reshape(n, 3)
+        dm = self._arr(dmom, 3*n, ctypes.c_double).reshape(n, 3)
+        r = self._arr(rung, n, ctypes.c_int8)
+        rj = self._arr(rung_jumped, n, ctypes.c_int8)
+        cv = self._arr(conv, nconv, ctypes.c_double)
+        active = r >= lowest_active_rung
+        if apply:
+            m[active] += dm[active]
+        dm[active] = dm[active]*cv[rj[active]][:, None]
+        return 0
+
+    def pm_assign_rungs(self, h, acc, n, rung_factor, n_rungs, rung, rung_jumped, counts):
+        import ctypes
+        a = self._arr(acc, 3*n, ctypes.c_double).reshape(n, 3)
+        r = self._arr(rung, n, ctypes.c_int8)
+        rj = self._arr(rung_jumped, n, ctypes.c_int8)
+        new = self._get_rung(a, r, rung_factor, n_rungs)
+        r[:] = new
+        rj[:] = new
+        for q in range(n_rungs):
+            counts[q] = int((new == q).sum())
+        return 0
+
+    def pm_flag_rung_jumps(self, h, acc, n, rung, rung_jumped, lowest_active_rung, rf_up, rf_down, dt1, n_rungs, any_ref):
+        import ctypes
+        a = self._arr(acc, 3*n, ctypes.c_double).reshape(n, 3)
+        r = self._arr(rung, n, ctypes.c_int8)
+        rj = self._arr(rung_jumped, n, ctypes.c_int8)
+        dt = self._arr(dt1, 3*n_rungs - 1, ctypes.c_double)
+        considered = (r >= lowest_active_rung) & (dt[r] != 0)
+        up = considered & (self._get_rung(a, r, rf_up, n_rungs) > r)
+        down_index = np.minimum(r.astype(np.int64) + n_rungs, 3*n_rungs - 2)
+        down = considered & ~up & (dt[down_index] != -1) & (self._get_rung(a, r, rf_down, n_rungs) < r)
+        rj[up] = r[up] + 2*n_rungs
+        rj[down] = r[down] + n_rungs
+        any_ref._obj.value = int(up.any() or down.any())
+        return 0
+
+    def pm_apply_rung_jumps(self, h, n, rung, rung_jumped, n_rungs, counts):
+        import ctypes
+        r = self._arr(rung, n, ctypes.c_int8)
+        rj = self._arr(rung_jumped, n, ctypes.c_int8)
+        up, down = rj >= 2*n_rungs, (rj >= n_rungs) & (rj < 2*n_rungs)
+        r[up] += 1
+        r[down] -= 1
+        rj[up | down] = r[up | down]
+        for q in range(n_rungs):
+            counts[q] = int((r == q).sum())
+        return 0

@@ -131,3 +131,52 @@ primordial_spectrum = {{
     ratio = last[large_scales, 2]/first[large_scales, 2]/growth2
     print("P(k, a=1)/P(k, a=0.02)/D² on large scales:", ratio)
     assert np.all((0.9 < ratio) & (ratio < 1.15)), ratio      # measured: 1.02, 1.05 (a 16³ grid instead of 32³: 0.80, 0.73)
+
+
+def test_p3m_run_with_rungs_reproduces_reference_on_the_cpu(monkeypatch):
+    """The reference's short P³M run (8 rungs, sub-stepped drifts and rung-selective kicks, rung jumps;
+    tests/golden/run_p3m_8.npz) through concept_b200.main / .shortrange with every library entry point replaced by its
+    numpy model — the CPU counterpart of tests/test_gpu_p3m.py::test_p3m_run_with_rungs_reproduces_reference."""
+    import torch
+    from concept_b200 import commons, main, mesh
+    from concept_b200.species import Component
+    import ic_mock_context
+    d = np.load(os.path.join(GOLDEN, 'run_p3m_8.npz'))
+    commons.load_params('''
+boxsize = 8*Mpc
+potential_options = {'gridsize': {'gravity': {'p3m': 24}}}
+H0      = 70*km/s/Mpc
+Ωcdm    = 0.25
+Ωb      = 0.05
+a_begin = 0.02
+output_times = {'snapshot': (0.0245,)}
+select_forces = {'matter': {'gravity': 'p3m'}}
+''')
+    contexts = {}
+
+    def get_context(gridsize, dtype=None):
+        if int(gridsize) not in contexts:
+            ctx = ic_mock_context.PMKickMockContext(gridsize, commons.params.boxsize)
+            ctx.lib = ic_mock_context.ShortRangeFakeLib(None, commons.params.boxsize)
+            ctx._h = None
+            contexts[int(gridsize)] = ctx
+        return contexts[int(gridsize)]
+    monkeypatch.setattr(mesh, 'get_context', get_context)
+    monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
+    c = Component('matter', 'matter', N=d['pos0'].shape[0], mass=float(d['mass']))
+    c.populate(d['pos0'], 'pos')
+    c.populate(d['mom0'], 'mom')
+    snaps = {}
+    main.timeloop([c], on_dump=lambda comps, dt: snaps.update(final=(comps[0].pos_mv3.copy(), comps[0].mom_mv3.copy(),
+                                                                          commons.universals.t, comps[0].rung_indices[:comps[0].N_local].numpy().copy())))
+    pos, mom, t, rung = snaps['final']
+    L = float(d['boxsize'])
+    assert t == pytest.approx(float(d['t_final']), rel=1e-10)
+    diff = pos[:, None, :] - d['pos_final'][None, :, :]
+    diff -= L*np.round(diff/L)
+    dist = np.sqrt((diff**2).sum(-1))
+    match = dist.argmin(1)                      # the reference re-orders its particles (tile_sort): match by position
+    assert len(set(match.tolist())) == len(match)
+    assert np.mean(dist[np.arange(len(match)), match])/L < 1e-7
+    assert np.abs(mom - d['mom_final'][match]).max() < 1e-5*np.abs(d['mom_final']).max()
+    assert np.mean(rung == d['rung_final'][match]) > 0.99
