@@ -180,3 +180,66 @@ select_forces = {'matter': {'gravity': 'p3m'}}
     assert np.mean(dist[np.arange(len(match)), match])/L < 1e-7
     assert np.abs(mom - d['mom_final'][match]).max() < 1e-5*np.abs(d['mom_final']).max()
     assert np.mean(rung == d['rung_final'][match]) > 0.99
+
+
+def test_example_basic_defaults_step_on_the_cpu(monkeypatch, tmp_path):
+    """param/example_basic's settings at a small size (8³ particles, P³M grid 16 — forces default to P³M with 8
+    rungs): initial conditions from the parameter file, rung initialisation on the nearly uniform particle load,
+    four base steps of long-range kicks, sub-stepped drifts and rung-selective pair kicks.  Total momentum is
+    conserved (antisymmetric pair forces, momentum-conserving PM) and the particles stay in the box."""
+    import ctypes
+    import subprocess
+    import tempfile
+    import torch
+    from concept_b200 import commons, main, mesh
+    from concept_b200.species import Component
+    import ic_mock_context
+    here = os.path.dirname(os.path.abspath(__file__))
+    tmp = tempfile.mkdtemp(prefix='p3m_harness_')
+    src = os.path.join(tmp, 'ic_host_harness.cpp')
+    with open(os.path.join(here, 'ic_host_harness.cu')) as f, open(src, 'w') as g:
+        g.write(f.read())
+    lib = os.path.join(tmp, 'libic_harness.so')
+    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-I', '/usr/local/cuda/include',
+                    '-I', os.path.join(os.path.dirname(here), 'concept_b200', 'csrc'), src, '-o', lib], check=True)
+    harness = ctypes.CDLL(lib)
+    contexts = {}
+
+    def get_context(gridsize, dtype=None):
+        if int(gridsize) not in contexts:
+            ctx = ic_mock_context.PMKickMockContext(gridsize, commons.params.boxsize)
+            ctx.lib = ic_mock_context.ShortRangeFakeLib(harness, commons.params.boxsize)
+            ctx._h = None
+            contexts[int(gridsize)] = ctx
+        return contexts[int(gridsize)]
+    monkeypatch.setattr(mesh, 'get_context', get_context)
+    monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
+    param = tmp_path/'param'
+    param.write_text(f'''
+initial_conditions = {{
+    'species': 'matter',
+    'N'      : 8**3,
+}}
+output_dirs = '{tmp_path}/output'
+output_times = {{'powerspec': 1.0}}
+boxsize = 256*Mpc/h
+potential_options = 16
+H0 = 67*km/(s*Mpc)
+Ωb = 0.049
+Ωcdm = 0.27
+a_begin = 0.02
+primordial_spectrum = {{
+    'A_s': 2.1e-9,
+    'n_s': 0.96,
+}}
+''', encoding='utf-8')
+    states = []
+    components = main.run(str(param), max_steps=4, on_step=lambda *a: states.append(a))
+    c = components[0]
+    assert c.forces == {'gravity': 'p3m'} and commons.params.N_rungs == 8 and len(states) == 4
+    assert set(contexts) == {8, 16}                      # the lattice grid of the realisation and the P³M grid
+    assert commons.universals.a > 0.02
+    pos, mom = c.pos_local.numpy(), c.mom_local.numpy()
+    assert np.isfinite(pos).all() and pos.min() >= 0 and pos.max() < commons.params.boxsize
+    assert sum(c.rungs_N) == c.N_local
+    assert np.abs(mom.sum(axis=0)).max() < 1e-9*np.abs(mom).sum()
