@@ -1,9 +1,16 @@
-"""TEST INFRASTRUCTURE ONLY — a numpy model of the libpmgrav entry points that concept_b200.ic calls
-(include/pmgrav.h: pm_ic_lattice, pm_ic_potential, pm_slab_save, pm_fourier_operate, pm_fft_forward /
-pm_fft_backward, pm_kspace_potential, pm_ic_displace, pm_real_export, pm_ic_2lpt_source, pm_fourier_resize,
-pm_ic_wrap), one rank, fp64.  It lets the CPU suite run the *orchestration* of concept_b200/ic.py — the
-order of operations, factors and signs the host hands to the kernels — against the reference's golden
-vectors without a GPU.  The kernels themselves are checked by the `-m gpu` tests of tests/test_widen_ic.py.
+"""TEST INFRASTRUCTURE ONLY — numpy models of the libpmgrav entry points (include/pmgrav.h) that the host mirror
+sequences, one rank, fp64, so that the CPU suite can run the *host code* of concept_b200 — parameters, orchestration,
+factors and signs handed to the kernels, time loop, rung scheduling — against the reference's golden vectors
+without a GPU.  The kernels themselves are checked by the `-m gpu` tests.
+
+  MockContext          the initial-condition entry points (pm_ic_*, pm_fourier_operate, pm_fft_*, pm_kspace_potential,
+                       pm_real_export/import, pm_fourier_resize, pm_lpt_accumulate) as plain numpy
+  HostKernelContext    the same, with the element code of csrc/pm_ic_ops.cuh / pm_copy_ops.cuh itself, compiled for the
+                       CPU (tests/ic_host_harness.cu), on buffers laid out as on the device
+  MeshMockContext      + the mesh operators particle_mesh / powerspec sequence (deposit, deconvolution, gather, …),
+                       built from oracle/pm_oracle.py, and pm_fourier_copy_modes (device code on the CPU)
+  PMKickMockContext    + pm_kick_long, pm_drift, pm_sum_mom2: what main.timeloop needs
+  ShortRangeFakeLib    the P³M entry points shortrange.py calls with raw pointers
 
 Slab layout as on the device with one rank: complex [i][j][kk] (PM_TAP_FOURIER), real [i][j][k].
 """
