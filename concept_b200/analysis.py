@@ -225,3 +225,23 @@ def _upstream_to_global_mixed(components, gridsizes_upstream, gridsize, ctx_glob
                                             accumulate=not first)
             first = False
     ctx_global.fourier_operate(from_saved=True)          # working slab = accumulated global slab
+
+
+def get_linear_powerspec(component_or_components, k_magnitudes, a=-1):
+    """linear.get_linear_powerspec (linear.py:3074-3133): P_lin(k) = (ζ(k)·T_δ(a, k))² of the (combined) species, with the
+    δ transfer function from ic.compute_transfer — CLASS in the reference, concept_b200.linear (or installed tables)
+    here.  For several components the transfer functions are averaged with the weights ϱ̄ (one combined species)."""
+    from . import ic
+    components = component_or_components if isinstance(component_or_components, (list, tuple)) else [component_or_components]
+    if a == -1:
+        a = commons.universals.a
+    k_magnitudes = np.asarray(k_magnitudes, dtype=np.float64)
+    δ = np.zeros_like(k_magnitudes)
+    weight_total = 0.0
+    for component in components:
+        spline, _ = ic.compute_transfer(component, 0, -1, a=a)
+        values = spline.eval_array(k_magnitudes) if hasattr(spline, 'eval_array') else np.array([spline.eval(k) for k in k_magnitudes])
+        δ += component.ϱ_bar*values
+        weight_total += component.ϱ_bar
+    δ /= weight_total
+    return (ic.get_primordial_curvature_perturbation(k_magnitudes)*δ)**2

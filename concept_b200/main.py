@@ -385,7 +385,8 @@ def _wanted(kind, dump_time):
 def dump_powerspec(components, dump_time):
     """analysis.powerspec + save_powerspec (analysis.py:500-579, :796-836) with the defaults of powerspec_options
     (commons.py:3354-3385: PCS, deconvolution, bcc interlacing, k_max = Nyquist, grid 2·∛N).  Columns as in the
-    reference's text files: k, number of modes, P(k)."""
+    reference's text files: k, number of modes, P(k), linear P(k) (powerspec_select's default, commons.py:2636-2643).
+    Returns (k, power, n_modes)."""
     out_dir = _output_dir('powerspec')
     particle_components = [c for c in components if c.representation == 'particles']
     if not particle_components:
@@ -399,10 +400,12 @@ def dump_powerspec(components, dump_time):
         os.makedirs(out_dir, exist_ok=True)
         filename = os.path.join(out_dir, f'powerspec_a={dump_time.a:.2f}')
         names = ', '.join(c.name for c in particle_components)
+        power_linear = analysis.get_linear_powerspec(particle_components, k)
         header = (f'Power spectrum of {names} at a = {universals.a:.8g}, t = {universals.t:.8g} {commons.unit_time}, '
                   f'grid size {gridsize} (concept_b200)\n'
-                  f'k [{commons.unit_length}^-1]\tmodes\tpower [{commons.unit_length}^3]')
-        np.savetxt(filename, np.column_stack([k, n_modes, power]), fmt=('%.8e', '%d', '%.8e'), delimiter='\t', header=header)
+                  f'k [{commons.unit_length}^-1]\tmodes\tpower [{commons.unit_length}^3]\tlinear power [{commons.unit_length}^3]')
+        np.savetxt(filename, np.column_stack([k, n_modes, power, power_linear]), fmt=('%.8e', '%d', '%.8e', '%.8e'),
+                   delimiter='\t', header=header)
     return k, power, n_modes
 
 

@@ -122,7 +122,12 @@ primordial_spectrum = {{
     assert commons.universals.a == pytest.approx(1.0, rel=1e-12) and len(components) == 1 and components[0].N_local == 16**3
     first = np.loadtxt(os.path.join(str(tmp_path), 'output', 'powerspec_a=0.02'))
     last = np.loadtxt(os.path.join(str(tmp_path), 'output', 'powerspec_a=1.00'))
-    assert first.shape == last.shape and np.array_equal(first[:, 0], last[:, 0])
+    assert first.shape == last.shape and first.shape[1] == 4 and np.array_equal(first[:, 0], last[:, 0])
+    # the file's linear column is (ζ·T_δ)² at the dump's scale factor: it grows by D1² exactly …
+    D1 = linear.compute_cosmo().growth_unnormalised
+    assert np.allclose(last[:, 3]/first[:, 3], (D1(1.0)/D1(0.02))**2, rtol=1e-6)
+    # … and the power measured on the initial conditions follows it on large scales
+    assert np.all(np.abs(first[:3, 2]/first[:3, 3] - 1) < 0.35)
     cosmo = linear.compute_cosmo()
     growth2 = (cosmo.growth_fac_D1(1.0)/cosmo.growth_fac_D1(0.02))**2
     k_nyquist_particles = np.pi*16/commons.params.boxsize

@@ -442,9 +442,10 @@ def test_gpu_example_basic_initial_conditions_and_powerspec(tmp_path):
     dump_time = main.DumpTime(commons.universals.a)
     k, power, n_modes = main.dump_powerspec(components, dump_time)
     table = np.loadtxt(os.path.join(str(tmp_path), f'powerspec_a={dump_time.a:.2f}'))
-    assert table.shape == (len(k), 3) and np.allclose(table[:, 2], power, rtol=1e-7)
+    assert table.shape == (len(k), 4) and np.allclose(table[:, 2], power, rtol=1e-7)
     T, _ = linear.compute_transfer(c, 0, 64, a=commons.universals.a)
     linear_power = (T.eval_array(k)*ic.get_primordial_curvature_perturbation(k))**2
+    assert np.allclose(table[:, 3], linear_power, rtol=1e-7)       # the 'linear' column of powerspec_select's default
     k_nyquist = np.pi*64/p.boxsize
     good = (n_modes >= 100) & (k < 0.9*k_nyquist)
     assert good.sum() >= 8
