@@ -16,3 +16,21 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope='session')
+def host_kernels():
+    """The element code of the initial-condition / copy kernels (concept_b200/csrc/pm_ic_ops.cuh, pm_copy_ops.cuh)
+    compiled for the CPU (tests/ic_host_harness.cu) and loaded as a ctypes library — no GPU needed."""
+    import ctypes
+    import subprocess
+    import tempfile
+    tests = os.path.join(ROOT, 'tests')
+    d = tempfile.mkdtemp(prefix='ic_harness_')
+    src = os.path.join(d, 'ic_host_harness.cpp')
+    with open(os.path.join(tests, 'ic_host_harness.cu')) as f, open(src, 'w') as g:
+        g.write(f.read())
+    lib = os.path.join(d, 'libic_harness.so')
+    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-I', '/usr/local/cuda/include',
+                    '-I', os.path.join(ROOT, 'concept_b200', 'csrc'), src, '-o', lib], check=True)
+    return ctypes.CDLL(lib)

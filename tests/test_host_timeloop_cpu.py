@@ -73,27 +73,16 @@ def test_static_timestepping_record_then_replay(monkeypatch, tmp_path):
     assert np.abs(dx).max() < 1e-4
 
 
-def test_parameter_file_run_end_to_end_on_the_cpu(monkeypatch, tmp_path):
+def test_parameter_file_run_end_to_end_on_the_cpu(monkeypatch, tmp_path, host_kernels):
     """main.run on a small example_basic-like parameter file, kernels replaced by their numpy model / the device
     code compiled for the CPU: the initial conditions are realised from the `initial_conditions` dict, the PM time
     loop runs from a = 0.02 to 1 on a PM grid twice as fine as the particle lattice, power spectra are dumped at
     both ends — and the large-scale power has grown by the square of the linear growth factor."""
-    import ctypes
-    import subprocess
-    import tempfile
     import torch
     from concept_b200 import commons, linear, main, mesh
     from concept_b200.species import Component
     import ic_mock_context
-    here = os.path.dirname(os.path.abspath(__file__))
-    tmp = tempfile.mkdtemp(prefix='run_harness_')
-    src = os.path.join(tmp, 'ic_host_harness.cpp')
-    with open(os.path.join(here, 'ic_host_harness.cu')) as f, open(src, 'w') as g:
-        g.write(f.read())
-    lib = os.path.join(tmp, 'libic_harness.so')
-    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-I', '/usr/local/cuda/include',
-                    '-I', os.path.join(os.path.dirname(here), 'concept_b200', 'csrc'), src, '-o', lib], check=True)
-    monkeypatch.setattr(ic_mock_context.PMKickMockContext, 'lib', ctypes.CDLL(lib))
+    monkeypatch.setattr(ic_mock_context.PMKickMockContext, 'lib', host_kernels)
     contexts = {}
     monkeypatch.setattr(mesh, 'get_context', lambda gridsize, dtype=None: contexts.setdefault(
         int(gridsize), ic_mock_context.PMKickMockContext(gridsize, commons.params.boxsize)))
@@ -187,27 +176,16 @@ select_forces = {'matter': {'gravity': 'p3m'}}
     assert np.mean(rung == d['rung_final'][match]) > 0.99
 
 
-def test_example_basic_defaults_step_on_the_cpu(monkeypatch, tmp_path):
+def test_example_basic_defaults_step_on_the_cpu(monkeypatch, tmp_path, host_kernels):
     """param/example_basic's settings at a small size (8³ particles, P³M grid 16 — forces default to P³M with 8
     rungs): initial conditions from the parameter file, rung initialisation on the nearly uniform particle load,
     four base steps of long-range kicks, sub-stepped drifts and rung-selective pair kicks.  Total momentum is
     conserved (antisymmetric pair forces, momentum-conserving PM) and the particles stay in the box."""
-    import ctypes
-    import subprocess
-    import tempfile
     import torch
     from concept_b200 import commons, main, mesh
     from concept_b200.species import Component
     import ic_mock_context
-    here = os.path.dirname(os.path.abspath(__file__))
-    tmp = tempfile.mkdtemp(prefix='p3m_harness_')
-    src = os.path.join(tmp, 'ic_host_harness.cpp')
-    with open(os.path.join(here, 'ic_host_harness.cu')) as f, open(src, 'w') as g:
-        g.write(f.read())
-    lib = os.path.join(tmp, 'libic_harness.so')
-    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-I', '/usr/local/cuda/include',
-                    '-I', os.path.join(os.path.dirname(here), 'concept_b200', 'csrc'), src, '-o', lib], check=True)
-    harness = ctypes.CDLL(lib)
+    harness = host_kernels
     contexts = {}
 
     def get_context(gridsize, dtype=None):

@@ -197,23 +197,6 @@ def test_amplitudes_match_reference(path, monkeypatch):
             assert np.allclose(table, d[f'amplitudes{variable}'], rtol=1e-14, atol=0)
 
 
-@pytest.fixture(scope='module')
-def host_kernels():
-    """csrc/pm_ic_ops.cuh compiled for the CPU (tests/ic_host_harness.cu) as a ctypes library"""
-    import ctypes
-    import subprocess
-    import tempfile
-    root = os.path.dirname(HERE)
-    d = tempfile.mkdtemp(prefix='ic_harness_')
-    src = os.path.join(d, 'ic_host_harness.cpp')
-    with open(os.path.join(HERE, 'ic_host_harness.cu')) as f, open(src, 'w') as g:
-        g.write(f.read())
-    lib = os.path.join(d, 'libic_harness.so')
-    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-I', '/usr/local/cuda/include',
-                    '-I', os.path.join(root, 'concept_b200', 'csrc'), src, '-o', lib], check=True)
-    return ctypes.CDLL(lib)
-
-
 @pytest.mark.parametrize('kernels', ['numpy-model', 'device-code-on-cpu'])
 @pytest.mark.parametrize('path', CASES, ids=IDS)
 def test_orchestration_through_kernel_model(path, kernels, monkeypatch, host_kernels):

@@ -100,23 +100,12 @@ def _components(d):
 
 
 @pytest.mark.parametrize('path', CASES, ids=IDS)
-def test_orchestration_through_kernel_model(path, monkeypatch):
-    import ctypes
-    import subprocess
-    import tempfile
+def test_orchestration_through_kernel_model(path, monkeypatch, host_kernels):
     import torch
     from concept_b200 import commons, interactions, mesh
     from concept_b200.species import Component
     import ic_mock_context
-    root = os.path.dirname(HERE)
-    tmp = tempfile.mkdtemp(prefix='mg_harness_')
-    src = os.path.join(tmp, 'ic_host_harness.cpp')
-    with open(os.path.join(HERE, 'ic_host_harness.cu')) as f, open(src, 'w') as g:
-        g.write(f.read())
-    lib = os.path.join(tmp, 'libic_harness.so')
-    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-I', '/usr/local/cuda/include',
-                    '-I', os.path.join(root, 'concept_b200', 'csrc'), src, '-o', lib], check=True)
-    monkeypatch.setattr(ic_mock_context.MeshMockContext, 'lib', ctypes.CDLL(lib))
+    monkeypatch.setattr(ic_mock_context.MeshMockContext, 'lib', host_kernels)
     d = np.load(path)
     commons.load_params(_param_text(d))
     assert commons.shortrange_scale(int(d['gridsize_global'])) == pytest.approx(float(d['r_scale'])) or str(d['method']) == 'pm'
@@ -209,23 +198,12 @@ def _pk_product(d, comps):
 
 
 @pytest.mark.parametrize('path', PK_CASES, ids=PK_IDS)
-def test_group_powerspec_orchestration_through_kernel_model(path, monkeypatch):
-    import ctypes
-    import subprocess
-    import tempfile
+def test_group_powerspec_orchestration_through_kernel_model(path, monkeypatch, host_kernels):
     import torch
     from concept_b200 import commons, mesh
     from concept_b200.species import Component
     import ic_mock_context
-    root = os.path.dirname(HERE)
-    tmp = tempfile.mkdtemp(prefix='pk_harness_')
-    src = os.path.join(tmp, 'ic_host_harness.cpp')
-    with open(os.path.join(HERE, 'ic_host_harness.cu')) as f, open(src, 'w') as g:
-        g.write(f.read())
-    lib = os.path.join(tmp, 'libic_harness.so')
-    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-I', '/usr/local/cuda/include',
-                    '-I', os.path.join(root, 'concept_b200', 'csrc'), src, '-o', lib], check=True)
-    monkeypatch.setattr(ic_mock_context.MeshMockContext, 'lib', ctypes.CDLL(lib))
+    monkeypatch.setattr(ic_mock_context.MeshMockContext, 'lib', host_kernels)
     d = np.load(path)
     contexts = {}
     monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
