@@ -226,3 +226,51 @@ primordial_spectrum = {{
     assert np.isfinite(pos).all() and pos.min() >= 0 and pos.max() < commons.params.boxsize
     assert sum(c.rungs_N) == c.N_local
     assert np.abs(mom.sum(axis=0)).max() < 1e-9*np.abs(mom).sum()
+
+
+def test_gravity_plugin_surface(monkeypatch):
+    """concept_b200.gravity mirrors the reference's short-range plugin (gravity.py:51-67, :263-354): factors per rung,
+    the pair kick into Δmom of the active particles, and a loud refusal of caller-side tile selections."""
+    import torch
+    from concept_b200 import commons, gravity, mesh, shortrange
+    from concept_b200.species import Component
+    from oracle import pm_oracle as O
+    import ic_mock_context
+    d = np.load(os.path.join(GOLDEN, 'shortkick_p3m_G24.npz'))
+    commons.load_params('''
+boxsize = 8*Mpc
+potential_options = {'gridsize': {'gravity': {'p3m': 24}}}
+H0 = 70*km/s/Mpc
+Ωcdm = 0.25
+Ωb = 0.05
+a_begin = 0.02
+select_forces = {'matter': {'gravity': 'p3m'}}
+''')
+    ctx = ic_mock_context.PMKickMockContext(24, commons.params.boxsize)
+    ctx.lib, ctx._h = ic_mock_context.ShortRangeFakeLib(None, commons.params.boxsize), None
+    monkeypatch.setattr(mesh, 'get_context', lambda gridsize, dtype=None: ctx)
+    monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
+    c = Component('matter', 'matter', N=d['pos0'].shape[0], mass=float(d['mass']))
+    c.populate(d['pos0'], 'pos')
+    c.populate(d['mom0'], 'mom')
+    assert c.softening_length == pytest.approx(float(d['softening_length']), rel=1e-14)
+    assert gravity.combine_softening_lengths(0.1, 0.3) == pytest.approx(0.2)
+    shortrange.ensure_rung_state(c)
+    rung = d['rung_indices_init'].astype(np.int8)
+    c.rung_indices[:c.N_local] = torch.from_numpy(rung)
+    c.rung_indices_jumped[:c.N_local] = torch.from_numpy(rung)
+    c.lowest_active_rung = 1
+    ᔑdt_rungs = {('a**(-3*w_eff₀-3*w_eff₁-1)', 'matter', 'matter'): np.asarray(d['dt_rungs_pair'], dtype=np.float64)}
+    factors = gravity.compute_factors(c, c, ᔑdt_rungs)
+    assert np.allclose(factors, float(d['G_Newton'])*float(d['mass'])**2*d['dt_rungs_pair'], rtol=1e-15)
+    c.Δmom[:] = 7.0
+    gravity.gravity_pairwise_shortrange('gravity', c, c, ᔑdt_rungs)
+    table, maxr2 = O.shortrange_table(float(d['sr_scale']), float(d['sr_range']), int(d['sr_tablesize']), float(d['softening_length']))
+    S = O.shortrange_sums(d['pos0'], float(d['boxsize']), float(d['sr_range']), table, maxr2)
+    active = rung >= 1
+    got = c.Δmom[:c.N_local].numpy()
+    assert active.any() and (~active).any()
+    assert np.allclose(got[active], S[active]*factors[rung[active]][:, None], rtol=1e-12, atol=0)
+    assert np.all(got[~active] == 7.0)                      # inactive receivers keep their stored Δmom
+    with pytest.raises(commons.ConceptAbort):
+        gravity.gravity_pairwise_shortrange('gravity', c, c, ᔑdt_rungs, tile_indices_receiver=np.arange(3))
