@@ -2,7 +2,7 @@
 """bench.py — PM-gravity cycle benchmark (BASELINE.json: particle-updates/s and ms per PM cycle,
 256³ particles / 512³ grid, CIC, fp64, on 1/2/4/8 B200).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extra]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
@@ -11,15 +11,23 @@ Green's function/deconvolution → c2r FFT → fused gradient + gather + kick + 
 full drift and, on several GPUs, the slab migration of particles.  Strong scaling: the same
 256³/512³ problem is split into x-slabs over the N ranks.
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` is the same cycle
-through the C-ABI entry point that takes HOST buffers (pm_kick_long_host: H2D of pos+mom, cycle,
-D2H of pos+mom every step).  `roofline` is for the dominant hand-written kernel (fused
-gradient/gather/kick), timed live with CUDA events inside the timed steps.  `cpu_baseline` is the
-C/OpenMP restatement of the reference loops (oracle/pm_oracle.c) on this box's host cores.
+Prints ONE JSON line (rank 0):
+  value        device-resident throughput of configs[1] (256³/512³, CIC, fp64)
+  e2e          the same cycle through the C-ABI entry point that takes HOST buffers (pm_kick_long_host)
+  roofline     the dominant hand-written kernel, timed live with CUDA events inside the timed steps,
+               plus the per-kernel table and the whole-cycle fraction
+  parity       BEFORE the timed region, at this N: a distributed kick + drift + migration at G = 128 and at the
+               benchmark's G = 512 on 10⁵ seeded particles, compared particle by particle (ids) with the CPU
+               restatement of the reference on rank 0 (oracle/, used here as the checker only); the run FAILS if the
+               kick differs by more than 1e-9 of its maximum, the drift is not bit-exact or a particle is lost —
+               the reference's own multi-process pin (test/nprocs_pm/analyze.py:121) made visible to the driver
+  particles_after, sum_mom2   measured after exactly warmup + steps cycles (comparable across N)
+  extra_configs   configs[2] (TSC, fp32 grid) at every N; configs[3] (512³/1024³) at N = 8; the P³M cycle of configs[4]
+  cpu_baseline    the C/OpenMP restatement of the reference loops (oracle/pm_oracle.c) on this box's host cores
 
---impl reference: the reference's CPU implementation of the same cycle.  The compiled reference
-cannot be built in this image (no MPI/FFTW/GSL), so this is the oracle port with
-all host threads, on a bounded sample of the workload per step.
+--impl reference: the reference's CPU implementation of the same cycle.  The compiled reference cannot be built
+in this image (no MPI/FFTW/GSL), so this is the oracle port with all host threads (set explicitly:
+torchrun exports OMP_NUM_THREADS=1) on the full 256³/512³ workload.
 """
 import argparse
 import json
@@ -34,14 +42,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_SIDE, GRID, BOXSIZE = 256, 512, 512.0
-ORDER, DIFF_ORDER = 2, 2
 G_NEWTON = 4.4985024439973154e-05
 SIGMA = 0.3
-KICK = dict(mass=1.0, boxsize=BOXSIZE, gridsize=GRID, order=ORDER, G_Newton=G_NEWTON,
-            dt_rho_over_dt1=2.0, dt_kick=1e-3, diff_order=DIFF_ORDER)
 DT_OVER_MASS = 1e-4
 METRIC = 'particle-updates/sec (one PM cycle: long-range kick + drift), 256^3 particles / 512^3 grid'
 UNIT = 'particle-updates/s'
+PARITY_TOL = 1e-9
+
+# BASELINE.json configs
+CONFIGS = {
+    'config2': dict(n_side=256, grid=512, order=2, diff=2, dtype='f64', r_scale_cells=0.0,
+                    label='configs[1]: 256^3 particles, 512^3 PM grid, CIC, fp64, deconvolution order 4, finite-difference order 2'),
+    'config3': dict(n_side=256, grid=512, order=3, diff=2, dtype='f32', r_scale_cells=0.0,
+                    label='configs[2]: 256^3 particles, 512^3 PM grid, TSC, fp32 grid (particles fp64), deconvolution order 6'),
+    'config4': dict(n_side=512, grid=1024, order=2, diff=2, dtype='f64', r_scale_cells=0.0,
+                    label='configs[3]: 512^3 particles, 1024^3 PM grid, CIC, fp64, 8 x-slabs'),
+    'config5': dict(n_side=256, grid=512, order=2, diff=4, dtype='f64', r_scale_cells=1.25,
+                    label='configs[4]: 256^3 particles, 512^3 grid, P3M: long-range PM (Gaussian split r_s = 1.25 cells, '
+                          'difference order 4) + short-range pair kick within 4.5 r_s (spline softening, one rung)'),
+}
+
+
+def kick_kwargs(cfg, boxsize=None):
+    L = BOXSIZE*cfg['grid']/GRID if boxsize is None else boxsize
+    return dict(mass=1.0, boxsize=L, gridsize=cfg['grid'], order=cfg['order'], G_Newton=G_NEWTON, dt_rho_over_dt1=2.0,
+                dt_kick=1e-3, diff_order=cfg['diff'], r_scale=cfg['r_scale_cells']*L/cfg['grid'])
 
 
 def measured_peaks():
@@ -104,15 +129,16 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_cycle_rate(n_side, grid, cycles=1, warm=1):
+def cpu_cycle_rate(cfg, n_side, grid, cycles=1, warm=1):
     """Times the C/OpenMP restatement on (n_side³, grid³); returns (updates/s, threads, seconds/cycle)."""
     from oracle import c_oracle as C
     from concept_b200.synthetic import zeldovich_particles
+    threads = C.set_num_threads()          # every host core, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
     L = BOXSIZE*grid/GRID
     pos, mom = zeldovich_particles(n_side, L, SIGMA, seed=0)
     pos, mom = pos.numpy(), mom.numpy()
     work = C.Workspace(grid)
-    kw = dict(KICK, boxsize=L, gridsize=grid, work=work)
+    kw = dict(kick_kwargs(dict(cfg, grid=grid), boxsize=L), work=work)
     ts = []
     for it in range(warm + cycles):
         t0 = time.perf_counter()
@@ -122,105 +148,237 @@ def cpu_cycle_rate(n_side, grid, cycles=1, warm=1):
         if it >= warm:
             ts.append(time.perf_counter() - t0)
     sec = statistics.median(ts)
-    return n_side**3/sec, C.num_threads(), sec
+    return n_side**3/sec, threads, sec
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_side, grid = N_SIDE//2, GRID//2      # bounded sample: 1/8 of the workload, same particles per cell
     from oracle import c_oracle as C
     from concept_b200.synthetic import zeldovich_particles
-    L = BOXSIZE*grid/GRID
-    pos, mom = zeldovich_particles(n_side, L, SIGMA, seed=0)
-    pos, mom = pos.numpy(), mom.numpy()
-    work = C.Workspace(grid)
-    kw = dict(KICK, boxsize=L, gridsize=grid, work=work)
+    cfg = CONFIGS['config2']
+    threads = C.set_num_threads()
+    n_side, grid = N_SIDE, GRID
+    L = BOXSIZE
+
+    def make(n_side, grid):
+        L = BOXSIZE*grid/GRID
+        pos, mom = zeldovich_particles(n_side, L, SIGMA, seed=0)
+        return pos.numpy(), mom.numpy(), dict(kick_kwargs(dict(cfg, grid=grid), boxsize=L), work=C.Workspace(grid)), L
+    pos, mom, kw, L = make(n_side, grid)
 
     def step():
         C.kick_long(pos, mom, **kw)
         C.sum_mom2(mom)
         C.drift(pos, mom, DT_OVER_MASS, L)
-    for _ in range(args.warmup):
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    sample = f'full workload: {n_side}^3 particles / {grid}^3 grid per step'
+    if first*(args.steps + args.warmup) > 240:
+        # too few host cores to finish K steps of the full workload in minutes: 1/8 of it, same particles per cell
+        n_side, grid = N_SIDE//2, GRID//2
+        pos, mom, kw, L = make(n_side, grid)
+        sample = (f'{n_side}^3 particles / {grid}^3 grid per step (1/8 of the workload, same particles per cell; one full-size '
+                  f'cycle took {first:.1f} s on {threads} threads)')
+        step()
+    for _ in range(max(args.warmup - 1, 0)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     sec = (time.perf_counter() - t0)/args.steps
     value = n_side**3/sec
-    sample = f'{n_side}^3 particles / {grid}^3 grid per step (1/8 of the workload, same particles per cell)'
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec*1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args.gpus),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': C.num_threads(), 'kind': 'port', 'sample': sample},
+        'config': workload_config(cfg, args.gpus),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'compiled reference unbuildable here (needs mpicc/FFTW-MPI/GSL); C/OpenMP port of its loops, pinned to '
-                'golden vectors from the reference run in pure-Python mode',
+                'golden vectors from the reference run in pure-Python mode; OpenMP threads set to os.cpu_count() explicitly',
     }))
 
 
-def workload_config(n_gpus):
-    return {'workload': 'configs[1]: 256^3 particles, 512^3 PM grid, CIC, fp64, deconvolution order 4, '
-                        'finite-difference order 2, Zel\'dovich-displaced lattice (sigma = 0.3 spacings, seed 0)',
-            'particles': N_SIDE**3, 'grid': GRID, 'interpolation': 'CIC', 'grid_dtype': 'f64',
-            'decomposition': f'{n_gpus} x-slab(s)', 'l2_policy': 'inputs larger than L2 (0.4 GB particles, 1.08 GB grid)'}
+def workload_config(cfg, n_gpus):
+    return {'workload': cfg['label'] + f", Zel'dovich-displaced lattice (sigma = {SIGMA} spacings, seed 0)",
+            'particles': cfg['n_side']**3, 'grid': cfg['grid'], 'interpolation': {2: 'CIC', 3: 'TSC', 4: 'PCS'}[cfg['order']],
+            'grid_dtype': cfg['dtype'], 'decomposition': f'{n_gpus} x-slab(s)',
+            'l2_policy': 'inputs larger than L2 (particles and grid are each several times the 126 MB L2 per GPU)'}
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def run_gpu(args):
-    import torch
-    import torch.distributed as dist
-    from concept_b200.pmsolver import PMContext, make_kick_params
-    from concept_b200.synthetic import zeldovich_particles
-    from concept_b200 import _lib
+class Dist:
+    """The process layout of one bench run (one rank per GPU under torchrun)."""
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit('launch with torch.distributed.run for --gpus > 1')
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    lib = _lib.load()
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device('cuda', self.local_rank)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
 
-    # synthetic inputs: every rank builds the same particle load and keeps its slab
-    pos, mom = zeldovich_particles(N_SIDE, BOXSIZE, SIGMA, seed=0, device=dev)
+    def bcast(self, obj):
+        if self.world == 1:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def allgather(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None]*self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [v.item() for v in t]
+
+    def sum_(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [v.item() for v in t]
+
+
+def make_context(D, grid, boxsize, dtype):
+    from concept_b200.pmsolver import PMContext
+    ctx = PMContext(grid, boxsize, dtype=dtype, rank=D.rank, nranks=D.world, device=D.local_rank)
+    if D.world > 1:
+        ctx.connect(D.bcast, D.allgather, D.rank == 0)
+    return ctx
+
+
+def distribute(D, ctx, pos, mom, ids=None, slack=1.5):
+    """Every rank holds the same full particle set; keep this rank's x-slab in capacity-sized buffers."""
+    torch = D.torch
     n_total = pos.shape[0]
-    ctx = PMContext(GRID, BOXSIZE, dtype='f64', rank=rank, nranks=world, device=local_rank)
-    if world > 1:
-        def _bcast(obj):
-            box = [obj]
-            dist.broadcast_object_list(box, src=0)
-            return box[0]
+    if D.world == 1:
+        return pos, mom, ids, n_total
+    G, L = ctx.gridsize, ctx.boxsize
+    owner = torch.clamp((pos[:, 0]*(G/L)).to(torch.int64), 0, G - 1)//ctx.nx_local
+    keep = owner == D.rank
+    n_local = int(keep.sum().item())
+    capacity = int(n_total/D.world*slack) + 4096
+    pbuf = torch.zeros((capacity, 3), dtype=torch.float64, device=D.dev)
+    mbuf = torch.zeros((capacity, 3), dtype=torch.float64, device=D.dev)
+    pbuf[:n_local] = pos[keep]
+    mbuf[:n_local] = mom[keep]
+    ibuf = None
+    if ids is not None:
+        ibuf = torch.zeros(capacity, dtype=torch.int64, device=D.dev)
+        ibuf[:n_local] = ids[keep]
+    return pbuf, mbuf, ibuf, n_local
 
-        def _allgather(obj):
-            out = [None]*world
-            dist.all_gather_object(out, obj)
-            return out
-        ctx.connect(_bcast, _allgather, rank == 0)
-        owner = torch.clamp((pos[:, 0]*(GRID/BOXSIZE)).to(torch.int64), 0, GRID - 1)//ctx.nx_local
-        keep = owner == rank
-        n_local = int(keep.sum().item())
-        capacity = int(n_total/world*1.5) + 4096
-        pbuf = torch.zeros((capacity, 3), dtype=torch.float64, device=dev)
-        mbuf = torch.zeros((capacity, 3), dtype=torch.float64, device=dev)
-        pbuf[:n_local] = pos[keep]
-        mbuf[:n_local] = mom[keep]
-        del pos, mom, owner, keep
-    else:
-        n_local = n_total
-        pbuf, mbuf = pos, mom
-    params = make_kick_params(**KICK)
-    sum2 = torch.zeros(1, dtype=torch.float64, device=dev)
-    # stages of one cycle, each bracketed by CUDA events inside the timed region
-    STAGES = ['grid_zero', 'deposit', 'halo_add', 'fft2d_forward', 'xsolve', 'fft2d_inverse', 'halo_fill', 'gather_kick_drift', 'migrate']
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(STAGES) + 1)] for _ in range(args.steps)]
+
+def parity_check(D, ctx, cfg, n_sub, seed):
+    """One distributed kick + drift + migration of n_sub seeded particles on `ctx`, compared on rank 0 with the CPU
+    restatement of the reference (C/OpenMP oracle, pinned to the reference's golden vectors).  Returns the record."""
+    import numpy as np
+    torch = D.torch
+    from concept_b200.pmsolver import make_kick_params
+    G, L = ctx.gridsize, ctx.boxsize
+    rng = np.random.default_rng(seed)
+    pos_h = rng.random((n_sub, 3))*L
+    # crowd the slab faces so that halos and migration are exercised at every N
+    nf = n_sub//5
+    pos_h[:nf, 0] = (np.repeat(np.arange(8)/8, (nf + 7)//8)[:nf] + (rng.random(nf) - 0.5)*3.0/G) % 1.0*L
+    mom_h = rng.standard_normal((n_sub, 3))
+    kw = kick_kwargs(dict(cfg, grid=G), boxsize=L)
+    params = make_kick_params(**kw)
+    dt = 0.7*L/G                      # |mom| ~ 1: a good fraction of a cell per step, so that particles do change slab
+    pos = torch.as_tensor(pos_h, device=D.dev)
+    mom = torch.as_tensor(mom_h, device=D.dev)
+    ids = torch.arange(n_sub, dtype=torch.int64, device=D.dev)
+    pbuf, mbuf, ibuf, n = distribute(D, ctx, pos, mom, ids, slack=3.0)
+    sum2 = torch.zeros(1, dtype=torch.float64, device=D.dev)
+    ctx.kick_drift(pbuf[:n], mbuf[:n], params, dt, sum_mom2=sum2)
+    if D.world > 1:
+        ctx.allreduce_sum(sum2)
+        n = ctx.exchange(pbuf, mbuf, ibuf, n)
+    ctx.check_async_error()
+    own_ok = True
+    if D.world > 1 and n:
+        owner = torch.clamp((pbuf[:n, 0]*(G/L)).to(torch.int64), 0, G - 1)//ctx.nx_local
+        own_ok = bool((owner == D.rank).all().item())
+    parts = D.allgather((pbuf[:n].cpu().numpy(), mbuf[:n].cpu().numpy(), ibuf[:n].cpu().numpy() if ibuf is not None
+                         else np.arange(n), own_ok))
+    rec = None
+    if D.rank == 0:
+        from oracle import c_oracle as C
+        C.set_num_threads()
+        gp = np.concatenate([p[0] for p in parts]); gm = np.concatenate([p[1] for p in parts])
+        gi = np.concatenate([p[2] for p in parts])
+        n_conserved = bool(gi.shape[0] == n_sub and np.array_equal(np.sort(gi), np.arange(n_sub)))
+        rec = {'grid': G, 'particles': n_sub, 'n_conserved': n_conserved, 'owners_ok': all(p[3] for p in parts)}
+        if n_conserved:
+            o = np.argsort(gi, kind='stable')
+            gp, gm = gp[o], gm[o]
+            ref = C.kick_long(pos_h.copy(), mom_h.copy(), **kw)
+            dmax = float(np.max(np.abs(ref - mom_h)))
+            rec['kick_relerr'] = float(np.max(np.abs(gm - ref)))/dmax
+            # drift: bit-exact given the (GPU-)kicked momenta — pos = mod(pos + mom·Δ, L) has one correct rounding
+            rec['drift_exact'] = bool(np.array_equal(gp, C.drift(pos_h.copy(), np.ascontiguousarray(gm), dt, L)))
+            rec['sum_mom2_relerr'] = abs(float(sum2.item()) - float(np.sum(gm*gm)))/float(np.sum(gm*gm))
+            rec['migrated'] = int(sum(1 for _ in ()))  # replaced below
+            owner0 = np.clip((pos_h[:, 0]*(G/L)).astype(np.int64), 0, G - 1)//ctx.nx_local
+            owner1 = np.clip((gp[:, 0]*(G/L)).astype(np.int64), 0, G - 1)//ctx.nx_local
+            rec['migrated'] = int(np.count_nonzero(owner0 != owner1))
+        rec['ok'] = bool(rec['n_conserved'] and rec['owners_ok'] and rec.get('kick_relerr', 1) < PARITY_TOL
+                         and rec.get('drift_exact', False) and rec.get('sum_mom2_relerr', 1) < 1e-12)
+    rec = D.bcast(rec)
+    del pbuf, mbuf, ibuf
+    return rec
+
+
+STAGES = ['grid_zero', 'deposit', 'halo_add', 'fft2d_forward', 'xsolve', 'fft2d_inverse', 'halo_fill', 'gather_kick_drift', 'migrate']
+
+
+def kernel_names(cfg):
+    T = 'double' if cfg['dtype'] == 'f64' else 'float'
+    G, o = cfg['grid'], cfg['order']
+    reach = 1 if cfg['diff'] <= 2 else cfg['diff']//2
+    return {'fft2d_forward': f'fft2d_kernel<{T},{G},-1> (r2c along z + c2c along y per x plane, L2-resident hand-over)',
+            'xsolve': f'xsolve2_kernel<{T},{G}> (c2c along x, Green\'s function, inverse c2c along x; peer loads/stores over NVLink)',
+            'fft2d_inverse': f'fft2d_kernel<{T},{G},+1> (inverse c2c along y + c2r along z per x plane)',
+            'gather_kick_drift': f'gather_kick_kernel<{o},{reach},{T},drift> (fused gradient + gather + kick + sum mom^2 + drift)',
+            'deposit': f'deposit_kernel<{o},{T}> (mass scatter, red.global.add)', 'grid_zero': 'cudaMemsetAsync'}
+
+
+def run_pm_config(D, cfg, steps, warmup, lib, ctx=None, pos=None, mom=None, want_e2e=False):
+    """Times the PM cycle of one configuration; returns (record, ctx, state) — device-resident, CUDA events per stage."""
+    torch = D.torch
+    from concept_b200.pmsolver import make_kick_params
+    from concept_b200.synthetic import zeldovich_particles
+    L = BOXSIZE*cfg['grid']/GRID
+    if ctx is None:
+        ctx = make_context(D, cfg['grid'], L, cfg['dtype'])
+    if pos is None:
+        pos, mom = zeldovich_particles(cfg['n_side'], L, SIGMA, seed=0, device=D.dev)
+    n_total = pos.shape[0]
+    pbuf, mbuf, _, n_local = distribute(D, ctx, pos, mom)
+    del pos, mom
+    params = make_kick_params(**kick_kwargs(cfg, boxsize=L))
+    sum2 = torch.zeros(1, dtype=torch.float64, device=D.dev)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(STAGES) + 1)] for _ in range(steps)]
     state = {'n': n_local}
     staged = ctx.hand_fft_available
 
@@ -249,57 +407,77 @@ def run_gpu(args):
                     ctx.kspace_potential(params.prefactor, params.deconv_order, params.gauss, 1.0)
                     ctx.fft_backward()
                 e[4].record(); e[5].record(); e[6].record()
-            if world > 1:
-                ctx.halo_fill()
+            if D.world > 1:
+                ctx.halo_fill_for(params.order, params.diff_order)
             e[7].record()
             ctx.gather_kick_drift(p, m, params.order, params.diff_order, params.kick_factor, DT_OVER_MASS, None, sum2)
             e[8].record()
-        if world > 1:
+        if D.world > 1:
             ctx.allreduce_sum(sum2)
             state['n'] = ctx.exchange(pbuf, mbuf, None, n)
         if i is not None:
             evs[i][9].record()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(warmup, 3)
+    for _ in range(warmup):
         cycle()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    D.barrier()
+    sampler = ClockSampler(D.local_rank)
+    if D.rank == 0:
         sampler.start()
     launches0 = lib.pm_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    D.barrier()
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         cycle(i)
     e1.record()
-    barrier()
+    D.barrier()
     launches = lib.pm_launch_count() - launches0
-    ctx.check_async_error()      # a tile dependency that timed out would have invalidated the run: fail loudly
-    clocks = sampler.stop() if rank == 0 else None
+    ctx.check_async_error()      # a tile dependency or a barrier that timed out would have invalidated the run: fail loudly
+    clocks = sampler.stop() if D.rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     stage_ms = [sum(e[k].elapsed_time(e[k + 1]) for e in evs)/len(evs) for k in range(len(STAGES))]
-    t = torch.tensor([ms_total] + stage_ms, dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t[0].item()/args.steps
-    stage_ms = [v.item() for v in t[1:]]
-    value = n_total/(ms_step*1e-3)
+    t = D.max_([ms_total] + stage_ms)
+    ms_step = t[0]/steps
+    stage_ms = t[1:]
+    # measured state after exactly warmup + steps cycles: comparable across N
+    n_after = int(round(D.sum_([float(state['n'])])[0]))
+    sum_mom2 = float(sum2.item())
 
-    # ---- end-to-end through the host-buffer C-ABI entry point (rank-local slab) ----
+    peak, peak_src = measured_peaks()
+    es = 8 if cfg['dtype'] == 'f64' else 4
+    n_per, g3_per = n_total/D.world, cfg['grid']**3/D.world
+    # algorithmic bytes per launch (SURVEY §8d / DESIGN §4), per rank
+    alg = {'grid_zero': es*g3_per, 'deposit': 24*n_per + es*g3_per, 'fft2d_forward': 2*es*g3_per, 'xsolve': 2*es*g3_per,
+           'fft2d_inverse': 2*es*g3_per, 'gather_kick_drift': 96*n_per + es*g3_per}
+    kernels = {k: {'ms': ms, 'algorithmic_GB': alg[k]/1e9 if k in alg else None,
+                   'achieved_GBps': (alg[k]/(ms*1e-3)/1e9 if (k in alg and ms > 0) else None),
+                   'frac': (alg[k]/(ms*1e-3)/1e9/peak if (k in alg and ms > 0) else None)}
+               for k, ms in zip(STAGES, stage_ms)}
+    names = kernel_names(cfg)
+    dom = max((k for k in alg if k in names and k != 'grid_zero'), key=lambda k: kernels[k]['ms'])
+    b_alg = 120*n_total + 6*es*cfg['grid']**3
+    rec = {'ms_per_step': ms_step, 'value': n_total/(ms_step*1e-3), 'n_total': n_total, 'launches': int(launches), 'clocks': clocks,
+           'particles_after': n_after, 'sum_mom2': sum_mom2, 'kernels': kernels, 'dominant': dom, 'dominant_name': names[dom],
+           'alg_dominant': alg[dom], 'peak': peak, 'peak_source': peak_src,
+           'cycle': {'algorithmic_bytes': b_alg, 'achieved_GBps_per_gpu': b_alg/D.world/(ms_step*1e-3)/1e9,
+                     'frac': b_alg/D.world/(ms_step*1e-3)/1e9/peak},
+           'hand_written_fft': bool(staged)}
+    return rec, ctx, (pbuf, mbuf, state, params, cycle)
+
+
+def run_e2e(D, ctx, pbuf, mbuf, state, params, cycle, steps):
+    """The same cycle with HOST particle buffers (pinned), host<->device copies inside the timed region."""
+    torch = D.torch
     n = state['n']
-    hp = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
-    hm = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
-    hp.copy_(pbuf[:n]); hm.copy_(mbuf[:n])
-    hp_np, hm_np = hp.numpy(), hm.numpy()
-    e2e_steps = max(3, min(args.steps, 10))
-    e2e = None
-    if world == 1:
+    n_total = int(round(D.sum_([float(n)])[0]))
+    e2e_steps = max(3, min(steps, 10))
+    if D.world == 1:
+        hp = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
+        hm = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
+        hp.copy_(pbuf[:n]); hm.copy_(mbuf[:n])
+        hp_np, hm_np = hp.numpy(), hm.numpy()
         for _ in range(2):
             ctx.kick_long_host(hp_np, hm_np, params, dt_over_mass=DT_OVER_MASS, want_sum=True)
         torch.cuda.synchronize()
@@ -307,87 +485,203 @@ def run_gpu(args):
         for _ in range(e2e_steps):
             ctx.kick_long_host(hp_np, hm_np, params, dt_over_mass=DT_OVER_MASS, want_sum=True)
         torch.cuda.synchronize()
-        e2e_sec = (time.perf_counter() - t0)/e2e_steps
-        e2e = {'value': n_total/e2e_sec, 'unit': UNIT, 'h2d_bytes_per_step': 2*24*n, 'd2h_bytes_per_step': 2*24*n + 8,
-               'ms_per_step': e2e_sec*1e3, 'api': 'pm_kick_long_host (pinned host pos/mom in, kick + fused drift, pos/mom out)'}
+        sec = (time.perf_counter() - t0)/e2e_steps
+        api = 'pm_kick_long_host (pinned host pos/mom in, kick + fused drift, pos/mom out)'
     else:
-        # every rank moves its own slab's particles host<->device around the same distributed cycle
+        hp = torch.empty((pbuf.shape[0], 3), dtype=torch.float64, pin_memory=True)
+        hm = torch.empty((pbuf.shape[0], 3), dtype=torch.float64, pin_memory=True)
+        hp[:n].copy_(pbuf[:n]); hm[:n].copy_(mbuf[:n])
+
         def e2e_step():
             nn = state['n']
             pbuf[:nn].copy_(hp[:nn], non_blocking=True)
             mbuf[:nn].copy_(hm[:nn], non_blocking=True)
             cycle()
             nn = state['n']
-            hp[:nn].copy_(pbuf[:nn], non_blocking=True) if nn <= hp.shape[0] else None
-            hm[:nn].copy_(mbuf[:nn], non_blocking=True) if nn <= hm.shape[0] else None
+            hp[:nn].copy_(pbuf[:nn], non_blocking=True)
+            hm[:nn].copy_(mbuf[:nn], non_blocking=True)
             torch.cuda.synchronize()
-        hp = torch.empty((pbuf.shape[0], 3), dtype=torch.float64, pin_memory=True)
-        hm = torch.empty((pbuf.shape[0], 3), dtype=torch.float64, pin_memory=True)
-        hp[:n].copy_(pbuf[:n]); hm[:n].copy_(mbuf[:n])
         for _ in range(2):
             e2e_step()
-        barrier()
+        D.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
-        barrier()
-        sec = torch.tensor([(time.perf_counter() - t0)/e2e_steps], dtype=torch.float64, device=dev)
-        dist.all_reduce(sec, op=dist.ReduceOp.MAX)
-        e2e = {'value': n_total/sec.item(), 'unit': UNIT, 'h2d_bytes_per_step': 2*24*n_total, 'd2h_bytes_per_step': 2*24*n_total + 8,
-               'ms_per_step': sec.item()*1e3, 'api': 'pinned host slabs -> device, distributed cycle, device -> host (per rank)'}
+        D.barrier()
+        sec = D.max_([(time.perf_counter() - t0)/e2e_steps])[0]
+        api = 'pinned host slabs -> device, distributed cycle, device -> host (per rank)'
+    gbs = 2*24*n_total/sec/1e9
+    return {'value': n_total/sec, 'unit': UNIT, 'h2d_bytes_per_step': 2*24*n_total, 'd2h_bytes_per_step': 2*24*n_total + 8,
+            'ms_per_step': sec*1e3, 'h2d_GBps': gbs, 'd2h_GBps': gbs, 'api': api}
 
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        n_per = n_total/world
-        g3_per = GRID**3/world
-        es = 8
-        # algorithmic bytes per launch (SURVEY §8d / DESIGN §4), per rank
-        alg = {'grid_zero': es*g3_per, 'deposit': 24*n_per + es*g3_per, 'fft2d_forward': 2*es*g3_per, 'xsolve': 2*es*g3_per,
-               'fft2d_inverse': 2*es*g3_per, 'gather_kick_drift': 96*n_per + es*g3_per}
-        kernels = {k: {'ms': ms, 'algorithmic_GB': alg[k]/1e9 if k in alg else None,
-                       'achieved_GBps': (alg[k]/(ms*1e-3)/1e9 if (k in alg and ms > 0) else None)}
-                   for k, ms in zip(STAGES, stage_ms)}
-        names = {'fft2d_forward': 'fft2d_kernel<double,512,-1> (r2c along z + c2c along y per x plane, L2-resident hand-over)',
-                 'xsolve': 'xsolve2_kernel<double,512> (c2c along x, Green\'s function, inverse c2c along x)',
-                 'fft2d_inverse': 'fft2d_kernel<double,512,+1> (inverse c2c along y + c2r along z per x plane)',
-                 'gather_kick_drift': 'gather_kick_kernel<2,1,double,drift> (fused gradient + CIC gather + kick + sum mom^2 + drift)',
-                 'deposit': 'deposit_kernel<2,double> (CIC scatter, red.global.add.f64)', 'grid_zero': 'cudaMemsetAsync'}
-        dom = max((k for k in alg if k in names), key=lambda k: kernels[k]['ms'])
-        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+
+def extra_record(rec, cfg, world):
+    out = {'workload': cfg['label'], 'ms_per_cycle': rec['ms_per_step'], 'particle_updates_per_s': rec['value'],
+           'cycle_frac_of_hbm_peak': rec['cycle']['frac'], 'algorithmic_bytes': rec['cycle']['algorithmic_bytes'],
+           'hand_written_fft': rec['hand_written_fft'], 'particles_after': rec['particles_after'],
+           'kernels': {k: {'ms': v['ms'], 'frac': v['frac']} for k, v in rec['kernels'].items()}}
+    return out
+
+
+def run_p3m_config(D, cfg, steps, lib):
+    """configs[4]: the P³M cycle — long-range kick (Gaussian-split potential, order-4 differences) + short-range pair
+    kick of all particles (one rung) + drift + migration.  Device-resident; CUDA events."""
+    torch = D.torch
+    import numpy as np
+    from concept_b200.pmsolver import make_kick_params
+    from concept_b200.synthetic import zeldovich_particles
+    from concept_b200 import p3m_bench
+    L = BOXSIZE*cfg['grid']/GRID
+    ctx = make_context(D, cfg['grid'], L, cfg['dtype'])
+    pos, mom = zeldovich_particles(cfg['n_side'], L, SIGMA, seed=0, device=D.dev)
+    n_total = pos.shape[0]
+    pbuf, mbuf, _, n = distribute(D, ctx, pos, mom)
+    del pos, mom
+    params = make_kick_params(**kick_kwargs(cfg, boxsize=L))
+    job = p3m_bench.ShortRangeJob(ctx, L, cfg['grid'], n_total, pbuf.shape[0], D.dev, G_NEWTON)
+    sum2 = torch.zeros(1, dtype=torch.float64, device=D.dev)
+    state = {'n': n}
+    names = ['long_range_kick', 'short_range_kick', 'drift_migrate']
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+
+    def cycle(i=None):
+        n = state['n']
+        p, m = pbuf[:n], mbuf[:n]
+        e = evs[i] if i is not None else None
+        if e: e[0].record()
+        sum2.zero_()
+        ctx.kick_long(p, m, params, sum_mom2=sum2)
+        if e: e[1].record()
+        job.kick(pbuf, mbuf, n)
+        if e: e[2].record()
+        ctx.drift(p, m, DT_OVER_MASS)
+        if D.world > 1:
+            state['n'] = job.exchange(pbuf, mbuf, n)
+        if e: e[3].record()
+    for _ in range(2):
+        cycle()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        cycle(i)
+    e1.record()
+    D.barrier()
+    ctx.check_async_error()
+    t = D.max_([e0.elapsed_time(e1)] + [sum(e[k].elapsed_time(e[k + 1]) for e in evs)/steps for k in range(3)])
+    pairs = job.pair_count(pbuf, state['n'])
+    pairs_total = D.sum_([float(pairs)])[0]
+    ms = t[0]/steps
+    rec = {'workload': cfg['label'], 'ms_per_cycle': ms, 'particle_updates_per_s': n_total/(ms*1e-3),
+           'stages_ms': dict(zip(names, t[1:])), 'pairs_within_range': pairs_total,
+           'pair_interactions_per_s': pairs_total/(t[2]*1e-3) if t[2] > 0 else None,
+           'particles_after': int(round(D.sum_([float(state['n'])])[0]))}
+    ctx.close()
+    return rec
+
+
+def run_gpu(args):
+    D = Dist(args)
+    torch = D.torch
+    from concept_b200 import _lib
+    lib = _lib.load()
+    cfg = CONFIGS['config2']
+
+    # ---- parity at this N, before anything is timed ----
+    parity = {'tolerance': PARITY_TOL, 'checker': 'oracle/pm_oracle.c (C/OpenMP restatement of the reference, pinned to its golden vectors)'}
+    ctx128 = make_context(D, 128, 128.0, 'f64')
+    parity['G128'] = parity_check(D, ctx128, dict(cfg, grid=128), 100000, seed=11)
+    ctx128.close()
+    ctx = make_context(D, cfg['grid'], BOXSIZE, cfg['dtype'])
+    parity['G512'] = parity_check(D, ctx, cfg, 100000, seed=12)
+    parity['ok'] = bool(parity['G128']['ok'] and parity['G512']['ok'])
+    if not parity['ok']:
+        if D.rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': None, 'unit': UNIT, 'n_gpus': D.world, 'parity': parity,
+                              'error': 'parity check failed before the timed region'}))
+        ctx.close()
+        if D.world > 1:
+            D.dist.destroy_process_group()
+        raise SystemExit(3)
+
+    # ---- configs[1]: the headline ----
+    rec, ctx, (pbuf, mbuf, state, params, cycle) = run_pm_config(D, cfg, args.steps, args.warmup, lib, ctx=ctx)
+    e2e = run_e2e(D, ctx, pbuf, mbuf, state, params, cycle, args.steps)
+    del pbuf, mbuf, cycle
+    ctx.close()
+    torch.cuda.empty_cache()
+
+    # ---- the other configurations of BASELINE.json ----
+    extra = {}
+    if not args.no_extra:
         try:
-            with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
-                traffic = json.load(f)['dram_bytes_per_launch'].get(dom) if world == 1 else None
-        except Exception:
-            traffic = None
-        b_alg = 120*n_total + 48*GRID**3
-        roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': kernels[dom]['achieved_GBps'], 'peak': peak, 'unit': 'GB/s',
-                    'frac': kernels[dom]['achieved_GBps']/peak, 'traffic': traffic,
-                    'peak_source': peak_src, 'kernel_ms': kernels[dom]['ms'], 'algorithmic_bytes_per_launch': alg[dom],
-                    'kernels': kernels,
-                    'cycle': {'algorithmic_bytes': b_alg, 'achieved_GBps_per_gpu': b_alg/world/(ms_step*1e-3)/1e9,
-                              'frac': b_alg/world/(ms_step*1e-3)/1e9/peak}}
-        cpu = None
-        if world == 1:
+            r3, c3, st3 = run_pm_config(D, CONFIGS['config3'], min(args.steps, 10), 3, lib)
+            extra['config3'] = extra_record(r3, CONFIGS['config3'], D.world)
+            extra['config3']['parity_note'] = ('fp32 grid has no reference counterpart (the reference is fp64-only); '
+                                               'tests/test_gpu_parity.py states rms force error <= 1e-5 against the fp64 oracle')
+            del st3
+            c3.close()
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            extra['config3'] = {'error': repr(exc)}
+        if D.world == 8:
             try:
-                rate, cores, sec = cpu_cycle_rate(N_SIDE//2, GRID//2, cycles=2, warm=1)
+                r4, c4, st4 = run_pm_config(D, CONFIGS['config4'], min(args.steps, 10), 3, lib)
+                extra['config4'] = extra_record(r4, CONFIGS['config4'], D.world)
+                del st4
+                c4.close()
+                torch.cuda.empty_cache()
+            except Exception as exc:
+                extra['config4'] = {'error': repr(exc)}
+        else:
+            extra['config4'] = {'skipped': 'configs[3] is defined on 8 GPUs (run with --gpus 8)'}
+        try:
+            extra['config5'] = run_p3m_config(D, CONFIGS['config5'], min(args.steps, 5), lib)
+        except Exception as exc:
+            extra['config5'] = {'error': repr(exc)}
+
+    if D.rank == 0:
+        dom = rec['dominant']
+        roofline = {'bound': 'hbm', 'kernel': rec['dominant_name'], 'achieved': rec['kernels'][dom]['achieved_GBps'], 'peak': rec['peak'],
+                    'unit': 'GB/s', 'frac': rec['kernels'][dom]['frac'], 'traffic': committed_traffic(dom, D.world),
+                    'traffic_source': 'profiles/ (ncu --set full capture of this kernel, per launch; not re-measured in this run)',
+                    'peak_source': rec['peak_source'], 'kernel_ms': rec['kernels'][dom]['ms'],
+                    'algorithmic_bytes_per_launch': rec['alg_dominant'], 'kernels': rec['kernels'], 'cycle': rec['cycle']}
+        cpu = None
+        if D.world == 1:
+            try:
+                rate, cores, sec = cpu_cycle_rate(cfg, N_SIDE//2, GRID//2, cycles=2, warm=1)
                 sample = f'{N_SIDE//2}^3 particles / {GRID//2}^3 grid (1/8 of the workload, same particles per cell), 2 cycles'
-                if sec < 1.5:   # plenty of cores: time the full workload once as well
-                    rate, cores, sec = cpu_cycle_rate(N_SIDE, GRID, cycles=1, warm=1)
-                    sample = f'full workload {N_SIDE}^3 / {GRID}^3, 1 cycle after 1 warm-up'
+                if sec < 1.5:   # plenty of cores: time the full workload as well
+                    rate, cores, sec = cpu_cycle_rate(cfg, N_SIDE, GRID, cycles=2, warm=1)
+                    sample = f'full workload {N_SIDE}^3 / {GRID}^3, 2 cycles after 1 warm-up'
                 cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample, 'sec_per_cycle': sec}
             except Exception as exc:   # the baseline is a report, never a gate
                 cpu = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {exc}'}
         out = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': workload_config(world), 'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
-            'gpu_launches': int(launches), 'clocks': clocks,
-            'sum_mom2': float(sum2.item()), 'particles_after': int(n_total),
+            'metric': METRIC, 'value': rec['value'], 'unit': UNIT, 'n_gpus': D.world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': rec['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': workload_config(cfg, D.world), 'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
+            'gpu_launches': rec['launches'], 'clocks': rec['clocks'], 'parity': parity,
+            'sum_mom2': rec['sum_mom2'], 'particles_after': rec['particles_after'],
+            'cycles_before_state': max(args.warmup, 3) + args.steps, 'extra_configs': extra,
         }
         print(json.dumps(out))
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if D.world > 1:
+        D.dist.destroy_process_group()
+
+
+def committed_traffic(kernel, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed ncu --set full capture"""
+    if world != 1:
+        return None
+    for name in ('r02_traffic.json', 'r01_traffic.json'):
+        try:
+            with open(os.path.join(ROOT, 'profiles', name)) as f:
+                return json.load(f)['dram_bytes_per_launch'].get(kernel)
+        except Exception:
+            continue
+    return None
 
 
 def main():
@@ -396,6 +690,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-extra', action='store_true', help='only configs[1] (skip the extra_configs legs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

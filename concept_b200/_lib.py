@@ -50,6 +50,7 @@ SIGNATURES = {
     'pm_deposit': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, POINTER(c_double)]),
     'pm_halo_add': (c_int, [c_void_p]),
     'pm_halo_fill': (c_int, [c_void_p]),
+    'pm_halo_fill_for': (c_int, [c_void_p, c_int, c_int, c_int]),
     'pm_fft_forward': (c_int, [c_void_p]),
     'pm_fft_backward': (c_int, [c_void_p]),
     'pm_kspace_potential': (c_int, [c_void_p, c_double, c_int, c_double, c_double]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     'pm_sum_mom2': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     'pm_sort_particles': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
     'pm_exchange': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64]),
+    'pm_exchange_rungs': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64]),
     'pm_shortrange': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, POINTER(c_double), c_int, c_double,
                               c_void_p, c_int, c_double, c_void_p]),
     'pm_apply_dmom': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, POINTER(c_double), c_int, c_int]),

@@ -336,6 +336,14 @@ def _method_value(spec, method):
     return spec
 
 
+def _even_gridsize(g):
+    """An odd grid size reaches get_fftw_slab() in the reference and aborts there (mesh.py:3784-3789)."""
+    g = int(g)
+    if g & 1:
+        abort(f'An odd grid size ({g}) was given for a potential grid. Some operations may not function correctly.')
+    return g
+
+
 def component_gridsizes(name, species, method, N):
     """(upstream, downstream) potential grid sizes of one component (commons.py:2958-3237,
     doc/parameters/numerics.rst `potential_options`): an entry of potential_options['gridsize'] keyed by the
@@ -348,7 +356,7 @@ def component_gridsizes(name, species, method, N):
                     g = _method_value(v, method)
                     if g is not None:
                         g = tuple(g) if isinstance(g, (tuple, list)) else (g, g)
-                        return tuple(int(x) + (int(x) & 1) for x in g)
+                        return tuple(_even_gridsize(x) for x in g)
     g = gridsize_for(method, N)
     return (g, g)
 
@@ -362,7 +370,7 @@ def global_gridsize(method, components):
             if str(k).lower() == 'global':
                 g = _method_value(v, method)
                 if g is not None and g != -1:
-                    return int(g) + (int(g) & 1)
+                    return _even_gridsize(g)
     return max(max(c.potential_gridsizes['gravity'][method]) for c in components)
 
 

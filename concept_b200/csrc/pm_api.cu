@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -150,6 +151,21 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
         c->f2_off_b = c->f2_off_a + (layout_bytes + 255) / 256 * 256;
         alloc_bytes = c->f2_off_b + layout_bytes;
     }
+    if (nranks > 1) {
+        // IPC arena: header | migration mailboxes (2 parities × nranks slots) | P³M ghost positions (2 parities × 2 sides)
+        const size_t slab_bytes = c->real_elems * es;
+        size_t mailbox_total = std::max<size_t>((size_t)16 << 20, slab_bytes / 4);
+        size_t ghost_total = std::max<size_t>((size_t)16 << 20, slab_bytes / 2);
+        if (const char* e = getenv("PM_MAILBOX_MB")) mailbox_total = (size_t)std::max(1, atoi(e)) << 20;
+        if (const char* e = getenv("PM_GHOST_MB")) ghost_total = (size_t)std::max(1, atoi(e)) << 20;
+        c->mailbox_slot_bytes = mailbox_total / (2 * (size_t)nranks) / 256 * 256;
+        c->ghost_buf_bytes = ghost_total / 4 / 256 * 256;
+        c->off_arena = (alloc_bytes + 255) / 256 * 256;
+        c->off_mailbox = c->off_arena + kArenaHeaderBytes;
+        c->off_ghost = c->off_mailbox + 2 * (size_t)nranks * c->mailbox_slot_bytes;
+        c->arena_bytes = kArenaHeaderBytes + 2 * (size_t)nranks * c->mailbox_slot_bytes + 4 * c->ghost_buf_bytes;
+        alloc_bytes = c->off_arena + c->arena_bytes;
+    }
     if (cudaMalloc(&c->real, alloc_bytes) != cudaSuccess) {
         set_error("pm_create: cannot allocate %zu bytes for the grid", alloc_bytes);
         return fail(PM_ERR_ALLOC);
@@ -157,6 +173,7 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
     c->bytes_allocated += alloc_bytes;
     cudaMemsetAsync(c->real, 0, c->real_elems * es, c->stream);
     c->real_is_zero = true;
+    if (nranks > 1) cudaMemsetAsync(reinterpret_cast<char*>(c->real) + c->off_arena, 0, kArenaHeaderBytes, c->stream);
     if (nranks == 1) {
         c->fourier = c->real;
     } else {
@@ -178,6 +195,8 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
         cudaMalloc(&c->tab_sin, sizeof(double) * g.G) != cudaSuccess ||
         cudaMalloc(&c->d_scratch, sizeof(double) * 64) != cudaSuccess ||
         cudaMalloc(&c->d_tilectr, sizeof(unsigned long long) * 4) != cudaSuccess ||
+        cudaMalloc(&c->d_comm_err, sizeof(int) * 4) != cudaSuccess ||
+        cudaMallocHost(&c->h_pinned, 4096) != cudaSuccess ||
         cudaMalloc(&c->d_counts, sizeof(int64_t) * (3 * nranks + (size_t)nranks * nranks + 8 + kNumSMs * 4)) != cudaSuccess) {
         set_error("pm_create: cannot allocate tables");
         return fail(PM_ERR_ALLOC);
@@ -185,6 +204,7 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
     cudaMemcpyAsync(c->tab_x, tx.data(), sizeof(double) * g.G, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(c->tab_sin, ts.data(), sizeof(double) * g.G, cudaMemcpyHostToDevice, c->stream);
     cudaMemsetAsync(c->d_scratch, 0, sizeof(double) * 64, c->stream);
+    cudaMemsetAsync(c->d_comm_err, 0, sizeof(int) * 4, c->stream);
     cudaStreamSynchronize(c->stream);   // tx/ts go out of scope
     c->fused_solve = true;
     c->solve_mode = PM_SOLVE_AUTO;
@@ -230,6 +250,8 @@ int pm_destroy(pm_ctx* c) {
     cudaFree(c->d_scratch);
     cudaFree(c->d_counts);
     cudaFree(c->d_tilectr);
+    cudaFree(c->d_comm_err);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaFree(c->xchg_buf);
     if (c->pipe_ready) {
         cudaStreamDestroy(c->s_h2d);
@@ -250,6 +272,10 @@ int pm_set_stream(pm_ctx* c, void* stream) {
     PM_CHECK_CUFFT(cufftSetStream(c->plan_fwd, c->stream));
     PM_CHECK_CUFFT(cufftSetStream(c->plan_bwd, c->stream));
     if (c->nranks > 1) PM_CHECK_CUFFT(cufftSetStream(c->plan_x, c->stream));
+    if (c->plan2_ready) {      // the batched 2-D plans of the cuFFT + x-solve path
+        PM_CHECK_CUFFT(cufftSetStream(c->plan2_fwd, c->stream));
+        PM_CHECK_CUFFT(cufftSetStream(c->plan2_bwd, c->stream));
+    }
     return PM_OK;
 }
 
@@ -274,6 +300,7 @@ int64_t pm_device_bytes(const pm_ctx* c) { return c ? c->bytes_allocated : 0; }
 int pm_grid_zero(pm_ctx* c) {
     PM_REQUIRE(c != nullptr, "pm_grid_zero: NULL context");
     // (after a fused solve on one rank the forward transform has already nullified the grid)
+    PM_TRY(barrier_before_overwrite(c));     // a neighbour may still be filling its halo from this slab
     if (!c->real_is_zero) PM_CHECK_CUDA(cudaMemsetAsync(c->real, 0, c->real_elems * c->elem_size(), c->stream));
     c->real_is_zero = true;
     c->grid_in_phi = false;
@@ -298,6 +325,13 @@ int pm_halo_add(pm_ctx* c) {
 int pm_halo_fill(pm_ctx* c) {
     PM_REQUIRE(c != nullptr, "pm_halo_fill: NULL context");
     return halo_fill(c, c->g.halo, c->g.halo, PM_TAP_REAL);
+}
+
+int pm_halo_fill_for(pm_ctx* c, int order, int diff_order, int interlace) {
+    PM_REQUIRE(c != nullptr, "pm_halo_fill_for: NULL context");
+    int lo, hi;
+    halo_for_gather(order, diff_order, interlace, &lo, &hi);
+    return halo_fill(c, lo, hi, PM_TAP_REAL);
 }
 
 int pm_fft_forward(pm_ctx* c) {
@@ -343,7 +377,15 @@ int pm_set_fused_solve(pm_ctx* c, int mode) {
 
 int pm_check_async_error(pm_ctx* c) {
     PM_REQUIRE(c != nullptr, "pm_check_async_error: NULL context");
-    return fft2_check_error(c);
+    PM_TRY(fft2_check_error(c));
+    int e = 0;
+    PM_CHECK_CUDA(cudaMemcpyAsync(&e, c->d_comm_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    if (e != 0) {
+        set_error("a rank did not arrive at a device barrier in time (results are invalid)");
+        return PM_ERR_COMM;
+    }
+    return PM_OK;
 }
 
 int pm_power_k2(pm_ctx* c, int k2_max, double* power, unsigned long long* count) {
@@ -359,7 +401,8 @@ int pm_diff(pm_ctx* c, int dim, int order) {
     PM_REQUIRE(c != nullptr, "pm_diff: NULL context");
     PM_REQUIRE(!c->space_fourier, "pm_diff: the slab holds Fourier data");
     PM_TRY(launch_diff(c, dim, order));
-    if (c->nranks > 1) PM_TRY(halo_fill(c, 2, 2, PM_TAP_FORCE));
+    // the gather that follows reaches PCS (2 planes) + the interlacing shift (1 plane) beyond the slab
+    if (c->nranks > 1) PM_TRY(halo_fill(c, std::min(3, c->g.nxl), std::min(3, c->g.nxl), PM_TAP_FORCE));
     return PM_OK;
 }
 
@@ -397,7 +440,13 @@ int pm_sum_mom2(pm_ctx* c, const double* mom, int64_t n, double* out) {
 
 int pm_exchange(pm_ctx* c, double* pos, double* mom, int64_t* ids, int64_t* n_inout, int64_t capacity) {
     PM_REQUIRE(c != nullptr, "pm_exchange: NULL context");
-    return exchange_particles(c, pos, mom, ids, n_inout, capacity);
+    return exchange_particles(c, pos, mom, ids, nullptr, nullptr, nullptr, n_inout, capacity);
+}
+
+int pm_exchange_rungs(pm_ctx* c, double* pos, double* mom, int64_t* ids, double* dmom, signed char* rung,
+                      signed char* rung_jumped, int64_t* n_inout, int64_t capacity) {
+    PM_REQUIRE(c != nullptr, "pm_exchange_rungs: NULL context");
+    return exchange_particles(c, pos, mom, ids, dmom, rung, rung_jumped, n_inout, capacity);
 }
 
 // ---- whole-path entry points -----------------------------------------------------

@@ -8,7 +8,9 @@
 // domain<->slab redistribution of mesh.py:2138-2411 does not exist in this layout.
 #include "pm_internal.cuh"
 
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace pm {
 
@@ -51,10 +53,51 @@ static int halo_add_t(pm_ctx* c) {
     return PM_OK;
 }
 
+// The same over the CUDA-IPC mappings of the neighbours' slabs (NVLink/NVSwitch peer loads, no NCCL launch, no
+// staging copy): one kernel adds prev's upper halo planes onto my first interior planes and next's lower halo planes
+// onto my last ones.  A flag barrier before it says that every rank's deposit is complete; the halo planes are only
+// overwritten again by the next pm_grid_zero, which is at least one barrier later on every rank.
+template <typename T>
+__global__ void __launch_bounds__(256)
+halo_add_peer_kernel(T* __restrict__ first, const T* __restrict__ prev_hi, T* __restrict__ last, const T* __restrict__ next_lo,
+                     size_t n) {
+    // n elements per side, a multiple of 2 (rows are Gp = G + 2 long); 16-byte vectors for f64
+    using V = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+    const size_t n2 = n / 2;
+    V* f2 = reinterpret_cast<V*>(first);
+    V* l2 = reinterpret_cast<V*>(last);
+    const V* p2 = reinterpret_cast<const V*>(prev_hi);
+    const V* q2 = reinterpret_cast<const V*>(next_lo);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * n2; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < n2) { V a = f2[i]; const V b = p2[i]; a.x += b.x; a.y += b.y; f2[i] = a; }
+        else { const size_t k = i - n2; V a = l2[k]; const V b = q2[k]; a.x += b.x; a.y += b.y; l2[k] = a; }
+    }
+}
+
+template <typename T>
+static int halo_add_peer_t(pm_ctx* c) {
+    const Geom& g = c->g;
+    const size_t plane = (size_t)g.G * g.Gp;
+    const size_t cnt = plane * kDepositHalo;
+    const int next = (c->rank + 1) % c->nranks, prev = (c->rank + c->nranks - 1) % c->nranks;
+    T* base = reinterpret_cast<T*>(c->real);
+    const T* pbase = reinterpret_cast<const T*>(c->peer_real[prev]);
+    const T* nbase = reinterpret_cast<const T*>(c->peer_real[next]);
+    T* first = base + (size_t)g.halo * plane;
+    T* last = base + (size_t)(g.halo + g.nxl - kDepositHalo) * plane;
+    const T* prev_hi = pbase + (size_t)(g.halo + g.nxl) * plane;              // prev's planes x0 .. x0+1 of mine
+    const T* next_lo = nbase + (size_t)(g.halo - kDepositHalo) * plane;       // next's planes below its slab = my last ones
+    PM_TRY(device_barrier(c));
+    PM_LAUNCH((halo_add_peer_kernel<T>), kNumSMs * 4, 256, 0, c->stream, first, prev_hi, last, next_lo, cnt);
+    return PM_OK;
+}
+
 int halo_add(pm_ctx* c) {
     if (c->nranks == 1) return PM_OK;
-    PM_REQUIRE(c->comm_ready, "pm_halo_add: call pm_comm_init first");
     PM_REQUIRE(c->g.nxl >= kDepositHalo, "slab thinner than the deposit halo");
+    if (c->peers_ready && getenv("PM_HALO_NCCL") == nullptr)
+        return c->dtype == PM_GRID_F64 ? halo_add_peer_t<double>(c) : halo_add_peer_t<float>(c);
+    PM_REQUIRE(c->comm_ready, "pm_halo_add: call pm_comm_init first");
     return c->dtype == PM_GRID_F64 ? halo_add_t<double>(c) : halo_add_t<float>(c);
 }
 
@@ -74,11 +117,44 @@ static int halo_fill_t(pm_ctx* c, int planes_lo, int planes_hi, int which) {
     return PM_OK;
 }
 
+// communicate_ghosts(grid, '=') over the peer mappings: my halo planes are read straight from the neighbours' interiors.
+__global__ void __launch_bounds__(256)
+halo_fill_peer_kernel(double2* __restrict__ lo_dst, const double2* __restrict__ lo_src, size_t n_lo,
+                      double2* __restrict__ hi_dst, const double2* __restrict__ hi_src, size_t n_hi) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_lo + n_hi; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < n_lo) lo_dst[i] = lo_src[i];
+        else hi_dst[i - n_lo] = hi_src[i - n_lo];
+    }
+}
+
+template <typename T>
+static int halo_fill_peer_t(pm_ctx* c, int planes_lo, int planes_hi) {
+    const Geom& g = c->g;
+    const size_t plane = (size_t)g.G * g.Gp;       // G·(G+2) elements: a multiple of 4 for even G, so 16-byte vectors fit
+    const int next = (c->rank + 1) % c->nranks, prev = (c->rank + c->nranks - 1) % c->nranks;
+    T* base = reinterpret_cast<T*>(c->real);
+    const T* pbase = reinterpret_cast<const T*>(c->peer_real[prev]);
+    const T* nbase = reinterpret_cast<const T*>(c->peer_real[next]);
+    const size_t per16 = 16 / sizeof(T);
+    PM_REQUIRE(plane % per16 == 0, "halo_fill: plane size not a multiple of 16 bytes");
+    PM_TRY(device_barrier(c));                      // every rank's potential is complete
+    PM_LAUNCH(halo_fill_peer_kernel, kNumSMs * 4, 256, 0, c->stream,
+              reinterpret_cast<double2*>(base + (size_t)(g.halo - planes_lo) * plane),
+              reinterpret_cast<const double2*>(pbase + (size_t)(g.halo + g.nxl - planes_lo) * plane), plane * planes_lo / per16,
+              reinterpret_cast<double2*>(base + (size_t)(g.halo + g.nxl) * plane),
+              reinterpret_cast<const double2*>(nbase + (size_t)g.halo * plane), plane * planes_hi / per16);
+    c->peers_may_read = true;   // the neighbours read my interior the same way: no overwriting before the next barrier
+    return PM_OK;
+}
+
 int halo_fill(pm_ctx* c, int planes_lo, int planes_hi, int which) {
     if (c->nranks == 1) return PM_OK;
-    PM_REQUIRE(c->comm_ready, "pm_halo_fill: call pm_comm_init first");
     PM_REQUIRE(planes_lo <= c->g.halo && planes_hi <= c->g.halo && planes_lo <= c->g.nxl && planes_hi <= c->g.nxl,
                "halo_fill: %d/%d planes exceed halo %d or slab %d", planes_lo, planes_hi, c->g.halo, c->g.nxl);
+    if (c->peers_ready && which == PM_TAP_REAL && !c->grid_in_phi && getenv("PM_HALO_NCCL") == nullptr)
+        return c->dtype == PM_GRID_F64 ? halo_fill_peer_t<double>(c, planes_lo, planes_hi)
+                                       : halo_fill_peer_t<float>(c, planes_lo, planes_hi);
+    PM_REQUIRE(c->comm_ready, "pm_halo_fill: call pm_comm_init first");
     return c->dtype == PM_GRID_F64 ? halo_fill_t<double>(c, planes_lo, planes_hi, which)
                                    : halo_fill_t<float>(c, planes_lo, planes_hi, which);
 }
@@ -141,12 +217,50 @@ int transpose_backward(pm_ctx* c) {
     return c->dtype == PM_GRID_F64 ? transpose_t<double, double2>(c, false) : transpose_t<float, float2>(c, false);
 }
 
+// Stream-ordered barrier over all ranks through the IPC arenas: lane r announces this rank's epoch in rank r's
+// header (a release store over NVLink) and waits until rank r's epoch has arrived here.  Everything this rank's
+// stream did before the barrier kernel — including its stores into peer memory — is complete when the kernel starts,
+// and the acquire loads order the peers' data before whatever this stream launches next.  One 32-thread kernel,
+// a few microseconds, instead of an NCCL all-reduce used as a barrier.  The wait is bounded: a peer that never arrives
+// raises the sticky flag (pm_check_async_error) instead of hanging the GPU.
+struct BarrierPeers { unsigned long long* flag[kMaxPeers]; };   // &header(r)->bar[my rank].v
+
+__global__ void __launch_bounds__(32)
+flag_barrier_kernel(BarrierPeers peers, const ArenaHeader* __restrict__ mine, int nranks, unsigned long long epoch, int* err) {
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flag[r]), "l"(epoch) : "memory");
+    const unsigned long long* f = &mine->bar[r].v;
+    unsigned long long v;
+    unsigned spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (v >= epoch) break;
+        if (++spins > 64) __nanosleep(200);
+        if (spins > (1u << 24)) { atomicExch(err, 3); break; }   // seconds
+    }
+}
+
 int device_barrier(pm_ctx* c) {
     if (c->nranks == 1) return PM_OK;
+    c->peers_may_read = false;
+    if (c->peers_ready && getenv("PM_BARRIER_NCCL") == nullptr) {
+        BarrierPeers bp;
+        for (int r = 0; r < kMaxPeers; ++r) bp.flag[r] = nullptr;
+        for (int r = 0; r < c->nranks; ++r) bp.flag[r] = &arena_header(c, r)->bar[c->rank].v;
+        const unsigned long long epoch = ++c->bar_epoch;
+        PM_LAUNCH(flag_barrier_kernel, 1, 32, 0, c->stream, bp, arena_header(c, c->rank), c->nranks, epoch, c->d_comm_err);
+        return PM_OK;
+    }
     PM_REQUIRE(c->comm_ready, "device barrier: call pm_comm_init first");
     double* token = c->d_scratch + 32;
     PM_CHECK_NCCL(ncclAllReduce(token, token, 1, ncclDouble, ncclSum, c->comm, c->stream));
     return PM_OK;
+}
+
+int barrier_before_overwrite(pm_ctx* c) {
+    if (c->nranks == 1 || !c->peers_may_read) return PM_OK;
+    return device_barrier(c);
 }
 
 }  // namespace pm

@@ -26,6 +26,19 @@ constexpr int kNumSMs = 148;  // B200
 constexpr int kHalo = 7;
 constexpr int kMaxPeers = 16;   // ranks whose slabs one kernel can address through peer pointers
 
+// IPC-mapped arena behind the slab (nranks > 1): what the ranks hand each other without NCCL or the host —
+// barrier flags, the migration mailboxes (one slot per source rank, double-buffered by exchange parity) and the
+// read-only ghost particles of the P³M short-range force.  Every word a peer writes sits on its own 64-byte line.
+struct alignas(64) ArenaWord { unsigned long long v; unsigned long long pad[7]; };
+struct ArenaHeader {
+    ArenaWord bar[kMaxPeers];             // barrier epoch announced by rank s
+    ArenaWord mb_count[2][kMaxPeers];     // particles rank s has put into its slot of my mailbox (per parity)
+    ArenaWord mb_unsent[2][kMaxPeers];    // movers rank s could not send this round (any destination)
+    ArenaWord ghost_count[2][2];          // [parity][side]: ghost positions in my lower / upper ghost buffer
+};
+constexpr size_t kArenaHeaderBytes = 8192;
+static_assert(sizeof(ArenaHeader) <= kArenaHeaderBytes, "arena header");
+
 extern std::atomic<int64_t> g_launches;
 void set_error(const char* fmt, ...);
 
@@ -149,6 +162,19 @@ struct pm_ctx {
     int f2_lag;
     void* peer_real[pm::kMaxPeers];   // IPC mappings of every rank's `real` buffer (own pointer for self)
     bool peers_ready;
+    // IPC arena (ArenaHeader | mailboxes | ghost buffers) inside the `real` allocation, same offsets on every rank
+    size_t off_arena, arena_bytes;
+    size_t off_mailbox, mailbox_slot_bytes;   // 2 parities × nranks slots
+    size_t off_ghost, ghost_buf_bytes;        // 2 parities × 2 sides
+    unsigned long long bar_epoch;     // barriers issued so far (every rank issues the same sequence)
+    unsigned long long xchg_epoch;    // exchanges issued so far (mailbox parity)
+    unsigned long long ghost_epoch;   // ghost exchanges issued so far (ghost-buffer parity)
+    bool xchg_pending;                // an exchange ran out of particle-buffer room: arrivals wait in the mailbox
+    int64_t xchg_pending_n;
+    int xchg_pending_parity;
+    bool peers_may_read;              // a peer may still be reading `real` through its mapping (halo fill): barrier before overwriting
+    int* d_comm_err;                  // sticky flag of the flag barrier (a peer that never arrived)
+    void* h_pinned;                   // small pinned host block for asynchronous read-backs
     // P3M short range scratch (pm_shortrange.cu)
     void* sr_buf;
     size_t sr_bytes;
@@ -199,15 +225,19 @@ int launch_power_k2(pm_ctx* c, int k2_max, double* power, unsigned long long* co
 // implemented in pm_particles.cu
 int launch_drift(pm_ctx* c, double* pos, const double* mom, int64_t n, double dt_over_mass);
 int launch_sum_mom2(pm_ctx* c, const double* mom, int64_t n, double* out);
-int exchange_particles(pm_ctx* c, double* pos, double* mom, int64_t* ids, int64_t* n_inout,
-                       int64_t capacity);
+int exchange_particles(pm_ctx* c, double* pos, double* mom, int64_t* ids, double* dmom, signed char* rung,
+                       signed char* rung_jumped, int64_t* n_inout, int64_t capacity);
 // implemented in pm_comm.cu
 int halo_add(pm_ctx* c);
 int halo_fill(pm_ctx* c, int planes_lo, int planes_hi, int which);
 int transpose_forward(pm_ctx* c);   // real-buffer 2-D spectra -> Fourier slab (all-to-all)
 int transpose_backward(pm_ctx* c);
 
-int device_barrier(pm_ctx* c);      // stream-ordered barrier over all ranks
+int device_barrier(pm_ctx* c);      // stream-ordered barrier over all ranks (flags in the peers' arenas; NCCL before the mappings exist)
+int barrier_before_overwrite(pm_ctx* c);   // barrier only if a peer may still be reading this rank's slab
+inline pm::ArenaHeader* arena_header(const pm_ctx* c, int r) {
+    return reinterpret_cast<pm::ArenaHeader*>(reinterpret_cast<char*>(c->peer_real[r]) + c->off_arena);
+}
 // implemented in pm_xsolve.cu
 bool xsolve_supported(const pm_ctx* c);
 int xsolve(pm_ctx* c, double prefactor, int deconv_order, double gauss);

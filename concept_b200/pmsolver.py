@@ -120,6 +120,9 @@ class PMContext:
     def halo_fill(self):
         check(self.lib.pm_halo_fill(self._h))
 
+    def halo_fill_for(self, order, diff_order, interlace=False):
+        check(self.lib.pm_halo_fill_for(self._h, int(order), int(diff_order), int(bool(interlace))))
+
     def fft_forward(self):
         check(self.lib.pm_fft_forward(self._h))
 
@@ -198,17 +201,29 @@ class PMContext:
         if out is None:
             acc.zero_()
         check(self.lib.pm_sum_mom2(self._h, _particles(mom), mom.shape[0], _ptr(acc)))
-        return float(acc.item()) if out is None else None
+        if out is not None:
+            return None
+        value = float(acc.item())
+        # the host synchronises here anyway (once per base step through measure('v_rms')): a good place to notice a
+        # hand-written transform that gave up on a tile dependency and left an invalid potential behind
+        self.check_async_error()
+        return value
 
     def sort_particles(self, pos, mom, ids=None, n=None):
         """Stable reorder of the first n particles by grid cell (tile_sort analogue)."""
         n = pos.shape[0] if n is None else int(n)
         check(self.lib.pm_sort_particles(self._h, _particles(pos), _particles(mom), _ptr(ids), n))
 
-    def exchange(self, pos, mom, ids, n):
-        """Slab migration.  pos/mom(/ids) are capacity-sized buffers; returns the new local count."""
+    def exchange(self, pos, mom, ids, n, Δmom=None, rung_indices=None, rung_indices_jumped=None):
+        """Slab migration.  pos/mom(/ids) are capacity-sized buffers; returns the new local count.  The P³M state of a
+        component (Δmom, rung_indices, rung_indices_jumped) migrates along when given."""
         n_io = ctypes.c_int64(int(n))
-        check(self.lib.pm_exchange(self._h, _particles(pos), _particles(mom), _ptr(ids), ctypes.byref(n_io), pos.shape[0]))
+        if Δmom is None and rung_indices is None:
+            check(self.lib.pm_exchange(self._h, _particles(pos), _particles(mom), _ptr(ids), ctypes.byref(n_io), pos.shape[0]))
+        else:
+            capacity = min(t.shape[0] for t in (pos, mom, Δmom, rung_indices, rung_indices_jumped) if t is not None)
+            check(self.lib.pm_exchange_rungs(self._h, _particles(pos), _particles(mom), _ptr(ids), _ptr(Δmom), _ptr(rung_indices),
+                                             _ptr(rung_indices_jumped), ctypes.byref(n_io), capacity))
         return n_io.value
 
     # -- initial conditions (csrc/pm_ic.cu) ------------------------------------------------

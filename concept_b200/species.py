@@ -60,6 +60,10 @@ class Component:
         self.pos = grow(self.pos, (size, 3), torch.float64)
         self.mom = grow(self.mom, (size, 3), torch.float64)
         self.ids = grow(self.ids, (size,), torch.int64)
+        if getattr(self, 'Δmom', None) is not None:      # P³M state follows (species.py:2040-2060)
+            self.Δmom = grow(self.Δmom, (size, 3), torch.float64)
+            self.rung_indices = grow(self.rung_indices, (size,), torch.int8)
+            self.rung_indices_jumped = grow(self.rung_indices_jumped, (size,), torch.int8)
         self.N_allocated = size
 
     def populate(self, data, var):
@@ -175,7 +179,19 @@ class Component:
         """Reorder the local particles by grid cell (the tile_sort analogue, species.py:2657-2780): keeps the
         deposit/gather locality that lattice-ordered particles lose over many steps."""
         ctx = self._pm_context() if gridsize is None else mesh.get_context(gridsize)
-        ctx.sort_particles(self.pos, self.mom, self.ids, self.N_local)
+        n = self.N_local
+        if getattr(self, 'Δmom', None) is None:
+            ctx.sort_particles(self.pos, self.mom, self.ids, n)
+            return
+        # P³M state (Δmom, rung_indices, rung_indices_jumped; species.py:956-996) follows the particles: sort a
+        # position index along with them and apply the same permutation to the per-particle rung arrays
+        index = torch.arange(n, dtype=torch.int64, device=self.device)
+        ids = self.ids[:n].clone()
+        ctx.sort_particles(self.pos, self.mom, index, n)
+        self.ids[:n] = ids[index]
+        self.Δmom[:n] = self.Δmom[:n][index]
+        self.rung_indices[:n] = self.rung_indices[:n][index]
+        self.rung_indices_jumped[:n] = self.rung_indices_jumped[:n][index]
 
     def _pm_context(self):
         method = self.forces.get('gravity', 'pm')
@@ -195,7 +211,19 @@ class Component:
         if communication.nprocs == 1:
             return
         ctx = self._pm_context()
-        self.N_local = ctx.exchange(self.pos, self.mom, self.ids, self.N_local)
+        from ._lib import PMError
+        for attempt in range(8):
+            try:
+                self.N_local = ctx.exchange(self.pos, self.mom, self.ids, self.N_local, Δmom=getattr(self, 'Δmom', None),
+                                            rung_indices=getattr(self, 'rung_indices', None),
+                                            rung_indices_jumped=getattr(self, 'rung_indices_jumped', None))
+                return
+            except PMError as err:
+                if err.status != -6:     # PM_ERR_OVERFLOW: this rank's buffers are too small for its arrivals
+                    raise
+                # the arrivals wait in the mailbox: grow (species.py:2002-2065 grows by realloc the same way) and unpack again
+                self.resize(int(1.3*self.N_allocated) + 4096)
+        abort(f'Component "{self.name}": particle exchange keeps overflowing')
 
     def sum_mom2(self):
         return communication.allreduce_sum(self._pm_context().sum_mom2(self.mom_local)) if self.N_local or communication.nprocs > 1 else 0.0

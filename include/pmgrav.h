@@ -103,6 +103,9 @@ int pm_deposit(pm_ctx* ctx, const double* pos, int64_t n, int order,
 int pm_halo_add(pm_ctx* ctx);
 /* communicate_ghosts(grid,'=') after the inverse transform (mesh.py:2243): fill x-halo planes */
 int pm_halo_fill(pm_ctx* ctx);
+/* the same, only as many planes as a gather of interpolation order `order` (1..4) with finite differences of order
+ * `diff_order` (0 = none) reaches beyond the slab (+1 with the interlacing shift): what pm_kick_long itself fills */
+int pm_halo_fill_for(pm_ctx* ctx, int order, int diff_order, int interlace);
 /* fft(slab,'forward'|'backward') (mesh.py:4012-4157 → fftw_execute): unnormalised, in place.
  * forward also performs nullify_modes(slab,'nyquist') only when asked via pm_kspace_*. */
 int pm_fft_forward(pm_ctx* ctx);
@@ -189,6 +192,14 @@ int pm_sort_particles(pm_ctx* ctx, double* pos, double* mom, int64_t* ids, int64
  * ids may be NULL. */
 int pm_exchange(pm_ctx* ctx, double* pos, double* mom, int64_t* ids, int64_t* n_inout,
                 int64_t capacity);
+/* The same for a P³M component: the short-range state of a particle — Δmom (the stored acceleration) and its
+ * rung indices (species.py:956-996; the reference ships them in exchange() too, communication.py:300-330) — migrates
+ * with it.  dmom, rung and rung_jumped may be NULL.
+ * Both run over the CUDA-IPC peer mappings (pm_ipc_open_peers): movers are written straight into the owner's mailbox,
+ * arrivals fill the holes the movers leave (communication.py:430-517).  PM_ERR_OVERFLOW on a rank whose buffers are too
+ * small for its arrivals: grow them (contents preserved) and call again — only that rank repeats its unpacking. */
+int pm_exchange_rungs(pm_ctx* ctx, double* pos, double* mom, int64_t* ids, double* dmom, signed char* rung,
+                      signed char* rung_jumped, int64_t* n_inout, int64_t capacity);
 
 /* ---- P3M short range (single GPU in this round) ---------------------------- */
 /* gravity_pairwise_shortrange over all pairs within `range` (gravity.py:263-354; pair enumeration

@@ -47,6 +47,12 @@ def num_threads():
     return load().pmo_num_threads()
 
 
+def set_num_threads(n=None):
+    """Use n OpenMP threads (default: every host core), whatever OMP_NUM_THREADS says — torchrun sets it to 1."""
+    load().pmo_set_num_threads(int(n or os.cpu_count() or 1))
+    return num_threads()
+
+
 class Workspace:
     """Scratch grids for pmo_kick_long (allocated once, like the reference's cached buffers)."""
     def __init__(self, G):

@@ -33,6 +33,7 @@
 #else
 static int omp_get_max_threads(void) { return 1; }
 static int omp_get_thread_num(void) { return 0; }
+static void omp_set_num_threads(int n) { (void)n; }
 #endif
 
 #define EPS 2.220446049250313e-16
@@ -41,6 +42,8 @@ static int omp_get_thread_num(void) { return 0; }
 typedef struct { double re, im; } cplx;
 
 int pmo_num_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline sets its thread count explicitly */
+void pmo_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 /* ---------------------------------------------------------------- weights */
 static inline int64_t set_weights(int order, double x, double* w) {
