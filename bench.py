@@ -303,13 +303,19 @@ def parity_check(D, ctx, cfg, n_sub, seed):
     pos_h[:nf, 0] = (np.repeat(np.arange(8)/8, (nf + 7)//8)[:nf] + (rng.random(nf) - 0.5)*3.0/G) % 1.0*L
     mom_h = rng.standard_normal((n_sub, 3))
     kw = kick_kwargs(dict(cfg, grid=G), boxsize=L)
-    params = make_kick_params(**kw)
     dt = 0.7*L/G                      # |mom| ~ 1: a good fraction of a cell per step, so that particles do change slab
     pos = torch.as_tensor(pos_h, device=D.dev)
     mom = torch.as_tensor(mom_h, device=D.dev)
     ids = torch.arange(n_sub, dtype=torch.int64, device=D.dev)
     pbuf, mbuf, ibuf, n = distribute(D, ctx, pos, mom, ids, slack=3.0)
     sum2 = torch.zeros(1, dtype=torch.float64, device=D.dev)
+    # calibrate the particle mass (the kick scales with mass²) so that max|Δmom| ≈ max|mom| ≈ 1: the comparison below then
+    # measures the kick itself and not the rounding of mom + Δmom
+    probe = torch.zeros_like(mbuf[:n])
+    ctx.kick_long(pbuf[:n], probe, make_kick_params(**kw))
+    dmax = D.max_([float(probe.abs().max().item()) if n else 0.0])[0]
+    kw['mass'] = kw['mass']*(1.0/dmax)**0.5
+    params = make_kick_params(**kw)
     ctx.kick_drift(pbuf[:n], mbuf[:n], params, dt, sum_mom2=sum2)
     if D.world > 1:
         ctx.allreduce_sum(sum2)
@@ -335,10 +341,10 @@ def parity_check(D, ctx, cfg, n_sub, seed):
             ref = C.kick_long(pos_h.copy(), mom_h.copy(), **kw)
             dmax = float(np.max(np.abs(ref - mom_h)))
             rec['kick_relerr'] = float(np.max(np.abs(gm - ref)))/dmax
+            rec['max_dmom_over_max_mom'] = dmax/float(np.max(np.abs(mom_h)))
             # drift: bit-exact given the (GPU-)kicked momenta — pos = mod(pos + mom·Δ, L) has one correct rounding
             rec['drift_exact'] = bool(np.array_equal(gp, C.drift(pos_h.copy(), np.ascontiguousarray(gm), dt, L)))
             rec['sum_mom2_relerr'] = abs(float(sum2.item()) - float(np.sum(gm*gm)))/float(np.sum(gm*gm))
-            rec['migrated'] = int(sum(1 for _ in ()))  # replaced below
             owner0 = np.clip((pos_h[:, 0]*(G/L)).astype(np.int64), 0, G - 1)//ctx.nx_local
             owner1 = np.clip((gp[:, 0]*(G/L)).astype(np.int64), 0, G - 1)//ctx.nx_local
             rec['migrated'] = int(np.count_nonzero(owner0 != owner1))

@@ -40,8 +40,14 @@ namespace pm {
 using namespace fftc;
 
 constexpr int kFftThreads = 256;
-constexpr int kFft2dOcc = 3;      // CTAs per SM: independent barrier domains hide each other's LDS/DP/STS phases
-constexpr int kXSolveOcc = 2;      // measured: 3 (table of Green's-function factors read from global, 85 registers) is 13 % slower
+#ifndef PM_FFT2D_OCC
+#define PM_FFT2D_OCC 3
+#endif
+#ifndef PM_XSOLVE_OCC
+#define PM_XSOLVE_OCC 2
+#endif
+constexpr int kFft2dOcc = PM_FFT2D_OCC;      // CTAs per SM: independent barrier domains hide each other's LDS/DP/STS phases
+constexpr int kXSolveOcc = PM_XSOLVE_OCC;    // measured: 3 (table of Green's-function factors read from global, 85 registers) is 13 % slower
 
 // ---- PTX helpers: mbarrier + bulk asynchronous copy ----------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -120,6 +120,36 @@ PM_HD void cmul(T& r, T& i, const V w) {
     r = t;
 }
 
+// Powers w⁰ … w^(R−1) of one table entry w = e^{−2πi·m/NT}.  The twiddles of a butterfly are the powers of ONE root
+// (ω64^(a·b3), ωN^(a·q) for a = 0 … R−1), so a thread loads that root once and multiplies — the kernels are bound by
+// the shared-memory/L1 data pipe (ncu r01: 42 % of all LDS were twiddle loads) and have FP64 issue slots to spare.
+// Squarings for even powers, one product for odd ones: at most ⌈log₂R⌉ roundings deep (≈ 3 ulp for R = 8).
+template <int R, typename T, typename V>
+PM_HD void tw_powers(const V w, T (&pr)[R], T (&pi)[R]) {
+    pr[0] = (T)1; pi[0] = (T)0;
+    if constexpr (R > 1) { pr[1] = w.x; pi[1] = w.y; }
+#pragma unroll
+    for (int m = 2; m < R; ++m) {
+        if ((m & 1) == 0) {
+            const T a = pr[m / 2], b = pi[m / 2];
+            pr[m] = (a - b) * (a + b);
+            pi[m] = (a + a) * b;
+        } else {
+            const T a = pr[m - 1], b = pi[m - 1];
+            pr[m] = fma_(a, w.x, -(b * w.y));
+            pi[m] = fma_(a, w.y, b * w.x);
+        }
+    }
+}
+// (r, i) ·= (wr, wi) (DIR < 0) or ·= conj (DIR > 0)
+template <int DIR, typename T>
+PM_HD void cmul2(T& r, T& i, const T wr, const T wi_in) {
+    const T wi = DIR < 0 ? wi_in : -wi_in;
+    const T t = fma_(r, wr, -(i * wi));
+    i = fma_(r, wi, i * wr);
+    r = t;
+}
+
 // ---------------------------------------------------------------------------------------------
 // layouts
 // ---------------------------------------------------------------------------------------------
@@ -272,12 +302,13 @@ PM_HD void dit_stageB(V* tile, const V* twB, int tid, int nthr) {
         L::template decode<P>(b, c, u);
         const int b3 = u & 7, a1 = u >> 3;
         const int p0 = 64 * a1 + b3;
-        T r[8], i[8];
+        T r[8], i[8], wr[8], wi[8];
+        tw_powers<8>(twB[8 + b3], wr, wi);     // ω64^(a2·b3), a2 = 0 … 7
 #pragma unroll
         for (int a2 = 0; a2 < 8; ++a2) {
             const V v = tile[L::idx_s8(p0, a2, c)];
             r[a2] = v.x; i[a2] = v.y;
-            if (a2) cmul<DIR>(r[a2], i[a2], twB[a2 * 8 + b3]);
+            if (a2) cmul2<DIR>(r[a2], i[a2], wr[a2], wi[a2]);
         }
         dft8<DIR>(r, i);
 #pragma unroll
@@ -296,12 +327,13 @@ PM_HD void dit_stageC(const V* tile, const V* twC, int tid, int nthr, const Sink
     for (int b = tid; b < 64 * L::C; b += nthr) {
         int c, q;
         L::template decode<64>(b, c, q);
-        T r[R1], i[R1];
+        T r[R1], i[R1], wr[R1], wi[R1];
+        tw_powers<R1>(twC[TWS * 64 + q], wr, wi);     // ωN^(a1·q)
 #pragma unroll
         for (int a1 = 0; a1 < R1; ++a1) {
             const V v = tile[L::idx_s64(q, a1, c)];
             r[a1] = v.x; i[a1] = v.y;
-            if (a1) cmul<DIR>(r[a1], i[a1], twC[(a1 * TWS) * 64 + q]);
+            if (a1) cmul2<DIR>(r[a1], i[a1], wr[a1], wi[a1]);
         }
         dftR<R1, DIR>(r, i);
 #pragma unroll
@@ -318,9 +350,11 @@ template <class L, typename T, int N, int TWS, int DIR, typename V>
 PM_HD void dif_stage1_regs(T (&r)[N / 64], T (&i)[N / 64], V* tile, const V* twC, int c, int q) {
     constexpr int R1 = N / 64;
     dftR<R1, DIR>(r, i);
+    T wr[R1], wi[R1];
+    tw_powers<R1>(twC[TWS * 64 + q], wr, wi);
 #pragma unroll
     for (int b1 = 0; b1 < R1; ++b1) {
-        if (b1) cmul<DIR>(r[b1], i[b1], twC[(b1 * TWS) * 64 + q]);
+        if (b1) cmul2<DIR>(r[b1], i[b1], wr[b1], wi[b1]);
         V v; v.x = r[b1]; v.y = i[b1];
         tile[L::idx_s64(q, b1, c)] = v;
     }
@@ -342,9 +376,11 @@ PM_HD void dif_stage2(V* tile, const V* twB, int tid, int nthr) {
             r[a2] = v.x; i[a2] = v.y;
         }
         dft8<DIR>(r, i);
+        T wr[8], wi[8];
+        tw_powers<8>(twB[8 + a3], wr, wi);     // ω64^(a3·b2)
 #pragma unroll
         for (int b2 = 0; b2 < 8; ++b2) {
-            if (b2) cmul<DIR>(r[b2], i[b2], twB[b2 * 8 + a3]);
+            if (b2) cmul2<DIR>(r[b2], i[b2], wr[b2], wi[b2]);
             V v; v.x = r[b2]; v.y = i[b2];
             tile[L::idx_s8(p0, b2, c)] = v;
         }
@@ -434,6 +470,130 @@ PM_HD void c2r_pre(const Source& src, V* tile, const V* twR, int tid, int nthr) 
         if (k != kp) {
             const int a1 = kp % R1, a2 = (kp / R1) & 7, a3 = kp / (8 * R1);
             tile[L::idx(64 * a1 + 8 * a2 + a3, c)] = zp;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the real-transform pre/post-processing fused into the neighbouring stage of the z pass (no extra trip of the tile
+// through shared memory, one block barrier less per tile)
+// ---------------------------------------------------------------------------------------------
+// One mirror pair of r2c_post: Z_k, Z_{M−k} -> X_k, X_{M−k}; needs k ≤ M/2, kp = (M − k) mod M.
+template <typename T, int M, typename V, class Sink>
+PM_HD void r2c_pair(const V* twR, const Sink& sink, int c, int k, T zkr, T zki, int kp, T zpr, T zpi) {
+    const T er = (T)0.5 * (zkr + zpr), ei = (T)0.5 * (zki - zpi);
+    T orr = (T)0.5 * (zki + zpi), oi = (T)-0.5 * (zkr - zpr);
+    cmul<-1>(orr, oi, tw_r<M>(twR, k));
+    sink(c, k, er + orr, ei + oi);
+    if (k == 0) sink(c, M, (T)0, (T)0);
+    else if (k != kp) sink(c, kp, er - orr, -ei + oi);
+}
+template <typename T, int M, typename V, class Sink>
+PM_HD void r2c_pair_any(const V* twR, const Sink& sink, int c, int k, T zkr, T zki, int kp, T zpr, T zpi) {
+    if (k <= kp) r2c_pair<T, M>(twR, sink, c, k, zkr, zki, kp, zpr, zpi);
+    else r2c_pair<T, M>(twR, sink, c, kp, zpr, zpi, k, zkr, zki);
+}
+
+// Forward: DIT stage C of the M-point transform + r2c_post.  One item = row c and the column pair (qa, qb) = (m, 64 − m)
+// for m = 1 … 31, (0, 32) for m = 0: its outputs Z[64·b1 + qa], Z[64·b1 + qb] (b1 < R1) hold both members of every mirror
+// pair (k, M − k) they belong to, because M − (64·b1 + qa) = 64·(R1 − 1 − b1) + (64 − qa).
+template <class L, typename T, int M, typename V, class Sink>
+PM_HD void r2c_stageC_post(const V* tile, const V* twC, const V* twR, int tid, int nthr, const Sink& sink) {
+    constexpr int R1 = M / 64;
+    for (int b = tid; b < 32 * L::C; b += nthr) {
+        const int m = b & 31, c = b >> 5;
+        const int qa = m, qb = m ? 64 - m : 32;
+        T ar[R1], ai[R1], br[R1], bi[R1];
+        {
+            T wr[R1], wi[R1];
+            tw_powers<R1>(twC[2 * 64 + qa], wr, wi);     // ωM^(a1·qa) = ωG^(2·a1·qa)
+#pragma unroll
+            for (int a1 = 0; a1 < R1; ++a1) {
+                const V v = tile[L::idx_s64(qa, a1, c)];
+                ar[a1] = v.x; ai[a1] = v.y;
+                if (a1) cmul2<-1>(ar[a1], ai[a1], wr[a1], wi[a1]);
+            }
+            dftR<R1, -1>(ar, ai);
+            tw_powers<R1>(twC[2 * 64 + qb], wr, wi);
+#pragma unroll
+            for (int a1 = 0; a1 < R1; ++a1) {
+                const V v = tile[L::idx_s64(qb, a1, c)];
+                br[a1] = v.x; bi[a1] = v.y;
+                if (a1) cmul2<-1>(br[a1], bi[a1], wr[a1], wi[a1]);
+            }
+            dftR<R1, -1>(br, bi);
+        }
+        if (m != 0) {
+#pragma unroll
+            for (int b1 = 0; b1 < R1; ++b1)
+                r2c_pair_any<T, M>(twR, sink, c, 64 * b1 + qa, ar[b1], ai[b1], 64 * (R1 - 1 - b1) + qb, br[R1 - 1 - b1], bi[R1 - 1 - b1]);
+        } else {
+            // qa = 0: k = 64·b1 pairs with 64·(R1 − b1) (k = 0 and k = M/2 with themselves)
+#pragma unroll
+            for (int b1 = 0; b1 <= R1 / 2; ++b1) {
+                const int bp = (R1 - b1) % R1;
+                r2c_pair<T, M>(twR, sink, c, 64 * b1, ar[b1], ai[b1], 64 * bp, ar[bp], ai[bp]);
+            }
+            // qb = 32: k = 64·b1 + 32 pairs with 64·(R1 − 1 − b1) + 32
+#pragma unroll
+            for (int b1 = 0; b1 <= (R1 - 1) / 2; ++b1) {
+                const int bp = R1 - 1 - b1;
+                r2c_pair<T, M>(twR, sink, c, 64 * b1 + 32, br[b1], bi[b1], 64 * bp + 32, br[bp], bi[bp]);
+            }
+        }
+    }
+}
+
+// One mirror pair of c2r_pre: X_k, X_{M−k} -> Z_k, Z_{M−k}; needs 0 < k ≤ M/2.
+template <typename T, int M, typename V>
+PM_HD void c2r_pair(const V* twR, int k, const V xk, const V xp, T& zkr, T& zki, T& zpr, T& zpi) {
+    const T ar = xk.x + xp.x, ai = xk.y - xp.y;
+    T ur = xk.x - xp.x, ui = xk.y + xp.y;
+    cmul<+1>(ur, ui, tw_r<M>(twR, k));
+    zkr = ar - ui; zki = ai + ur;      // A + i·U
+    zpr = ar + ui; zpi = -ai + ur;     // conj(A) + i·conj(U)
+}
+
+// Inverse: c2r_pre + DIT stage A of the M-point transform.  One item = row c and the butterfly pair (ua, ub) = (m, P − m)
+// for m = 1 … P/2 − 1, (0, P/2) for m = 0 (P = M/8 butterflies per row): element a = u + P·a3 of butterfly u needs X_a and
+// X_{M−a}, and M − a = (P − u) + P·(7 − a3) is element 7 − a3 of butterfly P − u.  src(c, k) delivers X_k (k < M).
+template <class L, typename T, int M, typename V, class Source>
+PM_HD void c2r_pre_stageA(const Source& src, V* tile, const V* twR, int tid, int nthr) {
+    constexpr int R1 = M / 64, P = M / 8, H = P / 2;
+    for (int b = tid; b < H * L::C; b += nthr) {
+        const int m = b % H, c = b / H;
+        const int ua = m, ub = m ? P - m : H;
+        V xa[8], xb[8];
+#pragma unroll
+        for (int a3 = 0; a3 < 8; ++a3) { xa[a3] = src(c, ua + P * a3); xb[a3] = src(c, ub + P * a3); }
+        T zar[8], zai[8], zbr[8], zbi[8];
+        if (m != 0) {
+#pragma unroll
+            for (int a3 = 0; a3 < 8; ++a3) {
+                const int k = ua + P * a3;            // 0 < k < M, mirror M − k = ub + P·(7 − a3)
+                if (k <= M / 2) c2r_pair<T, M>(twR, k, xa[a3], xb[7 - a3], zar[a3], zai[a3], zbr[7 - a3], zbi[7 - a3]);
+                else c2r_pair<T, M>(twR, M - k, xb[7 - a3], xa[a3], zbr[7 - a3], zbi[7 - a3], zar[a3], zai[a3]);
+            }
+        } else {
+            // ua = 0: k = P·a3; k = 0 alone (X_M := 0, Im X_0 ignored), k = M/2 with itself, a3 = 1 … 3 with 8 − a3
+            zar[0] = xa[0].x; zai[0] = xa[0].x;
+            T dr, di;
+#pragma unroll
+            for (int a3 = 1; a3 < 4; ++a3) c2r_pair<T, M>(twR, P * a3, xa[a3], xa[8 - a3], zar[a3], zai[a3], zar[8 - a3], zai[8 - a3]);
+            c2r_pair<T, M>(twR, M / 2, xa[4], xa[4], zar[4], zai[4], dr, di);
+            // ub = P/2: k = P/2 + P·a3 with P/2 + P·(7 − a3)
+#pragma unroll
+            for (int a3 = 0; a3 < 4; ++a3) c2r_pair<T, M>(twR, H + P * a3, xb[a3], xb[7 - a3], zbr[a3], zbi[a3], zbr[7 - a3], zbi[7 - a3]);
+        }
+        dft8<+1>(zar, zai);
+        dft8<+1>(zbr, zbi);
+        const int pa = 64 * (ua % R1) + 8 * (ua / R1), pb = 64 * (ub % R1) + 8 * (ub / R1);
+#pragma unroll
+        for (int b3 = 0; b3 < 8; ++b3) {
+            V v; v.x = zar[b3]; v.y = zai[b3];
+            tile[L::idx_s1(pa, b3, c)] = v;
+            v.x = zbr[b3]; v.y = zbi[b3];
+            tile[L::idx_s1(pb, b3, c)] = v;
         }
     }
 }

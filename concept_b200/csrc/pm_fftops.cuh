@@ -111,7 +111,7 @@ struct SlabFFT {
                 a_plane[((size_t)(k / CY) * G + row0 + c) * CY + (k % CY)] = v;
             }
         };
-        static constexpr int kPhases = 4;
+        static constexpr int kPhases = 3;
         PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int nthr, T (&)[kRegs]) const {
             if (ph == 0) dit_stageA<LZ, T, M, -1>(RowSource{plane, row0}, tile, tid, nthr);
             else if (ph == 1) {
@@ -122,8 +122,7 @@ struct SlabFFT {
                 }
                 dit_stageB<LZ, T, M, -1>(tile, tw.B, tid, nthr);
             }
-            else if (ph == 2) dit_stageC<LZ, T, M, 2, -1>(tile, tw.C, tid, nthr, ToTile{tile});
-            else r2c_post<LZ, T, M>(tile, tw.R, tid, nthr, ToA{a_plane, row0});
+            else r2c_stageC_post<LZ, T, M>(tile, tw.C, tw.R, tid, nthr, ToA{a_plane, row0});   // last stage + real post-processing
         }
     };
 
@@ -133,11 +132,10 @@ struct SlabFFT {
         int row0;
         static constexpr bool kBulk = false;
         PM_HD TileLoad load(int) const { return TileLoad{plane + (size_t)row0 * Gp, 0, CZ * Gp * (int)sizeof(T)}; }
-        static constexpr int kPhases = 4;
+        static constexpr int kPhases = 3;
         PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int nthr, T (&)[kRegs]) const {
-            if (ph == 0) c2r_pre<LZ, T, M>(RowSource{plane, row0}, tile, tw.R, tid, nthr);
-            else if (ph == 1) dit_stageA_inplace<LZ, T, M, +1>(tile, tid, nthr);
-            else if (ph == 2) dit_stageB<LZ, T, M, +1>(tile, tw.B, tid, nthr);
+            if (ph == 0) c2r_pre_stageA<LZ, T, M>(RowSource{plane, row0}, tile, tw.R, tid, nthr);   // real pre-processing + first stage
+            else if (ph == 1) dit_stageB<LZ, T, M, +1>(tile, tw.B, tid, nthr);
             else dit_stageC<LZ, T, M, 2, +1>(tile, tw.C, tid, nthr, RowSink{plane, row0});   // z_m = x_2m + i·x_2m+1
         }
     };
@@ -243,12 +241,13 @@ struct SlabFFT {
                 for (int b = tid; b < 64 * CY; b += nthr) {
                     int c, q;
                     LY::template decode<64>(b, c, q);
-                    T r[R1], im[R1];
+                    T r[R1], im[R1], wr[R1], wi[R1];
+                    tw_powers<R1>(tw.C[64 + q], wr, wi);     // ωG^(a1·q): forward stage C and, conjugated, inverse stage 1
 #pragma unroll
                     for (int a1 = 0; a1 < R1; ++a1) {
                         const V v = tile[LY::idx_s64(q, a1, c)];
                         r[a1] = v.x; im[a1] = v.y;
-                        if (a1) cmul<-1>(r[a1], im[a1], tw.C[a1 * 64 + q]);
+                        if (a1) cmul2<-1>(r[a1], im[a1], wr[a1], wi[a1]);
                     }
                     dftR<R1, -1>(r, im);
                     const int kk = kt * CY + c;
@@ -260,7 +259,13 @@ struct SlabFFT {
                         const T f = (T)factor(64 * b1 + q, sep_jk, kj2_kk2, line_nyq);
                         r[b1] *= f; im[b1] *= f;
                     }
-                    dif_stage1_regs<LY, T, G, 1, +1>(r, im, tile, tw.C, c, q);
+                    dftR<R1, +1>(r, im);
+#pragma unroll
+                    for (int b1 = 0; b1 < R1; ++b1) {
+                        if (b1) cmul2<+1>(r[b1], im[b1], wr[b1], wi[b1]);
+                        V v; v.x = r[b1]; v.y = im[b1];
+                        tile[LY::idx_s64(q, b1, c)] = v;
+                    }
                 }
             } else if (ph == 4) dif_stage2<LY, T, G, +1>(tile, tw.B, tid, nthr);
             else dif_stage3<LY, T, G, +1>(tile, tid, nthr, ToA{g, j, kt});

@@ -194,6 +194,30 @@ static double test_real(int nthr) {
             const T got = (n & 1) ? zim[c * M + n / 2] : zre[c * M + n / 2];
             err = fmax(err, fabs((double)(got - expect)) / (2.0 * M));
         }
+    // ---- the fused variants the kernels use: last stage + r2c_post, c2r_pre + first stage
+    for (int t = 0; t < nthr; ++t) dit_stageA<L, T, M, -1>(src, tile.data(), t, nthr);
+    for (int t = 0; t < nthr; ++t) dit_stageB<L, T, M, -1>(tile.data(), tw.B, t, nthr);
+    std::fill(ore.begin(), ore.end(), (T)99); std::fill(oim.begin(), oim.end(), (T)99);
+    for (int t = 0; t < nthr; ++t) r2c_stageC_post<L, T, M>(tile.data(), tw.C, tw.R, t, nthr, st);
+    for (int c = 0; c < C; ++c)
+        for (int k = 0; k <= M; ++k) {
+            if (k < M) {
+                err = fmax(err, fabs((double)(ore[c * (M + 1) + k] - Xr[c][k])));
+                err = fmax(err, fabs((double)(oim[c * (M + 1) + k] - Xi[c][k])));
+            } else {
+                err = fmax(err, fabs((double)ore[c * (M + 1) + k]) + fabs((double)oim[c * (M + 1) + k]));
+            }
+        }
+    for (int t = 0; t < nthr; ++t) c2r_pre_stageA<L, T, M>(spec, tile.data(), tw.R, t, nthr);
+    for (int t = 0; t < nthr; ++t) dit_stageB<L, T, M, +1>(tile.data(), tw.B, t, nthr);
+    std::fill(zre.begin(), zre.end(), (T)99); std::fill(zim.begin(), zim.end(), (T)99);
+    for (int t = 0; t < nthr; ++t) dit_stageC<L, T, M, 2, +1>(tile.data(), tw.C, t, nthr, stz);
+    for (int c = 0; c < C; ++c)
+        for (int n = 0; n < 2 * M; ++n) {
+            const long double expect = 2.0L * M * x[c][n] - Xr[c][M] * ((n & 1) ? -1 : 1);
+            const T got = (n & 1) ? zim[c * M + n / 2] : zre[c * M + n / 2];
+            err = fmax(err, fabs((double)(got - expect)) / (2.0 * M));
+        }
     return err;
 }
 
@@ -292,5 +316,6 @@ int main(int argc, char** argv) {
     report("real f64 M=128 C=16", test_real<double, 128, 16>(512), 1e-12);
     report("real f64 M=64  C=16", test_real<double, 64, 16>(512), 1e-12);
     report("real f32 M=256 C=16", test_real<float, 256, 16>(512), 2e-4);
+    report("real f64 M=512 C=8", test_real<double, 512, 8>(256), 1e-12);
     return fails;
 }
