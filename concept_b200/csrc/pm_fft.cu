@@ -39,12 +39,27 @@ namespace pm {
 
 using namespace fftc;
 
-constexpr int kFftThreads = 256;
+#ifndef PM_FFT2D_THREADS
+#define PM_FFT2D_THREADS 128
+#endif
+#ifndef PM_FFT2D_DOUBLE_BUFFER
+#define PM_FFT2D_DOUBLE_BUFFER 0
+#endif
+#ifndef PM_XSOLVE_THREADS
+#define PM_XSOLVE_THREADS 128
+#endif
+#ifndef PM_XSOLVE_DOUBLE_BUFFER
+#define PM_XSOLVE_DOUBLE_BUFFER 1
+#endif
+constexpr int kFftThreads = PM_XSOLVE_THREADS;     // x solve
+constexpr bool kXSolveDouble = PM_XSOLVE_DOUBLE_BUFFER != 0;
+constexpr int kFft2dThreads = PM_FFT2D_THREADS;    // 2-D transforms: small CTAs, many per SM; every warp owns a z row
+constexpr bool kFft2dDouble = PM_FFT2D_DOUBLE_BUFFER != 0;   // second tile buffer (bulk copy of the next y tile under the current one)
 #ifndef PM_FFT2D_OCC
-#define PM_FFT2D_OCC 3
+#define PM_FFT2D_OCC 4
 #endif
 #ifndef PM_XSOLVE_OCC
-#define PM_XSOLVE_OCC 2
+#define PM_XSOLVE_OCC 3
 #endif
 constexpr int kFft2dOcc = PM_FFT2D_OCC;      // CTAs per SM: independent barrier domains hide each other's LDS/DP/STS phases
 constexpr int kXSolveOcc = PM_XSOLVE_OCC;    // measured: 3 (table of Green's-function factors read from global, 85 registers) is 13 % slower
@@ -99,7 +114,7 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 // tile's dependency is met — started its copy into the other buffer.  A CTA blocks on a dependency only
 // between tiles (holding no unfinished work); dependencies point to strictly lower tickets and first-pass
 // tiles have none, so the CTA with the lowest blocked ticket can always proceed.
-template <class Job, typename V>
+template <bool DOUBLE, class Job, typename V>
 __device__ __forceinline__ void run_tiles(Job& job, unsigned* ticket, V* buf0, V* buf1, int* err) {
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ int s_next[2], s_loaded[2];
@@ -140,12 +155,14 @@ __device__ __forceinline__ void run_tiles(Job& job, unsigned* ticket, V* buf0, V
     int cur = s_next[1];
     for (int it = 0; cur >= 0; ++it) {
         const int b = it & 1;
-        V* bufc = b ? buf1 : buf0;
-        V* bufn = b ? buf0 : buf1;
+        V* bufc = (DOUBLE && b) ? buf1 : buf0;
+        V* bufn = (DOUBLE && !b) ? buf1 : buf0;
         if (tid == 0) {
+            // take the next ticket now; start its copy at once if it does not need the buffer in use (second buffer, or a
+            // tile that is read directly and only prefetched into L2) and its dependency is met
             const int nxt = fetch();
             int loaded = 0;
-            if (nxt >= 0 && ready(nxt)) {
+            if (nxt >= 0 && (DOUBLE || !job.uses_buffer(nxt)) && ready(nxt)) {
                 issue(nxt, bufn, &mbar[b ^ 1]);     // bufn: tile it−1 finished before the barrier that ended it
                 loaded = 1;
             }
@@ -169,25 +186,35 @@ __device__ __forceinline__ void run_tiles(Job& job, unsigned* ticket, V* buf0, V
     }
 }
 
-// copy the B | C (| R) tables to shared memory; visible after the first barrier of run_tiles
+// copy the twiddle tables to shared memory; visible after the first barrier of run_tiles.  The butterflies form their
+// twiddles as powers of ONE root (tw_powers), so only rows 0 … 2 of the C table are ever read (TWS ∈ {1, 2}):
+// B[64] | C rows 0-2 [192] | R[G/8 + 1]
+constexpr int kTwCRows = 3;
 template <typename V>
-__device__ __forceinline__ Twiddles<V> load_twiddles(V* smem, const void* gmem, int G, bool with_r) {
-    const int n = 64 + G + (with_r ? G / 8 + 1 : 0);
-    for (int m = threadIdx.x; m < n; m += kFftThreads) smem[m] = reinterpret_cast<const V*>(gmem)[m];
+__device__ __forceinline__ Twiddles<V> load_twiddles(V* smem, const void* gmem, int G, bool with_r, int nthr) {
+    const V* g = reinterpret_cast<const V*>(gmem);
+    const int crows = G / 64 < kTwCRows ? G / 64 : kTwCRows;
+    for (int m = threadIdx.x; m < 64 + 64 * crows; m += nthr) smem[m] = g[m];
+    if (with_r)
+        for (int m = threadIdx.x; m < G / 8 + 1; m += nthr) smem[64 + 64 * kTwCRows + m] = g[64 + G + m];
     Twiddles<V> tw;
     tw.B = smem;
     tw.C = smem + 64;
-    tw.R = smem + 64 + G;
+    tw.R = smem + 64 + 64 * kTwCRows;
     return tw;
 }
+template <int G> constexpr int smem_twiddle_entries() { return 64 + 64 * kTwCRows + G / 8 + 1; }
 
-template <class Op, typename V, typename T, int NREGS>
+template <class Op, typename V, typename T, int NREGS, int NTHR>
 __device__ __forceinline__ void run_phases(const Op& op, V* buf, const Twiddles<V>& tw) {
     T rg[NREGS];
 #pragma unroll
     for (int ph = 0; ph < Op::kPhases; ++ph) {
-        op.phase(ph, buf, tw, threadIdx.x, kFftThreads, rg);
-        if (ph + 1 < Op::kPhases) __syncthreads();
+        op.phase(ph, buf, tw, threadIdx.x, NTHR, rg);
+        if (ph + 1 < Op::kPhases) {
+            if constexpr (Op::kWarpPrivate) __syncwarp();     // the warp works on its own row: no block barrier
+            else __syncthreads();
+        }
     }
 }
 
@@ -229,7 +256,7 @@ struct Fft2dParams {
 
 template <typename T, int G, int DIR>
 struct Fft2dJob {
-    using S = SlabFFT<T, G, kFftThreads>;
+    using S = SlabFFT<T, G, kFft2dThreads>;
     using V = typename S::V;
     // forward: first pass z (kZTilesPerPlane tiles), second y;  inverse: first y, second z
     static constexpr int nA = DIR < 0 ? S::kZTilesPerPlane : S::kYTilesPerPlane;
@@ -261,6 +288,7 @@ struct Fft2dJob {
         return (p.mode == 0 && !(item >> 30)) ? p.done + ((item >> 10) & 0xfffff) : nullptr;
     }
     __device__ __forceinline__ bool is_z(int item) const { return (DIR < 0) == ((item >> 30) == 0); }
+    __device__ __forceinline__ bool uses_buffer(int item) const { return !is_z(item); }   // z tiles are read directly (L2 prefetch only)
     __device__ __forceinline__ int plane_of(int item) const { return (item >> 10) & 0xfffff; }
     __device__ __forceinline__ T* plane(int item) const {
         return reinterpret_cast<T*>(p.interior) + (size_t)plane_of(item) * G * S::Gp;
@@ -291,34 +319,34 @@ struct Fft2dJob {
         if (is_z(item)) {
             // (self-cleaning density grid: the forward z tiles nullify the rows they have consumed — plain stores;
             // bulk stores from a block of zeros in shared memory were measured slower, 1.01 vs 0.97 ms)
-            if constexpr (DIR < 0) run_phases<typename S::ZFwd, V, T, S::kRegs>(zfwd(item), buf, tw);
-            else run_phases<typename S::ZInv, V, T, S::kRegs>(zinv(item), buf, tw);
+            if constexpr (DIR < 0) run_phases<typename S::ZFwd, V, T, S::kRegs, kFft2dThreads>(zfwd(item), buf, tw);
+            else run_phases<typename S::ZInv, V, T, S::kRegs, kFft2dThreads>(zinv(item), buf, tw);
         } else {
             if constexpr (DIR < 0) {
                 // the A block is in shared memory now and nobody reads it again before the x solve rewrites
                 // it: drop its (dirty) L2 lines instead of letting them be written back to HBM
                 const typename S::YFwd op = yfwd(item);
                 const char* blk = reinterpret_cast<const char*>(op.a_tile);
-                for (int o = threadIdx.x * 128; o < G * S::CY * (int)sizeof(V); o += kFftThreads * 128)
+                for (int o = threadIdx.x * 128; o < G * S::CY * (int)sizeof(V); o += kFft2dThreads * 128)
                     asm volatile("discard.global.L2 [%0], 128;" ::"l"(__cvta_generic_to_global(blk + o)) : "memory");
-                run_phases<typename S::YFwd, V, T, S::kRegs>(op, buf, tw);
+                run_phases<typename S::YFwd, V, T, S::kRegs, kFft2dThreads>(op, buf, tw);
             } else {
-                run_phases<typename S::YInv, V, T, S::kRegs>(yinv(item), buf, tw);
+                run_phases<typename S::YInv, V, T, S::kRegs, kFft2dThreads>(yinv(item), buf, tw);
             }
         }
     }
 };
 
 template <typename T, int G, int DIR>
-__global__ void __launch_bounds__(kFftThreads, kFft2dOcc) fft2d_kernel(const __grid_constant__ Fft2dParams p) {
-    using S = SlabFFT<T, G, kFftThreads>;
+__global__ void __launch_bounds__(kFft2dThreads, kFft2dOcc) fft2d_kernel(const __grid_constant__ Fft2dParams p) {
+    using S = SlabFFT<T, G, kFft2dThreads>;
     using V = typename S::V;
     extern __shared__ __align__(128) unsigned char fft_smem[];
     V* buf0 = reinterpret_cast<V*>(fft_smem);
-    V* buf1 = buf0 + S::kBufElems;
-    const Twiddles<V> tw = load_twiddles(buf1 + S::kBufElems, p.tw, G, true);
+    V* buf1 = buf0 + (kFft2dDouble ? S::kBufElems : 0);
+    const Twiddles<V> tw = load_twiddles(buf1 + S::kBufElems, p.tw, G, true, kFft2dThreads);
     Fft2dJob<T, G, DIR> job(p, tw);
-    run_tiles(job, p.ticket, buf0, buf1, p.err);
+    run_tiles<kFft2dDouble>(job, p.ticket, buf0, buf1, p.err);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -347,6 +375,7 @@ struct XSolveJob {
     __device__ __forceinline__ const unsigned* dep(int) const { return nullptr; }
     __device__ __forceinline__ unsigned dep_need() const { return 0; }
     __device__ __forceinline__ unsigned* signal(int) const { return nullptr; }
+    __device__ __forceinline__ bool uses_buffer(int) const { return true; }
     __device__ __forceinline__ typename S::XSolve op(int item) const {
         const int jl = item / S::NKT, kt = item - jl * S::NKT;
         return typename S::XSolve{xg, j0 + jl, kt};
@@ -356,7 +385,7 @@ struct XSolveJob {
         issue_loads(o, o.nloads(), buf, bar);
     }
     __device__ __forceinline__ void process(int item, V* buf) const {
-        run_phases<typename S::XSolve, V, T, S::kRegs>(op(item), buf, tw);
+        run_phases<typename S::XSolve, V, T, S::kRegs, kFftThreads>(op(item), buf, tw);
     }
 };
 
@@ -366,9 +395,9 @@ __global__ void __launch_bounds__(kFftThreads, kXSolveOcc) xsolve2_kernel(const 
     using V = typename S::V;
     extern __shared__ __align__(128) unsigned char fft_smem[];
     V* buf0 = reinterpret_cast<V*>(fft_smem);
-    V* buf1 = buf0 + S::kYTileElems;
-    const Twiddles<V> tw = load_twiddles(buf1 + S::kYTileElems, p.tw, G, false);
-    double* sep = reinterpret_cast<double*>(buf1 + S::kYTileElems + 64 + G);
+    V* buf1 = buf0 + (kXSolveDouble ? S::kYTileElems : 0);
+    const Twiddles<V> tw = load_twiddles(buf1 + S::kYTileElems, p.tw, G, false, kFftThreads);
+    double* sep = reinterpret_cast<double*>(buf1 + S::kYTileElems + 64 + 64 * kTwCRows);
     __shared__ typename S::XGeom s_xg;
     for (int m = threadIdx.x; m < G; m += kFftThreads) sep[m] = p.xg.sep[m];
     if (threadIdx.x == 0) {
@@ -376,7 +405,7 @@ __global__ void __launch_bounds__(kFftThreads, kXSolveOcc) xsolve2_kernel(const 
         s_xg.sep = sep;
     }
     XSolveJob<T, G> job{&s_xg, tw, p.j0, p.njl};
-    run_tiles(job, p.ticket, buf0, buf1, p.err);
+    run_tiles<kXSolveDouble>(job, p.ticket, buf0, buf1, p.err);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -431,18 +460,18 @@ int make_fft2_tables(pm_ctx* c) {
 
 template <typename T, int G>
 static size_t fft2d_smem() {
-    using S = SlabFFT<T, G, kFftThreads>;
-    return sizeof(typename S::V) * ((size_t)2 * S::kBufElems + twiddle_entries<G>());
+    using S = SlabFFT<T, G, kFft2dThreads>;
+    return sizeof(typename S::V) * ((size_t)(kFft2dDouble ? 2 : 1) * S::kBufElems + smem_twiddle_entries<G>());
 }
 template <typename T, int G>
 static size_t xsolve2_smem() {
     using S = SlabFFT<T, G, kFftThreads>;
-    return sizeof(typename S::V) * ((size_t)2 * S::kYTileElems + 64 + G) + sizeof(double) * G;
+    return sizeof(typename S::V) * ((size_t)(kXSolveDouble ? 2 : 1) * S::kYTileElems + 64 + 64 * kTwCRows) + sizeof(double) * G;
 }
 
 template <typename T, int G, int DIR>
 static int launch_fft2d(pm_ctx* c, int mode) {
-    using S = SlabFFT<T, G, kFftThreads>;
+    using S = SlabFFT<T, G, kFft2dThreads>;
     Fft2dParams p;
     // one rank: the density grid cleans itself and the potential goes to `phi` (pm_internal.cuh)
     const bool self_clean = c->nranks == 1 && c->phi != nullptr;
@@ -463,7 +492,7 @@ static int launch_fft2d(pm_ctx* c, int mode) {
                                                          : ((mode == 1) == (DIR < 0) ? S::kZTilesPerPlane : S::kYTilesPerPlane));
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * kFft2dOcc);
     if (mode != 0) PM_CHECK_CUDA(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned), c->stream));
-    PM_LAUNCH((fft2d_kernel<T, G, DIR>), grid, kFftThreads, smem, c->stream, p);
+    PM_LAUNCH((fft2d_kernel<T, G, DIR>), grid, kFft2dThreads, smem, c->stream, p);
     return PM_OK;
 }
 

@@ -125,8 +125,10 @@ PM_HD void cmul(T& r, T& i, const V w) {
 // the shared-memory/L1 data pipe (ncu r01: 42 % of all LDS were twiddle loads) and have FP64 issue slots to spare.
 // Squarings for even powers, one product for odd ones: at most ⌈log₂R⌉ roundings deep (≈ 3 ulp for R = 8).
 template <int R, typename T, typename V>
-PM_HD void tw_powers(const V w, T (&pr)[R], T (&pi)[R]) {
+PM_HD void tw_powers(const V* wp, T (&pr)[R], T (&pi)[R]) {
     pr[0] = (T)1; pi[0] = (T)0;
+    if constexpr (R == 1) return;      // (the table entry may not even exist then)
+    const V w = *wp;
     if constexpr (R > 1) { pr[1] = w.x; pi[1] = w.y; }
 #pragma unroll
     for (int m = 2; m < R; ++m) {
@@ -303,7 +305,7 @@ PM_HD void dit_stageB(V* tile, const V* twB, int tid, int nthr) {
         const int b3 = u & 7, a1 = u >> 3;
         const int p0 = 64 * a1 + b3;
         T r[8], i[8], wr[8], wi[8];
-        tw_powers<8>(twB[8 + b3], wr, wi);     // ω64^(a2·b3), a2 = 0 … 7
+        tw_powers<8>(&twB[8 + b3], wr, wi);     // ω64^(a2·b3), a2 = 0 … 7
 #pragma unroll
         for (int a2 = 0; a2 < 8; ++a2) {
             const V v = tile[L::idx_s8(p0, a2, c)];
@@ -328,7 +330,7 @@ PM_HD void dit_stageC(const V* tile, const V* twC, int tid, int nthr, const Sink
         int c, q;
         L::template decode<64>(b, c, q);
         T r[R1], i[R1], wr[R1], wi[R1];
-        tw_powers<R1>(twC[TWS * 64 + q], wr, wi);     // ωN^(a1·q)
+        tw_powers<R1>(&twC[TWS * 64 + q], wr, wi);     // ωN^(a1·q)
 #pragma unroll
         for (int a1 = 0; a1 < R1; ++a1) {
             const V v = tile[L::idx_s64(q, a1, c)];
@@ -351,7 +353,7 @@ PM_HD void dif_stage1_regs(T (&r)[N / 64], T (&i)[N / 64], V* tile, const V* twC
     constexpr int R1 = N / 64;
     dftR<R1, DIR>(r, i);
     T wr[R1], wi[R1];
-    tw_powers<R1>(twC[TWS * 64 + q], wr, wi);
+    tw_powers<R1>(&twC[TWS * 64 + q], wr, wi);
 #pragma unroll
     for (int b1 = 0; b1 < R1; ++b1) {
         if (b1) cmul2<DIR>(r[b1], i[b1], wr[b1], wi[b1]);
@@ -377,7 +379,7 @@ PM_HD void dif_stage2(V* tile, const V* twB, int tid, int nthr) {
         }
         dft8<DIR>(r, i);
         T wr[8], wi[8];
-        tw_powers<8>(twB[8 + a3], wr, wi);     // ω64^(a3·b2)
+        tw_powers<8>(&twB[8 + a3], wr, wi);     // ω64^(a3·b2)
 #pragma unroll
         for (int b2 = 0; b2 < 8; ++b2) {
             if (b2) cmul2<DIR>(r[b2], i[b2], wr[b2], wi[b2]);
@@ -506,7 +508,7 @@ PM_HD void r2c_stageC_post(const V* tile, const V* twC, const V* twR, int tid, i
         T ar[R1], ai[R1], br[R1], bi[R1];
         {
             T wr[R1], wi[R1];
-            tw_powers<R1>(twC[2 * 64 + qa], wr, wi);     // ωM^(a1·qa) = ωG^(2·a1·qa)
+            tw_powers<R1>(&twC[2 * 64 + qa], wr, wi);     // ωM^(a1·qa) = ωG^(2·a1·qa)
 #pragma unroll
             for (int a1 = 0; a1 < R1; ++a1) {
                 const V v = tile[L::idx_s64(qa, a1, c)];
@@ -514,7 +516,7 @@ PM_HD void r2c_stageC_post(const V* tile, const V* twC, const V* twR, int tid, i
                 if (a1) cmul2<-1>(ar[a1], ai[a1], wr[a1], wi[a1]);
             }
             dftR<R1, -1>(ar, ai);
-            tw_powers<R1>(twC[2 * 64 + qb], wr, wi);
+            tw_powers<R1>(&twC[2 * 64 + qb], wr, wi);
 #pragma unroll
             for (int a1 = 0; a1 < R1; ++a1) {
                 const V v = tile[L::idx_s64(qb, a1, c)];

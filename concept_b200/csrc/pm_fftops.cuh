@@ -58,10 +58,10 @@ struct SlabFFT {
     static constexpr int Gc = M + 1;
     static constexpr int Gp = 2 * Gc;
     static constexpr int CY = 64 / (int)sizeof(V);   // columns per y/x tile: 4 in fp64, 8 in fp32
-    static constexpr int CZ = 8;                     // rows per z tile
+    static constexpr int CZ = NTHR / 32;             // rows per z tile: every warp owns one whole row (no block barrier inside)
     static constexpr int NKT = M / CY;               // column tiles
     using LY = ColSwz<CY>;
-    using LZ = RowSwz<M, CZ, Gc>;
+    using LZ = RowSwz<M, 1, Gc>;                     // the warp's private row
     static constexpr int kYTileElems = G * CY;
     static constexpr int kZTileElems = CZ * M;
     static constexpr int kBufElems = (kZTileElems > kYTileElems) ? kZTileElems : kYTileElems;
@@ -74,18 +74,18 @@ struct SlabFFT {
     static PM_HD size_t a_index(int il, int kt, int j, int c) { return (((size_t)il * NKT + kt) * G + j) * CY + c; }
     static PM_HD size_t b_index(int kt, int j, int il, int c, int nxl) { return (((size_t)kt * G + j) * nxl + il) * CY + c; }
 
-    struct RowSink {     // complex slot k of row c of a padded real plane
-        T* plane; int row0;
-        PM_HD void operator()(int c, int k, T r, T i) const {
+    struct RowSink {     // complex slot k of one row of a padded real plane
+        T* plane; int row;
+        PM_HD void operator()(int, int k, T r, T i) const {
             V v; v.x = r; v.y = i;
-            reinterpret_cast<V*>(plane + (size_t)(row0 + c) * Gp)[k] = v;
+            reinterpret_cast<V*>(plane + (size_t)row * Gp)[k] = v;
         }
     };
 
-    struct RowSource {     // complex element k of row c, straight from global memory (L2: the rows were prefetched)
-        const T* plane; int row0;
-        PM_HD V operator()(int c, int k) const {
-            return ld_stream(reinterpret_cast<const V*>(plane + (size_t)(row0 + c) * Gp) + k);
+    struct RowSource {     // complex element k of one row, straight from global memory (L2: the rows were prefetched)
+        const T* plane; int row;
+        PM_HD V operator()(int, int k) const {
+            return ld_stream(reinterpret_cast<const V*>(plane + (size_t)row * Gp) + k);
         }
     };
 
@@ -98,31 +98,30 @@ struct SlabFFT {
         int row0;         // first of the CZ rows
         bool clear;       // nullify the rows once they are read (self-cleaning density grid)
         static constexpr bool kBulk = false;
+        static constexpr bool kWarpPrivate = true;      // phases are separated by __syncwarp(), not by a block barrier
         PM_HD TileLoad load(int) const { return TileLoad{plane + (size_t)row0 * Gp, 0, CZ * Gp * (int)sizeof(T)}; }
-        struct ToTile {
-            V* tile;
-            PM_HD void operator()(int c, int idx, T r, T i) const { V v; v.x = r; v.y = i; tile[LZ::idx(idx, c)] = v; }
-        };
         struct ToA {
-            V* a_plane; int row0;
-            PM_HD void operator()(int c, int k, T r, T i) const {
+            V* a_plane; int row;
+            PM_HD void operator()(int, int k, T r, T i) const {
                 if (k >= M) return;     // the Nyquist column is not stored
                 V v; v.x = r; v.y = i;
-                a_plane[((size_t)(k / CY) * G + row0 + c) * CY + (k % CY)] = v;
+                a_plane[((size_t)(k / CY) * G + row) * CY + (k % CY)] = v;
             }
         };
         static constexpr int kPhases = 3;
-        PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int nthr, T (&)[kRegs]) const {
-            if (ph == 0) dit_stageA<LZ, T, M, -1>(RowSource{plane, row0}, tile, tid, nthr);
+        PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int, T (&)[kRegs]) const {
+            const int warp = tid >> 5, lane = tid & 31, row = row0 + warp;
+            V* mine = tile + warp * M;
+            if (ph == 0) dit_stageA<LZ, T, M, -1>(RowSource{plane, row}, mine, lane, 32);
             else if (ph == 1) {
-                if (clear) {     // every thread of the tile has consumed its rows by now
+                if (clear) {     // every lane of the warp has consumed the row by now
                     V zero; zero.x = 0; zero.y = 0;
-                    V* rows = reinterpret_cast<V*>(plane + (size_t)row0 * Gp);
-                    for (int e = tid; e < CZ * Gc; e += nthr) rows[e] = zero;
+                    V* cells = reinterpret_cast<V*>(plane + (size_t)row * Gp);
+                    for (int e = lane; e < Gc; e += 32) cells[e] = zero;
                 }
-                dit_stageB<LZ, T, M, -1>(tile, tw.B, tid, nthr);
+                dit_stageB<LZ, T, M, -1>(mine, tw.B, lane, 32);
             }
-            else r2c_stageC_post<LZ, T, M>(tile, tw.C, tw.R, tid, nthr, ToA{a_plane, row0});   // last stage + real post-processing
+            else r2c_stageC_post<LZ, T, M>(mine, tw.C, tw.R, lane, 32, ToA{a_plane, row});   // last stage + real post-processing
         }
     };
 
@@ -131,12 +130,15 @@ struct SlabFFT {
         T* plane;
         int row0;
         static constexpr bool kBulk = false;
+        static constexpr bool kWarpPrivate = true;
         PM_HD TileLoad load(int) const { return TileLoad{plane + (size_t)row0 * Gp, 0, CZ * Gp * (int)sizeof(T)}; }
         static constexpr int kPhases = 3;
-        PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int nthr, T (&)[kRegs]) const {
-            if (ph == 0) c2r_pre_stageA<LZ, T, M>(RowSource{plane, row0}, tile, tw.R, tid, nthr);   // real pre-processing + first stage
-            else if (ph == 1) dit_stageB<LZ, T, M, +1>(tile, tw.B, tid, nthr);
-            else dit_stageC<LZ, T, M, 2, +1>(tile, tw.C, tid, nthr, RowSink{plane, row0});   // z_m = x_2m + i·x_2m+1
+        PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int, T (&)[kRegs]) const {
+            const int warp = tid >> 5, lane = tid & 31, row = row0 + warp;
+            V* mine = tile + warp * M;
+            if (ph == 0) c2r_pre_stageA<LZ, T, M>(RowSource{plane, row}, mine, tw.R, lane, 32);   // real pre-processing + first stage
+            else if (ph == 1) dit_stageB<LZ, T, M, +1>(mine, tw.B, lane, 32);
+            else dit_stageC<LZ, T, M, 2, +1>(mine, tw.C, lane, 32, RowSink{plane, row});   // z_m = x_2m + i·x_2m+1
         }
     };
 
@@ -146,6 +148,7 @@ struct SlabFFT {
         V* b;             // this rank's B
         int il, kt, nxl;
         static constexpr bool kBulk = true;
+        static constexpr bool kWarpPrivate = false;
         PM_HD TileLoad load(int) const { return TileLoad{a_tile, 0, G * CY * (int)sizeof(V)}; }
         struct ToB {
             V* b; int il, kt, nxl;
@@ -170,6 +173,7 @@ struct SlabFFT {
         T* plane;         // padded real plane, written through its complex view [G][Gc]
         int kt;
         static constexpr bool kBulk = true;
+        static constexpr bool kWarpPrivate = false;
         PM_HD TileLoad load(int) const { return TileLoad{a_tile, 0, G * CY * (int)sizeof(V)}; }
         struct ToRows {
             T* plane; int kt;
@@ -202,6 +206,7 @@ struct SlabFFT {
         int j;        // global j row
         int kt;       // column tile
         static constexpr bool kBulk = true;
+        static constexpr bool kWarpPrivate = false;
         PM_HD int nloads() const { return g->nranks; }
         PM_HD TileLoad load(int r) const {
             const int nxl = 1 << g->nxl_shift;
@@ -242,7 +247,7 @@ struct SlabFFT {
                     int c, q;
                     LY::template decode<64>(b, c, q);
                     T r[R1], im[R1], wr[R1], wi[R1];
-                    tw_powers<R1>(tw.C[64 + q], wr, wi);     // ωG^(a1·q): forward stage C and, conjugated, inverse stage 1
+                    tw_powers<R1>(&tw.C[64 + q], wr, wi);     // ωG^(a1·q): forward stage C and, conjugated, inverse stage 1
 #pragma unroll
                     for (int a1 = 0; a1 < R1; ++a1) {
                         const V v = tile[LY::idx_s64(q, a1, c)];
