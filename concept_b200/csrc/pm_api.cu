@@ -145,7 +145,7 @@ int pm_create(pm_ctx** out, int gridsize, double boxsize, int grid_dtype, int ra
     };
     // the hand-written transform (pm_fft.cu) keeps two intermediate copies of the Fourier slab behind the grid
     size_t alloc_bytes = c->real_elems * es;
-    if (gridsize == 128 || gridsize == 256 || gridsize == 512) {
+    if (gridsize == 128 || gridsize == 256 || gridsize == 512 || gridsize == 1024) {
         const size_t layout_bytes = (size_t)g.nxl * (gridsize / 2) * gridsize * 2 * es;
         c->f2_off_a = (alloc_bytes + 255) / 256 * 256;
         c->f2_off_b = c->f2_off_a + (layout_bytes + 255) / 256 * 256;

@@ -51,9 +51,6 @@ using namespace fftc;
 #ifndef PM_XSOLVE_DOUBLE_BUFFER
 #define PM_XSOLVE_DOUBLE_BUFFER 1
 #endif
-constexpr int kFftThreads = PM_XSOLVE_THREADS;     // x solve
-constexpr bool kXSolveDouble = PM_XSOLVE_DOUBLE_BUFFER != 0;
-constexpr int kFft2dThreads = PM_FFT2D_THREADS;    // 2-D transforms: small CTAs, many per SM; every warp owns a z row
 constexpr bool kFft2dDouble = PM_FFT2D_DOUBLE_BUFFER != 0;   // second tile buffer (bulk copy of the next y tile under the current one)
 #ifndef PM_FFT2D_OCC
 #define PM_FFT2D_OCC 4
@@ -61,8 +58,19 @@ constexpr bool kFft2dDouble = PM_FFT2D_DOUBLE_BUFFER != 0;   // second tile buff
 #ifndef PM_XSOLVE_OCC
 #define PM_XSOLVE_OCC 3
 #endif
-constexpr int kFft2dOcc = PM_FFT2D_OCC;      // CTAs per SM: independent barrier domains hide each other's LDS/DP/STS phases
-constexpr int kXSolveOcc = PM_XSOLVE_OCC;    // measured: 3 (table of Green's-function factors read from global, 85 registers) is 13 % slower
+// Kernel shapes per grid size.  Small CTAs, several per SM (independent barrier domains hide each other's LDS / FP64 / STS
+// phases); a y or x tile is G × 64 bytes of columns, so G = 1024 doubles the tile (64 KB) and takes twice the threads.
+// Measured on B200 at 512³ fp64 (profiles/r02_fft_config_sweep.md): 2-D transforms 128 threads × 4 CTAs, one tile
+// buffer; x solve 128 threads × 3 CTAs, two tile buffers.
+template <int G>
+struct FftCfg {
+    static constexpr bool kBig = G >= 1024;
+    static constexpr int kThreads2d = kBig ? 256 : PM_FFT2D_THREADS;     // every warp owns a z row
+    static constexpr int kOcc2d = kBig ? 2 : PM_FFT2D_OCC;
+    static constexpr int kThreadsX = kBig ? 256 : PM_XSOLVE_THREADS;
+    static constexpr int kOccX = kBig ? 1 : PM_XSOLVE_OCC;      // radix-16 stage: 16 complex values + their twiddles per thread
+    static constexpr bool kDoubleX = kBig ? true : (PM_XSOLVE_DOUBLE_BUFFER != 0);
+};
 
 // ---- PTX helpers: mbarrier + bulk asynchronous copy ----------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -256,7 +264,7 @@ struct Fft2dParams {
 
 template <typename T, int G, int DIR>
 struct Fft2dJob {
-    using S = SlabFFT<T, G, kFft2dThreads>;
+    using S = SlabFFT<T, G, FftCfg<G>::kThreads2d>;
     using V = typename S::V;
     // forward: first pass z (kZTilesPerPlane tiles), second y;  inverse: first y, second z
     static constexpr int nA = DIR < 0 ? S::kZTilesPerPlane : S::kYTilesPerPlane;
@@ -319,32 +327,32 @@ struct Fft2dJob {
         if (is_z(item)) {
             // (self-cleaning density grid: the forward z tiles nullify the rows they have consumed — plain stores;
             // bulk stores from a block of zeros in shared memory were measured slower, 1.01 vs 0.97 ms)
-            if constexpr (DIR < 0) run_phases<typename S::ZFwd, V, T, S::kRegs, kFft2dThreads>(zfwd(item), buf, tw);
-            else run_phases<typename S::ZInv, V, T, S::kRegs, kFft2dThreads>(zinv(item), buf, tw);
+            if constexpr (DIR < 0) run_phases<typename S::ZFwd, V, T, S::kRegs, FftCfg<G>::kThreads2d>(zfwd(item), buf, tw);
+            else run_phases<typename S::ZInv, V, T, S::kRegs, FftCfg<G>::kThreads2d>(zinv(item), buf, tw);
         } else {
             if constexpr (DIR < 0) {
                 // the A block is in shared memory now and nobody reads it again before the x solve rewrites
                 // it: drop its (dirty) L2 lines instead of letting them be written back to HBM
                 const typename S::YFwd op = yfwd(item);
                 const char* blk = reinterpret_cast<const char*>(op.a_tile);
-                for (int o = threadIdx.x * 128; o < G * S::CY * (int)sizeof(V); o += kFft2dThreads * 128)
+                for (int o = threadIdx.x * 128; o < G * S::CY * (int)sizeof(V); o += FftCfg<G>::kThreads2d * 128)
                     asm volatile("discard.global.L2 [%0], 128;" ::"l"(__cvta_generic_to_global(blk + o)) : "memory");
-                run_phases<typename S::YFwd, V, T, S::kRegs, kFft2dThreads>(op, buf, tw);
+                run_phases<typename S::YFwd, V, T, S::kRegs, FftCfg<G>::kThreads2d>(op, buf, tw);
             } else {
-                run_phases<typename S::YInv, V, T, S::kRegs, kFft2dThreads>(yinv(item), buf, tw);
+                run_phases<typename S::YInv, V, T, S::kRegs, FftCfg<G>::kThreads2d>(yinv(item), buf, tw);
             }
         }
     }
 };
 
 template <typename T, int G, int DIR>
-__global__ void __launch_bounds__(kFft2dThreads, kFft2dOcc) fft2d_kernel(const __grid_constant__ Fft2dParams p) {
-    using S = SlabFFT<T, G, kFft2dThreads>;
+__global__ void __launch_bounds__(FftCfg<G>::kThreads2d, FftCfg<G>::kOcc2d) fft2d_kernel(const __grid_constant__ Fft2dParams p) {
+    using S = SlabFFT<T, G, FftCfg<G>::kThreads2d>;
     using V = typename S::V;
     extern __shared__ __align__(128) unsigned char fft_smem[];
     V* buf0 = reinterpret_cast<V*>(fft_smem);
     V* buf1 = buf0 + (kFft2dDouble ? S::kBufElems : 0);
-    const Twiddles<V> tw = load_twiddles(buf1 + S::kBufElems, p.tw, G, true, kFft2dThreads);
+    const Twiddles<V> tw = load_twiddles(buf1 + S::kBufElems, p.tw, G, true, FftCfg<G>::kThreads2d);
     Fft2dJob<T, G, DIR> job(p, tw);
     run_tiles<kFft2dDouble>(job, p.ticket, buf0, buf1, p.err);
 }
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(kFft2dThreads, kFft2dOcc) fft2d_kernel(const _
 // ---------------------------------------------------------------------------------------------
 template <typename T, int G>
 struct XSolveKParams {
-    typename SlabFFT<T, G, kFftThreads>::XGeom xg;
+    typename SlabFFT<T, G, FftCfg<G>::kThreadsX>::XGeom xg;
     const void* tw;
     int j0, njl;
     unsigned* ticket;
@@ -363,7 +371,7 @@ struct XSolveKParams {
 
 template <typename T, int G>
 struct XSolveJob {
-    using S = SlabFFT<T, G, kFftThreads>;
+    using S = SlabFFT<T, G, FftCfg<G>::kThreadsX>;
     using V = typename S::V;
     const typename S::XGeom* xg;   // in shared memory
     Twiddles<V> tw;
@@ -385,13 +393,15 @@ struct XSolveJob {
         issue_loads(o, o.nloads(), buf, bar);
     }
     __device__ __forceinline__ void process(int item, V* buf) const {
-        run_phases<typename S::XSolve, V, T, S::kRegs, kFftThreads>(op(item), buf, tw);
+        run_phases<typename S::XSolve, V, T, S::kRegs, FftCfg<G>::kThreadsX>(op(item), buf, tw);
     }
 };
 
 template <typename T, int G>
-__global__ void __launch_bounds__(kFftThreads, kXSolveOcc) xsolve2_kernel(const __grid_constant__ XSolveKParams<T, G> p) {
-    using S = SlabFFT<T, G, kFftThreads>;
+__global__ void __launch_bounds__(FftCfg<G>::kThreadsX, FftCfg<G>::kOccX) xsolve2_kernel(const __grid_constant__ XSolveKParams<T, G> p) {
+    using S = SlabFFT<T, G, FftCfg<G>::kThreadsX>;
+    constexpr bool kXSolveDouble = FftCfg<G>::kDoubleX;
+    constexpr int kFftThreads = FftCfg<G>::kThreadsX;
     using V = typename S::V;
     extern __shared__ __align__(128) unsigned char fft_smem[];
     V* buf0 = reinterpret_cast<V*>(fft_smem);
@@ -413,7 +423,7 @@ __global__ void __launch_bounds__(kFftThreads, kXSolveOcc) xsolve2_kernel(const 
 // ---------------------------------------------------------------------------------------------
 bool fft2_supported(const pm_ctx* c) {
     const int G = c->g.G;
-    if (!(G == 128 || G == 256 || G == 512)) return false;
+    if (!(G == 128 || G == 256 || G == 512 || G == 1024)) return false;
     if (c->nranks > kMaxFftPeers) return false;
     if (c->g.nxl & (c->g.nxl - 1)) return false;   // slabs must be a power of two thick
     if (c->g.nxl >= (1 << 20)) return false;
@@ -442,7 +452,7 @@ static int make_fft2_tables_t(pm_ctx* c) {
 
 int make_fft2_tables(pm_ctx* c) {
     const int G = c->g.G;
-    if (!(G == 128 || G == 256 || G == 512)) return PM_OK;
+    if (!(G == 128 || G == 256 || G == 512 || G == 1024)) return PM_OK;
     PM_TRY(c->dtype == PM_GRID_F64 ? make_fft2_tables_t<double>(c) : make_fft2_tables_t<float>(c));
     // counters: [0] ticket fwd, [1] ticket x, [2] ticket inv, [3] unused, [4 …) done fwd, then done inv;
     // one more entry after those f2_nctr: the sticky error flag
@@ -460,18 +470,18 @@ int make_fft2_tables(pm_ctx* c) {
 
 template <typename T, int G>
 static size_t fft2d_smem() {
-    using S = SlabFFT<T, G, kFft2dThreads>;
+    using S = SlabFFT<T, G, FftCfg<G>::kThreads2d>;
     return sizeof(typename S::V) * ((size_t)(kFft2dDouble ? 2 : 1) * S::kBufElems + smem_twiddle_entries<G>());
 }
 template <typename T, int G>
 static size_t xsolve2_smem() {
-    using S = SlabFFT<T, G, kFftThreads>;
-    return sizeof(typename S::V) * ((size_t)(kXSolveDouble ? 2 : 1) * S::kYTileElems + 64 + 64 * kTwCRows) + sizeof(double) * G;
+    using S = SlabFFT<T, G, FftCfg<G>::kThreadsX>;
+    return sizeof(typename S::V) * ((size_t)(FftCfg<G>::kDoubleX ? 2 : 1) * S::kYTileElems + 64 + 64 * kTwCRows) + sizeof(double) * G;
 }
 
 template <typename T, int G, int DIR>
 static int launch_fft2d(pm_ctx* c, int mode) {
-    using S = SlabFFT<T, G, kFft2dThreads>;
+    using S = SlabFFT<T, G, FftCfg<G>::kThreads2d>;
     Fft2dParams p;
     // one rank: the density grid cleans itself and the potential goes to `phi` (pm_internal.cuh)
     const bool self_clean = c->nranks == 1 && c->phi != nullptr;
@@ -490,15 +500,15 @@ static int launch_fft2d(pm_ctx* c, int mode) {
     PM_CHECK_CUDA(cudaFuncSetAttribute(fft2d_kernel<T, G, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (int64_t)c->g.nxl * (mode == 0 ? S::kZTilesPerPlane + S::kYTilesPerPlane
                                                          : ((mode == 1) == (DIR < 0) ? S::kZTilesPerPlane : S::kYTilesPerPlane));
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * kFft2dOcc);
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * FftCfg<G>::kOcc2d);
     if (mode != 0) PM_CHECK_CUDA(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned), c->stream));
-    PM_LAUNCH((fft2d_kernel<T, G, DIR>), grid, kFft2dThreads, smem, c->stream, p);
+    PM_LAUNCH((fft2d_kernel<T, G, DIR>), grid, FftCfg<G>::kThreads2d, smem, c->stream, p);
     return PM_OK;
 }
 
 template <typename T, int G>
 static int launch_xsolve2(pm_ctx* c, double prefactor) {
-    using S = SlabFFT<T, G, kFftThreads>;
+    using S = SlabFFT<T, G, FftCfg<G>::kThreadsX>;
     using V = typename S::V;
     const Geom& g = c->g;
     XSolveKParams<T, G> p;
@@ -521,8 +531,8 @@ static int launch_xsolve2(pm_ctx* c, double prefactor) {
     const size_t smem = xsolve2_smem<T, G>();
     PM_CHECK_CUDA(cudaFuncSetAttribute(xsolve2_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (int64_t)g.njl * S::NKT;
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * kXSolveOcc);
-    PM_LAUNCH((xsolve2_kernel<T, G>), grid, kFftThreads, smem, c->stream, p);
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * FftCfg<G>::kOccX);
+    PM_LAUNCH((xsolve2_kernel<T, G>), grid, FftCfg<G>::kThreadsX, smem, c->stream, p);
     return PM_OK;
 }
 
@@ -572,7 +582,8 @@ int solve_fft2(pm_ctx* c, double prefactor, int deconv_order, double gauss, bool
     switch (c->g.G) {
         case 128: s = f64 ? solve_fft2_tg<double, 128>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 128>(c, prefactor, l2_fused, stage); break;
         case 256: s = f64 ? solve_fft2_tg<double, 256>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 256>(c, prefactor, l2_fused, stage); break;
-        default:  s = f64 ? solve_fft2_tg<double, 512>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 512>(c, prefactor, l2_fused, stage); break;
+        case 512: s = f64 ? solve_fft2_tg<double, 512>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 512>(c, prefactor, l2_fused, stage); break;
+        default:  s = f64 ? solve_fft2_tg<double, 1024>(c, prefactor, l2_fused, stage) : solve_fft2_tg<float, 1024>(c, prefactor, l2_fused, stage); break;
     }
     if (s == PM_OK && c->nranks == 1 && c->phi != nullptr) {
         if (stage == 0 || stage == 1) c->real_is_zero = true;     // the forward z pass has nullified what it read

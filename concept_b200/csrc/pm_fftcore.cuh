@@ -103,11 +103,54 @@ PM_HD void dft8(T (&r)[8], T (&i)[8]) {
     r[3] = b6r + b7r; i[3] = b6i + b7i; r[7] = b6r - b7r; i[7] = b6i - b7i;
 }
 
+// 16 points as 4 × 4: n = 4·n1 + n2, k = k1 + 4·k2; 4-point transforms over n1, twiddles ω16^(n2·k1), 4-point transforms over n2
+template <int DIR, typename T>
+PM_HD void dft16(T (&r)[16], T (&i)[16]) {
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173;   // cos, sin of π/8
+    const T h = (T)0.70710678118654752440;
+    T yr[4][4], yi[4][4];      // [n2][k1]
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        T ar[4], ai[4];
+#pragma unroll
+        for (int n1 = 0; n1 < 4; ++n1) { ar[n1] = r[4 * n1 + n2]; ai[n1] = i[4 * n1 + n2]; }
+        dft4<DIR>(ar, ai);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) { yr[n2][k1] = ar[k1]; yi[n2][k1] = ai[k1]; }
+    }
+    // ω16^m = (cos(mπ/8), ∓sin(mπ/8)) for DIR = ∓1; m = n2·k1
+    auto tw = [&](T& xr, T& xi, T wr, T ws) {      // multiply by (wr, DIR < 0 ? −ws : +ws)
+        const T wi = DIR < 0 ? -ws : ws;
+        const T t = fma_(xr, wr, -(xi * wi));
+        xi = fma_(xr, wi, xi * wr);
+        xr = t;
+    };
+    tw(yr[1][1], yi[1][1], c1, s1);     // m = 1
+    tw(yr[1][2], yi[1][2], h, h);       // 2
+    tw(yr[1][3], yi[1][3], s1, c1);     // 3
+    tw(yr[2][1], yi[2][1], h, h);       // 2
+    tw(yr[2][2], yi[2][2], (T)0, (T)1); // 4
+    tw(yr[2][3], yi[2][3], -h, h);      // 6
+    tw(yr[3][1], yi[3][1], s1, c1);     // 3
+    tw(yr[3][2], yi[3][2], -h, h);      // 6
+    tw(yr[3][3], yi[3][3], -c1, -s1);   // 9: cos(9π/8) = −cos(π/8), sin(9π/8) = −sin(π/8)
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        T ar[4], ai[4];
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) { ar[n2] = yr[n2][k1]; ai[n2] = yi[n2][k1]; }
+        dft4<DIR>(ar, ai);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) { r[k1 + 4 * k2] = ar[k2]; i[k1 + 4 * k2] = ai[k2]; }
+    }
+}
+
 template <int R, int DIR, typename T>
 PM_HD void dftR(T (&r)[R], T (&i)[R]) {
     if constexpr (R == 2) dft2<DIR>(r, i);
     else if constexpr (R == 4) dft4<DIR>(r, i);
     else if constexpr (R == 8) dft8<DIR>(r, i);
+    else if constexpr (R == 16) dft16<DIR>(r, i);
     // R == 1: identity
 }
 

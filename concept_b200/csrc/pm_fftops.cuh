@@ -69,7 +69,7 @@ struct SlabFFT {
     static constexpr int kYTilesPerPlane = NKT;
     static constexpr int kNbtY = ((G / 8) * CY + NTHR - 1) / NTHR;            // first-stage butterflies per thread, y/x tiles
     static constexpr int kRegs = 16 * kNbtY;
-    static_assert(G % 64 == 0 && M % 64 == 0 && G / 64 <= 8, "G must be 128, 256 or 512");
+    static_assert(G % 64 == 0 && M % 64 == 0 && G / 64 <= 16, "G must be 128, 256, 512 or 1024");
 
     static PM_HD size_t a_index(int il, int kt, int j, int c) { return (((size_t)il * NKT + kt) * G + j) * CY + c; }
     static PM_HD size_t b_index(int kt, int j, int il, int c, int nxl) { return (((size_t)kt * G + j) * nxl + il) * CY + c; }

@@ -140,8 +140,8 @@ class PMContext:
 
     @property
     def hand_fft_available(self):
-        """True when pm_solve_fused runs the hand-written slab transform (G ∈ {128, 256, 512})."""
-        return self.gridsize in (128, 256, 512) and self.fused_solve_available
+        """True when pm_solve_fused runs the hand-written slab transform (G ∈ {128, 256, 512, 1024})."""
+        return self.gridsize in (128, 256, 512, 1024) and self.fused_solve_available
 
     @property
     def fused_solve_available(self):

@@ -304,6 +304,7 @@ int main(int argc, char** argv) {
         printf("%-40s max err %.3e %s\n", name, err, err < tol ? "ok" : "FAIL");
         if (!(err < tol)) ++fails;
     };
+    report("col f64 N=1024 C=4 nthr=256", test_complex<double, 1024, 4, false>(256), 1e-12);
     report("col f64 N=512 C=8  nthr=512", test_complex<double, 512, 8, false>(512), 1e-12);
     report("col f64 N=256 C=8  nthr=512", test_complex<double, 256, 8, false>(512), 1e-12);
     report("col f64 N=128 C=8  nthr=512", test_complex<double, 128, 8, false>(512), 1e-12);
