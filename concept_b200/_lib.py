@@ -75,6 +75,7 @@ SIGNATURES = {
     'pm_exchange_rungs': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64]),
     'pm_shortrange': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, POINTER(c_double), c_int, c_double,
                               c_void_p, c_int, c_double, c_void_p]),
+    'pm_shortrange_stats': (c_int, [c_void_p, c_int, POINTER(c_int64), POINTER(c_int64)]),
     'pm_apply_dmom': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, POINTER(c_double), c_int, c_int]),
     'pm_assign_rungs': (c_int, [c_void_p, c_void_p, c_int64, c_double, c_int, c_void_p, c_void_p, POINTER(c_int64)]),
     'pm_flag_rung_jumps': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_double, c_double,

@@ -60,6 +60,17 @@ def allreduce_sum(value):
     return float(t.item())
 
 
+def allreduce_ints(values):
+    """Element-wise sum of a list of python ints over the ranks (rung populations, flags)."""
+    if nprocs == 1:
+        return [int(v) for v in values]
+    import torch.distributed as dist
+    dev = torch.device('cuda', local_rank) if dist.get_backend() == 'nccl' else torch.device('cpu')
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    return [int(v) for v in t.tolist()]
+
+
 def allgather(obj):
     if nprocs == 1:
         return [obj]

@@ -180,6 +180,7 @@ struct pm_ctx {
     size_t sr_bytes;
     void* sr_tmp;
     size_t sr_tmp_bytes;
+    bool sr_want_stats;       // the pair kernel counts pairs and candidates (pm_shortrange_stats)
     // pm_kick_long_host: copy streams and events of the chunked H2D / compute / D2H pipeline
     cudaStream_t s_h2d, s_d2h;
     cudaEvent_t ev_pipe[3 * 16];

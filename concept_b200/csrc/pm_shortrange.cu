@@ -12,148 +12,329 @@
 //   get_rung / assign_rungs / flag_rung_jumps / apply_rung_jumps   species.py:2340-2545
 #include "pm_internal.cuh"
 
+#include <algorithm>
+#include <cmath>
+
 #include <cub/device/device_scan.cuh>
 
 namespace pm {
 
+// Cell list: cells of side ≥ range/S (S = 2 when the box allows it), z fastest, so that the (2S+1) cells of a z run are one
+// contiguous stretch of the cell-sorted positions.  One rank: cells cover the periodic box in all three dimensions.  Several
+// ranks: in x the cells cover the slab plus one `range` of read-only ghost particles on either side (the analogue of
+// sendrecv_component with tile selection, interactions.py:518-590, communication.py:847-1175); ghosts that come across the
+// periodic boundary arrive already shifted by ±L, so x needs no minimum image there.
 struct CellGeom {
-    int nc;             // cells per side
-    double inv_cell;    // nc / L
+    int ncx, nc;            // cells along x, cells along y and z
+    int S;                  // neighbour reach in cells
+    int periodic_x;         // one rank: x wraps like y and z
+    double inv_cell_x, inv_cell;
+    double x_origin;        // x of the lower edge of cell 0
     double L;
 };
 
-__device__ __forceinline__ int cell_coord(double x, const CellGeom& g) {
-    int c = (int)(x * g.inv_cell);
+__device__ __forceinline__ int cell_1d(double u, double inv_cell, int n) {
+    int c = (int)(u * inv_cell);
     if (c < 0) c = 0;
-    if (c >= g.nc) c = g.nc - 1;
+    if (c >= n) c = n - 1;
     return c;
+}
+__device__ __forceinline__ int cell_index(double x, double y, double z, const CellGeom& g) {
+    return (cell_1d(x - g.x_origin, g.inv_cell_x, g.ncx) * g.nc + cell_1d(y, g.inv_cell, g.nc)) * g.nc + cell_1d(z, g.inv_cell, g.nc);
+}
+
+// the particles of the pair kernel: local ones followed by the ghosts of the lower and the upper neighbour
+struct SrParticles {
+    const double* pos;                      // local, AoS
+    int64_t n;
+    const double* ghost[2];                 // ghost positions (AoS), NULL on one rank
+    const unsigned long long* nghost[2];    // their counts (device: written by the neighbours)
+    int64_t ghost_cap;
+};
+__device__ __forceinline__ int64_t sr_total(const SrParticles& p, int64_t* g0, int64_t* g1) {
+    *g0 = p.ghost[0] ? min((int64_t)*p.nghost[0], p.ghost_cap) : 0;
+    *g1 = p.ghost[1] ? min((int64_t)*p.nghost[1], p.ghost_cap) : 0;
+    return p.n + *g0 + *g1;
+}
+__device__ __forceinline__ const double* sr_pos(const SrParticles& p, int64_t i, int64_t g0) {
+    if (i < p.n) return p.pos + 3 * i;
+    i -= p.n;
+    if (i < g0) return p.ghost[0] + 3 * i;
+    return p.ghost[1] + 3 * (i - g0);
 }
 
 __global__ void __launch_bounds__(256)
-cell_count_kernel(const double* __restrict__ pos, int64_t n, CellGeom g, int* __restrict__ cell_of,
-                  int* __restrict__ count) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (cell_coord(pos[3 * i], g) * g.nc + cell_coord(pos[3 * i + 1], g)) * g.nc + cell_coord(pos[3 * i + 2], g);
+cell_count_kernel(SrParticles p, CellGeom g, int* __restrict__ cell_of, int* __restrict__ count) {
+    int64_t g0, g1;
+    const int64_t total = sr_total(p, &g0, &g1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* q = sr_pos(p, i, g0);
+        const int c = cell_index(q[0], q[1], q[2], g);
         cell_of[i] = c;
         atomicAdd(&count[c], 1);
     }
 }
 
 __global__ void __launch_bounds__(256)
-cell_scatter_kernel(const double* __restrict__ pos, int64_t n, const int* __restrict__ cell_of,
-                    const int* __restrict__ offset, int* __restrict__ cursor, double* __restrict__ pos_s,
-                    int* __restrict__ idx_s) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+cell_scatter_kernel(SrParticles p, const int* __restrict__ cell_of, const int* __restrict__ offset, int* __restrict__ cursor,
+                    double* __restrict__ pos_s, int* __restrict__ idx_s) {
+    int64_t g0, g1;
+    const int64_t total = sr_total(p, &g0, &g1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* q = sr_pos(p, i, g0);
         const int c = cell_of[i];
         const int slot = offset[c] + atomicAdd(&cursor[c], 1);
-        pos_s[3 * slot] = pos[3 * i];
-        pos_s[3 * slot + 1] = pos[3 * i + 1];
-        pos_s[3 * slot + 2] = pos[3 * i + 2];
-        idx_s[slot] = (int)i;
+        pos_s[3 * slot] = q[0];
+        pos_s[3 * slot + 1] = q[1];
+        pos_s[3 * slot + 2] = q[2];
+        idx_s[slot] = i < p.n ? (int)i : -1;      // ghosts only supply
+    }
+}
+
+// receivers of this call in cell order: slots of local particles on active rungs
+__global__ void __launch_bounds__(256)
+active_list_kernel(const int* __restrict__ idx_s, const int* __restrict__ offset, int ncell_total,
+                   const signed char* __restrict__ rung, int lowest_active_rung, int* __restrict__ list,
+                   unsigned int* __restrict__ nlist) {
+    const int total = offset[ncell_total];
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += gridDim.x * blockDim.x) {
+        const int s = base + lane;
+        bool act = false;
+        if (s < total) {
+            const int i = idx_s[s];
+            act = i >= 0 && rung[i] >= lowest_active_rung;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (m == 0) continue;
+        unsigned b0 = 0;
+        if (lane == 0) b0 = atomicAdd(nlist, (unsigned)__popc(m));
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
+        if (act) list[b0 + __popc(m & ((1u << lane) - 1))] = s;
     }
 }
 
 struct PairParams {
     double range2;      // range²
     double scaling;     // (T − 1)/r²_max
-    double L, half_L;
+    double L;
     int lowest_active_rung;
 };
 
-// One thread per receiver (in cell order).  Gather form: no atomics on Δmom.
+// One thread per receiver.  Gather form: no atomics on Δmom; a pair is evaluated from both sides (its two
+// receivers may sit on different rungs, or on different ranks).  The (2S+1)² z runs around the receiver's cell are
+// contiguous stretches of pos_s; runs that wrap around the box carry their image shift, so the pair loop itself has no
+// minimum-image logic: x⃗ = (x⃗_i − x⃗_j) − shift, r² = x·x + y·y + z·z in the reference's order (gravity.py:306-327).
 __global__ void __launch_bounds__(128)
 shortrange_kernel(const double* __restrict__ pos_s, const int* __restrict__ idx_s, const int* __restrict__ offset,
-                  int64_t n, CellGeom g, PairParams pp, const double* __restrict__ table,
-                  const signed char* __restrict__ rung, const signed char* __restrict__ rung_jumped,
-                  const double* __restrict__ factors, double* __restrict__ dmom) {
-    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const int i = idx_s[s];
-    if (rung[i] < pp.lowest_active_rung) return;      // inactive receivers get nothing (interactions.py:1700-1706)
-    const double xi = pos_s[3 * s], yi = pos_s[3 * s + 1], zi = pos_s[3 * s + 2];
-    const int cx = cell_coord(xi, g), cy = cell_coord(yi, g), cz = cell_coord(zi, g);
-    double sx = 0, sy = 0, sz = 0;
-    for (int dx = -1; dx <= 1; ++dx) {
-        const int nx = (cx + dx + g.nc) % g.nc;
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int ny = (cy + dy + g.nc) % g.nc;
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int nz = (cz + dz + g.nc) % g.nc;
-                const int c = (nx * g.nc + ny) * g.nc + nz;
-                const int jb = offset[c], je = offset[c + 1];
-                for (int j = jb; j < je; ++j) {
-                    if (j == s) continue;
-                    double x = xi - pos_s[3 * j], y = yi - pos_s[3 * j + 1], z = zi - pos_s[3 * j + 2];
-                    // periodic minimum image (periodic_offset_x/y/z of the reference's tile pairing)
-                    if (x > pp.half_L) x -= pp.L; else if (x < -pp.half_L) x += pp.L;
-                    if (y > pp.half_L) y -= pp.L; else if (y < -pp.half_L) y += pp.L;
-                    if (z > pp.half_L) z -= pp.L; else if (z < -pp.half_L) z += pp.L;
-                    const double r2 = x * x + y * y + z * z;
-                    if (r2 > pp.range2) continue;
-                    const double f = table[(int)(r2 * pp.scaling)];
-                    sx += x * f; sy += y * f; sz += z * f;
+                  const int* __restrict__ list, const unsigned int* __restrict__ nlist, CellGeom g, PairParams pp,
+                  const double* __restrict__ table, const signed char* __restrict__ rung_jumped,
+                  const double* __restrict__ factors, double* __restrict__ dmom, unsigned long long* __restrict__ stats) {
+    const unsigned int nrecv = *nlist;
+    unsigned long long hits = 0, cands = 0;
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < nrecv; t += gridDim.x * blockDim.x) {
+        const int s = list ? list[t] : (int)t;
+        const int i = idx_s[s];
+        if (i < 0) continue;
+        const double xi = pos_s[3 * (size_t)s], yi = pos_s[3 * (size_t)s + 1], zi = pos_s[3 * (size_t)s + 2];
+        const int cx = cell_1d(xi - g.x_origin, g.inv_cell_x, g.ncx), cy = cell_1d(yi, g.inv_cell, g.nc), cz = cell_1d(zi, g.inv_cell, g.nc);
+        double ax = 0, ay = 0, az = 0;
+        const bool zwrap = cz - g.S < 0 || cz + g.S >= g.nc;
+        for (int dx = -g.S; dx <= g.S; ++dx) {
+            int nx = cx + dx;
+            double sx = 0;
+            if (nx < 0) { if (!g.periodic_x) continue; nx += g.ncx; sx = -g.L; }
+            else if (nx >= g.ncx) { if (!g.periodic_x) continue; nx -= g.ncx; sx = g.L; }
+            for (int dy = -g.S; dy <= g.S; ++dy) {
+                int ny = cy + dy;
+                double sy = 0;
+                if (ny < 0) { ny += g.nc; sy = -g.L; }
+                else if (ny >= g.nc) { ny -= g.nc; sy = g.L; }
+                const int row = (nx * g.nc + ny) * g.nc;
+                const int nseg = zwrap ? 2 * g.S + 1 : 1;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    int jb, je;
+                    double sz = 0;
+                    if (!zwrap) {
+                        jb = offset[row + cz - g.S];
+                        je = offset[row + cz + g.S + 1];
+                    } else {
+                        int nz = cz - g.S + seg;
+                        if (nz < 0) { nz += g.nc; sz = -g.L; }
+                        else if (nz >= g.nc) { nz -= g.nc; sz = g.L; }
+                        jb = offset[row + nz];
+                        je = offset[row + nz + 1];
+                    }
+                    const double bx = xi - sx, by = yi - sy, bz = zi - sz;     // (x_i − shift) − x_j
+                    cands += (unsigned long long)(je - jb);
+                    for (int j = jb; j < je; ++j) {
+                        if (j == s) continue;
+                        const double x = bx - pos_s[3 * (size_t)j], y = by - pos_s[3 * (size_t)j + 1], z = bz - pos_s[3 * (size_t)j + 2];
+                        const double r2 = x * x + y * y + z * z;
+                        if (r2 > pp.range2) continue;
+                        const double f = __ldg(table + (int)(r2 * pp.scaling));
+                        ax += x * f; ay += y * f; az += z * f;
+                        ++hits;
+                    }
                 }
             }
         }
+        const double factor = factors[rung_jumped[i]];
+        dmom[3 * (size_t)i] = ax * factor;
+        dmom[3 * (size_t)i + 1] = ay * factor;
+        dmom[3 * (size_t)i + 2] = az * factor;
     }
-    const double factor = factors[rung_jumped[i]];
-    dmom[3 * (size_t)i] = sx * factor;
-    dmom[3 * (size_t)i + 1] = sy * factor;
-    dmom[3 * (size_t)i + 2] = sz * factor;
+    if (stats != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            hits += __shfl_xor_sync(0xffffffffu, hits, o);
+            cands += __shfl_xor_sync(0xffffffffu, cands, o);
+        }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(stats, hits); atomicAdd(stats + 1, cands); }
+    }
+}
+
+// ---- ghosts over the peer mappings -------------------------------------------------------------------------------
+struct GhostTargets {
+    double* buf[2];                 // [0]: the lower neighbour's UPPER ghost buffer, [1]: the upper neighbour's LOWER ghost buffer
+    double shift[2];                // added to x on the way (±L across the periodic boundary, else 0)
+};
+
+__global__ void __launch_bounds__(256)
+ghost_pack_kernel(const double* __restrict__ pos, int64_t n, double x_lo, double x_hi, double range, GhostTargets gt,
+                  int64_t cap, unsigned long long* __restrict__ counts /* [2] local */) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = pos[3 * i];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const bool near_face = side == 0 ? (x - x_lo < range) : (x_hi - x <= range);
+            if (!near_face) continue;
+            const unsigned long long k = atomicAdd(&counts[side], 1ULL);
+            if (k >= (unsigned long long)cap) continue;      // counted all the same: the receiver sees the overflow
+            double* q = gt.buf[side] + 3 * k;
+            q[0] = x + gt.shift[side];
+            q[1] = pos[3 * i + 1];
+            q[2] = pos[3 * i + 2];
+        }
+    }
+}
+
+__global__ void ghost_publish_kernel(ArenaHeader* lower, ArenaHeader* upper, int parity, const unsigned long long* __restrict__ counts) {
+    if (threadIdx.x == 0) lower->ghost_count[parity][1].v = counts[0];    // my low-face particles are its upper ghosts
+    if (threadIdx.x == 1) upper->ghost_count[parity][0].v = counts[1];
 }
 
 static int ensure_bytes(pm_ctx* c, void** buf, size_t* have, size_t need) {
     if (need <= *have) return PM_OK;
     if (*buf) { cudaFree(*buf); c->bytes_allocated -= *have; }
-    PM_CHECK_CUDA(cudaMalloc(buf, need));
-    *have = need;
-    c->bytes_allocated += need;
+    PM_CHECK_CUDA(cudaMalloc(buf, need + need / 8));
+    *have = need + need / 8;
+    c->bytes_allocated += *have;
     return PM_OK;
 }
 
 int shortrange(pm_ctx* c, const double* pos, int64_t n, const signed char* rung, const signed char* rung_jumped,
                int lowest_active_rung, const double* factors_host, int nfactors, double range,
                const double* table_dev, int tablesize, double maxr2, double* dmom) {
-    PM_REQUIRE(c->nranks == 1, "pm_shortrange: the P3M short-range force is single-GPU in this round");
-    PM_REQUIRE(n < (int64_t)1 << 31, "pm_shortrange: too many particles for 32-bit cell lists");
     PM_REQUIRE(nfactors > 0 && nfactors <= 64, "pm_shortrange: nfactors = %d", nfactors);
-    if (n == 0) return PM_OK;
+    const int P = c->nranks;
+    const double L = c->boxsize, W = L / P;
+    // ---- ghosts (several ranks): every rank takes part, also one without particles
+    SrParticles sp;
+    sp.pos = pos; sp.n = n;
+    sp.ghost[0] = sp.ghost[1] = nullptr;
+    sp.nghost[0] = sp.nghost[1] = nullptr;
+    sp.ghost_cap = 0;
+    int64_t max_total = n;
+    unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(c->d_counts) + 3 * P + (size_t)P * P;   // [4] scratch words
+    if (P > 1) {
+        PM_REQUIRE(c->peers_ready, "pm_shortrange: call pm_ipc_open_peers first (ghost particles travel over the peer mappings)");
+        PM_REQUIRE(W >= 2 * range, "pm_shortrange: slabs of width %g are thinner than twice the short-range range %g", W, range);
+        const int parity = (int)(c->ghost_epoch++ & 1);
+        const int lower = (c->rank + P - 1) % P, upper = (c->rank + 1) % P;
+        const int64_t cap = (int64_t)(c->ghost_buf_bytes / 24);
+        auto ghost_buf = [&](int r, int side) {
+            return reinterpret_cast<double*>(reinterpret_cast<char*>(c->peer_real[r]) + c->off_ghost +
+                                             ((size_t)parity * 2 + side) * c->ghost_buf_bytes);
+        };
+        GhostTargets gt;
+        gt.buf[0] = ghost_buf(lower, 1);
+        gt.buf[1] = ghost_buf(upper, 0);
+        gt.shift[0] = c->rank == 0 ? L : 0.0;            // across x = 0: they appear beyond the upper face of rank P − 1
+        gt.shift[1] = c->rank == P - 1 ? -L : 0.0;
+        unsigned long long* d_gc = d_stats + 2;
+        PM_CHECK_CUDA(cudaMemsetAsync(d_gc, 0, 2 * sizeof(unsigned long long), c->stream));
+        if (n > 0)
+            PM_LAUNCH(ghost_pack_kernel, kNumSMs * 4, 256, 0, c->stream, pos, n, c->rank * W, (c->rank + 1) * W, range, gt, cap, d_gc);
+        PM_LAUNCH(ghost_publish_kernel, 1, 32, 0, c->stream, arena_header(c, lower), arena_header(c, upper), parity, d_gc);
+        PM_TRY(device_barrier(c));
+        sp.ghost[0] = ghost_buf(c->rank, 0);
+        sp.ghost[1] = ghost_buf(c->rank, 1);
+        sp.nghost[0] = &arena_header(c, c->rank)->ghost_count[parity][0].v;
+        sp.nghost[1] = &arena_header(c, c->rank)->ghost_count[parity][1].v;
+        sp.ghost_cap = cap;
+        max_total = n + 2 * cap;
+    }
+    PM_REQUIRE(max_total < ((int64_t)1 << 31), "pm_shortrange: too many particles for 32-bit cell lists");
+    if (max_total == 0) return PM_OK;
+    // ---- cell geometry
     CellGeom g;
-    g.L = c->boxsize;
-    g.nc = (int)floor(c->boxsize / range);
+    g.L = L;
+    g.S = 2;
+    g.nc = (int)floor(L / (range / g.S));
+    if (g.nc < 2 * g.S + 1) { g.S = 1; g.nc = (int)floor(L / range); }
     // the reference requires at least 4 tiles across the box (species.py:3971-3975); 3 is the minimum for
     // a 27-cell neighbourhood without double counting
-    PM_REQUIRE(g.nc >= 3, "pm_shortrange: range %g is too large for the box %g (need boxsize/range >= 3)", range, c->boxsize);
-    if (g.nc > 256) g.nc = 256;
-    g.inv_cell = g.nc / c->boxsize;
-    const size_t ncell = (size_t)g.nc * g.nc * g.nc;
-    // scratch: cell_of[n] idx_s[n] count[ncell+1] offset[ncell+1] pos_s[3n] factors[64]
-    const size_t need = sizeof(int) * (2 * (size_t)n + 2 * (ncell + 1)) + sizeof(double) * (3 * (size_t)n + 64) + 256;
+    PM_REQUIRE(g.nc >= 3, "pm_shortrange: range %g is too large for the box %g (need boxsize/range >= 3)", range, L);
+    if (g.nc > 400) g.nc = 400;
+    g.inv_cell = g.nc / L;
+    if (P == 1) {
+        g.periodic_x = 1;
+        g.ncx = g.nc;
+        g.inv_cell_x = g.inv_cell;
+        g.x_origin = 0;
+    } else {
+        g.periodic_x = 0;
+        const double cell = L / g.nc;                          // same cell size as in y and z (≥ range/S)
+        g.x_origin = c->rank * W - range;
+        g.ncx = (int)ceil((W + 2 * range) / cell);
+        g.inv_cell_x = 1.0 / cell;
+    }
+    const size_t ncell = (size_t)g.ncx * g.nc * g.nc;
+    // scratch: pos_s[3·total] factors[64] | cell_of[total] idx_s[total] list[total] count[ncell+1] offset[ncell+1] nlist
+    const size_t tot = (size_t)max_total;
+    const size_t need = sizeof(double) * (3 * tot + 64) + sizeof(int) * (3 * tot + 2 * (ncell + 1) + 8) + 256;
     PM_TRY(ensure_bytes(c, &c->sr_buf, &c->sr_bytes, need));
     double* pos_s = reinterpret_cast<double*>(c->sr_buf);
-    double* d_factors = pos_s + 3 * n;
+    double* d_factors = pos_s + 3 * tot;
     int* cell_of = reinterpret_cast<int*>(d_factors + 64);
-    int* idx_s = cell_of + n;
-    int* count = idx_s + n;
+    int* idx_s = cell_of + tot;
+    int* list = idx_s + tot;
+    int* count = list + tot;
     int* offset = count + (ncell + 1);
+    unsigned int* nlist = reinterpret_cast<unsigned int*>(offset + (ncell + 1));
     PM_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (ncell + 1), c->stream));
     PM_CHECK_CUDA(cudaMemcpyAsync(d_factors, factors_host, sizeof(double) * nfactors, cudaMemcpyHostToDevice, c->stream));
-    PM_LAUNCH(cell_count_kernel, kNumSMs * 4, 256, 0, c->stream, pos, n, g, cell_of, count);
+    const int blocks = (int)std::min<int64_t>((max_total + 255) / 256, (int64_t)kNumSMs * 8);
+    PM_LAUNCH(cell_count_kernel, blocks, 256, 0, c->stream, sp, g, cell_of, count);
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, count, offset, (int)(ncell + 1), c->stream);
     PM_TRY(ensure_bytes(c, &c->sr_tmp, &c->sr_tmp_bytes, tmp_bytes));
     PM_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(c->sr_tmp, tmp_bytes, count, offset, (int)(ncell + 1), c->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PM_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (ncell + 1), c->stream));   // reuse as cursor
-    PM_LAUNCH(cell_scatter_kernel, kNumSMs * 4, 256, 0, c->stream, pos, n, cell_of, offset, count, pos_s, idx_s);
+    PM_LAUNCH(cell_scatter_kernel, blocks, 256, 0, c->stream, sp, cell_of, offset, count, pos_s, idx_s);
+    PM_CHECK_CUDA(cudaMemsetAsync(nlist, 0, sizeof(unsigned int), c->stream));
+    PM_LAUNCH(active_list_kernel, blocks, 256, 0, c->stream, idx_s, offset, (int)ncell, rung, lowest_active_rung, list, nlist);
     PairParams pp;
     pp.range2 = range * range;
     pp.scaling = (tablesize - 1) / maxr2;
-    pp.L = c->boxsize;
-    pp.half_L = 0.5 * c->boxsize;
+    pp.L = L;
     pp.lowest_active_rung = lowest_active_rung;
-    PM_LAUNCH(shortrange_kernel, (unsigned)((n + 127) / 128), 128, 0, c->stream, pos_s, idx_s, offset, n, g, pp,
-              table_dev, rung, rung_jumped, d_factors, dmom);
+    PM_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), c->stream));
+    const int pblocks = (int)std::min<int64_t>((std::max<int64_t>(n, 1) + 127) / 128, (int64_t)kNumSMs * 16);
+    PM_LAUNCH(shortrange_kernel, pblocks, 128, 0, c->stream, pos_s, idx_s, offset, list, nlist, g, pp, table_dev, rung_jumped,
+              d_factors, dmom, c->sr_want_stats ? d_stats : nullptr);
     return PM_OK;
 }
 
@@ -281,6 +462,20 @@ int pm_shortrange(pm_ctx* c, const double* pos, int64_t n, const signed char* ru
     PM_REQUIRE(c && (n == 0 || (pos && rung && rung_jumped && factors_host && table_dev && dmom)), "pm_shortrange: NULL argument");
     return shortrange(c, pos, n, rung, rung_jumped, lowest_active_rung, factors_host, nfactors, range, table_dev,
                       tablesize, maxr2, dmom);
+}
+
+int pm_shortrange_stats(pm_ctx* c, int enable, int64_t* pairs_out, int64_t* candidates_out) {
+    PM_REQUIRE(c != nullptr, "pm_shortrange_stats: NULL context");
+    if (pairs_out || candidates_out) {
+        unsigned long long h[2] = {0, 0};
+        const unsigned long long* d = reinterpret_cast<unsigned long long*>(c->d_counts) + 3 * c->nranks + (size_t)c->nranks * c->nranks;
+        PM_CHECK_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        PM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+        if (pairs_out) *pairs_out = (int64_t)h[0];
+        if (candidates_out) *candidates_out = (int64_t)h[1];
+    }
+    c->sr_want_stats = enable != 0;
+    return PM_OK;
 }
 
 int pm_apply_dmom(pm_ctx* c, double* mom, double* dmom, int64_t n, const signed char* rung,

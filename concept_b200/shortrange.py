@@ -7,7 +7,9 @@ get_shortrange_table (gravity.py:373-421), compute_factors (gravity.py:51-67), g
 
 The host keeps the reference's schedule (which rungs are kicked when, over which time interval, with
 which ᔑdt_rungs index); pairs, Δmom, accelerations and rung indices live on the GPU (pm_shortrange,
-pm_apply_dmom, pm_assign_rungs, pm_flag_rung_jumps, pm_apply_rung_jumps).  Single GPU in this round.
+pm_apply_dmom, pm_assign_rungs, pm_flag_rung_jumps, pm_apply_rung_jumps).  On several GPUs the particles within `range` of a slab
+face reach the neighbour as read-only ghosts inside pm_shortrange (the analogue of domain_domain's sendrecv_component,
+interactions.py:398-590), rung populations are summed over the ranks, and Δmom / rung indices migrate with their particles.
 """
 import ctypes
 import math
@@ -55,6 +57,11 @@ def get_softened_r3inv(r2, ϵ):
 def get_shortrange_table(gridsize, softening, device):
     """gravity.py:373-421, cached per (grid size, softening); returns (device tensor, maxr2, range, size)"""
     scale, rng, size = shortrange_params(gridsize)
+    return build_shortrange_table(scale, rng, size, softening, device)
+
+
+def build_shortrange_table(scale, rng, size, softening, device):
+    """The tabulation itself (gravity.py:395-421) for an explicit scale r_s, range and table size"""
     key = (scale, rng, size, softening, str(device))
     if key in _tables:
         return _tables[key]
@@ -89,7 +96,9 @@ def ensure_rung_state(c):
 
 
 def _set_populations(c, counts):
-    c.rungs_N = [int(v) for v in counts]
+    # the reference keeps per-process populations and reduces the lowest/highest populated rung over the processes
+    # (species.py:2547-2598); every rank must follow the same kick schedule, so the populations are summed right away
+    c.rungs_N = communication.allreduce_ints([int(v) for v in counts])
     populated = [r for r, v in enumerate(c.rungs_N) if v > 0]
     c.lowest_populated_rung = populated[0] if populated else N_rungs() - 1
     c.highest_populated_rung = populated[-1] if populated else 0
@@ -117,7 +126,7 @@ def flag_rung_jumps(c, Δt, Δt_jump_fac, fac_softening):
                                      c.rung_indices_jumped.data_ptr(), int(c.lowest_active_rung),
                                      get_rung_factor(c, Δt*Δt_jump_fac, fac_softening), get_rung_factor(c, Δt/Δt_jump_fac, fac_softening),
                                      dt1.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), N_rungs(), ctypes.byref(any_jump)))
-    return bool(any_jump.value)
+    return bool(communication.allreduce_ints([int(any_jump.value)])[0])     # any process (species.py:2506-2510)
 
 
 def apply_rung_jumps(c):
@@ -142,8 +151,6 @@ def apply_and_convert_Δmom(c, apply):
 # The pair interaction (interactions.component_component with gravity_pairwise_shortrange)
 # ---------------------------------------------------------------------------------------------
 def component_component(force, receivers, suppliers, ᔑdt_rungs_arg):
-    if communication.nprocs > 1:
-        abort('The P³M short-range force is single-GPU in this round (SURVEY.md §8e lists the ghost-particle exchange)')
     if len(receivers) != 1 or len(suppliers) != 1 or receivers[0] is not suppliers[0]:
         abort('concept_b200: the short-range force is implemented for one particle component')
     c = receivers[0]
@@ -277,3 +284,44 @@ def driftkick_short(components, Δt, sync_time):
         for c, jumped in zip(particle_components, any_rung_jumps):
             if jumped:
                 apply_rung_jumps(c)
+
+
+# ---------------------------------------------------------------------------------------------
+# The pair kick on bare device arrays (bench.py's configs[4] leg, tools): one rung, all particles active
+# ---------------------------------------------------------------------------------------------
+class PairKick:
+    """mom += G·m²·Δt·Σ_j (x⃗_i − x⃗_j)·table[r²] over all pairs within the range (gravity.py:263-354 with one rung), on
+    capacity-sized device arrays as bench.py keeps them.  scale r_s = 1.25 cells, range 4.5·r_s, 4096 table entries and
+    spline softening 0.025·L/∛N are the reference's defaults (commons.py:3254-3269, :3862-3873)."""
+
+    def __init__(self, ctx, boxsize, gridsize, n_total, capacity, G_Newton, mass=1.0, dt=1e-3):
+        self.ctx = ctx
+        dev = ctx.torch_device
+        self.scale = 1.25*boxsize/gridsize
+        self.range = 4.5*self.scale
+        softening = 0.025*boxsize/round(n_total**(1/3))
+        self.table, self.maxr2, _, self.size = build_shortrange_table(self.scale, self.range, 2**12, softening, dev)
+        self.dmom = torch.zeros((capacity, 3), dtype=torch.float64, device=dev)
+        self.rung = torch.zeros(capacity, dtype=torch.int8, device=dev)
+        self.factors = (ctypes.c_double*1)(G_Newton*mass*mass*dt)
+        self.conv = (ctypes.c_double*1)(1.0)
+
+    def kick(self, pos, mom, n):
+        ctx = self.ctx
+        check(ctx.lib.pm_shortrange(ctx._h, pos.data_ptr(), int(n), self.rung.data_ptr(), self.rung.data_ptr(), 0, self.factors, 1,
+                                    self.range, self.table.data_ptr(), self.size, self.maxr2, self.dmom.data_ptr()))
+        check(ctx.lib.pm_apply_dmom(ctx._h, mom.data_ptr(), self.dmom.data_ptr(), int(n), self.rung.data_ptr(), self.rung.data_ptr(),
+                                    0, self.conv, 1, 1))
+
+    def exchange(self, pos, mom, n):
+        return self.ctx.exchange(pos, mom, None, n, Δmom=self.dmom, rung_indices=self.rung, rung_indices_jumped=self.rung)
+
+    def pair_stats(self, pos, n):
+        """(pairs within the range, candidates examined) of one pair kernel over the current particles"""
+        ctx = self.ctx
+        check(ctx.lib.pm_shortrange_stats(ctx._h, 1, None, None))
+        check(ctx.lib.pm_shortrange(ctx._h, pos.data_ptr(), int(n), self.rung.data_ptr(), self.rung.data_ptr(), 0, self.factors, 1,
+                                    self.range, self.table.data_ptr(), self.size, self.maxr2, self.dmom.data_ptr()))
+        pairs, cands = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(ctx.lib.pm_shortrange_stats(ctx._h, 0, ctypes.byref(pairs), ctypes.byref(cands)))
+        return pairs.value//2, cands.value

@@ -201,7 +201,9 @@ int pm_exchange(pm_ctx* ctx, double* pos, double* mom, int64_t* ids, int64_t* n_
 int pm_exchange_rungs(pm_ctx* ctx, double* pos, double* mom, int64_t* ids, double* dmom, signed char* rung,
                       signed char* rung_jumped, int64_t* n_inout, int64_t capacity);
 
-/* ---- P3M short range (single GPU in this round) ---------------------------- */
+/* ---- P3M short range --------------------------------------------------------------
+ * On several ranks every rank calls pm_shortrange together: particles within `range` of a slab face are handed to the
+ * neighbour as read-only ghosts over the CUDA-IPC peer mappings (pm_ipc_open_peers) before the pair kernel runs. */
 /* gravity_pairwise_shortrange over all pairs within `range` (gravity.py:263-354; pair enumeration
  * interactions.py:1353-1791), gather form:
  *   dmom[i] = factors[rung_jumped[i]] · Σ_{j≠i, r²≤range²} (x_i − x_j)·table[int(r²·(tablesize−1)/maxr2)]
@@ -212,6 +214,10 @@ int pm_shortrange(pm_ctx* ctx, const double* pos, int64_t n, const signed char* 
                   const signed char* rung_jumped, int lowest_active_rung, const double* factors_host,
                   int nfactors, double range, const double* table_dev, int tablesize, double maxr2,
                   double* dmom);
+/* Counters of the pair kernel (measurement aid): with enable != 0 every following pm_shortrange counts the pairs within
+ * the range (each counted from both sides) and the candidates it looked at; the counts of the last such call are returned
+ * (host-synchronising).  Either output may be NULL. */
+int pm_shortrange_stats(pm_ctx* ctx, int enable, int64_t* pairs_out, int64_t* candidates_out);
 /* apply_Δmom (species.py:2253-2266; skipped when apply = 0, the "fake" kick) then
  * convert_Δmom_to_acc (species.py:2290-2325): dmom *= conv[rung_jumped], active rungs only */
 int pm_apply_dmom(pm_ctx* ctx, double* mom, double* dmom, int64_t n, const signed char* rung,
