@@ -84,9 +84,7 @@ cell_scatter_kernel(SrParticles p, const int* __restrict__ cell_of, const int* _
         const double* q = sr_pos(p, i, g0);
         const int c = cell_of[i];
         const int slot = offset[c] + atomicAdd(&cursor[c], 1);
-        pos_s[3 * slot] = q[0];
-        pos_s[3 * slot + 1] = q[1];
-        pos_s[3 * slot + 2] = q[2];
+        reinterpret_cast<double4*>(pos_s)[slot] = make_double4(q[0], q[1], q[2], 0.0);   // one 32-byte sector per particle
         idx_s[slot] = i < p.n ? (int)i : -1;      // ghosts only supply
     }
 }
@@ -119,24 +117,28 @@ struct PairParams {
     double scaling;     // (T − 1)/r²_max
     double L;
     int lowest_active_rung;
+    int zero_bin;       // index of the 0.0 appended to the device copy of the table
 };
 
 // One thread per receiver.  Gather form: no atomics on Δmom; a pair is evaluated from both sides (its two
 // receivers may sit on different rungs, or on different ranks).  The (2S+1)² z runs around the receiver's cell are
 // contiguous stretches of pos_s; runs that wrap around the box carry their image shift, so the pair loop itself has no
 // minimum-image logic: x⃗ = (x⃗_i − x⃗_j) − shift, r² = x·x + y·y + z·z in the reference's order (gravity.py:306-327).
+template <bool STATS>
 __global__ void __launch_bounds__(128)
-shortrange_kernel(const double* __restrict__ pos_s, const int* __restrict__ idx_s, const int* __restrict__ offset,
+shortrange_kernel(const double* __restrict__ pos_s_, const int* __restrict__ idx_s, const int* __restrict__ offset,
                   const int* __restrict__ list, const unsigned int* __restrict__ nlist, CellGeom g, PairParams pp,
                   const double* __restrict__ table, const signed char* __restrict__ rung_jumped,
                   const double* __restrict__ factors, double* __restrict__ dmom, unsigned long long* __restrict__ stats) {
+    const double4* __restrict__ pos_s = reinterpret_cast<const double4*>(pos_s_);
     const unsigned int nrecv = *nlist;
     unsigned long long hits = 0, cands = 0;
     for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < nrecv; t += gridDim.x * blockDim.x) {
         const int s = list ? list[t] : (int)t;
         const int i = idx_s[s];
         if (i < 0) continue;
-        const double xi = pos_s[3 * (size_t)s], yi = pos_s[3 * (size_t)s + 1], zi = pos_s[3 * (size_t)s + 2];
+        const double4 pi = pos_s[s];
+        const double xi = pi.x, yi = pi.y, zi = pi.z;
         const int cx = cell_1d(xi - g.x_origin, g.inv_cell_x, g.ncx), cy = cell_1d(yi, g.inv_cell, g.nc), cz = cell_1d(zi, g.inv_cell, g.nc);
         double ax = 0, ay = 0, az = 0;
         const bool zwrap = cz - g.S < 0 || cz + g.S >= g.nc;
@@ -166,25 +168,38 @@ shortrange_kernel(const double* __restrict__ pos_s, const int* __restrict__ idx_
                         je = offset[row + nz + 1];
                     }
                     const double bx = xi - sx, by = yi - sy, bz = zi - sz;     // (x_i − shift) − x_j
-                    cands += (unsigned long long)(je - jb);
-                    for (int j = jb; j < je; ++j) {
-                        if (j == s) continue;
-                        const double x = bx - pos_s[3 * (size_t)j], y = by - pos_s[3 * (size_t)j + 1], z = bz - pos_s[3 * (size_t)j + 2];
-                        const double r2 = x * x + y * y + z * z;
-                        if (r2 > pp.range2) continue;
-                        const double f = __ldg(table + (int)(r2 * pp.scaling));
-                        ax += x * f; ay += y * f; az += z * f;
-                        ++hits;
+                    if (STATS) cands += (unsigned long long)(je - jb);
+                    // Branch-free pair loop, four candidates in flight: a candidate beyond the range (or past the end of
+                    // the run) reads the zero appended to the table, so it adds exactly nothing; the receiver itself has
+                    // x⃗ = 0 and adds nothing either.  r² keeps the reference's operation order — it decides the table bin.
+                    for (int j0 = jb; j0 < je; j0 += 4) {
+                        double x[4], y[4], z[4], f[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {      // (the array has slack behind its last particle: reading past a run is harmless)
+                            const double4 q = pos_s[j0 + u];
+                            x[u] = bx - q.x; y[u] = by - q.y; z[u] = bz - q.z;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const double r2 = x[u] * x[u] + y[u] * y[u] + z[u] * z[u];
+                            const bool hit = (r2 <= pp.range2) & (j0 + u < je);
+                            const int bin = hit ? (int)(r2 * pp.scaling) : pp.zero_bin;
+                            f[u] = __ldg(table + bin);
+                            if (STATS) hits += hit ? 1u : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { ax = fma(x[u], f[u], ax); ay = fma(y[u], f[u], ay); az = fma(z[u], f[u], az); }
                     }
                 }
             }
         }
+        if (STATS) --hits;     // the receiver itself
         const double factor = factors[rung_jumped[i]];
         dmom[3 * (size_t)i] = ax * factor;
         dmom[3 * (size_t)i + 1] = ay * factor;
         dmom[3 * (size_t)i + 2] = az * factor;
     }
-    if (stats != nullptr) {
+    if (STATS) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             hits += __shfl_xor_sync(0xffffffffu, hits, o);
@@ -230,6 +245,8 @@ static int ensure_bytes(pm_ctx* c, void** buf, size_t* have, size_t need) {
     PM_CHECK_CUDA(cudaMalloc(buf, need + need / 8));
     *have = need + need / 8;
     c->bytes_allocated += *have;
+    // never-written slots must hold finite numbers: the pair loop reads up to three slots past a run (and masks them)
+    PM_CHECK_CUDA(cudaMemsetAsync(*buf, 0, *have, c->stream));
     return PM_OK;
 }
 
@@ -303,11 +320,14 @@ int shortrange(pm_ctx* c, const double* pos, int64_t n, const signed char* rung,
     const size_t ncell = (size_t)g.ncx * g.nc * g.nc;
     // scratch: pos_s[3·total] factors[64] | cell_of[total] idx_s[total] list[total] count[ncell+1] offset[ncell+1] nlist
     const size_t tot = (size_t)max_total;
-    const size_t need = sizeof(double) * (3 * tot + 64) + sizeof(int) * (3 * tot + 2 * (ncell + 1) + 8) + 256;
+    const size_t need = sizeof(double) * (4 * (tot + 8) + 64 + (size_t)tablesize + 8) + sizeof(int) * (3 * tot + 2 * (ncell + 1) + 8) + 256;
     PM_TRY(ensure_bytes(c, &c->sr_buf, &c->sr_bytes, need));
-    double* pos_s = reinterpret_cast<double*>(c->sr_buf);
-    double* d_factors = pos_s + 3 * tot;
-    int* cell_of = reinterpret_cast<int*>(d_factors + 64);
+    double* pos_s = reinterpret_cast<double*>(c->sr_buf);       // double4 per particle (cudaMalloc alignment)
+    double* d_factors = pos_s + 4 * (tot + 8);
+    double* d_table = d_factors + 64;          // the caller's table followed by a zero (what a non-pair reads)
+    int* cell_of = reinterpret_cast<int*>(d_table + tablesize + 8);
+    PM_CHECK_CUDA(cudaMemcpyAsync(d_table, table_dev, sizeof(double) * tablesize, cudaMemcpyDeviceToDevice, c->stream));
+    PM_CHECK_CUDA(cudaMemsetAsync(d_table + tablesize, 0, sizeof(double) * 8, c->stream));
     int* idx_s = cell_of + tot;
     int* list = idx_s + tot;
     int* count = list + tot;
@@ -331,10 +351,15 @@ int shortrange(pm_ctx* c, const double* pos, int64_t n, const signed char* rung,
     pp.scaling = (tablesize - 1) / maxr2;
     pp.L = L;
     pp.lowest_active_rung = lowest_active_rung;
+    pp.zero_bin = tablesize;
     PM_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), c->stream));
     const int pblocks = (int)std::min<int64_t>((std::max<int64_t>(n, 1) + 127) / 128, (int64_t)kNumSMs * 16);
-    PM_LAUNCH(shortrange_kernel, pblocks, 128, 0, c->stream, pos_s, idx_s, offset, list, nlist, g, pp, table_dev, rung_jumped,
-              d_factors, dmom, c->sr_want_stats ? d_stats : nullptr);
+    if (c->sr_want_stats)
+        PM_LAUNCH(shortrange_kernel<true>, pblocks, 128, 0, c->stream, pos_s, idx_s, offset, list, nlist, g, pp, d_table, rung_jumped,
+                  d_factors, dmom, d_stats);
+    else
+        PM_LAUNCH(shortrange_kernel<false>, pblocks, 128, 0, c->stream, pos_s, idx_s, offset, list, nlist, g, pp, d_table, rung_jumped,
+                  d_factors, dmom, d_stats);
     return PM_OK;
 }
 

@@ -105,7 +105,7 @@ select_forces = {{'matter': {{'gravity': 'p3m'}}}}
         rung_of = lambda ids: ((ids*7919) % 5).to(torch.int8)
         n = c.N_local
         c.rung_indices[:n] = rung_of(c.ids[:n])
-        jumped_of = lambda ids: (rung_of(ids) + 8*((ids % 7) == 0).to(torch.int8) + 16*((ids % 11) == 3).to(torch.int8)).to(torch.int8)
+        jumped_of = lambda ids: (rung_of(ids) + 8*((ids % 7) == 0).to(torch.int8) + 16*((ids % 7) == 3).to(torch.int8)).to(torch.int8)
         c.rung_indices_jumped[:n] = jumped_of(c.ids[:n])
         factors = np.linspace(1.0, 3.3, 23)
         table, maxr2, rng_sr, size = shortrange.get_shortrange_table(Gp, c.softening_length, c.device)
@@ -128,7 +128,7 @@ select_forces = {{'matter': {{'gravity': 'p3m'}}}}
         oks = communication.allgather((state_ok, n2))
         if rank == 0:
             rung_h = ((np.arange(Np)*7919) % 5).astype(np.int8)
-            jumped_h = (rung_h + 8*((np.arange(Np) % 7) == 0) + 16*((np.arange(Np) % 11) == 3)).astype(np.int64)
+            jumped_h = (rung_h + 8*((np.arange(Np) % 7) == 0) + 16*((np.arange(Np) % 7) == 3)).astype(np.int64)
             tab_o, maxr2_o = O.shortrange_table(*shortrange.shortrange_params(Gp)[:2], size, c.softening_length)
             active = rung_h >= 2
             ref = O.shortrange_sums(pos, Lp, rng_sr, tab_o, maxr2_o, active=active)*factors[jumped_h][:, None]
