@@ -418,6 +418,27 @@ __global__ void __launch_bounds__(FftCfg<G>::kThreadsX, FftCfg<G>::kOccX) xsolve
     run_tiles<kXSolveDouble>(job, p.ticket, buf0, buf1, p.err);
 }
 
+// B [kt][j][il][c] -> A [il][kt][j][c] on this rank (64-byte elements; 16 × 16 of them through shared memory so that both
+// sides move 1 KB runs): the hand-over to the inverse y pass when the x solve wrote its results in place into B.
+__global__ void __launch_bounds__(256)
+b_to_a_kernel(const uint4* __restrict__ b, uint4* __restrict__ a, int nxl, int rows /* NKT·G */) {
+    __shared__ uint4 tile[16][16 * 4 + 1];
+    const int tiles_il = nxl / 16, tiles_r = rows / 16;
+    for (int t = blockIdx.x; t < tiles_il * tiles_r; t += gridDim.x) {
+        const int il0 = (t % tiles_il) * 16, r0 = (t / tiles_il) * 16;
+        __syncthreads();
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {         // row r0 + rr: 16 planes × 4 uint4 contiguous
+            const int rr = e / 64, w = e % 64;
+            tile[rr][w] = b[((size_t)(r0 + rr) * nxl + il0) * 4 + w];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {         // plane il0 + pl: 16 rows × 4 uint4 contiguous
+            const int pl = e / 64, w = e % 64;
+            a[((size_t)(il0 + pl) * rows + r0) * 4 + w] = tile[w / 4][pl * 4 + (w % 4)];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -513,12 +534,18 @@ static int launch_xsolve2(pm_ctx* c, double prefactor) {
     const Geom& g = c->g;
     XSolveKParams<T, G> p;
     for (int r = 0; r < kMaxFftPeers; ++r) { p.xg.a[r] = nullptr; p.xg.b[r] = nullptr; }
+    // (timing experiments only — the results are wrong: PM_X_LOCAL bit 0 keeps all stores, bit 1 all loads on this rank)
+    static const int x_local = getenv("PM_X_LOCAL") ? atoi(getenv("PM_X_LOCAL")) : 0;
     for (int r = 0; r < c->nranks; ++r) {
         char* base = reinterpret_cast<char*>(c->nranks == 1 ? c->real : c->peer_real[r]);
-        p.xg.a[r] = reinterpret_cast<V*>(base + c->f2_off_a);
-        p.xg.b[r] = reinterpret_cast<const V*>(base + c->f2_off_b);
+        char* own = reinterpret_cast<char*>(c->real);
+        p.xg.a[r] = reinterpret_cast<V*>(((x_local & 1) ? own : base) + c->f2_off_a);
+        p.xg.b[r] = reinterpret_cast<const V*>(((x_local & 2) ? own : base) + c->f2_off_b);
     }
     p.xg.nranks = c->nranks;
+    // several ranks: results return to the B pieces (contiguous per peer), then one local re-layout pass B -> A
+    static const int x_inplace = getenv("PM_X_INPLACE") ? atoi(getenv("PM_X_INPLACE")) : -1;
+    p.xg.in_place = x_inplace >= 0 ? (x_inplace != 0 && g.nxl % 16 == 0) : (c->nranks > 1 && G >= 1024 && g.nxl % 16 == 0);
     p.xg.nxl_shift = 0;
     while ((1 << p.xg.nxl_shift) < g.nxl) ++p.xg.nxl_shift;
     p.xg.sep = c->xs_sep;
@@ -533,6 +560,7 @@ static int launch_xsolve2(pm_ctx* c, double prefactor) {
     const int64_t tiles = (int64_t)g.njl * S::NKT;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * FftCfg<G>::kOccX);
     PM_LAUNCH((xsolve2_kernel<T, G>), grid, FftCfg<G>::kThreadsX, smem, c->stream, p);
+    c->f2_x_in_place = p.xg.in_place != 0;
     return PM_OK;
 }
 
@@ -553,6 +581,12 @@ static int solve_fft2_tg(pm_ctx* c, double prefactor, bool l2_fused, int stage) 
         if (c->nranks > 1) PM_TRY(device_barrier(c));   // every rank's 2-D spectra are complete
         PM_TRY((launch_xsolve2<T, G>(c, prefactor)));
         if (c->nranks > 1) PM_TRY(device_barrier(c));   // all peers have written our planes
+        if (c->f2_x_in_place) {
+            using S = SlabFFT<T, G, FftCfg<G>::kThreadsX>;
+            const int rows = S::NKT * G;
+            PM_LAUNCH(b_to_a_kernel, kNumSMs * 8, 256, 0, c->stream, reinterpret_cast<const uint4*>(c->f2_b),
+                      reinterpret_cast<uint4*>(c->f2_a), c->g.nxl, rows);
+        }
     }
     if (stage == 0 || stage == 3) {
         if (l2_fused) {

@@ -197,6 +197,7 @@ struct SlabFFT {
         V* a[kMaxFftPeers];          // rank r's A
         const V* b[kMaxFftPeers];    // rank r's B
         int nranks;
+        int in_place;                // results go back into the B piece they came from (contiguous per rank) instead of A
         int nxl_shift;               // planes per rank = 1 << nxl_shift
         const double* sep;           // separable factor per axis index l < G: (x_l/sin x_l)^D·exp(−gauss·k_l²)
         double prefactor;            // −L²·G_N/π
@@ -216,7 +217,12 @@ struct SlabFFT {
             const XGeom* g; int j, kt;
             PM_HD void operator()(int c, int i, T r, T im) const {
                 V v; v.x = r; v.y = im;
-                g->a[i >> g->nxl_shift][a_index(i & ((1 << g->nxl_shift) - 1), kt, j, c)] = v;
+                const int rk = i >> g->nxl_shift, il = i & ((1 << g->nxl_shift) - 1);
+                // in place: the nxl·64-byte piece of rank rk's B that this tile loaded — consecutive planes are consecutive
+                // 64-byte segments, a few pages per peer.  (Straight into A, consecutive planes lie one plane of A apart:
+                // at G = 1024 that is 8 MB, and 64-byte stores scattered like that over a peer's 8 GB ran at 5 GB/s.)
+                if (g->in_place) const_cast<V*>(g->b[rk])[b_index(kt, j, il, c, 1 << g->nxl_shift)] = v;
+                else g->a[rk][a_index(il, kt, j, c)] = v;
             }
         };
         // per-mode factor in separable form: Π_l sep[l] · prefactor/k²; zero on the Nyquist planes and at

@@ -160,6 +160,7 @@ struct pm_ctx {
     unsigned* f2_ctr;         // tickets, per-plane completion counters, error flag (last entry)
     size_t f2_nctr;
     int f2_lag;
+    bool f2_x_in_place;       // the last x solve left its results in B (several ranks): re-layout before the inverse y pass
     void* peer_real[pm::kMaxPeers];   // IPC mappings of every rank's `real` buffer (own pointer for self)
     bool peers_ready;
     // IPC arena (ArenaHeader | mailboxes | ghost buffers) inside the `real` allocation, same offsets on every rank

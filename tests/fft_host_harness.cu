@@ -265,6 +265,7 @@ static int solve3d(const char* fin, const char* fsep, const char* fout, double p
     typename S::XGeom xg;
     for (int r = 0; r < kMaxFftPeers; ++r) { xg.a[r] = r < nranks ? A[r].data() : nullptr; xg.b[r] = r < nranks ? B[r].data() : nullptr; }
     xg.nranks = nranks;
+    xg.in_place = 0;
     xg.nxl_shift = 0;
     while ((1 << xg.nxl_shift) < nxl) ++xg.nxl_shift;
     xg.sep = sep.data();
