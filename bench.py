@@ -588,6 +588,28 @@ def run_p3m_config(D, cfg, steps, lib):
     return rec
 
 
+def run_example_basic():
+    """configs[0]: the reference's param/example_basic, unmodified (vendored byte-identical as tests/golden/example_basic),
+    through `python -m concept_b200 -p`: 64³ particles realised on the fly, P³M on a 128³ grid with 8 rungs, a = 0.02 → 1,
+    power spectrum at a = 1.  Wall time of the whole process (imports, initial conditions, time loop, output)."""
+    import tempfile
+    import numpy as np
+    with tempfile.TemporaryDirectory(prefix='example_basic_') as tmp:
+        env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
+        t0 = time.perf_counter()
+        r = subprocess.run([sys.executable, '-m', 'concept_b200', '-p', os.path.join(ROOT, 'tests', 'golden', 'example_basic')],
+                           cwd=tmp, env=env, capture_output=True, text=True, timeout=1200)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {'error': (r.stdout[-500:] + r.stderr[-500:])}
+        k, modes, power, linear = np.loadtxt(os.path.join(tmp, 'output', 'example_basic', 'powerspec_a=1.00')).T
+    large = (modes >= 100) & (k < 0.1)
+    return {'workload': 'configs[0]: param/example_basic unmodified (64^3 particles, P3M grid 128, 8 rungs, a = 0.02 -> 1)',
+            'wall_s': wall, 'finished': 'a = 1' in r.stdout.splitlines()[-1],
+            'P_over_linear_large_scales': [float(v) for v in power[large]/linear[large]],
+            'P_over_linear_at_k_max': float(power[-1]/linear[-1])}
+
+
 def run_gpu(args):
     D = Dist(args)
     torch = D.torch
@@ -647,6 +669,13 @@ def run_gpu(args):
             extra['config5'] = run_p3m_config(D, CONFIGS['config5'], min(args.steps, 5), lib)
         except Exception as exc:
             extra['config5'] = {'error': repr(exc)}
+        if D.world == 1:
+            try:
+                extra['config1'] = run_example_basic()
+            except Exception as exc:
+                extra['config1'] = {'error': repr(exc)}
+        else:
+            extra['config1'] = {'skipped': 'configs[0] (param/example_basic, 64^3 particles) is run by the one-GPU bench'}
 
     if D.rank == 0:
         dom = rec['dominant']

@@ -440,6 +440,42 @@ def test_gpu_example_basic_initial_conditions_and_powerspec(tmp_path):
     mesh.free_contexts()
 
 
+EXAMPLE_BASIC_SHA256 = '3131b62e31673345ad282766d55d53dbb9857ef73c8f8f265775387166be3b34'
+
+
+def test_vendored_example_basic_is_the_reference_file():
+    """tests/golden/example_basic is param/example_basic of the reference, byte for byte (40 lines of parameters, no code)"""
+    import hashlib
+    with open(os.path.join(HERE, 'golden', 'example_basic'), 'rb') as f:
+        assert hashlib.sha256(f.read()).hexdigest() == EXAMPLE_BASIC_SHA256
+
+
+@pytest.mark.gpu
+def test_gpu_example_basic_runs_unmodified_to_a1(tmp_path):
+    """BASELINE.json configs[0] / north star: `concept -p param/example_basic` — here `python -m concept_b200 -p` on the
+    unmodified file: 64³ particles realised on the fly, P³M on a 128³ grid with 8 rungs, a = 0.02 → 1, power spectrum
+    dumped at a = 1.  Physics check in the spirit of test/concept_vs_class_pm/analyze.py:56 (10 %): the large-scale
+    power follows linear growth; the small scales have gone non-linear (the short-range force is at work)."""
+    import subprocess
+    import sys
+    import time
+    root = os.path.dirname(HERE)
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    t0 = time.time()
+    r = subprocess.run([sys.executable, '-m', 'concept_b200', '-p', os.path.join(HERE, 'golden', 'example_basic')], cwd=str(tmp_path),
+                       env=env, capture_output=True, text=True, timeout=1500)
+    wall = time.time() - t0
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'a = 1' in r.stdout.splitlines()[-1]
+    table = np.loadtxt(os.path.join(str(tmp_path), 'output', 'example_basic', 'powerspec_a=1.00'))
+    k, modes, power, linear_power = table.T
+    large = (modes >= 100) & (k < 0.1)
+    assert large.sum() >= 2 and np.abs(power[large]/linear_power[large] - 1).max() < 0.1
+    small = k > 0.9
+    assert (power[small]/linear_power[small]).min() > 4
+    print(f'example_basic to a = 1: {wall:.1f} s wall')
+
+
 @pytest.mark.parametrize('rank', [0, 1])
 def test_replicated_realisation_keeps_the_rank_slab(rank, monkeypatch):
     """Two ranks (host logic only, kernels replaced by their numpy model): every rank realises the whole set and
