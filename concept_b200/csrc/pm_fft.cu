@@ -62,13 +62,14 @@ constexpr bool kFft2dDouble = PM_FFT2D_DOUBLE_BUFFER != 0;   // second tile buff
 // phases); a y or x tile is G × 64 bytes of columns, so G = 1024 doubles the tile (64 KB) and takes twice the threads.
 // Measured on B200 at 512³ fp64 (profiles/r02_fft_config_sweep.md): 2-D transforms 128 threads × 4 CTAs, one tile
 // buffer; x solve 128 threads × 3 CTAs, two tile buffers.
-template <int G>
+template <typename T, int G>
 struct FftCfg {
     static constexpr bool kBig = G >= 1024;
+    static constexpr bool kF32 = sizeof(T) == 4;      // fp32 x solve: 256 threads × 2 CTAs measured faster (0.38 vs 0.43 ms)
     static constexpr int kThreads2d = kBig ? 256 : PM_FFT2D_THREADS;     // every warp owns a z row
     static constexpr int kOcc2d = kBig ? 2 : PM_FFT2D_OCC;
-    static constexpr int kThreadsX = kBig ? 256 : PM_XSOLVE_THREADS;
-    static constexpr int kOccX = kBig ? 1 : PM_XSOLVE_OCC;      // radix-16 stage: 16 complex values + their twiddles per thread
+    static constexpr int kThreadsX = (kBig || kF32) ? 256 : PM_XSOLVE_THREADS;
+    static constexpr int kOccX = kBig ? 1 : (kF32 ? 2 : PM_XSOLVE_OCC);      // radix-16 stage: 16 complex values + their twiddles per thread
     static constexpr bool kDoubleX = kBig ? true : (PM_XSOLVE_DOUBLE_BUFFER != 0);
 };
 
@@ -264,7 +265,7 @@ struct Fft2dParams {
 
 template <typename T, int G, int DIR>
 struct Fft2dJob {
-    using S = SlabFFT<T, G, FftCfg<G>::kThreads2d>;
+    using S = SlabFFT<T, G, FftCfg<T, G>::kThreads2d>;
     using V = typename S::V;
     // forward: first pass z (kZTilesPerPlane tiles), second y;  inverse: first y, second z
     static constexpr int nA = DIR < 0 ? S::kZTilesPerPlane : S::kYTilesPerPlane;
@@ -327,32 +328,32 @@ struct Fft2dJob {
         if (is_z(item)) {
             // (self-cleaning density grid: the forward z tiles nullify the rows they have consumed — plain stores;
             // bulk stores from a block of zeros in shared memory were measured slower, 1.01 vs 0.97 ms)
-            if constexpr (DIR < 0) run_phases<typename S::ZFwd, V, T, S::kRegs, FftCfg<G>::kThreads2d>(zfwd(item), buf, tw);
-            else run_phases<typename S::ZInv, V, T, S::kRegs, FftCfg<G>::kThreads2d>(zinv(item), buf, tw);
+            if constexpr (DIR < 0) run_phases<typename S::ZFwd, V, T, S::kRegs, FftCfg<T, G>::kThreads2d>(zfwd(item), buf, tw);
+            else run_phases<typename S::ZInv, V, T, S::kRegs, FftCfg<T, G>::kThreads2d>(zinv(item), buf, tw);
         } else {
             if constexpr (DIR < 0) {
                 // the A block is in shared memory now and nobody reads it again before the x solve rewrites
                 // it: drop its (dirty) L2 lines instead of letting them be written back to HBM
                 const typename S::YFwd op = yfwd(item);
                 const char* blk = reinterpret_cast<const char*>(op.a_tile);
-                for (int o = threadIdx.x * 128; o < G * S::CY * (int)sizeof(V); o += FftCfg<G>::kThreads2d * 128)
+                for (int o = threadIdx.x * 128; o < G * S::CY * (int)sizeof(V); o += FftCfg<T, G>::kThreads2d * 128)
                     asm volatile("discard.global.L2 [%0], 128;" ::"l"(__cvta_generic_to_global(blk + o)) : "memory");
-                run_phases<typename S::YFwd, V, T, S::kRegs, FftCfg<G>::kThreads2d>(op, buf, tw);
+                run_phases<typename S::YFwd, V, T, S::kRegs, FftCfg<T, G>::kThreads2d>(op, buf, tw);
             } else {
-                run_phases<typename S::YInv, V, T, S::kRegs, FftCfg<G>::kThreads2d>(yinv(item), buf, tw);
+                run_phases<typename S::YInv, V, T, S::kRegs, FftCfg<T, G>::kThreads2d>(yinv(item), buf, tw);
             }
         }
     }
 };
 
 template <typename T, int G, int DIR>
-__global__ void __launch_bounds__(FftCfg<G>::kThreads2d, FftCfg<G>::kOcc2d) fft2d_kernel(const __grid_constant__ Fft2dParams p) {
-    using S = SlabFFT<T, G, FftCfg<G>::kThreads2d>;
+__global__ void __launch_bounds__(FftCfg<T, G>::kThreads2d, FftCfg<T, G>::kOcc2d) fft2d_kernel(const __grid_constant__ Fft2dParams p) {
+    using S = SlabFFT<T, G, FftCfg<T, G>::kThreads2d>;
     using V = typename S::V;
     extern __shared__ __align__(128) unsigned char fft_smem[];
     V* buf0 = reinterpret_cast<V*>(fft_smem);
     V* buf1 = buf0 + (kFft2dDouble ? S::kBufElems : 0);
-    const Twiddles<V> tw = load_twiddles(buf1 + S::kBufElems, p.tw, G, true, FftCfg<G>::kThreads2d);
+    const Twiddles<V> tw = load_twiddles(buf1 + S::kBufElems, p.tw, G, true, FftCfg<T, G>::kThreads2d);
     Fft2dJob<T, G, DIR> job(p, tw);
     run_tiles<kFft2dDouble>(job, p.ticket, buf0, buf1, p.err);
 }
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(FftCfg<G>::kThreads2d, FftCfg<G>::kOcc2d) fft2
 // ---------------------------------------------------------------------------------------------
 template <typename T, int G>
 struct XSolveKParams {
-    typename SlabFFT<T, G, FftCfg<G>::kThreadsX>::XGeom xg;
+    typename SlabFFT<T, G, FftCfg<T, G>::kThreadsX>::XGeom xg;
     const void* tw;
     int j0, njl;
     unsigned* ticket;
@@ -371,7 +372,7 @@ struct XSolveKParams {
 
 template <typename T, int G>
 struct XSolveJob {
-    using S = SlabFFT<T, G, FftCfg<G>::kThreadsX>;
+    using S = SlabFFT<T, G, FftCfg<T, G>::kThreadsX>;
     using V = typename S::V;
     const typename S::XGeom* xg;   // in shared memory
     Twiddles<V> tw;
@@ -393,15 +394,15 @@ struct XSolveJob {
         issue_loads(o, o.nloads(), buf, bar);
     }
     __device__ __forceinline__ void process(int item, V* buf) const {
-        run_phases<typename S::XSolve, V, T, S::kRegs, FftCfg<G>::kThreadsX>(op(item), buf, tw);
+        run_phases<typename S::XSolve, V, T, S::kRegs, FftCfg<T, G>::kThreadsX>(op(item), buf, tw);
     }
 };
 
 template <typename T, int G>
-__global__ void __launch_bounds__(FftCfg<G>::kThreadsX, FftCfg<G>::kOccX) xsolve2_kernel(const __grid_constant__ XSolveKParams<T, G> p) {
-    using S = SlabFFT<T, G, FftCfg<G>::kThreadsX>;
-    constexpr bool kXSolveDouble = FftCfg<G>::kDoubleX;
-    constexpr int kFftThreads = FftCfg<G>::kThreadsX;
+__global__ void __launch_bounds__(FftCfg<T, G>::kThreadsX, FftCfg<T, G>::kOccX) xsolve2_kernel(const __grid_constant__ XSolveKParams<T, G> p) {
+    using S = SlabFFT<T, G, FftCfg<T, G>::kThreadsX>;
+    constexpr bool kXSolveDouble = FftCfg<T, G>::kDoubleX;
+    constexpr int kFftThreads = FftCfg<T, G>::kThreadsX;
     using V = typename S::V;
     extern __shared__ __align__(128) unsigned char fft_smem[];
     V* buf0 = reinterpret_cast<V*>(fft_smem);
@@ -491,18 +492,18 @@ int make_fft2_tables(pm_ctx* c) {
 
 template <typename T, int G>
 static size_t fft2d_smem() {
-    using S = SlabFFT<T, G, FftCfg<G>::kThreads2d>;
+    using S = SlabFFT<T, G, FftCfg<T, G>::kThreads2d>;
     return sizeof(typename S::V) * ((size_t)(kFft2dDouble ? 2 : 1) * S::kBufElems + smem_twiddle_entries<G>());
 }
 template <typename T, int G>
 static size_t xsolve2_smem() {
-    using S = SlabFFT<T, G, FftCfg<G>::kThreadsX>;
-    return sizeof(typename S::V) * ((size_t)(FftCfg<G>::kDoubleX ? 2 : 1) * S::kYTileElems + 64 + 64 * kTwCRows) + sizeof(double) * G;
+    using S = SlabFFT<T, G, FftCfg<T, G>::kThreadsX>;
+    return sizeof(typename S::V) * ((size_t)(FftCfg<T, G>::kDoubleX ? 2 : 1) * S::kYTileElems + 64 + 64 * kTwCRows) + sizeof(double) * G;
 }
 
 template <typename T, int G, int DIR>
 static int launch_fft2d(pm_ctx* c, int mode) {
-    using S = SlabFFT<T, G, FftCfg<G>::kThreads2d>;
+    using S = SlabFFT<T, G, FftCfg<T, G>::kThreads2d>;
     Fft2dParams p;
     // one rank: the density grid cleans itself and the potential goes to `phi` (pm_internal.cuh)
     const bool self_clean = c->nranks == 1 && c->phi != nullptr;
@@ -521,15 +522,15 @@ static int launch_fft2d(pm_ctx* c, int mode) {
     PM_CHECK_CUDA(cudaFuncSetAttribute(fft2d_kernel<T, G, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (int64_t)c->g.nxl * (mode == 0 ? S::kZTilesPerPlane + S::kYTilesPerPlane
                                                          : ((mode == 1) == (DIR < 0) ? S::kZTilesPerPlane : S::kYTilesPerPlane));
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * FftCfg<G>::kOcc2d);
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * FftCfg<T, G>::kOcc2d);
     if (mode != 0) PM_CHECK_CUDA(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned), c->stream));
-    PM_LAUNCH((fft2d_kernel<T, G, DIR>), grid, FftCfg<G>::kThreads2d, smem, c->stream, p);
+    PM_LAUNCH((fft2d_kernel<T, G, DIR>), grid, FftCfg<T, G>::kThreads2d, smem, c->stream, p);
     return PM_OK;
 }
 
 template <typename T, int G>
 static int launch_xsolve2(pm_ctx* c, double prefactor) {
-    using S = SlabFFT<T, G, FftCfg<G>::kThreadsX>;
+    using S = SlabFFT<T, G, FftCfg<T, G>::kThreadsX>;
     using V = typename S::V;
     const Geom& g = c->g;
     XSolveKParams<T, G> p;
@@ -558,8 +559,8 @@ static int launch_xsolve2(pm_ctx* c, double prefactor) {
     const size_t smem = xsolve2_smem<T, G>();
     PM_CHECK_CUDA(cudaFuncSetAttribute(xsolve2_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (int64_t)g.njl * S::NKT;
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * FftCfg<G>::kOccX);
-    PM_LAUNCH((xsolve2_kernel<T, G>), grid, FftCfg<G>::kThreadsX, smem, c->stream, p);
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * FftCfg<T, G>::kOccX);
+    PM_LAUNCH((xsolve2_kernel<T, G>), grid, FftCfg<T, G>::kThreadsX, smem, c->stream, p);
     c->f2_x_in_place = p.xg.in_place != 0;
     return PM_OK;
 }
@@ -582,7 +583,7 @@ static int solve_fft2_tg(pm_ctx* c, double prefactor, bool l2_fused, int stage) 
         PM_TRY((launch_xsolve2<T, G>(c, prefactor)));
         if (c->nranks > 1) PM_TRY(device_barrier(c));   // all peers have written our planes
         if (c->f2_x_in_place) {
-            using S = SlabFFT<T, G, FftCfg<G>::kThreadsX>;
+            using S = SlabFFT<T, G, FftCfg<T, G>::kThreadsX>;
             const int rows = S::NKT * G;
             PM_LAUNCH(b_to_a_kernel, kNumSMs * 8, 256, 0, c->stream, reinterpret_cast<const uint4*>(c->f2_b),
                       reinterpret_cast<uint4*>(c->f2_a), c->g.nxl, rows);

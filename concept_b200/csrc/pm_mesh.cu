@@ -11,6 +11,7 @@
 #include "pm_internal.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace pm {
 
@@ -536,6 +537,122 @@ gather_kick_kernel(const T* __restrict__ phi, double* __restrict__ pos,
     }
 }
 
+// ---------------------------------------------------------------------------
+// fused gradient + gather + kick, streaming form
+// ---------------------------------------------------------------------------
+// The force on a particle is linear in the potential: with 1-D interpolation weights w[a] on ORDER cells and the centred
+// difference D[a] = Σ_m ±c_m·(φ[a+m] − φ[a−m]) (mesh.py:4961-5015),
+//   Σ_a w[a]·D[a] = Σ_u φ[u]·w'[u],   w'[u] = Σ_m ±c_m·(w[u−m] − w[u+m])      over W = ORDER + 2·REACH cells,
+// so the three force components are three separable sums over the W³ neighbourhood (minus the parts where two axes are
+// both outside the interpolation stencil).  Row by row along z: S0 = Σ_c wz[c]·φ, Sz = Σ_c wz'[c]·φ, then
+//   F_x += (wx'[t]·wy[b])·S0,   F_y += (wx[t]·wy'[b])·S0,   F_z += (wx[t]·wy[b])·Sz.
+// The same ORDER³ + 3·ORDER²·2·REACH distinct loads as the line form above, but nothing lives longer than one row:
+// ~50 registers instead of 100+ (TSC/PCS ran at one 128-thread CTA per SM).  The sums are a reassociation of the
+// reference's nest (differences are taken after the weighting); the stated kick tolerance is 1e-9 of the largest kick.
+template <int ORDER, int REACH>
+__device__ __forceinline__ void diff_weights(const double (&w)[ORDER], const FD& fd, double (&wd)[ORDER + 2 * REACH]) {
+    constexpr int W = ORDER + 2 * REACH;
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+        // cell u − REACH relative to the first stencil cell
+        double v = 0;
+#pragma unroll
+        for (int m = 1; m <= REACH; ++m) {
+            const int lo = u - REACH - m, hi = u - REACH + m;           // stencil cells whose difference touches this cell
+            const double wl = (lo >= 0 && lo < ORDER) ? w[lo] : 0.0;     // … as their upper neighbour (+)
+            const double wh = (hi >= 0 && hi < ORDER) ? w[hi] : 0.0;     // … as their lower neighbour (−)
+            const double wc = (u - REACH >= 0 && u - REACH < ORDER) ? w[u - REACH] : 0.0;
+            const double term = fd.forward ? (wl - wc) : (wl - wh);     // order 1: (φ[a+1] − φ[a])/Δx
+            v += ((m & 1) ? fd.c[m - 1] : -fd.c[m - 1]) * term;
+        }
+        wd[u] = v;
+    }
+}
+
+template <int ORDER, int REACH, typename T, bool DRIFT>
+__global__ void __launch_bounds__(kGkBlock, 4)
+gather_kick2_kernel(const T* __restrict__ phi, double* __restrict__ pos,
+                    double* __restrict__ mom, int64_t n, Geom g, Coord co, FD fd, double factor,
+                    double* __restrict__ sum_mom2, unsigned long long* __restrict__ tile_counter,
+                    double drift_dt, double boxsize) {
+    __shared__ double sred[kGkBlock / 32];
+    __shared__ int64_t s_slot;
+    constexpr int W = ORDER + 2 * REACH;
+    constexpr int64_t kChunk = (int64_t)kGkBlock * kGkChunkTiles;
+    double mom2_acc = 0;
+    const int64_t nchunks = (n + kChunk - 1) / kChunk;
+    for (int64_t chunk = next_chunk(tile_counter, &s_slot); chunk < nchunks; chunk = next_chunk(tile_counter, &s_slot)) {
+        const int64_t end = min(n, (chunk + 1) * kChunk);
+        for (int64_t ip = chunk * kChunk + threadIdx.x; ip < end; ip += kGkBlock) {
+            double* pp = pos + ip * 3;
+            const double px = __ldcs(pp), py = __ldcs(pp + 1), pz = __ldcs(pp + 2);
+            double wx[ORDER], wy[ORDER], wz[ORDER], dx[W], dy[W], dz[W];
+            const int ix = weights_1d<ORDER>((px - co.off[0]) * co.scale, wx);
+            const int iy = weights_1d<ORDER>((py - co.off[1]) * co.scale, wy);
+            const int iz = weights_1d<ORDER>((pz - co.off[2]) * co.scale, wz);
+            diff_weights<ORDER, REACH>(wx, fd, dx);
+            diff_weights<ORDER, REACH>(wy, fd, dy);
+            diff_weights<ORDER, REACH>(wz, fd, dz);
+            int oz[W];
+#pragma unroll
+            for (int t = 0; t < W; ++t) oz[t] = wrap(iz + t - REACH, g.G);
+            double vx = 0, vy = 0, vz = 0;
+#pragma unroll
+            for (int t = 0; t < W; ++t) {
+                const bool tcore = t >= REACH && t < REACH + ORDER;
+                const int lx = local_plane(ix + t - REACH, g);
+                const T* plane = phi + (size_t)(lx < 0 ? 0 : lx) * g.G * g.Gp;
+#pragma unroll
+                for (int b = 0; b < W; ++b) {
+                    const bool bcore = b >= REACH && b < REACH + ORDER;
+                    if (!tcore && !bcore) continue;
+                    const T* row = plane + (size_t)wrap(iy + b - REACH, g.G) * g.Gp;
+                    double s0 = 0, sz = 0;
+                    if (tcore && bcore) {
+#pragma unroll
+                        for (int cc = 0; cc < W; ++cc) {
+                            const double v = (double)row[oz[cc]];
+                            sz += dz[cc] * v;
+                            if (cc >= REACH && cc < REACH + ORDER) s0 += wz[cc - REACH] * v;
+                        }
+                        vz += (wx[t - REACH] * wy[b - REACH]) * sz;
+                        vx += (dx[t] * wy[b - REACH]) * s0;
+                        vy += (wx[t - REACH] * dy[b]) * s0;
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < ORDER; ++cc) s0 += wz[cc] * (double)row[oz[cc + REACH]];
+                        if (bcore) vx += (dx[t] * wy[b - REACH]) * s0;       // x arm
+                        else vy += (wx[t - REACH] * dy[b]) * s0;             // y arm
+                    }
+                }
+            }
+            if (factor != 1) { vx *= factor; vy *= factor; vz *= factor; }
+            double* m = mom + ip * 3;
+            const double mx = __ldcs(m) + vx, my = __ldcs(m + 1) + vy, mz = __ldcs(m + 2) + vz;
+            __stcs(m, mx); __stcs(m + 1, my); __stcs(m + 2, mz);
+            mom2_acc += mx * mx + my * my + mz * mz;
+            if constexpr (DRIFT) {
+                // Component.drift (species.py:2191-2196) with the freshly kicked momenta
+                __stcs(pp, mod_box(px + mx * drift_dt, boxsize));
+                __stcs(pp + 1, mod_box(py + my * drift_dt, boxsize));
+                __stcs(pp + 2, mod_box(pz + mz * drift_dt, boxsize));
+            }
+        }
+    }
+    if (sum_mom2 != nullptr) {
+        __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mom2_acc += __shfl_xor_sync(0xffffffffu, mom2_acc, o);
+        if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = mom2_acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0;
+            for (int w = 0; w < kGkBlock / 32; ++w) t += sred[w];
+            atomicAdd(sum_mom2, t);
+        }
+    }
+}
+
 template <typename T>
 static int gather_kick_dispatch(pm_ctx* c, double* pos, double* mom, int64_t n, int order,
                                 const FD& fd, double factor, const Coord& co, double* sum_mom2,
@@ -545,9 +662,20 @@ static int gather_kick_dispatch(pm_ctx* c, double* pos, double* mom, int64_t n, 
     const T* phi = reinterpret_cast<const T*>(c->grid_read());
     unsigned long long* ctr = c->d_tilectr + 1;
     PM_CHECK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), c->stream));
+    // the streaming form for the wide stencils (TSC, PCS, differences of order ≥ 4); CIC with two-point differences keeps
+    // the line form (measured on B200, profiles/r02_gather_forms.md); PM_GATHER_FORM=1|2 forces one of them
+    static const int form_env = getenv("PM_GATHER_FORM") ? atoi(getenv("PM_GATHER_FORM")) : 0;
+    const bool streaming = form_env ? form_env == 2 : !(order <= 2 && fd.reach == 1);
 #define PM_GK(O, R)                                                                                     \
     do {                                                                                                \
-        if (drift)                                                                                      \
+        if (streaming) {                                                                                \
+            if (drift)                                                                                  \
+                PM_LAUNCH((gather_kick2_kernel<O, R, T, true>), grid, kGkBlock, 0, c->stream, phi, pos, mom, n, \
+                          c->g, co, fd, factor, sum_mom2, ctr, drift_dt, c->boxsize);                   \
+            else                                                                                        \
+                PM_LAUNCH((gather_kick2_kernel<O, R, T, false>), grid, kGkBlock, 0, c->stream, phi, pos, mom, n, \
+                          c->g, co, fd, factor, sum_mom2, ctr, drift_dt, c->boxsize);                   \
+        } else if (drift)                                                                               \
             PM_LAUNCH((gather_kick_kernel<O, R, T, true>), grid, kGkBlock, 0, c->stream, phi, pos, mom, n, \
                       c->g, co, fd, factor, sum_mom2, ctr, drift_dt, c->boxsize);                       \
         else                                                                                            \
