@@ -524,7 +524,8 @@ static int launch_fft2d(pm_ctx* c, int mode) {
                                                          : ((mode == 1) == (DIR < 0) ? S::kZTilesPerPlane : S::kYTilesPerPlane));
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * FftCfg<T, G>::kOcc2d);
     if (mode != 0) PM_CHECK_CUDA(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned), c->stream));
-    PM_LAUNCH((fft2d_kernel<T, G, DIR>), grid, FftCfg<T, G>::kThreads2d, smem, c->stream, p);
+    constexpr int kThreads = FftCfg<T, G>::kThreads2d;
+    PM_LAUNCH((fft2d_kernel<T, G, DIR>), grid, kThreads, smem, c->stream, p);
     return PM_OK;
 }
 
@@ -560,7 +561,8 @@ static int launch_xsolve2(pm_ctx* c, double prefactor) {
     PM_CHECK_CUDA(cudaFuncSetAttribute(xsolve2_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (int64_t)g.njl * S::NKT;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * FftCfg<T, G>::kOccX);
-    PM_LAUNCH((xsolve2_kernel<T, G>), grid, FftCfg<T, G>::kThreadsX, smem, c->stream, p);
+    constexpr int kThreads = FftCfg<T, G>::kThreadsX;
+    PM_LAUNCH((xsolve2_kernel<T, G>), grid, kThreads, smem, c->stream, p);
     c->f2_x_in_place = p.xg.in_place != 0;
     return PM_OK;
 }
