@@ -656,8 +656,13 @@ def run_gpu(args):
             extra['config3'] = {'error': repr(exc)}
         if D.world == 8:
             try:
-                r4, c4, st4 = run_pm_config(D, CONFIGS['config4'], min(args.steps, 10), 3, lib)
+                c4 = make_context(D, CONFIGS['config4']['grid'], BOXSIZE*2, 'f64')
+                # parity of the 1024³ distributed path first (same checker, 10⁵ particles; the oracle needs ~30 GB of host memory)
+                parity['G1024'] = parity_check(D, c4, CONFIGS['config4'], 100000, seed=13)
+                parity['ok'] = bool(parity['ok'] and parity['G1024']['ok'])
+                r4, c4, st4 = run_pm_config(D, CONFIGS['config4'], min(args.steps, 10), 3, lib, ctx=c4)
                 extra['config4'] = extra_record(r4, CONFIGS['config4'], D.world)
+                extra['config4']['parity'] = parity['G1024']
                 del st4
                 c4.close()
                 torch.cuda.empty_cache()

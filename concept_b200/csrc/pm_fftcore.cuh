@@ -173,6 +173,15 @@ PM_HD void tw_powers(const V* wp, T (&pr)[R], T (&pi)[R]) {
     if constexpr (R == 1) return;      // (the table entry may not even exist then)
     const V w = *wp;
     if constexpr (R > 1) { pr[1] = w.x; pi[1] = w.y; }
+#ifdef PM_TW_SERIAL
+#pragma unroll
+    for (int m = 2; m < R; ++m) {      // w^m = w^(m−1)·w: one product each, R − 2 roundings deep
+        const T a = pr[m - 1], b = pi[m - 1];
+        pr[m] = fma_(a, w.x, -(b * w.y));
+        pi[m] = fma_(a, w.y, b * w.x);
+    }
+    return;
+#endif
 #pragma unroll
     for (int m = 2; m < R; ++m) {
         if ((m & 1) == 0) {

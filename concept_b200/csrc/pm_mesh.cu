@@ -140,6 +140,10 @@ __device__ __forceinline__ int64_t next_chunk(unsigned long long* counter, int64
 // ---------------------------------------------------------------------------
 constexpr int kDepBlock = 256;
 
+__device__ __forceinline__ void red_add_v2(float* addr8, float a, float b) {     // addr8: 8-byte aligned
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(addr8)), "f"(a), "f"(b) : "memory");
+}
+
 template <int ORDER, typename T>
 __global__ void __launch_bounds__(kDepBlock)
 deposit_kernel(const double* __restrict__ pos, int64_t n, T* __restrict__ grid, Geom g, Coord co,
@@ -174,6 +178,28 @@ deposit_kernel(const double* __restrict__ pos, int64_t n, T* __restrict__ grid, 
                 for (int b = 0; b < ORDER; ++b) {
                     const double wab = wa * wy[b];
                     T* row = plane + jy[b];
+                    if constexpr (sizeof(T) == 4 && ORDER >= 2) {
+                        // fp32 grid: the ORDER cells of a z run go out as 8-byte-aligned pairs (red.global.add.v2.f32,
+                        // REDG.E.ADD.F32x2) plus the odd ends — 18 instead of 27 reductions per TSC particle.  PTX has no
+                        // vector form for f64.
+                        if (iz >= 0 && iz + ORDER <= g.G) {
+                            float v[ORDER];
+#pragma unroll
+                            for (int cc = 0; cc < ORDER; ++cc) v[cc] = (float)(wab * wz[cc]);
+                            float* r0 = reinterpret_cast<float*>(row) + iz;
+                            if (iz & 1) {
+                                atomicAdd(r0, v[0]);
+#pragma unroll
+                                for (int cc = 1; cc + 1 < ORDER; cc += 2) red_add_v2(r0 + cc, v[cc], v[cc + 1]);
+                                if ((ORDER & 1) == 0) atomicAdd(r0 + ORDER - 1, v[ORDER - 1]);
+                            } else {
+#pragma unroll
+                                for (int cc = 0; cc + 1 < ORDER; cc += 2) red_add_v2(r0 + cc, v[cc], v[cc + 1]);
+                                if (ORDER & 1) atomicAdd(r0 + ORDER - 1, v[ORDER - 1]);
+                            }
+                            continue;
+                        }
+                    }
 #pragma unroll
                     for (int cc = 0; cc < ORDER; ++cc) {
                         atomicAdd(row + kz[cc], (T)(wab * wz[cc]));
