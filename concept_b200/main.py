@@ -144,89 +144,104 @@ def _remove_doppelgängers(x, y, rel_tol):
     return x[accepted].copy(), y[accepted].copy()
 
 
-def prepare_static_timestepping():
-    """main.py:499-656.  `static_timestepping` is None, a callable a ↦ Δa, or a path: an existing file of
-    (a, Δa) records is replayed (log–log interpolation within each stretch of growing Δa, exact look-up at the
-    recorded scale factors), otherwise the run records its own time-stepping to that path (see
-    get_base_timestep_size).  Every rank evaluates the same function of the same numbers: no broadcast needed."""
-    static_timestepping = commons.params.static_timestepping
-    if static_timestepping is None:
-        return None
-    if isinstance(static_timestepping, str):
-        if not os.path.exists(static_timestepping):
-            static_timestepping_dir = os.path.dirname(static_timestepping)
-            if static_timestepping_dir and communication.master:
-                os.makedirs(static_timestepping_dir, exist_ok=True)
-            masterprint(f'Static time-stepping information will be written to "{static_timestepping}"')
-            return None
-        if os.path.isdir(static_timestepping):
-            abort(f'Supplied static_timestepping = "{static_timestepping}" is a directory, not a file')
-        import collections
-        import scipy.interpolate
-        table_a, table_Δa = (arr.copy() for arr in np.loadtxt(static_timestepping, unpack=True, ndmin=2))
-        data = collections.defaultdict(list)
-        for a, Δa in zip(table_a, table_Δa):
-            data[float(a)].append(float(Δa))
-        for Δa_list in data.values():
-            Δa_list.reverse()
-        table_a, table_Δa = _remove_doppelgängers(table_a, table_Δa, Δt_reltol)
-        mask = np.diff(table_Δa) < 0
-        for index in range(1, len(mask)):
-            mask[index] &= not mask[index - 1]
-        if len(mask):
-            mask[-1] = False
-        interval_indices = list(np.where(mask)[0] + 1)
-        a_intervals, a_right = [], 0
-        for index in interval_indices:
-            a_left, a_right = a_right, table_a[index]
-            a_intervals.append((a_left, a_right))
-        interval_indices.append(table_a.shape[0])
-        a_intervals.append((a_right, ထ))
-        interps, index_left = [], 0
-        for index_right in interval_indices:
-            xs, ys = np.log(table_a[index_left:index_right]), np.log(table_Δa[index_left:index_right])
-            if len(xs) == 1:
-                interps.append(lambda a, *, y=ys[0]: math.exp(float(y)))
-            else:
-                interps.append(lambda a, *, f=scipy.interpolate.interp1d(xs, ys, 'linear', fill_value='extrapolate'):
-                               math.exp(float(f(math.log(a)))))
-            index_left = index_right
-        n = int(math.ceil(math.log10(1/Δt_reltol) + 0.5))
+class StaticTimestepping:
+    """`static_timestepping` of the reference (main.py:499-656) as a look-up object: a ↦ Δt.
 
-        def static_timestepping_func(a=-1):
-            if a == -1:
-                a, t = universals.a, universals.t
-            else:
-                t = cosmic_time(a)
-            Δa_list = data.get(float(f'{{:.{n}e}}'.format(a)))
-            if Δa_list:
-                Δa = Δa_list.pop()
-            else:
-                for (a_left, a_right), interp in zip(a_intervals, interps):
-                    if a_right != ထ and math.isclose(float(a), float(a_right)):
-                        continue
-                    if math.isclose(float(a), float(a_left + machine_ϵ)):
-                        a = a_left
-                    if a_left <= a < a_right:
-                        break
-                else:
-                    abort(f'static_timestepping_func(): a = {a} not in any interval')
-                Δa = interp(a)
-            a_next = a + Δa
-            return cosmic_time(a_next) - t if a_next <= 1 else ထ
-        masterprint(f'Static time-stepping information will be read from "{static_timestepping}"')
-        return static_timestepping_func
-    if callable(static_timestepping):
-        def static_timestepping_func(a=-1):
-            if a == -1:
-                a, t = universals.a, universals.t
-            else:
-                t = cosmic_time(a)
-            a_next = a + static_timestepping(a)
-            return cosmic_time(a_next) - t if a_next <= 1 else ထ
+    Built from a callable a ↦ Δa or from a recorded file of (a, Δa) rows.  A recorded scale factor is answered with
+    the recorded Δa (rows of the same `a` are handed out in file order); any other `a` is interpolated
+    log–log within its *stretch* — the table is cut wherever Δa drops (a synchronisation in the recorded run), so an
+    interpolation never runs across such a drop.  Every rank evaluates the same function of the same numbers."""
+
+    def __init__(self, func=None):
+        self.func = func            # a -> Δa, or None when table-driven
+        self.recorded = {}          # rounded a -> recorded Δa values, next one last
+        self.lefts = []             # left edge of every stretch (first one 0)
+        self.stretches = []         # per stretch: (log a, log Δa) arrays
+        self.digits = int(math.ceil(math.log10(1/Δt_reltol) + 0.5))
+
+    # -- construction ------------------------------------------------------------------------
+    @classmethod
+    def from_file(cls, path):
+        self = cls()
+        a_rows, Δa_rows = (np.array(col, dtype=float) for col in np.loadtxt(path, unpack=True, ndmin=2))
+        for a, Δa in zip(a_rows[::-1], Δa_rows[::-1]):           # reversed: list.pop() then follows the file order
+            self.recorded.setdefault(float(a), []).append(float(Δa))
+        a_tab, Δa_tab = _remove_doppelgängers(a_rows, Δa_rows, Δt_reltol)
+        # a stretch ends where Δa drops; of two consecutive drops only the first counts, and never the last row
+        keep = []           # (row index of the drop, accepted)
+        for d in np.flatnonzero(np.diff(Δa_tab) < 0):
+            d = int(d)
+            suppressed = bool(keep) and keep[-1][1] and d == keep[-1][0] + 1      # directly after an accepted drop
+            keep.append((d, not suppressed))
+        starts = [d + 1 for d, accepted in keep if accepted and d != len(Δa_tab) - 2]
+        bounds = [0] + starts + [len(a_tab)]
+        self.lefts = [0.0] + [float(a_tab[i]) for i in starts]
+        self.stretches = [(np.log(a_tab[lo:hi]), np.log(Δa_tab[lo:hi])) for lo, hi in zip(bounds[:-1], bounds[1:])]
+        return self
+
+    # -- evaluation --------------------------------------------------------------------------
+    def _stretch_of(self, a):
+        """Index of the stretch holding a, and a snapped onto a stretch edge it is indistinguishable from."""
+        import bisect
+        i = bisect.bisect_right(self.lefts, a) - 1
+        if i + 1 < len(self.lefts) and math.isclose(float(a), self.lefts[i + 1]):
+            i += 1                                  # on the right edge: that point opens the next stretch
+        if i < 0:
+            abort(f'static time-stepping: a = {a} lies before the recorded stretches')
+        if math.isclose(float(a), float(self.lefts[i] + machine_ϵ)):
+            a = self.lefts[i]
+        return i, a
+
+    @staticmethod
+    def _loglog(xs, ys, a):
+        if len(xs) == 1:
+            return math.exp(float(ys[0]))
+        x = math.log(a)
+        hi = min(max(int(np.searchsorted(xs, x, side='left')), 1), len(xs) - 1)      # linear, extrapolating at both ends
+        lo = hi - 1
+        slope = (ys[hi] - ys[lo])/(xs[hi] - xs[lo])
+        return math.exp(float(slope*(x - xs[lo]) + ys[lo]))
+
+    def Δa(self, a):
+        if self.func is not None:
+            return self.func(a)
+        pending = self.recorded.get(float(f'{{:.{self.digits}e}}'.format(a)))
+        if pending:
+            return pending.pop()
+        i, a = self._stretch_of(a)
+        return self._loglog(*self.stretches[i], a)
+
+    def __call__(self, a=-1):
+        """Δt of the base step starting at scale factor a (default: now); ∞ past a = 1."""
+        if a == -1:
+            a, t = universals.a, universals.t
+        else:
+            t = cosmic_time(a)
+        a_next = a + self.Δa(a)
+        return cosmic_time(a_next) - t if a_next <= 1 else ထ
+
+
+def prepare_static_timestepping():
+    """main.py:499-656.  `static_timestepping` is None, a callable a ↦ Δa, or a path: an existing file of (a, Δa)
+    records is replayed, otherwise the run records its own time-stepping to that path (see get_base_timestep_size)."""
+    spec = commons.params.static_timestepping
+    if spec is None:
+        return None
+    if callable(spec):
         masterprint('Static time-stepping configured using supplied function')
-        return static_timestepping_func
-    abort(f'Could not interpret static_timestepping = {static_timestepping} of type {type(static_timestepping)}')
+        return StaticTimestepping(spec)
+    if not isinstance(spec, str):
+        abort(f'Could not interpret static_timestepping = {spec} of type {type(spec)}')
+    if os.path.isdir(spec):
+        abort(f'Supplied static_timestepping = "{spec}" is a directory, not a file')
+    if os.path.exists(spec):
+        masterprint(f'Static time-stepping information will be read from "{spec}"')
+        return StaticTimestepping.from_file(spec)
+    directory = os.path.dirname(spec)
+    if directory and communication.master:
+        os.makedirs(directory, exist_ok=True)
+    masterprint(f'Static time-stepping information will be written to "{spec}"')
+    return None
 
 
 def update_base_timestep_size(Δt, Δt_min, Δt_max, bottleneck, time_step=-1, time_step_last_sync=-1,
@@ -428,6 +443,126 @@ def dump(components, dump_time, on_dump=None):
     return False
 
 
+class _Leapfrog:
+    """The stepping state of one run (reference main.py:102-471 for particle components).
+
+    The integrator is kick-drift-kick with the long-range kicks half a step out of phase with the drifts.  The system
+    is *synchronised* (positions and momenta at the same time) at the start, at every dump and whenever the base step
+    Δt has to change; a synchronised state is left with half kicks (`_leave_synchronised_state`), every other step is a
+    drift over Δt followed by a long-range kick over Δt that is clipped at `sync_time` when a synchronisation is due
+    (`_drift_and_kick`).  `_plan` decides after each step whether the next one has to end synchronised."""
+
+    def __init__(self, components, static_timestepping_func, on_dump, on_step, max_steps):
+        self.components = components
+        self.static = static_timestepping_func
+        self.on_dump, self.on_step, self.max_steps = on_dump, on_step, max_steps
+        self.time_step = 0
+        self.announced_step = -1
+        self.last_sync_step = 0
+        self.synchronised = True
+        self.sync_time = ထ
+        self.limit_is_fresh = False        # Δt_max was measured at the current time already
+        self.Δt_shelved = -1               # the step size put aside while a dump forces a shorter one
+        initial_fac_times.add(universals.t)
+        self.Δt_max, self.bottleneck = get_base_timestep_size(components, self.static)
+        self.Δt = self.Δt_max
+
+    # -- pieces of a step --------------------------------------------------------------------
+    def _announce_step(self):
+        if self.time_step > self.announced_step:
+            self.announced_step = self.time_step
+            if self.synchronised:           # all rungs are synchronised: re-assign them (main.py:225-227)
+                _assign_rungs(self.components, self.Δt)
+            universals.time_step = self.time_step
+
+    def _measure_limit(self):
+        self.Δt_max, self.bottleneck = get_base_timestep_size(self.components, self.static)
+
+    def _leave_synchronised_state(self):
+        self.synchronised = False
+        kick_long(self.components, self.Δt, self.sync_time, 'init')
+        kick_short(self.components, self.Δt)
+
+    def _advance_clock(self, Δt_half):
+        universals.t += Δt_half
+        if universals.t + Δt_reltol*self.Δt + 2*machine_ϵ > self.sync_time:
+            universals.t = self.sync_time
+        universals.a = scale_factor(universals.t)
+
+    def _drift_and_kick(self):
+        driftkick_short(self.components, self.Δt, self.sync_time)
+        self._advance_clock(0.5*self.Δt)
+        kick_long(self.components, self.Δt, self.sync_time, 'full')
+        self._advance_clock(0.5*self.Δt)
+        if self.on_step is not None:
+            self.on_step(self.time_step, universals.t, universals.a, self.Δt)
+
+    def _plan(self, dump_time, after_half_kicks):
+        """Schedule a synchronisation if the dump is near, if Δt exceeds its limit, or (between synchronisations only)
+        if Δt may grow again after a full period."""
+        Δt = self.Δt
+        if dump_time.t - universals.t <= 1.5*Δt:
+            self.sync_time = dump_time.t
+            return
+        self._measure_limit()
+        too_large = Δt > self.Δt_max
+        may_grow = (not after_half_kicks and self.Δt_max > Δt_increase_min_factor*Δt
+                    and (self.time_step + 1 - self.last_sync_step) >= Δt_period)
+        if too_large or may_grow:
+            self.sync_time = universals.t + (0.5*Δt if after_half_kicks else Δt)
+            self.limit_is_fresh = True
+
+    def _cap_for_dump(self, t_dump):
+        room = t_dump - universals.t
+        if self.Δt > room:
+            self.Δt_shelved = self.Δt
+            self.Δt = room
+
+    def _resynchronised(self, dump_time, next_dump_time):
+        """The step just taken ended at sync_time.  Returns True when that was the dump."""
+        self.synchronised = True
+        self.sync_time = ထ
+        if self.Δt_shelved != -1:
+            self.Δt = max(self.Δt, self.Δt_shelved)
+            self.Δt_shelved = -1
+        if not self.limit_is_fresh:
+            self._measure_limit()
+        self.limit_is_fresh = False
+        self.Δt, self.bottleneck = update_base_timestep_size(
+            self.Δt, self.Δt_min, self.Δt_max, self.bottleneck, self.time_step, self.last_sync_step,
+            tolerate_danger=(self.bottleneck == bottleneck_static_timestepping))
+        self.time_step += 1
+        self.last_sync_step = self.time_step
+        if universals.t == dump_time.t:
+            dump(self.components, dump_time, self.on_dump)
+            if next_dump_time is not None:
+                self.Δt_max = next_dump_time.t - universals.t
+                self._cap_for_dump(next_dump_time.t)
+            return True
+        self.Δt_max = dump_time.t - universals.t
+        self._cap_for_dump(dump_time.t)
+        return False
+
+    # -- driver ------------------------------------------------------------------------------
+    def run_to(self, dump_time, next_dump_time):
+        """Step until `dump_time` has been dumped; False if max_steps ended the run first."""
+        while True:
+            if self.max_steps is not None and self.time_step >= self.max_steps:
+                return False
+            self._announce_step()
+            if self.synchronised:
+                self._leave_synchronised_state()
+                self._plan(dump_time, after_half_kicks=True)
+                continue
+            self._drift_and_kick()
+            if universals.t == self.sync_time:
+                if self._resynchronised(dump_time, next_dump_time):
+                    return True
+                continue
+            self.time_step += 1
+            self._plan(dump_time, after_half_kicks=False)
+
+
 def timeloop(components, on_dump=None, on_step=None, max_steps=None):
     """main.py:102-471 for particle components.  `components` replaces get_initial_conditions()
     (snapshot loading / IC generation are out of scope).  Returns the number of base steps taken."""
@@ -442,99 +577,15 @@ def timeloop(components, on_dump=None, on_step=None, max_steps=None):
         dump_times.pop(0)
         if not dump_times:
             return 0
-    static_timestepping_func = prepare_static_timestepping()
-    initial_fac_times.add(universals.t)
-    Δt_max, bottleneck = get_base_timestep_size(components, static_timestepping_func)
-    Δt_begin = Δt_max
-    if Δt_begin > dump_times[0].t - universals.t:
-        Δt_begin = dump_times[0].t - universals.t
-    Δt = Δt_begin
-    Δt_min = 1e-4*Δt_begin
+    stepper = _Leapfrog(components, prepare_static_timestepping(), on_dump, on_step, max_steps)
+    stepper.Δt = min(stepper.Δt, dump_times[0].t - universals.t)
+    stepper.Δt_min = 1e-4*stepper.Δt
     get_time_step_integrals(0, 0, components)
-    initialize_rung_populations(components, Δt)
-    time_step = 0
-    time_step_last_sync = 0
-    time_step_previous = -1
-    time_step_type = 'init'
-    sync_time = ထ
-    recompute_Δt_max = True
-    Δt_backup = -1
-    for dump_index, dump_time in enumerate(dump_times):
-        while True:
-            if max_steps is not None and time_step >= max_steps:
-                return time_step
-            if time_step > time_step_previous:
-                time_step_previous = time_step
-                # at an "init" step all rungs are synchronised: re-assign them (main.py:225-227)
-                if time_step_type == 'init':
-                    _assign_rungs(components, Δt)
-                universals.time_step = time_step
-            if time_step_type == 'init':
-                time_step_type = 'full'
-                kick_long(components, Δt, sync_time, 'init')
-                kick_short(components, Δt)
-                if dump_time.t - universals.t <= 1.5*Δt:
-                    sync_time = dump_time.t
-                    continue
-                Δt_max, bottleneck = get_base_timestep_size(components, static_timestepping_func)
-                if Δt > Δt_max:
-                    sync_time = universals.t + 0.5*Δt
-                    recompute_Δt_max = False
-                    continue
-            elif time_step_type == 'full':
-                driftkick_short(components, Δt, sync_time)
-                universals.t += 0.5*Δt
-                if universals.t + Δt_reltol*Δt + 2*machine_ϵ > sync_time:
-                    universals.t = sync_time
-                universals.a = scale_factor(universals.t)
-                kick_long(components, Δt, sync_time, 'full')
-                universals.t += 0.5*Δt
-                if universals.t + Δt_reltol*Δt + 2*machine_ϵ > sync_time:
-                    universals.t = sync_time
-                universals.a = scale_factor(universals.t)
-                if on_step is not None:
-                    on_step(time_step, universals.t, universals.a, Δt)
-                if universals.t == sync_time:
-                    time_step_type = 'init'
-                    sync_time = ထ
-                    if Δt_backup != -1:
-                        if Δt < Δt_backup:
-                            Δt = Δt_backup
-                        Δt_backup = -1
-                    if recompute_Δt_max:
-                        Δt_max, bottleneck = get_base_timestep_size(components, static_timestepping_func)
-                    recompute_Δt_max = True
-                    Δt, bottleneck = update_base_timestep_size(Δt, Δt_min, Δt_max, bottleneck, time_step, time_step_last_sync,
-                                                               tolerate_danger=(bottleneck == bottleneck_static_timestepping))
-                    time_step += 1
-                    time_step_last_sync = time_step
-                    if universals.t == dump_time.t:
-                        dump(components, dump_time, on_dump)
-                        if dump_index != len(dump_times) - 1:
-                            Δt_max = dump_times[dump_index + 1].t - universals.t
-                            if Δt > Δt_max:
-                                Δt_backup = Δt
-                                Δt = Δt_max
-                        break
-                    Δt_max = dump_time.t - universals.t
-                    if Δt > Δt_max:
-                        Δt_backup = Δt
-                        Δt = Δt_max
-                    continue
-                time_step += 1
-                if dump_time.t - universals.t <= 1.5*Δt:
-                    sync_time = dump_time.t
-                    continue
-                Δt_max, bottleneck = get_base_timestep_size(components, static_timestepping_func)
-                if Δt > Δt_max:
-                    sync_time = universals.t + Δt
-                    recompute_Δt_max = False
-                    continue
-                if Δt_max > Δt_increase_min_factor*Δt and (time_step + 1 - time_step_last_sync) >= Δt_period:
-                    sync_time = universals.t + Δt
-                    recompute_Δt_max = False
-                    continue
-    return time_step
+    initialize_rung_populations(components, stepper.Δt)
+    for dump_time, next_dump_time in zip(dump_times, dump_times[1:] + [None]):
+        if not stepper.run_to(dump_time, next_dump_time):
+            break
+    return stepper.time_step
 
 
 def get_initial_conditions(initial_conditions_touse=None, do_realization=True):
