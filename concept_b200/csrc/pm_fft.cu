@@ -45,6 +45,12 @@ using namespace fftc;
 #ifndef PM_FFT2D_DOUBLE_BUFFER
 #define PM_FFT2D_DOUBLE_BUFFER 0
 #endif
+#ifndef PM_FFT_Z_RPW_FWD
+#define PM_FFT_Z_RPW_FWD 1
+#endif
+#ifndef PM_FFT_Z_RPW_INV
+#define PM_FFT_Z_RPW_INV 2
+#endif
 #ifndef PM_XSOLVE_THREADS
 #define PM_XSOLVE_THREADS 128
 #endif
@@ -70,6 +76,9 @@ struct FftCfg {
     static constexpr int kOcc2d = kBig ? 2 : PM_FFT2D_OCC;
     static constexpr int kThreadsX = (kBig || kF32) ? 256 : PM_XSOLVE_THREADS;
     static constexpr int kOccX = kBig ? 1 : (kF32 ? 2 : PM_XSOLVE_OCC);      // radix-16 stage: 16 complex values + their twiddles per thread
+    // z rows per warp (their loads are in flight together): measured 1 for the forward pass (0.82 vs 0.87 ms), 2 for the
+    // inverse (0.73 vs 0.81 ms)
+    static constexpr int kRowsFwd = PM_FFT_Z_RPW_FWD, kRowsInv = PM_FFT_Z_RPW_INV;
     static constexpr bool kDoubleX = kBig ? true : (PM_XSOLVE_DOUBLE_BUFFER != 0);
 };
 
@@ -258,6 +267,7 @@ struct Fft2dParams {
     int nplanes;
     int mode;             // 0: both passes, dependency-ordered (L2-resident); 1: first pass only; 2: second pass only
     int lag;              // planes between the first and the second pass in ticket order (mode 0)
+    int discard;          // forward y tiles drop the consumed A block from L2
     unsigned* ticket;
     unsigned* done;       // [nplanes] finished first-pass tiles
     int* err;
@@ -265,7 +275,7 @@ struct Fft2dParams {
 
 template <typename T, int G, int DIR>
 struct Fft2dJob {
-    using S = SlabFFT<T, G, FftCfg<T, G>::kThreads2d>;
+    using S = SlabFFT<T, G, FftCfg<T, G>::kThreads2d, (DIR < 0 ? FftCfg<T, G>::kRowsFwd : FftCfg<T, G>::kRowsInv)>;
     using V = typename S::V;
     // forward: first pass z (kZTilesPerPlane tiles), second y;  inverse: first y, second z
     static constexpr int nA = DIR < 0 ? S::kZTilesPerPlane : S::kYTilesPerPlane;
@@ -336,6 +346,7 @@ struct Fft2dJob {
                 // it: drop its (dirty) L2 lines instead of letting them be written back to HBM
                 const typename S::YFwd op = yfwd(item);
                 const char* blk = reinterpret_cast<const char*>(op.a_tile);
+                if (p.discard)
                 for (int o = threadIdx.x * 128; o < G * S::CY * (int)sizeof(V); o += FftCfg<T, G>::kThreads2d * 128)
                     asm volatile("discard.global.L2 [%0], 128;" ::"l"(__cvta_generic_to_global(blk + o)) : "memory");
                 run_phases<typename S::YFwd, V, T, S::kRegs, FftCfg<T, G>::kThreads2d>(op, buf, tw);
@@ -348,7 +359,7 @@ struct Fft2dJob {
 
 template <typename T, int G, int DIR>
 __global__ void __launch_bounds__(FftCfg<T, G>::kThreads2d, FftCfg<T, G>::kOcc2d) fft2d_kernel(const __grid_constant__ Fft2dParams p) {
-    using S = SlabFFT<T, G, FftCfg<T, G>::kThreads2d>;
+    using S = typename Fft2dJob<T, G, DIR>::S;
     using V = typename S::V;
     extern __shared__ __align__(128) unsigned char fft_smem[];
     V* buf0 = reinterpret_cast<V*>(fft_smem);
@@ -485,14 +496,20 @@ int make_fft2_tables(pm_ctx* c) {
     // so that one CUDA-IPC handle exposes all three to the peers
     c->f2_a = reinterpret_cast<char*>(c->real) + c->f2_off_a;
     c->f2_b = reinterpret_cast<char*>(c->real) + c->f2_off_b;
-    c->f2_lag = 10;   // planes; > CTAs in flight / tiles per plane (444 / 96)
-    if (const char* e = getenv("PM_FFT_LAG")) c->f2_lag = std::max(1, atoi(e));
+    // planes between the two passes in ticket order; > CTAs in flight / tiles per plane.  Measured on B200 at 512³ fp64
+    // (profiles/r02_fft_config_sweep.md): forward 2/3/4/5/6/8/10 -> 0.92/0.87/0.84/0.82/0.82/0.86/0.89 ms,
+    // inverse 6/8/10/12/14 -> 0.86/0.82/0.81/0.82/0.83 ms
+    c->f2_lag = 5;
+    c->f2_lag_inv = 10;
+    if (const char* e = getenv("PM_FFT_LAG")) c->f2_lag = c->f2_lag_inv = std::max(1, atoi(e));
+    if (const char* e = getenv("PM_FFT_LAG_FWD")) c->f2_lag = std::max(1, atoi(e));
+    if (const char* e = getenv("PM_FFT_LAG_INV")) c->f2_lag_inv = std::max(1, atoi(e));
     return PM_OK;
 }
 
-template <typename T, int G>
+template <typename T, int G, int DIR>
 static size_t fft2d_smem() {
-    using S = SlabFFT<T, G, FftCfg<T, G>::kThreads2d>;
+    using S = typename Fft2dJob<T, G, DIR>::S;
     return sizeof(typename S::V) * ((size_t)(kFft2dDouble ? 2 : 1) * S::kBufElems + smem_twiddle_entries<G>());
 }
 template <typename T, int G>
@@ -503,7 +520,7 @@ static size_t xsolve2_smem() {
 
 template <typename T, int G, int DIR>
 static int launch_fft2d(pm_ctx* c, int mode) {
-    using S = SlabFFT<T, G, FftCfg<T, G>::kThreads2d>;
+    using S = typename Fft2dJob<T, G, DIR>::S;
     Fft2dParams p;
     // one rank: the density grid cleans itself and the potential goes to `phi` (pm_internal.cuh)
     const bool self_clean = c->nranks == 1 && c->phi != nullptr;
@@ -514,11 +531,13 @@ static int launch_fft2d(pm_ctx* c, int mode) {
     p.tw = c->f2_tw;
     p.nplanes = c->g.nxl;
     p.mode = mode;
-    p.lag = c->f2_lag;
+    p.lag = DIR < 0 ? c->f2_lag : c->f2_lag_inv;
+    static const int no_discard = getenv("PM_FFT_NO_DISCARD") ? atoi(getenv("PM_FFT_NO_DISCARD")) : 0;
+    p.discard = !no_discard;
     p.ticket = c->f2_ctr + (DIR < 0 ? 0 : 2);
     p.done = c->f2_ctr + 4 + (DIR < 0 ? 0 : c->g.nxl);
     p.err = reinterpret_cast<int*>(c->f2_ctr + c->f2_nctr);
-    const size_t smem = fft2d_smem<T, G>();
+    const size_t smem = fft2d_smem<T, G, DIR>();
     PM_CHECK_CUDA(cudaFuncSetAttribute(fft2d_kernel<T, G, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (int64_t)c->g.nxl * (mode == 0 ? S::kZTilesPerPlane + S::kYTilesPerPlane
                                                          : ((mode == 1) == (DIR < 0) ? S::kZTilesPerPlane : S::kYTilesPerPlane));

@@ -31,6 +31,8 @@ namespace fftc {
 
 constexpr int kMaxFftPeers = 16;
 
+
+
 // streaming global load: L2 only (the 2-D kernels hand rows from one SM to another inside a launch, which
 // L1 would not notice; nothing here is re-read anyway)
 template <typename V>
@@ -48,7 +50,10 @@ struct TileLoad {
     int bytes;         // multiple of 16; src and dst 16-byte aligned
 };
 
-template <typename T, int G_, int NTHR_>
+// several rows per warp only while the z tile still fits into the y-tile buffer: RPW·(NTHR/32)·(G/2) ≤ G·CY, CY ≥ 4
+constexpr bool rpw_fits(int G, int NTHR, int RPW) { return RPW * (NTHR / 32) * (G / 2) <= G * 4; }
+
+template <typename T, int G_, int NTHR_, int RPW_ = 1>
 struct SlabFFT {
     using V = typename Vec2<T>::type;
     using TW = Twiddles<V>;
@@ -58,10 +63,13 @@ struct SlabFFT {
     static constexpr int Gc = M + 1;
     static constexpr int Gp = 2 * Gc;
     static constexpr int CY = 64 / (int)sizeof(V);   // columns per y/x tile: 4 in fp64, 8 in fp32
-    static constexpr int CZ = NTHR / 32;             // rows per z tile: every warp owns one whole row (no block barrier inside)
+    // rows per warp, their loads in flight together; RPW·(NTHR/32) rows are as large as a y tile (G × 64 bytes) when
+    // NTHR = G/4·RPW/2 — at G = 1024 (256 threads) a second row would double the tile buffer
+    static constexpr int RPW = rpw_fits(G_, NTHR_, RPW_) ? RPW_ : 1;
+    static constexpr int CZ = RPW * (NTHR / 32);     // rows per z tile: every warp owns whole rows (no block barrier inside)
     static constexpr int NKT = M / CY;               // column tiles
     using LY = ColSwz<CY>;
-    using LZ = RowSwz<M, 1, Gc>;                     // the warp's private row
+    using LZ = RowSwz<M, RPW, Gc>;                   // the warp's private rows
     static constexpr int kYTileElems = G * CY;
     static constexpr int kZTileElems = CZ * M;
     static constexpr int kBufElems = (kZTileElems > kYTileElems) ? kZTileElems : kYTileElems;
@@ -74,18 +82,18 @@ struct SlabFFT {
     static PM_HD size_t a_index(int il, int kt, int j, int c) { return (((size_t)il * NKT + kt) * G + j) * CY + c; }
     static PM_HD size_t b_index(int kt, int j, int il, int c, int nxl) { return (((size_t)kt * G + j) * nxl + il) * CY + c; }
 
-    struct RowSink {     // complex slot k of one row of a padded real plane
+    struct RowSink {     // complex slot k of row `row + c` of a padded real plane
         T* plane; int row;
-        PM_HD void operator()(int, int k, T r, T i) const {
+        PM_HD void operator()(int c, int k, T r, T i) const {
             V v; v.x = r; v.y = i;
-            reinterpret_cast<V*>(plane + (size_t)row * Gp)[k] = v;
+            reinterpret_cast<V*>(plane + (size_t)(row + c) * Gp)[k] = v;
         }
     };
 
-    struct RowSource {     // complex element k of one row, straight from global memory (L2: the rows were prefetched)
+    struct RowSource {     // complex element k of row `row + c`, straight from global memory (L2: the rows were prefetched)
         const T* plane; int row;
-        PM_HD V operator()(int, int k) const {
-            return ld_stream(reinterpret_cast<const V*>(plane + (size_t)row * Gp) + k);
+        PM_HD V operator()(int c, int k) const {
+            return ld_stream(reinterpret_cast<const V*>(plane + (size_t)(row + c) * Gp) + k);
         }
     };
 
@@ -102,22 +110,22 @@ struct SlabFFT {
         PM_HD TileLoad load(int) const { return TileLoad{plane + (size_t)row0 * Gp, 0, CZ * Gp * (int)sizeof(T)}; }
         struct ToA {
             V* a_plane; int row;
-            PM_HD void operator()(int, int k, T r, T i) const {
+            PM_HD void operator()(int c, int k, T r, T i) const {
                 if (k >= M) return;     // the Nyquist column is not stored
                 V v; v.x = r; v.y = i;
-                a_plane[((size_t)(k / CY) * G + row) * CY + (k % CY)] = v;
+                a_plane[((size_t)(k / CY) * G + row + c) * CY + (k % CY)] = v;
             }
         };
         static constexpr int kPhases = 3;
         PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int, T (&)[kRegs]) const {
-            const int warp = tid >> 5, lane = tid & 31, row = row0 + warp;
-            V* mine = tile + warp * M;
+            const int warp = tid >> 5, lane = tid & 31, row = row0 + warp * RPW;
+            V* mine = tile + warp * (RPW * M);
             if (ph == 0) dit_stageA<LZ, T, M, -1>(RowSource{plane, row}, mine, lane, 32);
             else if (ph == 1) {
-                if (clear) {     // every lane of the warp has consumed the row by now
+                if (clear) {     // every lane of the warp has consumed the rows by now (they are contiguous)
                     V zero; zero.x = 0; zero.y = 0;
                     V* cells = reinterpret_cast<V*>(plane + (size_t)row * Gp);
-                    for (int e = lane; e < Gc; e += 32) cells[e] = zero;
+                    for (int e = lane; e < RPW * Gc; e += 32) cells[e] = zero;
                 }
                 dit_stageB<LZ, T, M, -1>(mine, tw.B, lane, 32);
             }
@@ -134,8 +142,8 @@ struct SlabFFT {
         PM_HD TileLoad load(int) const { return TileLoad{plane + (size_t)row0 * Gp, 0, CZ * Gp * (int)sizeof(T)}; }
         static constexpr int kPhases = 3;
         PM_HD void phase(int ph, V* tile, const TW& tw, int tid, int, T (&)[kRegs]) const {
-            const int warp = tid >> 5, lane = tid & 31, row = row0 + warp;
-            V* mine = tile + warp * M;
+            const int warp = tid >> 5, lane = tid & 31, row = row0 + warp * RPW;
+            V* mine = tile + warp * (RPW * M);
             if (ph == 0) c2r_pre_stageA<LZ, T, M>(RowSource{plane, row}, mine, tw.R, lane, 32);   // real pre-processing + first stage
             else if (ph == 1) dit_stageB<LZ, T, M, +1>(mine, tw.B, lane, 32);
             else dit_stageC<LZ, T, M, 2, +1>(mine, tw.C, lane, 32, RowSink{plane, row});   // z_m = x_2m + i·x_2m+1

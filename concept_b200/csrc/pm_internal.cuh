@@ -159,7 +159,7 @@ struct pm_ctx {
     size_t f2_off_a, f2_off_b; // their byte offsets from `real` (the same on every rank)
     unsigned* f2_ctr;         // tickets, per-plane completion counters, error flag (last entry)
     size_t f2_nctr;
-    int f2_lag;
+    int f2_lag, f2_lag_inv;   // planes between the two passes of the forward / inverse 2-D transform in ticket order
     bool f2_x_in_place;       // the last x solve left its results in B (several ranks): re-layout before the inverse y pass
     void* peer_real[pm::kMaxPeers];   // IPC mappings of every rank's `real` buffer (own pointer for self)
     bool peers_ready;

@@ -77,14 +77,16 @@ cell_count_kernel(SrParticles p, CellGeom g, int* __restrict__ cell_of, int* __r
 
 __global__ void __launch_bounds__(256)
 cell_scatter_kernel(SrParticles p, const int* __restrict__ cell_of, const int* __restrict__ offset, int* __restrict__ cursor,
-                    double* __restrict__ pos_s, int* __restrict__ idx_s) {
+                    double* __restrict__ pos_s, size_t stride, int* __restrict__ idx_s) {
     int64_t g0, g1;
     const int64_t total = sr_total(p, &g0, &g1);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const double* q = sr_pos(p, i, g0);
         const int c = cell_of[i];
         const int slot = offset[c] + atomicAdd(&cursor[c], 1);
-        reinterpret_cast<double4*>(pos_s)[slot] = make_double4(q[0], q[1], q[2], 0.0);   // one 32-byte sector per particle
+        pos_s[slot] = q[0];                    // structure of arrays: the lanes of a warp walk neighbouring stretches of the
+        pos_s[stride + slot] = q[1];           // sorted list, so one load instruction touches a few 128-byte lines per
+        pos_s[2 * stride + slot] = q[2];       // coordinate instead of one 32-byte record per lane
         idx_s[slot] = i < p.n ? (int)i : -1;      // ghosts only supply
     }
 }
@@ -126,19 +128,19 @@ struct PairParams {
 // minimum-image logic: x⃗ = (x⃗_i − x⃗_j) − shift, r² = x·x + y·y + z·z in the reference's order (gravity.py:306-327).
 template <bool STATS>
 __global__ void __launch_bounds__(128)
-shortrange_kernel(const double* __restrict__ pos_s_, const int* __restrict__ idx_s, const int* __restrict__ offset,
+shortrange_kernel(const double* __restrict__ xs, size_t stride, const int* __restrict__ idx_s, const int* __restrict__ offset,
                   const int* __restrict__ list, const unsigned int* __restrict__ nlist, CellGeom g, PairParams pp,
                   const double* __restrict__ table, const signed char* __restrict__ rung_jumped,
                   const double* __restrict__ factors, double* __restrict__ dmom, unsigned long long* __restrict__ stats) {
-    const double4* __restrict__ pos_s = reinterpret_cast<const double4*>(pos_s_);
+    const double* __restrict__ ys = xs + stride;
+    const double* __restrict__ zs = xs + 2 * stride;
     const unsigned int nrecv = *nlist;
     unsigned long long hits = 0, cands = 0;
     for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < nrecv; t += gridDim.x * blockDim.x) {
         const int s = list ? list[t] : (int)t;
         const int i = idx_s[s];
         if (i < 0) continue;
-        const double4 pi = pos_s[s];
-        const double xi = pi.x, yi = pi.y, zi = pi.z;
+        const double xi = xs[s], yi = ys[s], zi = zs[s];
         const int cx = cell_1d(xi - g.x_origin, g.inv_cell_x, g.ncx), cy = cell_1d(yi, g.inv_cell, g.nc), cz = cell_1d(zi, g.inv_cell, g.nc);
         double ax = 0, ay = 0, az = 0;
         const bool zwrap = cz - g.S < 0 || cz + g.S >= g.nc;
@@ -176,8 +178,7 @@ shortrange_kernel(const double* __restrict__ pos_s_, const int* __restrict__ idx
                         double x[4], y[4], z[4], f[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {      // (the array has slack behind its last particle: reading past a run is harmless)
-                            const double4 q = pos_s[j0 + u];
-                            x[u] = bx - q.x; y[u] = by - q.y; z[u] = bz - q.z;
+                            x[u] = bx - xs[j0 + u]; y[u] = by - ys[j0 + u]; z[u] = bz - zs[j0 + u];
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -320,10 +321,12 @@ int shortrange(pm_ctx* c, const double* pos, int64_t n, const signed char* rung,
     const size_t ncell = (size_t)g.ncx * g.nc * g.nc;
     // scratch: pos_s[3·total] factors[64] | cell_of[total] idx_s[total] list[total] count[ncell+1] offset[ncell+1] nlist
     const size_t tot = (size_t)max_total;
-    const size_t need = sizeof(double) * (4 * (tot + 8) + 64 + (size_t)tablesize + 8) + sizeof(int) * (3 * tot + 2 * (ncell + 1) + 8) + 256;
+    const size_t stride = (tot + 8 + 15) / 16 * 16;        // doubles per coordinate array (slack behind the last particle)
+    const size_t need = sizeof(double) * (3 * stride + 64 + (size_t)tablesize + 8) +
+                        sizeof(int) * (3 * tot + 2 * (ncell + 1) + 8) + 256;
     PM_TRY(ensure_bytes(c, &c->sr_buf, &c->sr_bytes, need));
-    double* pos_s = reinterpret_cast<double*>(c->sr_buf);       // double4 per particle (cudaMalloc alignment)
-    double* d_factors = pos_s + 4 * (tot + 8);
+    double* pos_s = reinterpret_cast<double*>(c->sr_buf);       // x | y | z of the cell-sorted particles
+    double* d_factors = pos_s + 3 * stride;
     double* d_table = d_factors + 64;          // the caller's table followed by a zero (what a non-pair reads)
     int* cell_of = reinterpret_cast<int*>(d_table + tablesize + 8);
     PM_CHECK_CUDA(cudaMemcpyAsync(d_table, table_dev, sizeof(double) * tablesize, cudaMemcpyDeviceToDevice, c->stream));
@@ -343,7 +346,8 @@ int shortrange(pm_ctx* c, const double* pos, int64_t n, const signed char* rung,
     PM_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(c->sr_tmp, tmp_bytes, count, offset, (int)(ncell + 1), c->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PM_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (ncell + 1), c->stream));   // reuse as cursor
-    PM_LAUNCH(cell_scatter_kernel, blocks, 256, 0, c->stream, sp, cell_of, offset, count, pos_s, idx_s);
+    PM_LAUNCH(cell_scatter_kernel, blocks, 256, 0, c->stream, sp, cell_of, offset, count, pos_s, stride, idx_s);
+    // (receivers in blocks of 4³ cells instead of the z-fastest cell order were measured too: no gain, 16.8 vs 16.5 ms)
     PM_CHECK_CUDA(cudaMemsetAsync(nlist, 0, sizeof(unsigned int), c->stream));
     PM_LAUNCH(active_list_kernel, blocks, 256, 0, c->stream, idx_s, offset, (int)ncell, rung, lowest_active_rung, list, nlist);
     PairParams pp;
@@ -355,10 +359,10 @@ int shortrange(pm_ctx* c, const double* pos, int64_t n, const signed char* rung,
     PM_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), c->stream));
     const int pblocks = (int)std::min<int64_t>((std::max<int64_t>(n, 1) + 127) / 128, (int64_t)kNumSMs * 16);
     if (c->sr_want_stats)
-        PM_LAUNCH(shortrange_kernel<true>, pblocks, 128, 0, c->stream, pos_s, idx_s, offset, list, nlist, g, pp, d_table, rung_jumped,
+        PM_LAUNCH(shortrange_kernel<true>, pblocks, 128, 0, c->stream, pos_s, stride, idx_s, offset, list, nlist, g, pp, d_table, rung_jumped,
                   d_factors, dmom, d_stats);
     else
-        PM_LAUNCH(shortrange_kernel<false>, pblocks, 128, 0, c->stream, pos_s, idx_s, offset, list, nlist, g, pp, d_table, rung_jumped,
+        PM_LAUNCH(shortrange_kernel<false>, pblocks, 128, 0, c->stream, pos_s, stride, idx_s, offset, list, nlist, g, pp, d_table, rung_jumped,
                   d_factors, dmom, d_stats);
     return PM_OK;
 }
