@@ -473,6 +473,37 @@ def run_pm_config(D, cfg, steps, warmup, lib, ctx=None, pos=None, mom=None, want
     return rec, ctx, (pbuf, mbuf, state, params, cycle)
 
 
+def run_particle_order(D, ctx, pbuf, mbuf, n, params):
+    """One GPU: what the memory order of the particles is worth — the same cycle on a randomly permuted array, the time of
+    pm_sort_particles (the tile_sort analogue), and the cycle after sorting."""
+    torch = D.torch
+    perm = torch.randperm(n, device=D.dev)
+    p, m = pbuf[:n][perm].contiguous(), mbuf[:n][perm].contiguous()
+    sum2 = torch.zeros(1, dtype=torch.float64, device=D.dev)
+
+    def timed(fn, reps):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)/reps
+    cyc = lambda: ctx.kick_drift(p, m, params, DT_OVER_MASS, sum_mom2=sum2)
+    shuffled = timed(cyc, 3)
+    ctx.sort_particles(p, m)          # warm-up (scratch allocation); the array is sorted now
+    q, r = p[perm % n].contiguous(), m[perm % n].contiguous()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ctx.sort_particles(q, r); e1.record(); torch.cuda.synchronize()
+    sort_ms = e0.elapsed_time(e1)
+    p, m = q, r
+    after = timed(lambda: ctx.kick_drift(p, m, params, DT_OVER_MASS, sum_mom2=sum2), 3)
+    return {'cycle_ms_random_order': shuffled, 'sort_ms': sort_ms, 'cycle_ms_after_sort': after,
+            'note': 'main.timeloop re-orders by grid cell at synchronised steps every cell_sort_period (default 64) base steps'}
+
+
 def run_e2e(D, ctx, pbuf, mbuf, state, params, cycle, steps):
     """The same cycle with HOST particle buffers (pinned), host<->device copies inside the timed region."""
     torch = D.torch
@@ -637,6 +668,12 @@ def run_gpu(args):
     # ---- configs[1]: the headline ----
     rec, ctx, (pbuf, mbuf, state, params, cycle) = run_pm_config(D, cfg, args.steps, args.warmup, lib, ctx=ctx)
     e2e = run_e2e(D, ctx, pbuf, mbuf, state, params, cycle, args.steps)
+    particle_order = None
+    if D.world == 1 and not args.no_extra:
+        try:
+            particle_order = run_particle_order(D, ctx, pbuf, mbuf, state['n'], params)
+        except Exception as exc:
+            particle_order = {'error': repr(exc)}
     del pbuf, mbuf, cycle
     ctx.close()
     torch.cuda.empty_cache()
@@ -706,7 +743,7 @@ def run_gpu(args):
             'data': 'synthetic', 'config': workload_config(cfg, D.world), 'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
             'gpu_launches': rec['launches'], 'clocks': rec['clocks'], 'parity': parity,
             'sum_mom2': rec['sum_mom2'], 'particles_after': rec['particles_after'],
-            'cycles_before_state': max(args.warmup, 3) + args.steps, 'extra_configs': extra,
+            'cycles_before_state': max(args.warmup, 3) + args.steps, 'particle_order': particle_order, 'extra_configs': extra,
         }
         print(json.dumps(out))
     if D.world > 1:

@@ -255,6 +255,9 @@ def load_params(path_or_text='', extra='', **overrides):
     p.Δa_max_early = float(up.get('Δa_max_early', 0.00153))
     p.Δa_max_late = float(up.get('Δa_max_late', 0.022))
     p.static_timestepping = up.get('static_timestepping', None)
+    # concept_b200 only: base steps between two re-orderings of the particles by grid cell (pm_sort_particles, the analogue of
+    # the tile sort the reference performs at its synchronised steps, main.py:270-305); 0 disables it
+    p.cell_sort_period = int(up.get('cell_sort_period', 64))
     p.cell_centered = bool(up.get('cell_centered', True))
     p.grid_dtype = str(up.get('grid_dtype', 'f64'))     # extension: 'f32' selects the mixed-precision grid
     # select_forces (commons.py:3664-3702): default for particles is gravity via P³M

@@ -498,9 +498,9 @@ int make_fft2_tables(pm_ctx* c) {
     c->f2_b = reinterpret_cast<char*>(c->real) + c->f2_off_b;
     // planes between the two passes in ticket order; > CTAs in flight / tiles per plane.  Measured on B200 at 512³ fp64
     // (profiles/r02_fft_config_sweep.md): forward 2/3/4/5/6/8/10 -> 0.92/0.87/0.84/0.82/0.82/0.86/0.89 ms,
-    // inverse 6/8/10/12/14 -> 0.86/0.82/0.81/0.82/0.83 ms
+    // inverse (two rows per warp) 6/8/10/12/16/20 -> 0.78/0.74/0.73/0.72/0.77/0.80 ms
     c->f2_lag = 5;
-    c->f2_lag_inv = 10;
+    c->f2_lag_inv = 12;
     if (const char* e = getenv("PM_FFT_LAG")) c->f2_lag = c->f2_lag_inv = std::max(1, atoi(e));
     if (const char* e = getenv("PM_FFT_LAG_FWD")) c->f2_lag = std::max(1, atoi(e));
     if (const char* e = getenv("PM_FFT_LAG_INV")) c->f2_lag_inv = std::max(1, atoi(e));

@@ -463,6 +463,7 @@ class _Leapfrog:
         self.sync_time = ထ
         self.limit_is_fresh = False        # Δt_max was measured at the current time already
         self.Δt_shelved = -1               # the step size put aside while a dump forces a shorter one
+        self.last_sort_step = 0
         initial_fac_times.add(universals.t)
         self.Δt_max, self.bottleneck = get_base_timestep_size(components, self.static)
         self.Δt = self.Δt_max
@@ -473,7 +474,22 @@ class _Leapfrog:
             self.announced_step = self.time_step
             if self.synchronised:           # all rungs are synchronised: re-assign them (main.py:225-227)
                 _assign_rungs(self.components, self.Δt)
+                self._restore_memory_order()
             universals.time_step = self.time_step
+
+    def _restore_memory_order(self):
+        """Deposit and gather rely on consecutive particles touching neighbouring grid rows (a randomly ordered array costs
+        3.6× the cycle time, bench.py `particle_order`).  Lattice-ordered initial conditions have that order and the hole-filling
+        migration keeps it, but it decays as structure forms; like the reference's tile sort at synchronised steps
+        (main.py:270-305) the particles are re-ordered by grid cell there, every `cell_sort_period` base steps (a sort costs
+        about 0.6 PM cycles)."""
+        period = commons.params.cell_sort_period
+        if period <= 0 or self.time_step - self.last_sort_step < period:
+            return
+        self.last_sort_step = self.time_step
+        for c in self.components:
+            if c.representation == 'particles' and c.N_local > 1:
+                c.cell_sort()
 
     def _measure_limit(self):
         self.Δt_max, self.bottleneck = get_base_timestep_size(self.components, self.static)

@@ -400,6 +400,18 @@ class PMKickMockContext(MeshMockContext):
         from oracle import pm_oracle as O
         pos.copy_(torch.from_numpy(O.drift(pos.numpy(), mom.numpy(), dt_over_mass, self.boxsize)))
 
+    def sort_particles(self, pos, mom, ids=None, n=None):
+        """pm_sort_particles: stable re-ordering by grid cell (x plane, y row, z)"""
+        import torch
+        n = pos.shape[0] if n is None else int(n)
+        G = self.gridsize
+        cell = np.clip((pos[:n].numpy()*(G/self.boxsize)).astype(np.int64), 0, G - 1)
+        order = torch.as_tensor(np.argsort((cell[:, 0]*G + cell[:, 1])*G + cell[:, 2], kind='stable'))
+        pos[:n] = pos[:n][order]
+        mom[:n] = mom[:n][order]
+        if ids is not None:
+            ids[:n] = ids[:n][order]
+
     def sum_mom2(self, mom, out=None):
         from oracle import pm_oracle as O
         return O.sum_mom2(mom.numpy())

@@ -135,7 +135,7 @@ select_forces = {'matter': {'gravity': 'pm'}}
     c.populate(d['pos0'], 'pos'); c.populate(d['mom0'], 'mom')
     snaps, steps = {}, []
     def on_dump(components, dump_time):
-        snaps[f'{dump_time.a:.6f}'] = (components[0].pos_mv3.copy(), components[0].mom_mv3.copy(), commons.universals.t)
+        snaps[f'{dump_time.a:.6f}'] = (*components[0].gather_global(), commons.universals.t)      # particles by id (the run re-orders them by cell)
     nsteps = main.timeloop([c], on_dump=on_dump, on_step=lambda *a: steps.append(a))
     assert sorted(snaps) == ['0.100000', '0.500000', '1.000000']
     assert nsteps == len(d['drift_dt']) == 142   # same number of base steps (drifts) as the reference

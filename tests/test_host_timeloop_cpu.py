@@ -38,7 +38,7 @@ def _run(monkeypatch, **overrides):
     snaps, steps = {}, []
 
     def on_dump(components, dump_time):
-        snaps[f'{dump_time.a:.6f}'] = (components[0].pos_mv3.copy(), components[0].mom_mv3.copy(), commons.universals.t)
+        snaps[f'{dump_time.a:.6f}'] = (*components[0].gather_global(), commons.universals.t)      # particles by id (the run re-orders them by cell)
     nsteps = main.timeloop([c], on_dump=on_dump, on_step=lambda *a: steps.append(a))
     return d, nsteps, steps, snaps
 
