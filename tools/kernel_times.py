@@ -28,6 +28,7 @@ def main():
     ap.add_argument('--reps', type=int, default=7)
     ap.add_argument('--tag', default='')
     ap.add_argument('--solve-mode', default='auto')
+    ap.add_argument('--sort', action='store_true', help='re-order the particles by grid cell first (pm_sort_particles)')
     ap.add_argument('--check', action='store_true', help='compare the potential with the cuFFT path of the same library')
     a = ap.parse_args()
     L = 512.0*a.grid/512
@@ -35,6 +36,8 @@ def main():
     N = pos.shape[0]
     ctx = PMContext(a.grid, L, dtype=a.dtype)
     ctx.set_fused_solve(a.solve_mode)
+    if a.sort:
+        ctx.sort_particles(pos, mom)
     p = make_kick_params(mass=1.0, boxsize=L, gridsize=a.grid, order=a.order, G_Newton=4.4985024439973154e-05,
                          dt_rho_over_dt1=2.0, dt_kick=1e-3, diff_order=a.diff)
     s = torch.zeros(1, dtype=torch.float64, device='cuda')
