@@ -50,8 +50,14 @@ struct TileLoad {
     int bytes;         // multiple of 16; src and dst 16-byte aligned
 };
 
+// Bytes of adjacent kk columns per y/x tile row (and per store segment into A, B and the complex rows): 64 or 128.
+// G = 1024 keeps 64 (a 128-byte tile would be 128 KB).
+#ifndef PM_FFT_CY_BYTES
+#define PM_FFT_CY_BYTES 64
+#endif
+constexpr int cy_bytes(int G) { return G >= 1024 ? 64 : PM_FFT_CY_BYTES; }
 // several rows per warp only while the z tile still fits into the y-tile buffer: RPW·(NTHR/32)·(G/2) ≤ G·CY, CY ≥ 4
-constexpr bool rpw_fits(int G, int NTHR, int RPW) { return RPW * (NTHR / 32) * (G / 2) <= G * 4; }
+constexpr bool rpw_fits(int G, int NTHR, int RPW) { return RPW * (NTHR / 32) * (G / 2) <= G * (cy_bytes(G) / 16); }
 
 template <typename T, int G_, int NTHR_, int RPW_ = 1>
 struct SlabFFT {
@@ -62,7 +68,7 @@ struct SlabFFT {
     static constexpr int M = G / 2;          // complex points of the packed real transform
     static constexpr int Gc = M + 1;
     static constexpr int Gp = 2 * Gc;
-    static constexpr int CY = 64 / (int)sizeof(V);   // columns per y/x tile: 4 in fp64, 8 in fp32
+    static constexpr int CY = cy_bytes(G_) / (int)sizeof(V);   // columns per y/x tile: 4 in fp64, 8 in fp32 (64-byte groups)
     // rows per warp, their loads in flight together; RPW·(NTHR/32) rows are as large as a y tile (G × 64 bytes) when
     // NTHR = G/4·RPW/2 — at G = 1024 (256 threads) a second row would double the tile buffer
     static constexpr int RPW = rpw_fits(G_, NTHR_, RPW_) ? RPW_ : 1;
