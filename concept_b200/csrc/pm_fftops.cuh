@@ -220,6 +220,8 @@ struct SlabFFT {
         const XGeom* g;
         int j;        // global j row
         int kt;       // column tile
+        V* stage = nullptr;   // in place with a staging tile: the results are laid out like the loaded tile (rank-major, each
+                              // rank's nxl·CY elements contiguous) and the caller sends every piece to its owner in one bulk copy
         static constexpr bool kBulk = true;
         static constexpr bool kWarpPrivate = false;
         PM_HD int nloads() const { return g->nranks; }
@@ -237,6 +239,13 @@ struct SlabFFT {
                 // at G = 1024 that is 8 MB, and 64-byte stores scattered like that over a peer's 8 GB ran at 5 GB/s.)
                 if (g->in_place) const_cast<V*>(g->b[rk])[b_index(kt, j, il, c, 1 << g->nxl_shift)] = v;
                 else g->a[rk][a_index(il, kt, j, c)] = v;
+            }
+        };
+        struct ToStage {
+            V* stage;
+            PM_HD void operator()(int c, int i, T r, T im) const {
+                V v; v.x = r; v.y = im;
+                stage[(size_t)i * CY + c] = v;
             }
         };
         // per-mode factor in separable form: Π_l sep[l] · prefactor/k²; zero on the Nyquist planes and at
@@ -293,6 +302,7 @@ struct SlabFFT {
                     }
                 }
             } else if (ph == 4) dif_stage2<LY, T, G, +1>(tile, tw.B, tid, nthr);
+            else if (g->in_place && stage != nullptr) dif_stage3<LY, T, G, +1>(tile, tid, nthr, ToStage{stage});
             else dif_stage3<LY, T, G, +1>(tile, tid, nthr, ToA{g, j, kt});
         }
     };
