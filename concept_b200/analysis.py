@@ -201,11 +201,8 @@ def _upstream_to_global_mixed(components, gridsizes_upstream, gridsize, ctx_glob
     """interpolate_upstream (mesh.py:492-616) for components with their own upstream grid sizes: every group is
     deposited on its own grid, transformed, and copied — with its deconvolution, interlacing phase and the half-cell
     phase between grids — into the global slab (add_upstream_to_global_slabs :618-710, copy_modes :980-1322), which
-    ends up in ctx_global's working slab.  One rank (see pm_fourier_copy_modes)."""
-    from . import communication, mesh
-    if communication.nprocs > 1:
-        commons.abort('Power spectra with component-specific upstream grid sizes need one rank '
-                      '(the cross-rank mode exchange of copy_modes, mesh.py:1105-1230, is not provided)')
+    ends up in ctx_global's working slab.  On several ranks pm_fourier_copy_modes exchanges the mode rows between them."""
+    from . import mesh
     nl = len(shifts)
     first = True
     for gridsize_upstream in sorted(set(gridsizes_upstream), key=lambda g: (g != gridsize, g)):

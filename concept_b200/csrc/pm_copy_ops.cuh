@@ -38,6 +38,27 @@ PM_HD double ipow(double f, int n) {
     return r;
 }
 
+// The value a shared mode (ki, kj, kk) of the source grid — v at source slab indices (is, js, kk) — takes in the destination:
+// source-grid deconvolution, 1/n_lattices, interlacing phase and the half-cell phase between the two grids.
+PM_HD double2 mode_value(const double2 v, int ki, int kj, int kk, int is, int js, const CopyParams& p, const double* tab_x,
+                         const double* tab_sin) {
+    double factor = 1;
+    if (p.deconv_order) {
+        // ((xi·xj)·xk)/((si·sj)·sk), then **D  (mesh.py:2795-2856)
+        factor = ((tab_x[is] * tab_x[js]) * tab_x[kk]) / ((tab_sin[is] * tab_sin[js]) * tab_sin[kk]);
+        factor = ipow(factor, p.deconv_order);
+    }
+    factor *= p.scale;
+    double theta = p.cell_phase * ((ki + kj) + kk);
+    if (p.rotate) theta += (ki * p.th[0] + kj * p.th[1]) + kk * p.th[2];
+    double sn, cs;
+    sincos(theta, &sn, &cs);
+    double2 o;
+    o.x = factor * (v.x * cs - v.y * sn);
+    o.y = factor * (v.x * sn + v.y * cs);
+    return o;
+}
+
 // Mode idx of the destination slab.  Returns false when the mode lies outside the cube |k| < min(Gs, Gd)/2 that
 // the two grids share (Nyquist planes of the smaller grid excluded, mesh.py:1134-1135): '=' writes zero there,
 // '+=' leaves it alone.  tab_x / tab_sin: the SOURCE context's x_l = k_l·π/Gs + ε and sin x_l by slab index.
@@ -56,20 +77,7 @@ PM_HD bool copy_mode(int64_t idx, const double2* src, const CopyParams& p, const
     if (!(ki > -n && ki < n && kj > -n && kj < n && kk < n)) return false;
     const int is = ki < 0 ? ki + p.Gs : ki;
     const int js = kj < 0 ? kj + p.Gs : kj;
-    const double2 v = src[((int64_t)is * p.Gs + js) * Gcs + kk];
-    double factor = 1;
-    if (p.deconv_order) {
-        // ((xi·xj)·xk)/((si·sj)·sk), then **D  (mesh.py:2795-2856)
-        factor = ((tab_x[is] * tab_x[js]) * tab_x[kk]) / ((tab_sin[is] * tab_sin[js]) * tab_sin[kk]);
-        factor = ipow(factor, p.deconv_order);
-    }
-    factor *= p.scale;
-    double theta = p.cell_phase * ((ki + kj) + kk);
-    if (p.rotate) theta += (ki * p.th[0] + kj * p.th[1]) + kk * p.th[2];
-    double sn, cs;
-    sincos(theta, &sn, &cs);
-    out->x = factor * (v.x * cs - v.y * sn);
-    out->y = factor * (v.x * sn + v.y * cs);
+    *out = mode_value(src[((int64_t)is * p.Gs + js) * Gcs + kk], ki, kj, kk, is, js, p, tab_x, tab_sin);
     return true;
 }
 

@@ -188,12 +188,15 @@ def _particle_mesh_mixed_gridsizes(receivers, suppliers, gridsizes_upstream, gri
     potential is copied to every downstream grid size in use, where the downstream deconvolution, differentiation and
     interpolation happen.  A deconvolution is promoted to the global slab only if all grids on its side have the global
     size (interactions.py:2069-2080).  The accumulating global slab and the finished potential live in the saved
-    slabs of the contexts (pm_slab_save), the working slabs being transformed in place."""
+    slabs of the contexts (pm_slab_save), the working slabs being transformed in place.  On several ranks every grid is
+    slab-decomposed like the particles and pm_fourier_copy_modes exchanges the rows of the shared mode cube between the
+    ranks (the reference's subslab exchange, mesh.py:1105-1230)."""
     from . import communication
     p = commons.params
-    if communication.nprocs > 1:
-        abort('Component-specific upstream/downstream grid sizes need the cross-rank mode exchange of copy_modes '
-              '(mesh.py:1105-1230), which concept_b200 does not provide: use one grid size per potential on several GPUs')
+    for gridsize in set(gridsizes_upstream) | set(gridsizes_downstream) | {G}:
+        # every grid is cut into the same x-slabs as the particles (fft.c:105-212 asks for the same divisibility)
+        if gridsize % communication.nprocs or (communication.nprocs > 1 and gridsize//communication.nprocs < 8):
+            abort(f'Grid size {gridsize} cannot be cut into {communication.nprocs} slabs of at least 8 planes')
     if str(p.grid_dtype) not in ('f64', 'float64'):
         abort('Component-specific upstream/downstream grid sizes are available for fp64 grids only')
     L = p.boxsize

@@ -82,6 +82,60 @@ select_forces = {{'matter': {{'gravity': 'pm'}}}}
             if status != 'ok':
                 failures.append((G, order, diff, interlace))
         mesh.free_contexts()
+    # ---- component-specific upstream / downstream grid sizes on several ranks: every grid is slab-decomposed and
+    # pm_fourier_copy_modes moves the rows of the shared mode cube between the ranks (copy_modes' subslab exchange,
+    # mesh.py:1105-1230); compared with the oracle restatement of particle_mesh on rank 0
+    for Gg, grids, order, diff, interlace in [(128, {'cdm': (64, 128), 'baryons': (128, 64)}, 3, 4, False),
+                                              (64, {'cdm': (32, 64), 'baryons': (64, 32)}, 2, 0, True)]:
+        all_grids = {Gg} | {g for pair in grids.values() for g in pair}
+        if any(g % P or g//P < 8 for g in all_grids):
+            continue
+        interp = {2: 'CIC', 3: 'TSC', 4: 'PCS'}[order]
+        grids_txt = ''.join(f"        '{name}': {{'gravity': {{'pm': {pair}}}}},\n" for name, pair in grids.items())
+        commons.load_params(f"""
+boxsize = {L}*Mpc
+potential_options = {{
+    'gridsize': {{
+        'global': {{'gravity': {{'pm': {Gg}}}}},
+{grids_txt}    }},
+    'interpolation': {{'gravity': {{'pm': '{interp}'}}}},
+    'interlace': {{'gravity': {{'pm': ({interlace}, {interlace})}}}},
+    'differentiation': {{'default': {{'gravity': {{'pm': {diff if diff else "'fourier'"}}}}}}},
+}}
+select_forces = {{'all': {{'gravity': 'pm'}}}}
+Ωcdm = 0.25
+Ωb = 0.05
+""")
+        commons.universals.a = 0.5
+        rng = np.random.default_rng(500 + order)
+        species = {'cdm': 'cold dark matter', 'baryons': 'baryons'}
+        comps, host, ᔑdt = [], [], {'1': 0.0123}
+        for name, Nc, mass, dt_rho, dt_kick in [('cdm', 9000, 2.9, 0.024846, 0.012177), ('baryons', 7000, 4.2, 0.025338, 0.011808)]:
+            pos = rng.random((Nc, 3))*L
+            pos[:1600, 0] = (rng.random(1600)*0.02 + np.repeat(np.arange(8)/8, 200))*L % L   # crowd the slab faces
+            mom = rng.standard_normal((Nc, 3))*3.0
+            c = Component(name, species[name], N=Nc, mass=mass)
+            c.set_particles(pos, mom)
+            assert c.potential_gridsizes['gravity']['pm'] == grids[name], c.potential_gridsizes
+            ᔑdt['a**(-3*w_eff-1)', name] = dt_rho
+            ᔑdt['a**(-3*w_eff)', name] = dt_kick
+            comps.append(c)
+            host.append(dict(pos=pos, mom=mom, mass=mass, upstream=grids[name][0], downstream=grids[name][1], dt_rho=dt_rho,
+                             dt_kick=dt_kick, diff_order=diff))
+        interactions.gravity('pm', comps, comps, ᔑdt, 'long-range', False)
+        got = [c.gather_global()[1] for c in comps]
+        for g in all_grids:
+            mesh.get_context(g, 'f64').check_async_error()
+        if rank == 0:
+            ref = O.pm_kick_multigrid(host, boxsize=L, gridsize_global=Gg, order=order, G_Newton=commons.G_Newton, dt1=0.0123,
+                                      deconvolve=True, interlace=interlace)
+            errs = [relerr(m - h['mom'], r - h['mom']) for m, r, h in zip(got, ref, host)]
+            status = 'ok' if max(errs) < 1e-9 else 'FAIL'
+            print(f'[P={P}] mixed grid sizes global {Gg}, {grids}, order={order} diff={diff} interlace={interlace}: '
+                  f'kick relerr {max(errs):.2e}  {status}', flush=True)
+            if status != 'ok':
+                failures.append(('mixed', Gg))
+        mesh.free_contexts()
     # ---- P³M short range on several ranks: ghost particles across the slab faces (and across the periodic boundary),
     # receivers on active rungs only, Δmom / rung indices migrating with their particles
     import ctypes

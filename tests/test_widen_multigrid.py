@@ -120,7 +120,9 @@ def test_orchestration_through_kernel_model(path, monkeypatch, host_kernels):
     _assert_kicks(d, [c.mom_local.numpy() for c in comps])
 
 
-def test_mixed_gridsizes_need_one_rank(monkeypatch):
+def test_mixed_gridsizes_need_slabs_of_eight_planes(monkeypatch):
+    """On several ranks every grid is cut into x-slabs (tests/mgpu_check.py runs the exchange on GPUs): a grid that cannot
+    be cut aborts like the reference's slab decomposition (fft.c:105-212 / mesh.py:3779-3783)."""
     from concept_b200 import commons, communication, interactions
     d = np.load(CASES[0])
     commons.load_params(_param_text(d))
