@@ -136,6 +136,35 @@ select_forces = {{'all': {{'gravity': 'pm'}}}}
             if status != 'ok':
                 failures.append(('mixed', Gg))
         mesh.free_contexts()
+    # ---- P(k) estimator on several ranks (compute_powerspec, analysis.py:500-579): slab-decomposed PCS deposit on two
+    # interlaced lattices, distributed FFT, Σ|δ̂|² per k² all-reduced over the ranks; against the oracle estimator
+    from concept_b200 import analysis
+    Gk, Lk, Nk = 128, 500.0, 60_000
+    if Gk % P == 0 and Gk//P >= 8:
+        commons.load_params(f'boxsize = {Lk}*Mpc\nH0 = 70*km/s/Mpc\nΩcdm = 0.25\nΩb = 0.05\n')
+        commons.universals.a = 0.5
+        rng = np.random.default_rng(77)
+        pos = rng.random((Nk, 3))*Lk
+        centres = rng.random((40, 3))*Lk
+        pos[:Nk//2] = (centres[rng.integers(0, 40, Nk//2)] + rng.standard_normal((Nk//2, 3))*0.01*Lk) % Lk
+        c = Component('matter', 'matter', N=Nk, mass=1.7)
+        c.set_particles(pos, np.zeros((Nk, 3)))
+        centers, power, n_modes = analysis.powerspec([c], Gk)
+        mesh.get_context(Gk, 'f64').check_async_error()
+        mesh.free_contexts()
+        if rank == 0:
+            k2_max, _ = analysis.get_powerspec_bins(Gk, boxsize=Lk)
+            slab = O.density_fourier(pos, 1.7, 0.5, Lk, Gk, 4, True, True)
+            power_k2, count_k2 = O.power_by_k2(slab, k2_max)
+            _, idx, centers_ref, n_ref = analysis.get_powerspec_bins(Gk, n_modes_fine=count_k2, boxsize=Lk)
+            ref = np.zeros(len(centers_ref))
+            np.add.at(ref, idx, power_k2)
+            ref *= (0.5**(-3)*c.ϱ_bar)**(-2)*Lk**3/n_ref
+            e = float(np.max(np.abs(power/ref - 1)))
+            status = 'ok' if (np.array_equal(n_modes, n_ref) and e < 1e-9) else 'FAIL'
+            print(f'[P={P}] P(k) G={Gk}: mode counts equal {bool(np.array_equal(n_modes, n_ref))}, max |P/P_ref - 1| {e:.2e}  {status}', flush=True)
+            if status != 'ok':
+                failures.append(('powerspec', Gk))
     # ---- P³M short range on several ranks: ghost particles across the slab faces (and across the periodic boundary),
     # receivers on active rungs only, Δmom / rung indices migrating with their particles
     import ctypes
