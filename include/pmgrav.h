@@ -284,7 +284,9 @@ int pm_fourier_resize(pm_ctx* src, pm_ctx* dst);
  *   dst (+)= scale·[Π x_l/sin x_l]^deconv_order·e^{i(θ_cell + θ_shift)}·src
  * deconvolution and θ_shift = −2π/G_src·k·shift evaluated for the SOURCE grid, θ_cell = (π/G_dst − π/G_src)·(ki+kj+kk)
  * the half-cell offset between cell-centred grids.  '=' (accumulate == 0) nullifies every other mode of dst.
- * src_saved / dst_saved select the saved copy (pm_slab_save) instead of the working slab.  One rank per context. */
+ * src_saved / dst_saved select the saved copy (pm_slab_save) instead of the working slab.  Several ranks (both contexts
+ * distributed over the same ranks, a collective call): the rows of the shared cube are exchanged between the ranks that
+ * hold them in the two slab decompositions (the subslab exchange of mesh.py:1105-1230) over dst's communicator. */
 int pm_fourier_copy_modes(pm_ctx* src, pm_ctx* dst, int deconv_order, const double* shift, double scale,
                           int src_saved, int dst_saved, int accumulate);
 
