@@ -469,6 +469,14 @@ def run_pm_config(D, cfg, steps, warmup, lib, ctx=None, pos=None, mom=None, want
         fw['achieved_GBps_incl_zeroing'] = (alg['fft2d_forward'] + alg['grid_zero'])/(fw['ms']*1e-3)/1e9
         fw['frac_incl_zeroing'] = fw['achieved_GBps_incl_zeroing']/peak
         kernels['grid_zero'].update(achieved_GBps=None, frac=None, note='the grid is already nullified (self-cleaning forward transform)')
+    if D.world > 1 and staged:
+        # several ranks: the x solve is bound by NVLink, not HBM.  Per rank and direction: its own remote loads plus the peers'
+        # stores into it, 2·(P−1)/P of a rank's half-spectrum; reference 770 GB/s per direction (measured peer copy,
+        # B200_PROFILING.md; 900 nominal).  The stage time includes the two device barriers and the local B -> A re-layout.
+        nv = 2*(D.world - 1)/D.world*es*g3_per
+        xs = kernels['xsolve']
+        xs['nvlink'] = {'bytes_per_direction': nv, 'achieved_GBps': nv/(xs['ms']*1e-3)/1e9, 'peak_GBps': 770.0,
+                        'frac': nv/(xs['ms']*1e-3)/1e9/770.0}
     names = kernel_names(cfg)
     dom = max((k for k in alg if k in names and k != 'grid_zero'), key=lambda k: kernels[k]['ms'])
     b_alg = 120*n_total + 6*es*cfg['grid']**3
@@ -734,6 +742,10 @@ def run_gpu(args):
                     'traffic_source': 'profiles/ (ncu --set full capture of this kernel, per launch; not re-measured in this run)',
                     'peak_source': rec['peak_source'], 'kernel_ms': rec['kernels'][dom]['ms'],
                     'algorithmic_bytes_per_launch': rec['alg_dominant'], 'kernels': rec['kernels'], 'cycle': rec['cycle']}
+        if dom == 'xsolve' and rec['kernels'][dom].get('nvlink'):
+            roofline['note'] = ('on several ranks the dominant kernel moves its lines over NVLink: see "nvlink" '
+                                '(bytes per direction and rank against the measured 770 GB/s peer-copy rate); "frac" is its HBM fraction')
+            roofline['nvlink'] = rec['kernels'][dom]['nvlink']
         cpu = None
         if D.world == 1:
             try:
