@@ -1,10 +1,12 @@
-"""Mesh layer of the host mirror: a cache of libpmgrav contexts and thin wrappers with the
-reference's function names.
+"""Mesh layer of the host mirror: the cache of libpmgrav contexts and the one mesh function that forms scalars on the
+host.
 
-Reference counterparts (mesh.py): get_fftw_slab :3769-3866 (cached slabs + plans, never freed),
-interpolate_particles :1512, fft :4012, fourier_operate :3327, nullify_modes :3545,
-diff_domaingrid :4874, interpolate_domaingrid_to_particles :376.  The arithmetic lives in
-csrc/*.cu; nothing here touches grid values.
+Reference counterparts (mesh.py): get_fftw_slab :3769-3866 (cached slabs + plans, never freed) → get_context;
+free_fftw_slab :3897 → free_contexts; interpolate_particles :1512-1636 (its contribution scalar, :1542-1573) →
+interpolate_particles.  The other mesh operators of the reference (fft :4012, fourier_operate :3327, nullify_modes :3545,
+diff_domaingrid :4874, interpolate_domaingrid_to_particles :376, copy_modes :980) have no host-side body here: they are
+entry points of the C ABI (include/pmgrav.h), called as methods of the context (pmsolver.PMContext) from interactions.py and
+analysis.py.  Nothing here touches grid values.
 """
 import torch
 
