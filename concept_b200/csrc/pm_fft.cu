@@ -61,8 +61,14 @@ constexpr bool kFft2dDouble = PM_FFT2D_DOUBLE_BUFFER != 0;   // second tile buff
 #ifndef PM_FFT2D_OCC
 #define PM_FFT2D_OCC 4
 #endif
+#ifndef PM_FFT2D_OCC_F32
+#define PM_FFT2D_OCC_F32 PM_FFT2D_OCC     /* fp32 grids: half the registers per value */
+#endif
 #ifndef PM_XSOLVE_OCC
 #define PM_XSOLVE_OCC 3
+#endif
+#ifndef PM_XSOLVE_OCC_F32
+#define PM_XSOLVE_OCC_F32 2
 #endif
 // Kernel shapes per grid size.  Small CTAs, several per SM (independent barrier domains hide each other's LDS / FP64 / STS
 // phases); a y or x tile is G × 64 bytes of columns, so G = 1024 doubles the tile (64 KB) and takes twice the threads.
@@ -73,9 +79,9 @@ struct FftCfg {
     static constexpr bool kBig = G >= 1024;
     static constexpr bool kF32 = sizeof(T) == 4;      // fp32 x solve: 256 threads × 2 CTAs measured faster (0.38 vs 0.43 ms)
     static constexpr int kThreads2d = kBig ? 256 : PM_FFT2D_THREADS;     // every warp owns a z row
-    static constexpr int kOcc2d = kBig ? 2 : PM_FFT2D_OCC;
+    static constexpr int kOcc2d = kBig ? 2 : (kF32 ? PM_FFT2D_OCC_F32 : PM_FFT2D_OCC);
     static constexpr int kThreadsX = (kBig || kF32) ? 256 : PM_XSOLVE_THREADS;
-    static constexpr int kOccX = kBig ? 1 : (kF32 ? 2 : PM_XSOLVE_OCC);      // radix-16 stage: 16 complex values + their twiddles per thread
+    static constexpr int kOccX = kBig ? 1 : (kF32 ? PM_XSOLVE_OCC_F32 : PM_XSOLVE_OCC);      // radix-16 stage: 16 complex values + their twiddles per thread
     // z rows per warp (their loads are in flight together): measured 1 for the forward pass (0.82 vs 0.87 ms), 2 for the
     // inverse (0.73 vs 0.81 ms)
     static constexpr int kRowsFwd = PM_FFT_Z_RPW_FWD, kRowsInv = PM_FFT_Z_RPW_INV;

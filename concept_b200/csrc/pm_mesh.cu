@@ -595,8 +595,11 @@ __device__ __forceinline__ void diff_weights(const double (&w)[ORDER], const FD&
     }
 }
 
+#ifndef PM_GK2_OCC
+#define PM_GK2_OCC 4
+#endif
 template <int ORDER, int REACH, typename T, bool DRIFT>
-__global__ void __launch_bounds__(kGkBlock, 4)
+__global__ void __launch_bounds__(kGkBlock, PM_GK2_OCC)
 gather_kick2_kernel(const T* __restrict__ phi, double* __restrict__ pos,
                     double* __restrict__ mom, int64_t n, Geom g, Coord co, FD fd, double factor,
                     double* __restrict__ sum_mom2, unsigned long long* __restrict__ tile_counter,
