@@ -19,9 +19,12 @@ def cli(argv=None):
     commons.verbose = True
     try:
         components = main.run(args.params, '\n'.join(args.command_line_params), max_steps=args.max_steps)
-    finally:
+    except BaseException:
         mesh.free_contexts()
+        raise
+    mesh.free_contexts()
     commons.masterprint(f'concept_b200 run finished: {len(components)} component(s), a = {commons.universals.a:.6g}')
+    communication.finalize()
     return 0
 
 

@@ -40,6 +40,16 @@ def init(backend=None):
     return rank, nprocs
 
 
+def finalize():
+    """Leave the process group (end of a run under torchrun)."""
+    global _initialized
+    if nprocs > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    _initialized = False
+
+
 def bcast(obj, root=0):
     if nprocs == 1:
         return obj
