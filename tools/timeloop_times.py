@@ -13,7 +13,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from concept_b200 import main, mesh  # noqa: E402
+from concept_b200 import communication, main, mesh  # noqa: E402
 
 
 def run():
@@ -22,6 +22,7 @@ def run():
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--method', default='pm')
     a = ap.parse_args()
+    communication.init()
     n, G = a.size, 2*a.size
     param = f'''
 initial_conditions = {{'species': 'matter', 'N': {n}**3}}
@@ -46,11 +47,13 @@ primordial_spectrum = {{'A_s': 2.1e-9, 'n_s': 0.96}}
     torch.cuda.synchronize()
     dts = [1e3*(b[0] - a_[0]) for a_, b in zip(stamps, stamps[1:])]
     tail = sorted(dts[len(dts)//4:])
-    print(json.dumps({'particles': n**3, 'grid': G, 'method': a.method, 'steps': len(stamps),
-                      'setup_and_first_step_s': round(stamps[0][0] - t0, 3),
-                      'ms_per_base_step_median': round(tail[len(tail)//2], 3), 'ms_per_base_step_min': round(tail[0], 3),
-                      'ms_per_base_step_max': round(tail[-1], 3), 'a_reached': stamps[-1][1]}))
+    if communication.master:
+        print(json.dumps({'ranks': communication.nprocs, 'particles': n**3, 'grid': G, 'method': a.method, 'steps': len(stamps),
+                          'setup_and_first_step_s': round(stamps[0][0] - t0, 3),
+                          'ms_per_base_step_median': round(tail[len(tail)//2], 3), 'ms_per_base_step_min': round(tail[0], 3),
+                          'ms_per_base_step_max': round(tail[-1], 3), 'a_reached': stamps[-1][1]}))
     mesh.free_contexts()
+    communication.finalize()
 
 
 if __name__ == '__main__':
