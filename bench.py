@@ -520,6 +520,34 @@ def run_particle_order(D, ctx, pbuf, mbuf, n, params):
             'note': 'main.timeloop re-orders by grid cell at synchronised steps every cell_sort_period (default 64) base steps'}
 
 
+def run_clustered(D, ctx, cfg, params):
+    """One GPU: SURVEY §8d's second synthetic set — the same lattice displaced by sigma = 2 inter-particle spacings (four
+    grid cells: shell crossing everywhere, cells with many particles, reductions that collide) — in lattice order and after
+    pm_sort_particles."""
+    from concept_b200.synthetic import zeldovich_particles
+    torch = D.torch
+    L = float(cfg['grid'])
+    p, m = zeldovich_particles(cfg['n_side'], L, 2.0, seed=0, device=D.dev)
+    sum2 = torch.zeros(1, dtype=torch.float64, device=D.dev)
+
+    def timed(reps):
+        ctx.kick_drift(p, m, params, 0.0, sum_mom2=sum2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            ctx.kick_drift(p, m, params, 0.0, sum_mom2=sum2)      # no drift: the same particle set every time
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)/reps
+    lattice_order = timed(5)
+    ctx.sort_particles(p, m)
+    after = timed(5)
+    ctx.check_async_error()
+    return {'workload': 'the lattice of configs[1] displaced by sigma = 2.0 spacings (4 grid cells), kick without drift',
+            'cycle_ms_lattice_order': lattice_order, 'cycle_ms_after_sort': after}
+
+
 def run_e2e(D, ctx, pbuf, mbuf, state, params, cycle, steps):
     """The same cycle with HOST particle buffers (pinned), host<->device copies inside the timed region."""
     torch = D.torch
@@ -690,6 +718,10 @@ def run_gpu(args):
             particle_order = run_particle_order(D, ctx, pbuf, mbuf, state['n'], params)
         except Exception as exc:
             particle_order = {'error': repr(exc)}
+        try:
+            particle_order['clustered'] = run_clustered(D, ctx, cfg, params)
+        except Exception as exc:
+            particle_order['clustered'] = {'error': repr(exc)}
     del pbuf, mbuf, cycle
     ctx.close()
     torch.cuda.empty_cache()
