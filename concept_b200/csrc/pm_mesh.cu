@@ -598,8 +598,12 @@ __device__ __forceinline__ void diff_weights(const double (&w)[ORDER], const FD&
 #ifndef PM_GK2_OCC
 #define PM_GK2_OCC 4
 #endif
+// CTAs per SM (register cap).  Measured on B200 at 4 / 5 / 6 (profiles/r02_fft_config_sweep.md): TSC fp32, order-2 differences
+// 1.08 / 1.13 / 1.15 ms; TSC fp64, order-4 differences 2.56 / 2.31 / 3.30 ms; PCS fp64, order-4 differences 3.74 / 5.52 / 9.10 ms.
+template <int ORDER, int REACH, typename T>
+constexpr int gk2_occupancy() { return (ORDER == 3 && REACH == 2 && sizeof(T) == 8) ? 5 : PM_GK2_OCC; }
 template <int ORDER, int REACH, typename T, bool DRIFT>
-__global__ void __launch_bounds__(kGkBlock, PM_GK2_OCC)
+__global__ void __launch_bounds__(kGkBlock, gk2_occupancy<ORDER, REACH, T>())
 gather_kick2_kernel(const T* __restrict__ phi, double* __restrict__ pos,
                     double* __restrict__ mom, int64_t n, Geom g, Coord co, FD fd, double factor,
                     double* __restrict__ sum_mom2, unsigned long long* __restrict__ tile_counter,
