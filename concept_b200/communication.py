@@ -98,8 +98,16 @@ def barrier():
 
 def slab_owner(x, boxsize, gridsize, n_ranks=None):
     """Owner rank of positions x (numpy or torch): the slab holding cell int(x·G/L).
-    Same rule as owner_of() in csrc/pm_particles.cu (which_domain analogue, communication.py:756-772)."""
+    Same rule as owner_of() in csrc/pm_particles.cu (which_domain analogue, communication.py:756-772).
+    A grid size the ranks do not divide has no slabs (pm_create refuses it, like fft.c:105-212); a component whose own
+    grid is of that kind — it may still be analysed on other grids — is cut at x = r·L/P exactly, the slab boundaries of
+    every grid the ranks do divide."""
     n_ranks = nprocs if n_ranks is None else n_ranks
+    if gridsize % n_ranks:
+        if isinstance(x, torch.Tensor):
+            return torch.clamp((x*(n_ranks/boxsize)).to(torch.int64), 0, n_ranks - 1)
+        import numpy as np
+        return np.clip((np.asarray(x)*(n_ranks/boxsize)).astype(np.int64), 0, n_ranks - 1)
     nxl = gridsize//n_ranks
     if isinstance(x, torch.Tensor):
         cell = torch.clamp((x*(gridsize/boxsize)).to(torch.int64), 0, gridsize - 1)

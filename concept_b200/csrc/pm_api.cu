@@ -378,12 +378,17 @@ int pm_set_fused_solve(pm_ctx* c, int mode) {
 int pm_check_async_error(pm_ctx* c) {
     PM_REQUIRE(c != nullptr, "pm_check_async_error: NULL context");
     PM_TRY(fft2_check_error(c));
-    int e = 0;
-    PM_CHECK_CUDA(cudaMemcpyAsync(&e, c->d_comm_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int e[2] = {0, 0};
+    PM_CHECK_CUDA(cudaMemcpyAsync(e, c->d_comm_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
-    if (e != 0) {
+    if (e[0] != 0) {
         set_error("a rank did not arrive at a device barrier in time (results are invalid)");
         return PM_ERR_COMM;
+    }
+    if (e[1] != 0) {
+        set_error("pm_deposit: a particle lies outside this rank's x-slab plus halo — its mass was not deposited "
+                  "(particles must be distributed by x-slab: Component.set_particles / pm_exchange)");
+        return PM_ERR_ARG;
     }
     return PM_OK;
 }

@@ -147,7 +147,7 @@ __device__ __forceinline__ void red_add_v2(float* addr8, float a, float b) {    
 template <int ORDER, typename T>
 __global__ void __launch_bounds__(kDepBlock)
 deposit_kernel(const double* __restrict__ pos, int64_t n, T* __restrict__ grid, Geom g, Coord co,
-               double contribution, unsigned long long* __restrict__ tile_counter) {
+               double contribution, unsigned long long* __restrict__ tile_counter, int* __restrict__ lost) {
     __shared__ int64_t s_slot;
     constexpr int64_t kChunk = (int64_t)kDepBlock * kChunkTiles;
     const int64_t nchunks = (n + kChunk - 1) / kChunk;
@@ -171,7 +171,10 @@ deposit_kernel(const double* __restrict__ pos, int64_t n, T* __restrict__ grid, 
 #pragma unroll
             for (int a = 0; a < ORDER; ++a) {
                 const int lx = local_plane(ix + a, g);
-                if (lx < 0) continue;
+                if (lx < 0) {       // several ranks: a plane beyond the halo — the particle is not in this rank's slab and its
+                    *lost = 1;      // mass would vanish silently; sticky flag, reported by pm_check_async_error
+                    continue;
+                }
                 const double wa = wx[a] * contribution;
                 T* plane = grid + (size_t)lx * g.G * g.Gp;
 #pragma unroll
@@ -217,12 +220,13 @@ static int deposit_dispatch(pm_ctx* c, const double* pos, int64_t n, int order, 
     const int grid = (int)std::min<int64_t>(nchunks, (int64_t)kNumSMs * 8);
     T* gptr = reinterpret_cast<T*>(c->real);
     unsigned long long* ctr = c->d_tilectr;
+    int* lost = c->d_comm_err + 1;
     PM_CHECK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), c->stream));
     switch (order) {
-        case 1: PM_LAUNCH((deposit_kernel<1, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr); break;
-        case 2: PM_LAUNCH((deposit_kernel<2, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr); break;
-        case 3: PM_LAUNCH((deposit_kernel<3, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr); break;
-        case 4: PM_LAUNCH((deposit_kernel<4, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr); break;
+        case 1: PM_LAUNCH((deposit_kernel<1, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr, lost); break;
+        case 2: PM_LAUNCH((deposit_kernel<2, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr, lost); break;
+        case 3: PM_LAUNCH((deposit_kernel<3, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr, lost); break;
+        case 4: PM_LAUNCH((deposit_kernel<4, T>), grid, kDepBlock, 0, c->stream, pos, n, gptr, c->g, co, contribution, ctr, lost); break;
     }
     return PM_OK;
 }

@@ -27,12 +27,15 @@ def main():
     rank, P = communication.init()
     L, N = 60.0, 40000
     failures = []
+    # MGPU_ONLY=pm,mixed,powerspec,p3m restricts the run to some sections (development aid; default: all)
+    only = {w for w in os.environ.get('MGPU_ONLY', '').split(',') if w}
+    want = lambda section: not only or section in only
     # G = 128: hand-written slab transform, x-solve over CUDA-IPC peer pointers; G = 64: cuFFT 2-D + the
     # first-generation x-solve over peer pointers; G = 48: cuFFT + NCCL all-to-all transpose
     for G, order, diff, interlace, dtype in [(128, 2, 2, False, 'f64'), (128, 3, 4, False, 'f64'), (64, 2, 2, False, 'f64'), (64, 3, 4, False, 'f64'), (64, 4, 8, False, 'f64'),
                                              (64, 2, 0, False, 'f64'), (64, 3, 2, True, 'f64'),
                                              (48, 2, 2, False, 'f64'), (48, 3, 4, False, 'f64')]:
-        if G % P or G//P < 7:
+        if G % P or G//P < 7 or not want('pm'):
             continue
         interp = {2: 'CIC', 3: 'TSC', 4: 'PCS'}[order]
         commons.load_params(f'''
@@ -88,7 +91,7 @@ select_forces = {{'matter': {{'gravity': 'pm'}}}}
     for Gg, grids, order, diff, interlace in [(128, {'cdm': (64, 128), 'baryons': (128, 64)}, 3, 4, False),
                                               (64, {'cdm': (32, 64), 'baryons': (64, 32)}, 2, 0, True)]:
         all_grids = {Gg} | {g for pair in grids.values() for g in pair}
-        if any(g % P or g//P < 8 for g in all_grids):
+        if any(g % P or g//P < 8 for g in all_grids) or not want('mixed'):
             continue
         interp = {2: 'CIC', 3: 'TSC', 4: 'PCS'}[order]
         grids_txt = ''.join(f"        '{name}': {{'gravity': {{'pm': {pair}}}}},\n" for name, pair in grids.items())
@@ -140,7 +143,7 @@ select_forces = {{'all': {{'gravity': 'pm'}}}}
     # interlaced lattices, distributed FFT, Σ|δ̂|² per k² all-reduced over the ranks; against the oracle estimator
     from concept_b200 import analysis
     Gk, Lk, Nk = 128, 500.0, 60_000
-    if Gk % P == 0 and Gk//P >= 8:
+    if Gk % P == 0 and Gk//P >= 8 and want('powerspec'):
         commons.load_params(f'boxsize = {Lk}*Mpc\nH0 = 70*km/s/Mpc\nΩcdm = 0.25\nΩb = 0.05\n')
         commons.universals.a = 0.5
         rng = np.random.default_rng(77)
@@ -171,7 +174,7 @@ select_forces = {{'all': {{'gravity': 'pm'}}}}
     from concept_b200 import shortrange
     from concept_b200._lib import check
     Lp, Gp, Np = 60.0, 128, 12000
-    if Gp % P == 0 and Lp/P >= 2*4.5*1.25*Lp/Gp:
+    if Gp % P == 0 and Lp/P >= 2*4.5*1.25*Lp/Gp and want('p3m'):
         commons.load_params(f"""
 boxsize = {Lp}*Mpc
 potential_options = {{'gridsize': {{'gravity': {{'p3m': {Gp}}}}}}}

@@ -111,3 +111,21 @@ def test_two_rank_replicated_initial_conditions_over_gloo():
         p.join(180)
         assert p.exitcode == 0
     assert sorted(out.get(timeout=5) for _ in range(2)) == [(0, 'ok'), (1, 'ok')]
+
+
+def test_slab_owner_of_a_grid_the_ranks_do_not_divide():
+    """A component whose own grid size (default 2·∛N) is not divisible by the number of ranks is still cut at x = r·L/P —
+    the slab boundaries of the grids the ranks do divide.  (Cutting it by cells of its own grid put the boundaries of a
+    78³ grid on 8 ranks up to 8.6 cells of a 128³ grid away from that grid's slabs: the P(k) deposit lost mass.)"""
+    import numpy as np
+    import torch
+    from concept_b200 import communication
+    L = 500.0
+    x = np.random.default_rng(0).random(20000)*L
+    for P in (4, 8):
+        own = communication.slab_owner(x, L, 78, P)
+        assert np.array_equal(own, np.minimum((x/L*P).astype(np.int64), P - 1))
+        assert np.array_equal(communication.slab_owner(torch.as_tensor(x), L, 78, P).numpy(), own)
+        # and it agrees with the cell rule of a divisible grid away from the cell that holds the boundary
+        cells = communication.slab_owner(x, L, 128, P)
+        assert np.array_equal(own, cells)
