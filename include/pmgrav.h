@@ -144,8 +144,11 @@ int pm_solve_fused(pm_ctx* ctx, double prefactor, int deconv_order, double gauss
 int pm_solve_fused_stage(pm_ctx* ctx, double prefactor, int deconv_order, double gauss, int stage);
 int pm_fused_solve_available(const pm_ctx* ctx);
 int pm_set_fused_solve(pm_ctx* ctx, int mode);
-/* Host-synchronising check of the asynchronous give-up flag of the dependency-ordered kernels
- * (a tile dependency that was not satisfied within seconds); PM_ERR_ARG with a message if set. */
+/* Host-synchronising check of the sticky flags that kernels raise instead of hanging or failing silently: a tile
+ * dependency of the dependency-ordered transforms that was not satisfied within seconds, a rank that did not arrive at a
+ * device barrier (PM_ERR_COMM), and — several ranks — a deposit contribution that fell outside this rank's x-slab plus halo
+ * (the particle is not distributed by slab; the reference's domain decomposition makes that impossible by construction,
+ * communication.py:135-517).  Returns the error code with a message if any is set. */
 int pm_check_async_error(pm_ctx* ctx);
 /* The mode loop of compute_powerspec (analysis.py:500-547) on the Fourier slab: for every mode of
  * fourier_loop(gridsize, sparse=True, skip_origin=True, k2_max) (mesh.py:2615-2890)
