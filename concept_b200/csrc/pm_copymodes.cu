@@ -71,6 +71,17 @@ copy_modes_unpack_kernel(const double2* __restrict__ in, double2* __restrict__ d
     }
 }
 
+// stream-ordered scratch that is released on every way out of the function
+struct AsyncScratch {
+    void* ptr = nullptr;
+    cudaStream_t stream;
+    explicit AsyncScratch(cudaStream_t s) : stream(s) {}
+    ~AsyncScratch() { if (ptr) cudaFreeAsync(ptr, stream); }
+    AsyncScratch(const AsyncScratch&) = delete;
+    AsyncScratch& operator=(const AsyncScratch&) = delete;
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&ptr, bytes ? bytes : 16, stream); }
+};
+
 static int copy_modes_ranks(pm_ctx* src, pm_ctx* dst, const copyops::CopyParams& p, const double2* from, double2* onto,
                             bool accumulate) {
     const int P = dst->nranks, me = dst->rank;
@@ -96,11 +107,12 @@ static int copy_modes_ranks(pm_ctx* src, pm_ctx* dst, const copyops::CopyParams&
     const size_t row_elems = (size_t)W * n;            // complex values per row
     const size_t ns = send_off[P], nr = recv_off[P];
     cudaStream_t st = dst->stream;
-    double2 *d_send = nullptr, *d_recv = nullptr;
-    int* d_idx = nullptr;
-    PM_CHECK_CUDA(cudaMallocAsync(&d_send, sizeof(double2) * std::max<size_t>(ns * row_elems, 1), st));
-    PM_CHECK_CUDA(cudaMallocAsync(&d_recv, sizeof(double2) * std::max<size_t>(nr * row_elems, 1), st));
-    PM_CHECK_CUDA(cudaMallocAsync(&d_idx, sizeof(int) * std::max<size_t>(ns + 2 * nr, 1), st));
+    AsyncScratch b_send(st), b_recv(st), b_idx(st);
+    PM_CHECK_CUDA(b_send.alloc(sizeof(double2) * ns * row_elems));
+    PM_CHECK_CUDA(b_recv.alloc(sizeof(double2) * nr * row_elems));
+    PM_CHECK_CUDA(b_idx.alloc(sizeof(int) * (ns + 2 * nr)));
+    double2 *d_send = static_cast<double2*>(b_send.ptr), *d_recv = static_cast<double2*>(b_recv.ptr);
+    int* d_idx = static_cast<int*>(b_idx.ptr);
     if (ns) PM_CHECK_CUDA(cudaMemcpyAsync(d_idx, h_send.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, st));
     if (nr) {
         PM_CHECK_CUDA(cudaMemcpyAsync(d_idx + ns, h_kj.data(), sizeof(int) * nr, cudaMemcpyHostToDevice, st));
@@ -110,19 +122,18 @@ static int copy_modes_ranks(pm_ctx* src, pm_ctx* dst, const copyops::CopyParams&
     if (!accumulate) PM_CHECK_CUDA(cudaMemsetAsync(onto, 0, sizeof(double2) * dst->fourier_elems, st));   // modes outside the shared cube
     if (ns) PM_LAUNCH(copy_modes_pack_kernel, kNumSMs * 4, 256, 0, st, from, d_send, d_idx, (int)ns, n, p.Gs, njl_s);
     PM_CHECK_NCCL(ncclGroupStart());
-    for (int r = 0; r < P; ++r) {
+    ncclResult_t posted = ncclSuccess;
+    for (int r = 0; r < P && posted == ncclSuccess; ++r) {
         const size_t cs = (send_off[r + 1] - send_off[r]) * row_elems * 2, cr = (recv_off[r + 1] - recv_off[r]) * row_elems * 2;
-        if (cs) PM_CHECK_NCCL(ncclSend(d_send + send_off[r] * row_elems, cs, ncclDouble, r, dst->comm, st));
-        if (cr) PM_CHECK_NCCL(ncclRecv(d_recv + recv_off[r] * row_elems, cr, ncclDouble, r, dst->comm, st));
+        if (cs) posted = ncclSend(d_send + send_off[r] * row_elems, cs, ncclDouble, r, dst->comm, st);
+        if (cr && posted == ncclSuccess) posted = ncclRecv(d_recv + recv_off[r] * row_elems, cr, ncclDouble, r, dst->comm, st);
     }
-    PM_CHECK_NCCL(ncclGroupEnd());
+    PM_CHECK_NCCL(ncclGroupEnd());      // the group is closed whatever happened inside
+    PM_CHECK_NCCL(posted);
     if (nr)
         PM_LAUNCH(copy_modes_unpack_kernel, kNumSMs * 4, 256, 0, st, d_recv, onto, d_idx + ns, d_idx + ns + nr, (int)nr, n, p, njl_d,
                   src->tab_x, src->tab_sin, accumulate ? 1 : 0);
-    PM_CHECK_CUDA(cudaFreeAsync(d_send, st));
-    PM_CHECK_CUDA(cudaFreeAsync(d_recv, st));
-    PM_CHECK_CUDA(cudaFreeAsync(d_idx, st));
-    return PM_OK;
+    return PM_OK;      // the scratch is released in stream order behind the unpack kernel
 }
 
 }  // namespace pm
