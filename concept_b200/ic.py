@@ -20,6 +20,7 @@ private one-rank context and keeps its x-slab), see _get_context.
 Not built: fluid realisations and the non-linear ("structure": "non-linear") realisations.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -179,10 +180,12 @@ def generate_primordial_noise(gridsize, fixed_amplitude=False, phase_shift=0):
         ki, kk = fourier_curve_slice_order(G)
         n = len(ki)
         i_direct, i_conj = ki % G, (-ki) % G
-        for j in range(G):
+
+        def fill_slice(j):
+            # one kj slice: its four child streams are its own, its plane of the slab too — slices are independent
             kj = j - (G if j >= nyquist else 0)
             if kj == -nyquist:
-                continue
+                return
             streams = [common.spawn(spawn_key_offset + sign*kj) for common in (prng_amplitudes_common, prng_phases_common)
                        for sign in (+1, -1)]
             if fixed_amplitude:
@@ -191,9 +194,20 @@ def generate_primordial_noise(gridsize, fixed_amplitude=False, phase_shift=0):
                 r, r_conj = streams[0].rayleigh_array(n, scale), streams[1].rayleigh_array(n, scale)
             θ, θ_conj = streams[2].uniform_array(n, -π, π), streams[3].uniform_array(n, -π, π)
             direct = (kk != 0) | (ki < 0) | ((ki == 0) & (kj < 0))
-            slab[j, i_direct[direct], kk[direct]] = polar(r, θ)[direct]
-            conj = (kk == 0) & ((ki < 0) | ((ki == 0) & (kj >= 0)))
-            slab[j, i_conj[conj], 0] = np.conj(polar(r_conj, θ_conj)[conj])
+            slab[j, i_direct[direct], kk[direct]] = polar(r[direct], θ[direct])
+            conj = (kk == 0) & ((ki < 0) | ((ki == 0) & (kj >= 0)))      # a few modes of the kk = 0 plane only
+            slab[j, i_conj[conj], 0] = np.conj(polar(r_conj[conj], θ_conj[conj]))
+        # the draws and the cos/sin of a slice are numpy calls that release the GIL: slices run on a few host threads
+        # (every rank realises the whole noise, so the threads are shared out between the ranks of a node)
+        from . import communication
+        workers = max(1, min(16, (os.cpu_count() or 1)//max(1, communication.nprocs)))
+        if workers > 1 and G >= 64:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                list(pool.map(fill_slice, range(G)))
+        else:
+            for j in range(G):
+                fill_slice(j)
     else:
         abort(f'primordial_noise_imprinting = "{p.primordial_noise_imprinting}" not implemented')
     slab[0, 0, 0] = 0

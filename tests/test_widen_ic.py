@@ -145,6 +145,22 @@ def test_noise_is_nested_in_grid_size():
             assert large[kj % 12, ki % 12, 0] == np.conj(large[-kj % 12, -ki % 12, 0])
 
 
+def test_noise_slices_on_threads_equal_the_sequential_noise(monkeypatch):
+    """From 64³ on the kj slices are filled by a few host threads (their streams and slab planes are independent): the
+    result is the sequential one bit for bit, and the inner 8³ modes still equal the reference-pinned 8³ noise."""
+    import os
+    from concept_b200 import commons, ic
+    commons.load_params('boxsize = 8*Mpc\n')
+    monkeypatch.setattr(os, 'cpu_count', lambda: 8)
+    threaded = ic.generate_primordial_noise(64)
+    monkeypatch.setattr(os, 'cpu_count', lambda: 1)
+    sequential = ic.generate_primordial_noise(64)
+    assert np.array_equal(threaded, sequential)
+    small = ic.generate_primordial_noise(8)
+    k = np.arange(-3, 4)
+    assert np.array_equal(small[np.ix_(k % 8, k % 8, np.arange(4))], threaded[np.ix_(k % 64, k % 64, np.arange(4))])
+
+
 def test_fourier_curve_is_a_bijection():
     from concept_b200 import ic
     from oracle import ic_oracle as O
