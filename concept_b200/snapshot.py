@@ -63,11 +63,13 @@ def correct_float(val_raw):
 
 def _block(f, name, payload):
     """SnapFormat 2 block: 16-byte name record (name + size of the data record incl. its two markers)
-    followed by the Fortran-style data record (snapshot.py:1671-1711)."""
-    f.write(struct.pack('<I4sII', 8, name.ljust(4).encode('ascii'), len(payload) + 8, 8))
-    f.write(struct.pack('<I', len(payload)))
-    f.write(payload)
-    f.write(struct.pack('<I', len(payload)))
+    followed by the Fortran-style data record (snapshot.py:1671-1711).  payload: bytes or a contiguous numpy array
+    (written straight from its buffer)."""
+    size = payload.nbytes if isinstance(payload, np.ndarray) else len(payload)
+    f.write(struct.pack('<I4sII', 8, name.ljust(4).encode('ascii'), size + 8, 8))
+    f.write(struct.pack('<I', size))
+    f.write(memoryview(payload).cast('B') if isinstance(payload, np.ndarray) else payload)
+    f.write(struct.pack('<I', size))
 
 
 def write_gadget(filename, pos, mom, *, mass, a, boxsize, H0, Ωm, ids=None, bits_pos=32, bits_vel=32):
@@ -101,19 +103,21 @@ def write_gadget(filename, pos, mom, *, mass, a, boxsize, H0, Ωm, ids=None, bit
 
     def convert(data, unit, bits, wrap):
         dtype = np.float32 if bits == 32 else np.float64
-        out = (data.reshape(-1)*(1/unit)).astype(dtype)
+        # the product in fp64, rounded once to the file's precision (no fp64 temporary of the whole array)
+        out = np.empty(data.size, dtype=dtype)
+        np.multiply(data.reshape(-1), 1/unit, out=out, casting='same_kind')
         if wrap:     # round-off guard of the writer (snapshot.py:1381-1382)
             box = dtype(boxsize/unit)
-            over = out >= box
+            over = np.flatnonzero(out >= box)
             out[over] -= box
         return out
     with open(filename, 'wb') as f:
         _block(f, 'HEAD', raw)
-        _block(f, 'POS', convert(pos, unit_length, bits_pos, True).tobytes())
-        _block(f, 'VEL', convert(mom, unit_velocity*mass*a**1.5, bits_vel, False).tobytes())
+        _block(f, 'POS', convert(pos, unit_length, bits_pos, True))
+        _block(f, 'VEL', convert(mom, unit_velocity*mass*a**1.5, bits_vel, False))
         id_dtype = np.uint32 if N <= 2**32 else np.uint64
-        ids = np.arange(N, dtype=id_dtype) if ids is None else np.asarray(ids).astype(id_dtype)
-        _block(f, 'ID', ids.tobytes())
+        ids = np.arange(N, dtype=id_dtype) if ids is None else np.ascontiguousarray(np.asarray(ids).astype(id_dtype))
+        _block(f, 'ID', ids)
     return header
 
 
@@ -129,7 +133,7 @@ def read_gadget(filename):
             commons.abort(f'"{filename}" is not a SnapFormat 2 GADGET snapshot')
         o += 16
         size = struct.unpack_from('<I', blob, o)[0]
-        payload = blob[o + 4:o + 4 + size]
+        payload = memoryview(blob)[o + 4:o + 4 + size]          # a view: the blocks are hundreds of MB
         if struct.unpack_from('<I', blob, o + 4 + size)[0] != size:
             commons.abort(f'Corrupt block "{name.decode().strip()}" in "{filename}"')
         blocks[name.decode('ascii').strip()] = payload
