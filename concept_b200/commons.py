@@ -315,15 +315,43 @@ def p_finish(p):
     return p
 
 
+def _lattice_cells(N):
+    """Ñ = n³ of species.py:1137-1143: N, N/2 or N/4 for a simple-cubic, body-centred or face-centred pre-initial lattice"""
+    N = int(N)
+    for per_cell in (1, 2, 4):
+        if N % per_cell == 0:
+            n = round((N//per_cell)**(1/3))
+            if n**3 == N//per_cell:
+                return N//per_cell
+    return N
+
+
+def gridsize_value(g, N):
+    """A grid size given as a number or as an expression in 'N', 'Ñ', 'gridsize' (= ∛Ñ for particles) and 'nprocs',
+    e.g. '2*cbrt(N)' — Component.__init__'s to_float, species.py:1134-1157."""
+    if isinstance(g, str):
+        from . import communication
+        Ñ = _lattice_cells(N)
+        expr = g.replace('gridsize', repr(float(round(Ñ**(1/3))))).replace('nprocs', str(communication.nprocs))
+        names = {k: getattr(math, k) for k in ('sqrt', 'log', 'log2', 'log10', 'exp', 'floor', 'ceil', 'pi')}
+        names.update(cbrt=lambda x: x**(1/3), N=int(N), Ñ=Ñ, min=min, max=max, round=round, π=math.pi)
+        try:
+            g = eval(expr, {'__builtins__': {}}, names)
+        except Exception as exc:
+            abort(f'Could not understand the grid size "{g}": {exc}')
+    return int(round(float(g)))
+
+
 def gridsize_for(method, N):
-    """Default PM grid sizes: cbrt(N) for pm, 2·cbrt(N) for p3m (doc/parameters/numerics.rst:72-100)."""
+    """Default PM grid sizes: cbrt(Ñ) for pm, 2·cbrt(Ñ) for p3m, Ñ the cells of the pre-initial lattice
+    (doc/parameters/numerics.rst:72-100, species.py:1192-1207)."""
     g = params.gridsize_spec.get(method)
     if isinstance(g, (tuple, list)):
         g = g[0]
     if g is None or g == -1:
-        n = round(N**(1/3))
+        n = round(_lattice_cells(N)**(1/3))
         g = n if method == 'pm' else 2*n
-    g = int(g)
+    g = gridsize_value(g, N)
     return g + (g & 1)
 
 
@@ -359,7 +387,11 @@ def component_gridsizes(name, species, method, N):
                     g = _method_value(v, method)
                     if g is not None:
                         g = tuple(g) if isinstance(g, (tuple, list)) else (g, g)
-                        return tuple(_even_gridsize(x) for x in g)
+                        if len(g) == 1:
+                            g = g*2
+                        if -1 in g:
+                            break       # -1: the default for this component (species.py:1169-1171)
+                        return tuple(_even_gridsize(gridsize_value(x, N)) for x in g)
     g = gridsize_for(method, N)
     return (g, g)
 
@@ -373,7 +405,7 @@ def global_gridsize(method, components):
             if str(k).lower() == 'global':
                 g = _method_value(v, method)
                 if g is not None and g != -1:
-                    return _even_gridsize(g)
+                    return _even_gridsize(gridsize_value(g, max((c.N for c in components), default=0)))
     return max(max(c.potential_gridsizes['gravity'][method]) for c in components)
 
 

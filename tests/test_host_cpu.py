@@ -79,6 +79,27 @@ potential_options = {
     assert commons.gridsize_for('pm', 1000) == 12
 
 
+def test_gridsize_expressions_like_the_reference():
+    """Grid sizes may be expressions in N, Ñ, gridsize and nprocs (Component.__init__'s to_float, species.py:1134-1157; the
+    reference's own param/example_explanatory says 'p3m': ('2*cbrt(N)', '2*cbrt(N)')); the default is ∛Ñ (2·∛Ñ for P³M) with Ñ the
+    cells of the pre-initial lattice, also for bcc (N = 2n³) and fcc (N = 4n³) loads (species.py:1192-1207)."""
+    commons.load_params("""
+boxsize = 100*Mpc
+potential_options = {'gridsize': {'global': {'gravity': {'pm': 64, 'p3m': 128}},
+                                  'matter': {'gravity': {'p3m': ('2*cbrt(N)', '2*cbrt(N)')}},
+                                  'cdm': {'gravity': {'pm': 'gridsize', 'p3m': -1}}}}
+""")
+    assert commons.component_gridsizes('matter', 'matter', 'p3m', 64**3) == (128, 128)
+    assert commons.component_gridsizes('cdm', 'cold dark matter', 'pm', 2*24**3) == (24, 24)        # ∛Ñ of a bcc load
+    assert commons.component_gridsizes('cdm', 'cold dark matter', 'p3m', 16**3) == (128, 128)      # -1: the default (global)
+    assert commons.gridsize_value('cbrt(Ñ)', 4*10**3) == 10 and commons.gridsize_value('2*cbrt(N) + 2*nprocs', 8**3) == 18
+    assert commons.gridsize_value(47.6, 0) == 48
+    commons.load_params('boxsize = 100*Mpc\n')
+    assert commons.gridsize_for('pm', 2*24**3) == 24 and commons.gridsize_for('p3m', 4*10**3) == 20
+    with pytest.raises(commons.ConceptAbort):
+        commons.gridsize_value('2*cuberoot(N)', 8**3)
+
+
 def test_background_and_time_step_integrals_match_reference_run():
     """Every ᔑdt the reference used in its 160 kicks / 142 drifts is reproduced from our own
     background (same ODE solver settings, same natural cubic splines)."""
