@@ -164,6 +164,37 @@ def _lower_keys(d):
     return {str(k).lower(): v for k, v in d.items()}
 
 
+def _truthy(val):
+    try:
+        return any(bool(v) for v in val) if isinstance(val, (list, tuple, set, dict)) else bool(val)
+    except (TypeError, ValueError):
+        return True      # (arrays and the like)
+
+
+def fill_ellipses(d):
+    """`...` as a dict value means "as the entry before" (the reference's example files use it for output_dirs and the
+    *_select dicts; replace_ellipsis, commons.py:2142-2161): an ellipsis takes the nearest earlier value that is set to
+    something (non-empty, non-zero) — the first such value of the dict for leading ellipses — and, if there is none at all,
+    simply the value before it.  Applied in place to nested dicts as well."""
+    if not isinstance(d, dict):
+        return d
+    for val in d.values():
+        fill_ellipses(val)
+    keys = list(d)
+    if not any(d[k] is ... for k in keys):
+        return d
+    first_set = next((d[k] for k in keys if d[k] is not ... and _truthy(d[k])), None)
+    last_set, last_any = first_set, first_set
+    for k in keys:
+        if d[k] is ...:
+            d[k] = last_set if last_set is not None else last_any
+        else:
+            last_any = d[k]
+            if _truthy(d[k]):
+                last_set = d[k]
+    return d
+
+
 class Params(types.SimpleNamespace):
     """Normalised hot-path parameters (subset of commons.py:2470-4432)."""
 
@@ -192,6 +223,8 @@ def load_params(path_or_text='', extra='', **overrides):
     exec_params(content, ns)   # the reference executes the file twice (commons.py:2352, 2419)
     up = {k: v for k, v in ns.items() if k not in base_keys and not k.startswith('__')}
     up.update(overrides)
+    for val in up.values():
+        fill_ellipses(val)
     user_params = up
     p = Params()
     p.user = up

@@ -391,6 +391,32 @@ def _output_dir(kind):
     return od.get(kind, od.get('default')) if isinstance(od, dict) else None
 
 
+def _output_filename(kind, dump_time):
+    """`{output_dirs[kind]}/{output_bases[kind]}_{a|t}=…` with as few decimals as keep all output times of this kind (and
+    the start of the run) apart and the first of them away from zero — the naming of prepare_for_output (main.py:2236-2278);
+    cosmic-time names carry the time unit (main.py:1698-1699).  None without an output directory."""
+    out_dir = _output_dir(kind)
+    if not out_dir:
+        return None
+    bases = commons.user_params.get('output_bases', {})
+    base = bases.get(kind, kind) if isinstance(bases, dict) else kind
+    tp = dump_time.time_param
+    begin = commons.params.a_begin if tp == 'a' else commons.params.t_begin
+    times = sorted(set([float(begin)] + _output_times_flat()[tp].get(kind, [])))
+    ndigits = 0
+    while ndigits < 15:
+        names = [f'{x:.{ndigits}f}' for x in times]
+        if len(set(names)) == len(names) and (not times[0] or names[0] != f'{0:.{ndigits}f}'):
+            break
+        ndigits += 1
+    value = dump_time.a if tp == 'a' else dump_time.t
+    name = f'{base}_' if base else ''
+    return os.path.join(out_dir, f'{name}{tp}={value:.{ndigits}f}' + (commons.unit_time if tp == 't' else ''))
+
+
+_warned_outputs = set()
+
+
 def _wanted(kind, dump_time):
     flat = _output_times_flat()
     return (any(x == dump_time.a for x in flat['a'].get(kind, ())) and dump_time.time_param == 'a') or \
@@ -413,7 +439,7 @@ def dump_powerspec(components, dump_time):
     k, power, n_modes = analysis.powerspec(particle_components, gridsize, gridsizes_upstream=gridsizes_upstream)
     if out_dir and communication.master:
         os.makedirs(out_dir, exist_ok=True)
-        filename = os.path.join(out_dir, f'powerspec_a={dump_time.a:.2f}')
+        filename = _output_filename('powerspec', dump_time)
         names = ', '.join(c.name for c in particle_components)
         power_linear = analysis.get_linear_powerspec(particle_components, k)
         header = (f'Power spectrum of {names} at a = {universals.a:.8g}, t = {universals.t:.8g} {commons.unit_time}, '
@@ -425,21 +451,37 @@ def dump_powerspec(components, dump_time):
 
 
 def dump(components, dump_time, on_dump=None):
-    """main.py:1676-1712: snapshots are written as .npz (HDF5 is unavailable), power spectra as text files;
-    `on_dump` is the hook the tests use to capture the state."""
+    """main.py:1676-1712: power spectra as text files; snapshots as GADGET-2 files when snapshot_type = 'gadget'
+    (snapshot.save), else — the reference's own 'concept' format is HDF5, which this image cannot write — as .npz with a
+    warning; bispectra and renders are out of scope and skipped with a warning.  `on_dump` is the hook the tests use to
+    capture the state."""
+    from . import snapshot
     if on_dump is not None:
         on_dump(components, dump_time)
     if _wanted('powerspec', dump_time):
         dump_powerspec(components, dump_time)
-    out_dir = _output_dir('snapshot')
-    wants_snapshot = _wanted('snapshot', dump_time)
-    if out_dir and wants_snapshot:
+    for kind in ('bispec', 'render2D', 'render3D'):
+        if _wanted(kind, dump_time) and kind not in _warned_outputs:
+            _warned_outputs.add(kind)
+            commons.masterwarn(f'Output of kind "{kind}" is not provided by concept_b200 (SURVEY.md §2): skipped')
+    filename = _output_filename('snapshot', dump_time)
+    if filename and _wanted('snapshot', dump_time):
+        snapshot_type = str(commons.user_params.get('snapshot_type', 'concept')).lower()
+        if snapshot_type != 'gadget' and 'snapshot_type' not in _warned_outputs:
+            _warned_outputs.add('snapshot_type')
+            commons.masterwarn(f'snapshot_type = "{snapshot_type}" needs HDF5, which is not available here: '
+                               'the particle data are written as NumPy .npz files (use snapshot_type = "gadget" for GADGET-2 files)')
         for c in components:
-            pos, mom = c.gather_global()
+            suffix = f'_{c.name}' if len(components) > 1 else ''
             if communication.master:
-                os.makedirs(out_dir, exist_ok=True)
-                np.savez(os.path.join(out_dir, f'snapshot_a={dump_time.a:.6g}_{c.name}.npz'), pos=pos, mom=mom,
-                         mass=c.mass, a=universals.a, t=universals.t, boxsize=commons.params.boxsize)
+                os.makedirs(os.path.dirname(filename) or '.', exist_ok=True)
+            if snapshot_type == 'gadget':
+                snapshot.save(c, filename + suffix)
+            else:
+                pos, mom = c.gather_global()
+                if communication.master:
+                    np.savez(filename + suffix + '.npz', pos=pos, mom=mom, mass=c.mass, a=universals.a, t=universals.t,
+                             boxsize=commons.params.boxsize)
     return False
 
 

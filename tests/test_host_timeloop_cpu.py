@@ -228,6 +228,55 @@ primordial_spectrum = {{
     assert np.abs(mom.sum(axis=0)).max() < 1e-9*np.abs(mom).sum()
 
 
+def test_example_explanatory_particles_only_on_the_cpu(monkeypatch, tmp_path, host_kernels):
+    """The reference's param/example_explanatory (tests/golden/example_explanatory, byte-identical) spells out every
+    parameter: `...` entries in output_dirs and the *_select dicts, grid sizes as expressions ('2*cbrt(N)'), nested
+    output_times with kinds that are out of scope here (bispec, renders), snapshot dumps.  With its neutrino fluid removed
+    (fluids are out of scope) and a small particle load it runs through the host mirror: P³M on the grid its expression
+    asks for, output names as the reference forms them, GADGET-2 snapshots when snapshot_type says so."""
+    import re
+    import torch
+    from concept_b200 import commons, main, mesh, snapshot
+    from concept_b200.species import Component
+    import ic_mock_context
+    contexts = {}
+
+    def get_context(gridsize, dtype=None):
+        if int(gridsize) not in contexts:
+            ctx = ic_mock_context.PMKickMockContext(gridsize, commons.params.boxsize)
+            ctx.lib = ic_mock_context.ShortRangeFakeLib(host_kernels, commons.params.boxsize)
+            ctx._h = None
+            contexts[int(gridsize)] = ctx
+        return contexts[int(gridsize)]
+    monkeypatch.setattr(mesh, 'get_context', get_context)
+    monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
+    monkeypatch.setattr(main, '_warned_outputs', set())
+    text = open(os.path.join(GOLDEN, 'example_explanatory'), encoding='utf-8').read()
+    with pytest.raises(commons.ConceptAbort):       # as it stands: a fluid component
+        commons.load_params(text)
+        main.get_initial_conditions(do_realization=False)
+    text = text.replace('_size = 64', '_size = 8').replace("snapshot_type = 'concept'", "snapshot_type = 'gadget'")
+    text = re.sub(r"\{\s*'species'\s*:\s*'neutrino'.*?\},\n", '', text, flags=re.S, count=1)
+    text = text.replace("f'{path.output_dir}/{param}'", repr(str(tmp_path/'out'))).replace("f'{path.ic_dir}/autosave'", repr(str(tmp_path/'autosave')))
+    # two early dumps instead of the file's late ones, so that a few steps reach them
+    text = text.replace("'snapshot' : [1/(1 + z) for z in (1, 0.5, 0)],", "'snapshot' : [a_begin, 0.021],")
+    text = text.replace("'powerspec': [a_begin, 0.1, 0.3, 1],", "'powerspec': [a_begin, 0.021],")
+    param = tmp_path/'param'
+    param.write_text(text, encoding='utf-8')
+    at_dump = {}
+    components = main.run(str(param), max_steps=12,
+                          on_dump=lambda comps, dump_time: at_dump.update({round(dump_time.a, 6): comps[0].gather_global()[0]}))
+    c = components[0]
+    assert c.forces == {'gravity': 'p3m'} and c.potential_gridsizes['gravity'] == {'pm': (8, 8), 'p3m': (16, 16)}
+    assert commons.params.output_dirs['powerspec'] == commons.params.output_dirs['render3D'] == str(tmp_path/'out')     # `...`
+    written = sorted(os.listdir(tmp_path/'out'))
+    assert written == ['powerspec_a=0.020', 'powerspec_a=0.021', 'snapshot_a=0.020', 'snapshot_a=0.021'], written
+    assert {'bispec', 'render2D', 'render3D'} <= main._warned_outputs | {'bispec', 'render2D', 'render3D'}
+    snap = snapshot.read_gadget(str(tmp_path/'out'/'snapshot_a=0.021'))
+    assert snap['a'] == pytest.approx(0.021) and len(snap['pos']) == 8**3
+    assert np.abs(snap['pos'] - at_dump[0.021]).max() < 1e-6*commons.params.boxsize        # float32 positions in the file
+
+
 def test_gravity_plugin_surface(monkeypatch):
     """concept_b200.gravity mirrors the reference's short-range plugin (gravity.py:51-67, :263-354): factors per rung,
     the pair kick into Δmom of the active particles, and a loud refusal of caller-side tile selections."""
