@@ -237,6 +237,11 @@ def load_params(path_or_text='', extra='', **overrides):
     p.t_begin = float(up.get('t_begin', 0.0))
     p.enable_Hubble = bool(up.get('enable_Hubble', True))
     p.ρ_crit = 3*p.H0**2/(8*π*G_Newton)            # commons.py:4435
+    for key, ours in (('unit_length', unit_length), ('unit_time', unit_time), ('unit_mass', unit_mass)):
+        if str(up.get(key, ours)) != ours:
+            abort(f'{key} = "{up[key]}": concept_b200 works in the reference\'s default unit system ({unit_length}, {unit_time}, {unit_mass}) only')
+    if str(up.get('softening_kernel', 'spline')).lower() != 'spline':
+        abort(f'softening_kernel = "{up["softening_kernel"]}": only the (default) spline kernel is implemented')
     p.initial_conditions = up.get('initial_conditions', None)
     p.output_times = up.get('output_times', {})
     p.output_dirs = up.get('output_dirs', {})
@@ -373,6 +378,29 @@ def gridsize_value(g, N):
         except Exception as exc:
             abort(f'Could not understand the grid size "{g}": {exc}')
     return int(round(float(g)))
+
+
+def component_softening_length(name, species, N):
+    """select_softening_length (commons.py:3862-3873, doc/parameters/physics.rst): a length or an expression in boxsize, N
+    and the units, looked up by component name, species, 'particles', 'all', 'default'; default 0.025·boxsize/∛N."""
+    spec = user_params.get('select_softening_length', {})
+    value = '0.025*boxsize/cbrt(N)'
+    if isinstance(spec, dict):
+        lowered = _lower_keys(spec)
+        for key in (name, species, 'particles', 'all', 'default'):
+            if str(key).lower() in lowered:
+                value = lowered[str(key).lower()]
+                break
+    elif spec:
+        value = spec
+    if isinstance(value, str):
+        names = {k: getattr(units, k) for k in vars(units) if not k.startswith('_')}
+        names.update(cbrt=lambda x: x**(1/3), sqrt=math.sqrt, N=max(int(N), 1), boxsize=params.boxsize, π=math.pi, pi=math.pi)
+        try:
+            value = eval(value, {'__builtins__': {}}, names)
+        except Exception as exc:
+            abort(f'Could not understand the softening length "{value}": {exc}')
+    return float(value)
 
 
 def gridsize_for(method, N):

@@ -172,9 +172,13 @@ def save(component, filename):
     from . import communication
     p = commons.params
     pos, mom = component.gather_global()
+    # gadget_snapshot_params['dataformat'] (commons.py:2581-2600): 32 or 64 bits for positions and velocities
+    fmt = commons.user_params.get('gadget_snapshot_params', {})
+    fmt = {str(k).upper(): v for k, v in dict(fmt.get('dataformat', {})).items()} if isinstance(fmt, dict) else {}
+    bits = {key: (int(fmt[key]) if str(fmt.get(key, 32)).isdigit() else 32) for key in ('POS', 'VEL')}
     if communication.master:
         write_gadget(filename, pos, mom, mass=component.mass, a=commons.universals.a, boxsize=p.boxsize, H0=p.H0,
-                     Ωm=p.Ωb + p.Ωcdm)
+                     Ωm=p.Ωb + p.Ωcdm, bits_pos=bits['POS'], bits_vel=bits['VEL'])
     communication.barrier()
     return filename
 

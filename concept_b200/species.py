@@ -38,8 +38,8 @@ class Component:
             self.potential_gridsizes['gravity'][method] = (
                 commons.component_gridsizes(self.name, self.species, method, self.N) if self.N > 0 else (None, None))
             self.potential_differentiations['gravity'][method] = p.differentiation[method]
-        # softening_length default 0.025·L/∛N (commons.py:3862-3873)
-        self.softening_length = 0.025*p.boxsize/max(self.N, 1)**(1/3)
+        # select_softening_length, default 0.025·L/∛N (commons.py:3862-3873)
+        self.softening_length = commons.component_softening_length(self.name, self.species, self.N)
         self._ϱ_bar = -1
 
     # -- storage ------------------------------------------------------------------------------

@@ -100,6 +100,20 @@ potential_options = {'gridsize': {'global': {'gravity': {'pm': 64, 'p3m': 128}},
         commons.gridsize_value('2*cuberoot(N)', 8**3)
 
 
+def test_softening_length_units_and_kernel_parameters():
+    """select_softening_length (commons.py:3862-3873) by name / species / 'particles' / 'all', as a length or an expression;
+    a unit system or softening kernel other than the reference's defaults aborts instead of being ignored."""
+    from concept_b200.species import Component
+    commons.load_params("boxsize = 100*Mpc\nselect_softening_length = {'matter': '0.03*boxsize/cbrt(N)', 'all': 2*kpc}\n")
+    assert Component('matter', 'matter', N=1000, mass=1).softening_length == pytest.approx(0.3, rel=1e-14)
+    assert Component('b', 'baryons', N=1000, mass=1).softening_length == pytest.approx(0.002, rel=1e-14)
+    commons.load_params('boxsize = 100*Mpc\n')
+    assert Component('matter', 'matter', N=1000, mass=1).softening_length == 0.025*100.0/1000**(1/3)
+    for line in ("unit_length = 'kpc'", "unit_mass = 'm☉'", "softening_kernel = 'plummer'"):
+        with pytest.raises(commons.ConceptAbort):
+            commons.load_params('boxsize = 100*Mpc\n' + line + '\n')
+
+
 def test_background_and_time_step_integrals_match_reference_run():
     """Every ᔑdt the reference used in its 160 kicks / 142 drifts is reproduced from our own
     background (same ODE solver settings, same natural cubic splines)."""
