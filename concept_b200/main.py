@@ -432,11 +432,32 @@ def dump_powerspec(components, dump_time):
     particle_components = [c for c in components if c.representation == 'particles']
     if not particle_components:
         return None
-    # powerspec_options defaults: upstream grid size 2·∛N per particle component, global = the largest upstream size
-    gridsizes_upstream = [2*round(c.N**(1/3)) for c in particle_components]
+    # powerspec_options (commons.py:3354-3385): upstream grid size per component (default '2*cbrt(N)'), global grid size
+    # (default: the largest upstream size), interpolation, deconvolution, interlacing, k_max and the bins per decade — each
+    # looked up by component name, species, 'particles', 'all', 'default'
+    options = commons.user_params.get('powerspec_options', {})
+    options = {str(k).lower().replace('_', ' '): v for k, v in options.items()} if isinstance(options, dict) else {}
+
+    def option(name, component, default):
+        spec = options.get(name, default)
+        if isinstance(spec, dict) and name != 'bins per decade' or \
+                (name == 'bins per decade' and isinstance(spec, dict) and any(isinstance(v, dict) for v in spec.values())):
+            lowered = {str(k).lower(): v for k, v in spec.items()}
+            for key in (component.name, component.species, 'particles', 'all', 'default'):
+                if str(key).lower() in lowered:
+                    return lowered[str(key).lower()]
+            return default
+        return spec
+    first = particle_components[0]
+    gridsizes_upstream = [commons.gridsize_value(option('upstream gridsize', c, '2*cbrt(N)'), c.N) for c in particle_components]
     gridsizes_upstream = [g + (g & 1) for g in gridsizes_upstream]
-    gridsize = max(gridsizes_upstream)
-    k, power, n_modes = analysis.powerspec(particle_components, gridsize, gridsizes_upstream=gridsizes_upstream)
+    gridsize = option('global gridsize', first, -1)
+    gridsize = max(gridsizes_upstream) if gridsize in (-1, None) else commons.gridsize_value(gridsize, first.N)
+    k_max = option('k max', first, option('k_max', first, None))
+    k, power, n_modes = analysis.powerspec(
+        particle_components, gridsize, interpolation=option('interpolation', first, None), deconvolve=option('deconvolve', first, None),
+        interlace=option('interlace', first, None), k_max=k_max.lower() if isinstance(k_max, str) else k_max,
+        bins_per_decade=option('bins per decade', first, None), gridsizes_upstream=gridsizes_upstream)
     if out_dir and communication.master:
         os.makedirs(out_dir, exist_ok=True)
         filename = _output_filename('powerspec', dump_time)

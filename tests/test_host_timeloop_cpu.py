@@ -261,6 +261,9 @@ def test_example_explanatory_particles_only_on_the_cpu(monkeypatch, tmp_path, ho
     # two early dumps instead of the file's late ones, so that a few steps reach them
     text = text.replace("'snapshot' : [1/(1 + z) for z in (1, 0.5, 0)],", "'snapshot' : [a_begin, 0.021],")
     text = text.replace("'powerspec': [a_begin, 0.1, 0.3, 1],", "'powerspec': [a_begin, 0.021],")
+    # powerspec_options of the file, with a finer upstream grid for the particles than its '2*cbrt(N)'
+    assert "'particles': '2*cbrt(N)'," in text
+    text = text.replace("'particles': '2*cbrt(N)',", "'particles': '3*cbrt(N)',", 1)
     param = tmp_path/'param'
     param.write_text(text, encoding='utf-8')
     at_dump = {}
@@ -272,6 +275,7 @@ def test_example_explanatory_particles_only_on_the_cpu(monkeypatch, tmp_path, ho
     written = sorted(os.listdir(tmp_path/'out'))
     assert written == ['powerspec_a=0.020', 'powerspec_a=0.021', 'snapshot_a=0.020', 'snapshot_a=0.021'], written
     assert {'bispec', 'render2D', 'render3D'} <= main._warned_outputs | {'bispec', 'render2D', 'render3D'}
+    assert 'grid size 24 ' in open(tmp_path/'out'/'powerspec_a=0.021', encoding='utf-8').readline()       # 3·∛512
     snap = snapshot.read_gadget(str(tmp_path/'out'/'snapshot_a=0.021'))
     assert snap['a'] == pytest.approx(0.021) and len(snap['pos']) == 8**3
     assert np.abs(snap['pos'] - at_dump[0.021]).max() < 1e-6*commons.params.boxsize        # float32 positions in the file
