@@ -470,12 +470,37 @@ def global_gridsize(method, components):
     return max(max(c.potential_gridsizes['gravity'][method]) for c in components)
 
 
-def shortrange_scale(gridsize):
-    """shortrange_params['gravity']['scale'] = 1.25·boxsize/gridsize (commons.py:3254-3269)"""
+def _shortrange_expression(value, names):
+    if not isinstance(value, str):
+        return float(value)
+    env = {k: getattr(units, k) for k in vars(units) if not k.startswith('_')}
+    env.update(cbrt=lambda x: x**(1/3), sqrt=math.sqrt, π=math.pi, pi=math.pi, boxsize=params.boxsize, **names)
+    try:
+        return float(eval(value, {'__builtins__': {}}, env))
+    except Exception as exc:
+        abort(f'Could not understand the short-range parameter "{value}": {exc}')
+
+
+def _shortrange_gravity():
     sp = user_params.get('shortrange_params', {})
     if sp and not isinstance(list(sp.values())[0], dict):
         sp = {'gravity': sp}
-    scale = sp.get('gravity', {}).get('scale', None)
-    if scale is None or isinstance(scale, str):
+    return _lower_keys(sp.get('gravity', {})) if isinstance(sp, dict) else {}
+
+
+def shortrange_scale(gridsize):
+    """shortrange_params['gravity']['scale'], a length or an expression in boxsize and gridsize; default
+    '1.25*boxsize/gridsize' (commons.py:3254-3269)"""
+    scale = _shortrange_gravity().get('scale', None)
+    if scale is None:
         return 1.25*params.boxsize/gridsize
-    return float(scale)
+    return _shortrange_expression(scale, {'gridsize': gridsize})
+
+
+def shortrange_range(gridsize):
+    """shortrange_params['gravity']['range'], a length or an expression in scale, boxsize and gridsize; default '4.5*scale'"""
+    scale = shortrange_scale(gridsize)
+    rng = _shortrange_gravity().get('range', None)
+    if rng is None:
+        return 4.5*scale
+    return _shortrange_expression(rng, {'scale': scale, 'gridsize': gridsize})

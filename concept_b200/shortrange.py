@@ -32,13 +32,8 @@ def N_rungs():
 def shortrange_params(gridsize):
     """shortrange_params['gravity'] with its defaults (commons.py:3254-3269)"""
     scale = commons.shortrange_scale(gridsize)
-    sp = commons.user_params.get('shortrange_params', {})
-    if sp and not isinstance(list(sp.values())[0], dict):
-        sp = {'gravity': sp}
-    g = sp.get('gravity', {})
-    rng = g.get('range', None)
-    rng = 4.5*scale if rng is None or isinstance(rng, str) else float(rng)
-    tablesize = int(g.get('tablesize', 2**12))
+    rng = commons.shortrange_range(gridsize)
+    tablesize = int(commons._shortrange_gravity().get('tablesize', 2**12))
     return scale, rng, tablesize
 
 

@@ -114,6 +114,18 @@ def test_softening_length_units_and_kernel_parameters():
             commons.load_params('boxsize = 100*Mpc\n' + line + '\n')
 
 
+def test_shortrange_parameters_as_expressions():
+    """shortrange_params (commons.py:3254-3269): scale and range as lengths or as the expressions the reference's
+    example_explanatory spells out ('1.25*boxsize/gridsize', '4.5*scale'), with or without the 'gravity' level."""
+    from concept_b200 import shortrange
+    commons.load_params("boxsize = 100*Mpc\nshortrange_params = {'gravity': {'scale': '1.5*boxsize/gridsize', 'range': '4.0*scale', 'tablesize': 2048}}\n")
+    assert shortrange.shortrange_params(50) == (3.0, 12.0, 2048)
+    commons.load_params('boxsize = 100*Mpc\n')
+    assert shortrange.shortrange_params(50) == (2.5, 11.25, 4096)
+    commons.load_params("boxsize = 100*Mpc\nshortrange_params = {'scale': 3*Mpc}\n")
+    assert shortrange.shortrange_params(50) == (3.0, 13.5, 4096)
+
+
 def test_background_and_time_step_integrals_match_reference_run():
     """Every ᔑdt the reference used in its 160 kicks / 142 drifts is reproduced from our own
     background (same ODE solver settings, same natural cubic splines)."""
