@@ -67,11 +67,25 @@ def build_units(unit_length='Mpc', unit_time='Gyr', unit_mass='10¹⁰ m☉'):
     return u, r
 
 
-units, unit_relations = build_units()
-unit_length, unit_time, unit_mass = 'Mpc', 'Gyr', '10¹⁰ m☉'
-light_speed = units.ly/units.yr
-G_Newton = (unit_relations['G_Newton']/(unit_relations['m']**3/(unit_relations['kg']*unit_relations['s']**2))
-            * units.m**3/(units.kg*units.s**2))
+def set_unit_system(length='Mpc', time='Gyr', mass='10¹⁰ m☉'):
+    """The unit system every number of a run is expressed in (unit_length, unit_time, unit_mass of the parameter file,
+    commons.py:1935-1999); rebinds `units`, `G_Newton`, `light_speed` and the unit names of this module, which the other
+    modules always reach through `commons.`."""
+    global units, unit_relations, unit_length, unit_time, unit_mass, light_speed, G_Newton
+    r = _unit_relations()
+    mass = str(mass).replace(' ', '')
+    mass_names = {'10¹⁰m☉': '10¹⁰ m☉', '1e+10*m_sun': '10¹⁰ m☉', '1e10*m_sun': '10¹⁰ m☉', '10**10*m_sun': '10¹⁰ m☉', 'm☉': 'm_sun'}
+    mass = mass_names.get(mass, mass)
+    if str(length) not in r or str(time) not in r or (mass not in r and mass != '10¹⁰ m☉'):
+        abort(f'Unit system ({length}, {time}, {mass}) not understood')
+    units, unit_relations = build_units(str(length), str(time), mass)
+    unit_length, unit_time, unit_mass = str(length), str(time), ('m☉' if mass == 'm_sun' else mass)
+    light_speed = units.ly/units.yr
+    G_Newton = (unit_relations['G_Newton']/(unit_relations['m']**3/(unit_relations['kg']*unit_relations['s']**2))
+                * units.m**3/(units.kg*units.s**2))
+
+
+units = unit_relations = unit_length = unit_time = unit_mass = light_speed = G_Newton = None
 
 
 # ---------------------------------------------------------------------------
@@ -105,6 +119,9 @@ def abort(*args, exit_code=1):
     msg = ' '.join(str(a) for a in args)
     print('Aborting:', msg, file=sys.stderr)
     raise ConceptAbort(msg or exit_code)
+
+
+set_unit_system()
 
 
 # ---------------------------------------------------------------------------
@@ -217,6 +234,11 @@ def load_params(path_or_text='', extra='', **overrides):
     # h is defined from H0 after the file (commons.py:1785-1798) — but files use it (`256*Mpc/h`), so
     # it must be resolvable during the retry loop
     content += '\ntry:\n    h = H0/(100*km/(s*Mpc))\nexcept NameError:\n    h = 1\nh = float("{:.15f}".format(h))\n'
+    # the unit system first (its names are plain strings in the file); everything else is read in it
+    set_unit_system()
+    probe = _param_namespace(path)
+    exec_params(content, probe)
+    set_unit_system(probe.get('unit_length', 'Mpc'), probe.get('unit_time', 'Gyr'), probe.get('unit_mass', '10¹⁰ m☉'))
     ns = _param_namespace(path)
     base_keys = set(ns)
     exec_params(content, ns)
@@ -237,9 +259,6 @@ def load_params(path_or_text='', extra='', **overrides):
     p.t_begin = float(up.get('t_begin', 0.0))
     p.enable_Hubble = bool(up.get('enable_Hubble', True))
     p.ρ_crit = 3*p.H0**2/(8*π*G_Newton)            # commons.py:4435
-    for key, ours in (('unit_length', unit_length), ('unit_time', unit_time), ('unit_mass', unit_mass)):
-        if str(up.get(key, ours)) != ours:
-            abort(f'{key} = "{up[key]}": concept_b200 works in the reference\'s default unit system ({unit_length}, {unit_time}, {unit_mass}) only')
     if str(up.get('softening_kernel', 'spline')).lower() != 'spline':
         abort(f'softening_kernel = "{up["softening_kernel"]}": only the (default) spline kernel is implemented')
     p.initial_conditions = up.get('initial_conditions', None)

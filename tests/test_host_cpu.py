@@ -109,9 +109,29 @@ def test_softening_length_units_and_kernel_parameters():
     assert Component('b', 'baryons', N=1000, mass=1).softening_length == pytest.approx(0.002, rel=1e-14)
     commons.load_params('boxsize = 100*Mpc\n')
     assert Component('matter', 'matter', N=1000, mass=1).softening_length == 0.025*100.0/1000**(1/3)
-    for line in ("unit_length = 'kpc'", "unit_mass = 'm☉'", "softening_kernel = 'plummer'"):
-        with pytest.raises(commons.ConceptAbort):
-            commons.load_params('boxsize = 100*Mpc\n' + line + '\n')
+    with pytest.raises(commons.ConceptAbort):
+        commons.load_params("boxsize = 100*Mpc\nsoftening_kernel = 'plummer'\n")
+    commons.load_params('boxsize = 100*Mpc\n')
+
+
+def test_unit_system_of_the_parameter_file():
+    """unit_length / unit_time / unit_mass (commons.py:1935-1999; the reference's test/realize/param uses kpc): every number
+    of the run is expressed in them — lengths scale, Newton's constant and the critical density follow, rates do not change —
+    and the next parameter file starts from the defaults again."""
+    from concept_b200.species import Component
+    base = 'boxsize = 100*Mpc\nH0 = 70*km/(s*Mpc)\nΩb = 0.05\nΩcdm = 0.25\n'
+    p0 = commons.load_params(base)
+    G0, m0 = commons.G_Newton, Component('matter', 'matter', N=1000, mass=-1).softening_length
+    p1 = commons.load_params("unit_length = 'kpc'\nunit_mass = 'm☉'\n" + base)
+    assert commons.unit_length == 'kpc' and commons.unit_mass == 'm☉'
+    assert p1.boxsize == pytest.approx(1e3*p0.boxsize, rel=1e-14) and p1.H0 == pytest.approx(p0.H0, rel=1e-14)
+    assert commons.G_Newton == pytest.approx(G0*1e9/1e10, rel=1e-13)                 # length³ / mass
+    assert p1.ρ_crit == pytest.approx(p0.ρ_crit*1e10/1e9, rel=1e-13)                 # mass / length³
+    assert Component('matter', 'matter', N=1000, mass=-1).softening_length == pytest.approx(1e3*m0, rel=1e-14)
+    with pytest.raises(commons.ConceptAbort):
+        commons.load_params("unit_length = 'furlong'\n" + base)
+    commons.load_params(base)
+    assert commons.unit_length == 'Mpc' and commons.G_Newton == G0
 
 
 def test_shortrange_parameters_as_expressions():

@@ -127,6 +127,45 @@ primordial_spectrum = {{
     assert np.all((0.9 < ratio) & (ratio < 1.15)), ratio      # measured: 1.02, 1.05 (a 16³ grid instead of 32³: 0.80, 0.73)
 
 
+def test_run_is_invariant_under_the_unit_system(monkeypatch, tmp_path, host_kernels):
+    """The same parameter file in (Mpc, Gyr, 10¹⁰ m☉) and in (kpc, Myr, m☉): initial conditions, background, time-step
+    control and kicks go through every host module in the file's units — positions, momenta and the scale factor reached
+    after a few steps agree once converted (kernels replaced by their numpy model)."""
+    import torch
+    from concept_b200 import commons, main, mesh
+    from concept_b200.species import Component
+    import ic_mock_context
+    monkeypatch.setattr(ic_mock_context.PMKickMockContext, 'lib', host_kernels)
+    monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
+    results = {}
+    for tag, head in (('default', ''), ('small', "unit_length = 'kpc'\nunit_time = 'Myr'\nunit_mass = 'm☉'\n")):
+        contexts = {}
+        monkeypatch.setattr(mesh, 'get_context', lambda gridsize, dtype=None, contexts=contexts: contexts.setdefault(
+            int(gridsize), ic_mock_context.PMKickMockContext(gridsize, commons.params.boxsize)))
+        param = tmp_path/f'param_{tag}'
+        param.write_text(head + f"""
+initial_conditions = {{'species': 'matter', 'N': 8**3}}
+output_dirs = '{tmp_path}/output_{tag}'
+output_times = {{'powerspec': 1.0}}
+boxsize = 128*Mpc/h
+potential_options = 16
+select_forces = {{'matter': {{'gravity': 'pm'}}}}
+H0 = 67*km/(s*Mpc)
+Ωb = 0.049
+Ωcdm = 0.27
+a_begin = 0.02
+""", encoding='utf-8')
+        c = main.run(str(param), max_steps=5)[0]
+        u = commons.units
+        results[tag] = (c.pos_local.numpy()/u.Mpc, c.mom_local.numpy()/(u.m_sun*u.Mpc/u.Gyr), commons.universals.a,
+                        commons.universals.t/u.Gyr, c.mass/u.m_sun)
+    commons.load_params('boxsize = 8*Mpc\n')
+    (pos0, mom0, a0, t0, m0), (pos1, mom1, a1, t1, m1) = results['default'], results['small']
+    assert a1 == pytest.approx(a0, rel=1e-10) and t1 == pytest.approx(t0, rel=1e-10) and m1 == pytest.approx(m0, rel=1e-12)
+    assert np.abs(pos1 - pos0).max() < 1e-9*np.abs(pos0).max()
+    assert np.abs(mom1 - mom0).max() < 1e-8*np.abs(mom0).max()
+
+
 def test_p3m_run_with_rungs_reproduces_reference_on_the_cpu(monkeypatch):
     """The reference's short P³M run (8 rungs, sub-stepped drifts and rung-selective kicks, rung jumps;
     tests/golden/run_p3m_8.npz) through concept_b200.main / .shortrange with every library entry point replaced by its
