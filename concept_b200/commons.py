@@ -316,6 +316,9 @@ def load_params(path_or_text='', extra='', **overrides):
     # the tile sort the reference performs at its synchronised steps, main.py:270-305); 0 disables it
     p.cell_sort_period = int(up.get('cell_sort_period', 64))
     p.cell_centered = bool(up.get('cell_centered', True))
+    if not p.cell_centered:
+        abort('cell_centered = False (grid values at the cell vertices) is not implemented: the mesh kernels, the lattice of the '
+              'initial conditions and the phases between grids of different size assume cell-centred values (the default)')
     p.grid_dtype = str(up.get('grid_dtype', 'f64'))     # extension: 'f32' selects the mixed-precision grid
     # select_forces (commons.py:3664-3702): default for particles is gravity via P³M
     sf = up.get('select_forces', {})
