@@ -402,6 +402,21 @@ def gridsize_value(g, N):
     return int(round(float(g)))
 
 
+def component_differentiation(name, species, method):
+    """potential_options['differentiation'] is selected per component (Component.__init__, species.py:1217-1236): an entry
+    keyed by the component's name, its species, 'particles' or 'all' wins over 'default' (2 for PM, 4 for P³M);
+    'fourier' → 0."""
+    spec = params.potential_options_raw.get('differentiation') if isinstance(params.potential_options_raw, dict) else None
+    if isinstance(spec, dict):
+        lowered = _lower_keys(spec)
+        for key in (name, species, 'particles', 'all'):
+            if str(key).lower() in lowered:
+                v = _method_value(lowered[str(key).lower()], method)
+                if v is not None:
+                    return 0 if str(v).lower() == 'fourier' else int(v)
+    return params.differentiation[method]
+
+
 def component_softening_length(name, species, N):
     """select_softening_length (commons.py:3862-3873, doc/parameters/physics.rst): a length or an expression in boxsize, N
     and the units, looked up by component name, species, 'particles', 'all', 'default'; default 0.025·boxsize/∛N."""

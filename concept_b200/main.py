@@ -437,6 +437,9 @@ def dump_powerspec(components, dump_time):
     # looked up by component name, species, 'particles', 'all', 'default'
     options = commons.user_params.get('powerspec_options', {})
     options = {str(k).lower().replace('_', ' '): v for k, v in options.items()} if isinstance(options, dict) else {}
+    if 'gridsize' in options:       # one grid size for both (commons.py:3392-3398)
+        options.setdefault('upstream gridsize', options['gridsize'])
+        options.setdefault('global gridsize', options['gridsize'])
 
     def option(name, component, default):
         spec = options.get(name, default)
@@ -454,10 +457,13 @@ def dump_powerspec(components, dump_time):
     gridsize = option('global gridsize', first, -1)
     gridsize = max(gridsizes_upstream) if gridsize in (-1, None) else commons.gridsize_value(gridsize, first.N)
     k_max = option('k max', first, option('k_max', first, None))
+    bins_per_decade = option('bins per decade', first, None)
+    if bins_per_decade is not None and not isinstance(bins_per_decade, dict):
+        bins_per_decade = {'k_min': float(bins_per_decade)}        # the same number of bins in every decade
     k, power, n_modes = analysis.powerspec(
         particle_components, gridsize, interpolation=option('interpolation', first, None), deconvolve=option('deconvolve', first, None),
         interlace=option('interlace', first, None), k_max=k_max.lower() if isinstance(k_max, str) else k_max,
-        bins_per_decade=option('bins per decade', first, None), gridsizes_upstream=gridsizes_upstream)
+        bins_per_decade=bins_per_decade, gridsizes_upstream=gridsizes_upstream)
     if out_dir and communication.master:
         os.makedirs(out_dir, exist_ok=True)
         filename = _output_filename('powerspec', dump_time)

@@ -37,7 +37,7 @@ class Component:
         for method in ('pm', 'p3m'):
             self.potential_gridsizes['gravity'][method] = (
                 commons.component_gridsizes(self.name, self.species, method, self.N) if self.N > 0 else (None, None))
-            self.potential_differentiations['gravity'][method] = p.differentiation[method]
+            self.potential_differentiations['gravity'][method] = commons.component_differentiation(self.name, self.species, method)
         # select_softening_length, default 0.025·L/∛N (commons.py:3862-3873)
         self.softening_length = commons.component_softening_length(self.name, self.species, self.N)
         self._ϱ_bar = -1

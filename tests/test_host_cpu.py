@@ -134,6 +134,20 @@ def test_unit_system_of_the_parameter_file():
     assert commons.unit_length == 'Mpc' and commons.G_Newton == G0
 
 
+def test_differentiation_order_per_component():
+    """potential_options['differentiation'] keyed by component (the reference's test/concept_vs_class_pm/param asks for order 4
+    for 'matter'), species.py:1217-1236"""
+    from concept_b200.species import Component
+    commons.load_params("""
+boxsize = 100*Mpc
+potential_options = {'gridsize': {'gravity': {'pm': 16}},
+                     'differentiation': {'matter': {'gravity': {'pm': 4}}, 'baryons': {'gravity': {'pm': 'fourier'}}}}
+""")
+    assert Component('matter', 'matter', N=512, mass=1).potential_differentiations['gravity'] == {'pm': 4, 'p3m': 4}
+    assert Component('b', 'baryons', N=512, mass=1).potential_differentiations['gravity'] == {'pm': 0, 'p3m': 4}
+    assert Component('cdm', 'cold dark matter', N=512, mass=1).potential_differentiations['gravity'] == {'pm': 2, 'p3m': 4}
+
+
 def test_shortrange_parameters_as_expressions():
     """shortrange_params (commons.py:3254-3269): scale and range as lengths or as the expressions the reference's
     example_explanatory spells out ('1.25*boxsize/gridsize', '4.5*scale'), with or without the 'gravity' level."""
