@@ -314,7 +314,9 @@ def load_params(path_or_text='', extra='', **overrides):
     p.static_timestepping = up.get('static_timestepping', None)
     # concept_b200 only: base steps between two re-orderings of the particles by grid cell (pm_sort_particles, the analogue of
     # the tile sort the reference performs at its synchronised steps, main.py:270-305); 0 disables it
-    p.cell_sort_period = int(up.get('cell_sort_period', 64))
+    # particle_reordering (commons.py, default True): the periodic re-ordering of the particles in memory; here by grid cell
+    # every cell_sort_period base steps (0: never)
+    p.cell_sort_period = int(up.get('cell_sort_period', 64)) if up.get('particle_reordering', True) else 0
     p.cell_centered = bool(up.get('cell_centered', True))
     if not p.cell_centered:
         abort('cell_centered = False (grid values at the cell vertices) is not implemented: the mesh kernels, the lattice of the '

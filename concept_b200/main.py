@@ -468,12 +468,25 @@ def dump_powerspec(components, dump_time):
         os.makedirs(out_dir, exist_ok=True)
         filename = _output_filename('powerspec', dump_time)
         names = ', '.join(c.name for c in particle_components)
-        power_linear = analysis.get_linear_powerspec(particle_components, k)
+        # powerspec_select (commons.py:2636-2643): the linear-theory column unless it is switched off for these components
+        select = commons.user_params.get('powerspec_select', {})
+        want_linear = True
+        if isinstance(select, dict):
+            lowered = {str(key).lower(): val for key, val in select.items()}
+            for key in (first.name, first.species, 'particles', 'all', 'default'):
+                if str(key).lower() in lowered:
+                    val = lowered[str(key).lower()]
+                    want_linear = bool(val.get('linear', False)) if isinstance(val, dict) else bool(val)
+                    break
+        columns, fmt = [k, n_modes, power], ['%.8e', '%d', '%.8e']
         header = (f'Power spectrum of {names} at a = {universals.a:.8g}, t = {universals.t:.8g} {commons.unit_time}, '
                   f'grid size {gridsize} (concept_b200)\n'
-                  f'k [{commons.unit_length}^-1]\tmodes\tpower [{commons.unit_length}^3]\tlinear power [{commons.unit_length}^3]')
-        np.savetxt(filename, np.column_stack([k, n_modes, power, power_linear]), fmt=('%.8e', '%d', '%.8e', '%.8e'),
-                   delimiter='\t', header=header)
+                  f'k [{commons.unit_length}^-1]\tmodes\tpower [{commons.unit_length}^3]')
+        if want_linear:
+            columns.append(analysis.get_linear_powerspec(particle_components, k))
+            fmt.append('%.8e')
+            header += f'\tlinear power [{commons.unit_length}^3]'
+        np.savetxt(filename, np.column_stack(columns), fmt=tuple(fmt), delimiter='\t', header=header)
     return k, power, n_modes
 
 
