@@ -1,7 +1,8 @@
 """GADGET-2 snapshots: exchange particle data with a real CO*N*CEPT / GADGET run.
 
 Mirrors the reference's GadgetSnapshot (snapshot.py:640-2640) for what the PM path needs: one particle
-component stored as GADGET type 1 ("halo"), SnapFormat 2 (named blocks), a single file, POS and VEL in
+component stored as GADGET type 1 ("halo"), SnapFormat 2 (named blocks), written as a single file and read from one
+or several files, POS and VEL in
 32 or 64 bits, 32-bit IDs (64-bit above 2³² particles), GADGET units kpc/h, km/s, 10¹⁰ m☉/h
 (commons.py:2787-2804).  Conversions (snapshot.py:1520-1552, :1376-1383, :2560-2573):
 
@@ -121,9 +122,46 @@ def write_gadget(filename, pos, mom, *, mass, a, boxsize, H0, Ωm, ids=None, bit
     return header
 
 
+def _gadget_files(filename):
+    """The files of a snapshot: `filename` itself, or — a snapshot spread over several files (header NumFiles > 1) —
+    `filename.0`, `filename.1`, … next to each other, or the `*.0`, `*.1`, … inside the directory `filename` (how the
+    reference writes them, snapshot.py:1316-1323)."""
+    import glob
+    import os
+    import re
+    if os.path.isfile(filename):
+        return [filename]
+    if os.path.isdir(filename):
+        files = [f for f in glob.glob(os.path.join(filename, '*.*')) if re.search(r'\.\d+$', f)]
+    else:
+        files = [f for f in glob.glob(filename + '.*') if re.search(r'\.\d+$', f)]
+    if not files:
+        commons.abort(f'No GADGET snapshot at "{filename}"')
+    return sorted(files, key=lambda f: int(f.rsplit('.', 1)[1]))
+
+
 def read_gadget(filename):
-    """Read a single-file SnapFormat-2 GADGET snapshot with one populated particle type.
+    """Read a SnapFormat-2 GADGET snapshot with one populated particle type, in one file or spread over several.
     Returns dict(header, pos, mom, ids, mass, a, boxsize, H0, Ωm) in internal units."""
+    files = _gadget_files(filename)
+    if len(files) == 1:
+        return _read_gadget_file(files[0], single=True)
+    parts = [_read_gadget_file(f, single=False) for f in files]
+    first = parts[0]
+    if first['header']['NumFiles'] != len(files):
+        commons.abort(f'"{filename}": {len(files)} files found, the header says NumFiles = {first["header"]["NumFiles"]}')
+    out = dict(first)
+    out['pos'] = np.concatenate([q['pos'] for q in parts])
+    out['mom'] = np.concatenate([q['mom'] for q in parts])
+    out['ids'] = None if any(q['ids'] is None for q in parts) else np.concatenate([q['ids'] for q in parts])
+    t = first['type']
+    n_all = first['header']['Nall'][t] + 2**32*first['header']['NallHW'][t]
+    if len(out['pos']) != n_all:
+        commons.abort(f'"{filename}": the files hold {len(out["pos"])} particles, the header says {n_all}')
+    return out
+
+
+def _read_gadget_file(filename, single):
     with open(filename, 'rb') as f:
         blob = f.read()
     blocks, o = {}, 0
@@ -144,8 +182,10 @@ def read_gadget(filename):
         header[name] = list(vals) if len(vals) > 1 else vals[0]
         off += struct.calcsize('<' + fmt)
     types = [t for t in range(NUM_TYPES) if header['Npart'][t]]
-    if len(types) != 1 or header['NumFiles'] != 1:
-        commons.abort('concept_b200 reads single-file GADGET snapshots with one particle type')
+    if len(types) != 1:
+        commons.abort('concept_b200 reads GADGET snapshots with one particle type')
+    if single and header['NumFiles'] > 1:
+        commons.abort(f'"{filename}" is one of {header["NumFiles"]} files of a snapshot: give the common name (without .0)')
     t = types[0]
     N = header['Npart'][t]
     h, a = header['HubbleParam'], header['Time']
@@ -163,7 +203,7 @@ def read_gadget(filename):
         ids = np.frombuffer(blocks['ID'], dtype='<u4' if len(blocks['ID']) == 4*N else '<u8').astype(np.int64)
     u = commons.units
     return dict(header=header, pos=pos, mom=mom, ids=ids, mass=mass, a=a, boxsize=header['BoxSize']*unit_length,
-                H0=h*100*u.km/(u.s*u.Mpc), Ωm=header['Omega0'])
+                H0=h*100*u.km/(u.s*u.Mpc), Ωm=header['Omega0'], type=t)
 
 
 def save(component, filename):

@@ -57,6 +57,50 @@ def test_position_wrap_and_double_precision(tmp_path):
     assert abs(snapshot.read_gadget(fn)['pos'][0, 0] - pos[0, 0]) < 1e-12
 
 
+def _rewrite_header(path, **fields):
+    """patch header fields of a SnapFormat-2 file in place (the HEAD block starts 16 + 4 bytes into the file)"""
+    import struct
+    from concept_b200 import snapshot
+    with open(path, 'r+b') as f:
+        off = 20
+        for name, fmt in snapshot.HEADER_FIELDS:
+            if name in fields:
+                f.seek(off)
+                vals = fields[name] if isinstance(fields[name], (list, tuple)) else [fields[name]]
+                f.write(struct.pack('<' + fmt, *vals))
+            off += struct.calcsize('<' + fmt)
+
+
+def test_reader_of_a_snapshot_spread_over_several_files(tmp_path):
+    """GADGET snapshots of large runs come as name.0, name.1, … (header NumFiles > 1, Nall = total, Npart = this file) —
+    as files next to each other or inside a directory (how the reference writes them, snapshot.py:1316-1323)."""
+    from concept_b200 import commons, snapshot
+    commons.load_params('boxsize = 32*Mpc\nH0 = 70*km/(s*Mpc)\nΩb = 0.05\nΩcdm = 0.25\n')
+    p = commons.params
+    rng = np.random.default_rng(4)
+    N, cuts = 1000, [0, 300, 650, 1000]
+    pos, mom = rng.random((N, 3))*p.boxsize, rng.standard_normal((N, 3))
+    kw = dict(mass=2.5, a=0.5, boxsize=p.boxsize, H0=p.H0, Ωm=p.Ωm, bits_pos=64, bits_vel=64)
+    whole = tmp_path/'whole'
+    snapshot.write_gadget(str(whole), pos, mom, **kw)
+    ref = snapshot.read_gadget(str(whole))
+    for layout in ('flat', 'directory'):
+        base = tmp_path/layout
+        if layout == 'directory':
+            base.mkdir()
+        for i, (lo, hi) in enumerate(zip(cuts, cuts[1:])):
+            name = str(base/f'snapshot.{i}') if layout == 'directory' else f'{base}.{i}'
+            snapshot.write_gadget(name, pos[lo:hi], mom[lo:hi], ids=np.arange(lo, hi), **kw)
+            nall = [0]*6
+            nall[snapshot.HALO] = N
+            _rewrite_header(name, NumFiles=3, Nall=nall)
+        got = snapshot.read_gadget(str(base))
+        assert all(np.array_equal(got[key], ref[key]) for key in ('pos', 'mom', 'ids'))
+        assert got['mass'] == ref['mass'] and got['a'] == 0.5
+        with pytest.raises(commons.ConceptAbort):       # one file of several is not a snapshot
+            snapshot.read_gadget(str(base/'snapshot.1') if layout == 'directory' else f'{base}.1')
+
+
 @pytest.mark.gpu
 def test_component_save_load_round_trip(tmp_path):
     """snapshot.save / snapshot.load through a GPU-resident Component."""
