@@ -141,7 +141,8 @@ def _gadget_files(filename):
 
 
 def read_gadget(filename):
-    """Read a SnapFormat-2 GADGET snapshot with one populated particle type, in one file or spread over several.
+    """Read a GADGET snapshot (SnapFormat 2 with named blocks, or the older SnapFormat 1) with one populated particle type,
+    in one file or spread over several.
     Returns dict(header, pos, mom, ids, mass, a, boxsize, H0, Ωm) in internal units."""
     files = _gadget_files(filename)
     if len(files) == 1:
@@ -165,16 +166,28 @@ def _read_gadget_file(filename, single):
     with open(filename, 'rb') as f:
         blob = f.read()
     blocks, o = {}, 0
+    if len(blob) < 264:
+        commons.abort(f'"{filename}" is not a GADGET snapshot')
+    snapformat = {8: 2, HEADER_SIZE: 1}.get(struct.unpack_from('<I', blob, 0)[0])
+    if snapformat is None:
+        commons.abort(f'"{filename}" is not a GADGET snapshot of SnapFormat 1 or 2')
+    unnamed = iter(('HEAD', 'POS', 'VEL', 'ID', 'MASS'))       # SnapFormat 1: the blocks come in this order, without names
     while o < len(blob):
-        n, name, _, n2 = struct.unpack_from('<I4sII', blob, o)
-        if n != 8 or n2 != 8:
-            commons.abort(f'"{filename}" is not a SnapFormat 2 GADGET snapshot')
-        o += 16
+        if snapformat == 2:
+            n, name, _, n2 = struct.unpack_from('<I4sII', blob, o)
+            if n != 8 or n2 != 8:
+                commons.abort(f'"{filename}" is not a SnapFormat 2 GADGET snapshot')
+            name = name.decode('ascii').strip()
+            o += 16
+        else:
+            name = next(unnamed, None)
+            if name is None:
+                break                                           # further blocks (gas, …) are of no concern here
         size = struct.unpack_from('<I', blob, o)[0]
         payload = memoryview(blob)[o + 4:o + 4 + size]          # a view: the blocks are hundreds of MB
-        if struct.unpack_from('<I', blob, o + 4 + size)[0] != size:
-            commons.abort(f'Corrupt block "{name.decode().strip()}" in "{filename}"')
-        blocks[name.decode('ascii').strip()] = payload
+        if o + 8 + size > len(blob) or struct.unpack_from('<I', blob, o + 4 + size)[0] != size:
+            commons.abort(f'Corrupt block "{name}" in "{filename}"')
+        blocks[name] = payload
         o += size + 8
     head, header, off = blocks['HEAD'], {}, 0
     for name, fmt in HEADER_FIELDS:

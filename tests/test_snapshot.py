@@ -101,6 +101,30 @@ def test_reader_of_a_snapshot_spread_over_several_files(tmp_path):
             snapshot.read_gadget(str(base/'snapshot.1') if layout == 'directory' else f'{base}.1')
 
 
+def test_reader_of_snapformat_1(tmp_path):
+    """SnapFormat 1 (what GADGET's own initial-condition generators write by default): the same records without the
+    16-byte name records in front of them, in the order HEAD, POS, VEL, ID."""
+    from concept_b200 import commons, snapshot
+    commons.load_params('boxsize = 32*Mpc\nH0 = 70*km/(s*Mpc)\nΩb = 0.05\nΩcdm = 0.25\n')
+    p = commons.params
+    rng = np.random.default_rng(5)
+    pos, mom = rng.random((400, 3))*p.boxsize, rng.standard_normal((400, 3))
+    two = tmp_path/'format2'
+    snapshot.write_gadget(str(two), pos, mom, mass=1.5, a=0.25, boxsize=p.boxsize, H0=p.H0, Ωm=p.Ωm)
+    blob, out, o = two.read_bytes(), b'', 0
+    while o < len(blob):                      # drop the name records
+        size = int.from_bytes(blob[o + 16:o + 20], 'little')
+        out += blob[o + 16:o + 16 + size + 8]
+        o += 16 + size + 8
+    one = tmp_path/'format1'
+    one.write_bytes(out)
+    a, b = snapshot.read_gadget(str(one)), snapshot.read_gadget(str(two))
+    assert all(np.array_equal(a[key], b[key]) for key in ('pos', 'mom', 'ids')) and a['mass'] == b['mass'] and a['a'] == 0.25
+    with pytest.raises(commons.ConceptAbort):
+        (tmp_path/'junk').write_bytes(b'\x01'*400)
+        snapshot.read_gadget(str(tmp_path/'junk'))
+
+
 @pytest.mark.gpu
 def test_component_save_load_round_trip(tmp_path):
     """snapshot.save / snapshot.load through a GPU-resident Component."""
