@@ -104,6 +104,10 @@ class ConceptAbort(SystemExit):
 verbose = bool(int(os.environ.get('CONCEPT_B200_VERBOSE', '0')))
 
 
+def communication_master():
+    return int(os.environ.get('RANK', '0')) == 0
+
+
 def masterprint(*args, **kwargs):
     if verbose and int(os.environ.get('RANK', '0')) == 0:
         print(*args, **kwargs)

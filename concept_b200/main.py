@@ -423,12 +423,12 @@ def _wanted(kind, dump_time):
            (any(x == dump_time.t for x in flat['t'].get(kind, ())) and dump_time.time_param == 't')
 
 
-def dump_powerspec(components, dump_time):
+def dump_powerspec(components, dump_time, filename=None):
     """analysis.powerspec + save_powerspec (analysis.py:500-579, :796-836) with the defaults of powerspec_options
     (commons.py:3354-3385: PCS, deconvolution, bcc interlacing, k_max = Nyquist, grid 2·∛N).  Columns as in the
     reference's text files: k, number of modes, P(k), linear P(k) (powerspec_select's default, commons.py:2636-2643).
     Returns (k, power, n_modes)."""
-    out_dir = _output_dir('powerspec')
+    out_dir = os.path.dirname(filename) or '.' if filename else _output_dir('powerspec')
     particle_components = [c for c in components if c.representation == 'particles']
     if not particle_components:
         return None
@@ -466,7 +466,7 @@ def dump_powerspec(components, dump_time):
         bins_per_decade=bins_per_decade, gridsizes_upstream=gridsizes_upstream)
     if out_dir and communication.master:
         os.makedirs(out_dir, exist_ok=True)
-        filename = _output_filename('powerspec', dump_time)
+        filename = filename or _output_filename('powerspec', dump_time)
         names = ', '.join(c.name for c in particle_components)
         # powerspec_select (commons.py:2636-2643): the linear-theory column unless it is switched off for these components
         select = commons.user_params.get('powerspec_select', {})
@@ -711,6 +711,55 @@ def get_initial_conditions(initial_conditions_touse=None, do_realization=True):
         for component in to_realize:
             ic.realize_particles(component, universals.a, components_all=to_realize)
     return components + to_realize
+
+
+def _load_snapshot_for_utility(path, param, extra):
+    """Parameters for a utility run on a snapshot: the parameter file if one is given, else what the snapshot's header says
+    about the box and the cosmology (the reference compares the two and warns, utilities.py:470-477)."""
+    from . import snapshot
+    if param:
+        commons.load_params(param, extra)
+    else:
+        head = snapshot.read_gadget(path)
+        commons.load_params(f"boxsize = {head['boxsize']!r}\nH0 = {head['H0']!r}\nΩb = 0.049\nΩcdm = {head['Ωm'] - 0.049!r}\n"
+                            f"a_begin = {head['a']!r}\n", extra)
+    init_time()
+    component = snapshot.load(path)
+    universals.a = float(universals.a)
+    universals.t = cosmic_time(universals.a) if commons.params.enable_Hubble else universals.t
+    return component
+
+
+def utility_info(path):
+    """`concept -u info` (utilities.py, info): what a snapshot holds, one line per fact"""
+    from . import snapshot
+    d = snapshot.read_gadget(path)
+    u = commons.units
+    lines = [f'GADGET snapshot "{path}"',
+             f'  particles        {len(d["pos"])} (type {d["type"]})',
+             f'  particle mass    {d["mass"]:.8g} {commons.unit_mass}',
+             f'  a                {d["a"]:.8g}    (z = {1/d["a"] - 1:.6g})',
+             f'  boxsize          {d["boxsize"]:.8g} {commons.unit_length}',
+             f'  H0               {d["H0"]/(u.km/(u.s*u.Mpc)):.8g} km s⁻¹ Mpc⁻¹',
+             f'  Ωm               {d["Ωm"]:.8g}',
+             f'  files            {d["header"]["NumFiles"]}']
+    if commons.communication_master():
+        print('\n'.join(lines))
+    return d
+
+
+def utility_powerspec(path, param='', extra=''):
+    """`concept -u powerspec snapshot` (utilities.py:465-497): the power spectrum of a snapshot, written next to it as
+    `powerspec_<snapshot name>` (output_bases['powerspec'] + '_' + name)."""
+    component = _load_snapshot_for_utility(path, param, extra)
+    out_dir, basename = os.path.split(os.path.abspath(path.rstrip('/')))
+    bases = commons.user_params.get('output_bases', {})
+    base = bases.get('powerspec', 'powerspec') if isinstance(bases, dict) else 'powerspec'
+    filename = os.path.join(out_dir, f'{base}_{basename}' if base else basename)
+    if filename == os.path.abspath(path):
+        filename = os.path.join(out_dir, f'powerspec_{basename}')
+    dump_powerspec([component], DumpTime(a=universals.a), filename=filename)
+    return filename
 
 
 def run(param, extra='', on_dump=None, on_step=None, max_steps=None):

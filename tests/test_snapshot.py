@@ -125,6 +125,41 @@ def test_reader_of_snapformat_1(tmp_path):
         snapshot.read_gadget(str(tmp_path/'junk'))
 
 
+def test_cli_utilities_info_and_powerspec(monkeypatch, tmp_path, capsys, host_kernels):
+    """`python -m concept_b200 -u info SNAPSHOT` and `-u powerspec SNAPSHOT` (the reference's util/info, util/powerspec;
+    utilities.py:465-497): box and cosmology come from the snapshot when no parameter file is given, the spectrum is written
+    next to the snapshot as powerspec_<name> and equals analysis.powerspec of the loaded component (kernels replaced by
+    their numpy model)."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from concept_b200 import __main__ as cli, analysis, commons, mesh, snapshot
+    from concept_b200.species import Component
+    import ic_mock_context
+    monkeypatch.setattr(ic_mock_context.MeshMockContext, 'lib', host_kernels)
+    contexts = {}
+    monkeypatch.setattr(mesh, 'get_context', lambda gridsize, dtype=None: contexts.setdefault(
+        int(gridsize), ic_mock_context.MeshMockContext(gridsize, commons.params.boxsize)))
+    monkeypatch.setattr(mesh, 'free_contexts', lambda: contexts.clear())
+    monkeypatch.setattr(Component, 'device', property(lambda self: torch.device('cpu')))
+    commons.load_params('boxsize = 40*Mpc\nH0 = 70*km/(s*Mpc)\nΩb = 0.049\nΩcdm = 0.251\n')
+    p = commons.params
+    rng = np.random.default_rng(6)
+    pos, mom = rng.random((8**3, 3))*p.boxsize, rng.standard_normal((8**3, 3))
+    path = str(tmp_path/'snapshot_a=0.50')
+    snapshot.write_gadget(path, pos, mom, mass=3.0, a=0.5, boxsize=p.boxsize, H0=p.H0, Ωm=p.Ωm, bits_pos=64, bits_vel=64)
+    assert cli.cli(['-u', 'info', path]) == 0
+    out = capsys.readouterr().out
+    assert 'particles        512' in out and 'a                0.5 ' in out and 'boxsize          40 Mpc' in out
+    assert cli.cli(['-u', 'powerspec', path]) == 0
+    table = np.loadtxt(str(tmp_path/'powerspec_snapshot_a=0.50'))
+    assert commons.universals.a == 0.5 and commons.params.boxsize == pytest.approx(40.0, rel=1e-12)
+    c = snapshot.load(path)
+    k, power, n_modes = analysis.powerspec([c], 16, gridsizes_upstream=[16])
+    assert table.shape == (len(k), 4) and np.allclose(table[:, 0], k, rtol=1e-7) and np.allclose(table[:, 2], power, rtol=1e-7)
+    assert np.array_equal(table[:, 1], n_modes)
+
+
 @pytest.mark.gpu
 def test_component_save_load_round_trip(tmp_path):
     """snapshot.save / snapshot.load through a GPU-resident Component."""
