@@ -469,7 +469,7 @@ def run_pm_config(D, cfg, steps, warmup, lib, ctx=None, pos=None, mom=None, want
         fw['achieved_GBps_incl_zeroing'] = (alg['fft2d_forward'] + alg['grid_zero'])/(fw['ms']*1e-3)/1e9
         fw['frac_incl_zeroing'] = fw['achieved_GBps_incl_zeroing']/peak
         kernels['grid_zero'].update(achieved_GBps=None, frac=None, note='the grid is already nullified (self-cleaning forward transform)')
-    if D.world > 1 and staged:
+    if D.world > 1 and staged and kernels['xsolve']['ms'] > 0:
         # several ranks: the x solve is bound by NVLink, not HBM.  Per rank and direction: its own remote loads plus the peers'
         # stores into it, 2·(P−1)/P of a rank's half-spectrum; reference 770 GB/s per direction (measured peer copy,
         # B200_PROFILING.md; 900 nominal).  The stage time includes the two device barriers and the local B -> A re-layout.
